@@ -1,0 +1,153 @@
+"""
+Per-source and per-z-slice operands of the batched log-posterior kernel.
+
+The reference hands `ln_probab` a DATA object per source (DATA_AGNfitter.py:357-369:
+nus, fluxes, fluxerrs, z, dlum, lumfactor) and a parameter table P from
+PARAMETERSPACE_AGNfitter.Pdict (PARAMETERSPACE:31-102).  Here a whole catalogue becomes
+struct-of-arrays blocks, with every walker-independent quantity evaluated once on the host
+by agnfitter_b200.hostmath (reference arithmetic, reference operation order).
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import hostmath
+from .flatten import ModelSet
+
+# consts block layout, per source (float64)
+C_INV4PIDL2 = 0     # 1 / (4 pi dlum^2)                       PARAMETERSPACE:232, PRIORS:178
+C_NCONST = 4
+
+
+@dataclass
+class ZSlices:
+    cgal: np.ndarray      # [n_z, n_b]  -0.4 * k_Calzetti(band centre, rest frame)
+    cbbb: np.ndarray      # [n_z, n_b]  -0.4 * k_Prevot(band centre, rest frame)
+    xray: np.ndarray      # [n_z] uint64 bit b set: bands_b + log10(1+z) >= 16.685   DICTIONARIES:254-256
+    j1500: np.ndarray     # [n_z] int32 band read by prior_AGNfraction                PRIORS:166-167
+    omega: np.ndarray     # [n_z, n_b] trapezoid weights over observed band nu        PRIORS:89-91
+
+
+def make_zslices(ms: ModelSet) -> ZSlices:
+    n_z, n_b = ms.n_z, ms.n_b
+    if n_b > 64:
+        raise ValueError("at most 64 bands are supported (validity masks are 64-bit)")
+    cgal = np.zeros((n_z, n_b))
+    cbbb = np.zeros((n_z, n_b))
+    xray = np.zeros(n_z, dtype=np.uint64)
+    j1500 = np.zeros(n_z, dtype=np.int32)
+    omega = np.zeros((n_z, n_b))
+    for i, z in enumerate(ms.z_grid):
+        rest = ms.bands + np.log10((1 + z))
+        cbbb[i] = -0.4 * hostmath.prevot_k(rest)
+        cgal[i] = -0.4 * hostmath.calzetti_k(10 ** rest)
+        bits = 0
+        for b in np.nonzero(rest >= 16.685)[0]:
+            bits |= (1 << int(b))
+        xray[i] = np.uint64(bits)
+        j1500[i] = hostmath.band_1500(ms.bands, z)
+        omega[i] = hostmath.trapz_weights((10 ** rest) / (1 + z))
+    return ZSlices(cgal=cgal, cbbb=cbbb, xray=xray, j1500=j1500, omega=omega)
+
+
+def pdict_bounds(ms: ModelSet, z):
+    """P['min'], P['max'] for one source (PARAMETERSPACE:42-100)."""
+    mins, maxs = [], []
+    for f in ms.families:
+        if not f.fitted:
+            continue
+        for d in range(f.n_dim):
+            mins.append(float(np.min(f.keys_float[d])))
+            maxs.append(float(np.max(f.keys_float[d])))
+    agn_on = ms.settings['turn_on_AGN'] == True
+    mins += [-10., -10., -10.]
+    maxs += [10., 10., 10. if agn_on else -9.8]
+    if ms.bbb_has_norm:
+        mins.append(-10.)
+        maxs.append(10. if agn_on else -9.8)
+    if ms.radio:
+        mins.append(-10.)
+        maxs.append(10. if agn_on else -9.8)
+    agemax = None
+    for i, nm in enumerate(ms.par_names):
+        if nm in ('age', 'tau'):
+            if agemax is None:
+                agemax = float(np.log10(hostmath.maximal_age(z)))
+            maxs[i] = agemax
+        if nm == 'Tdust':
+            maxs[i] = 42.
+        if nm == 'EBVgal':
+            mins[i] = 0.05
+    return np.array(mins, dtype=np.float64), np.array(maxs, dtype=np.float64)
+
+
+@dataclass
+class SourceSet:
+    zi: np.ndarray          # [S] int32 z-slice of each source
+    y: np.ndarray           # [S, n_b] fluxes
+    isig: np.ndarray        # [S, n_b] 1/fluxerr
+    mask: np.ndarray        # [S] uint64 likelihood validity bits
+    pmin: np.ndarray        # [S, n_par]
+    pmax: np.ndarray        # [S, n_par]
+    consts: np.ndarray      # [S, C_NCONST]
+    agn_branch: np.ndarray  # [S] int32   0 faint / 1 bright                 PRIORS:182
+    irsyn_mode: np.ndarray  # [S] int32   0 off, +1, -1                        PRIORS:244-252
+    irsyn_j: np.ndarray     # [S] int32
+
+    @property
+    def S(self):
+        return len(self.zi)
+
+
+def make_sources(ms: ModelSet, z, dlum, nus, fluxes, fluxerrs, bounds_cache=None) -> SourceSet:
+    """z,dlum: [S]; nus/fluxes/fluxerrs: [S, n_b] (sorted by nu as DATA_all.PROPS leaves them).
+    Every source's z must be present in ms.z_grid (exact float match)."""
+    z = np.atleast_1d(np.asarray(z, dtype=np.float64))
+    dlum = np.atleast_1d(np.asarray(dlum, dtype=np.float64))
+    nus = np.atleast_2d(np.asarray(nus, dtype=np.float64))
+    fluxes = np.atleast_2d(np.asarray(fluxes, dtype=np.float64))
+    fluxerrs = np.atleast_2d(np.asarray(fluxerrs, dtype=np.float64))
+    S, n_b = fluxes.shape
+    if n_b != ms.n_b:
+        raise ValueError("catalogue has %d bands, dictionary has %d" % (n_b, ms.n_b))
+    zpos = {float(v): i for i, v in enumerate(ms.z_grid)}
+    try:
+        zi = np.array([zpos[float(v)] for v in z], dtype=np.int32)
+    except KeyError as e:
+        raise ValueError("source redshift %s has no dictionary z-slice" % e)
+
+    with np.errstate(divide="ignore"):
+        isig = 1.0 / fluxerrs
+    mask = np.zeros(S, dtype=np.uint64)
+    n_par = ms.n_par
+    pmin = np.empty((S, n_par))
+    pmax = np.empty((S, n_par))
+    consts = np.zeros((S, C_NCONST))
+    agn_branch = np.zeros(S, dtype=np.int32)
+    irsyn_mode = np.zeros(S, dtype=np.int32)
+    irsyn_j = np.zeros(S, dtype=np.int32)
+    want_agn = ms.settings.get('PRIOR_AGNfraction') == True
+    xr = ms.settings['XRAYS']
+    cache = {} if bounds_cache is None else bounds_cache
+    for s in range(S):
+        v = hostmath.likelihood_mask(nus[s], fluxes[s], z[s], xr)
+        bits = 0
+        for b in np.nonzero(v)[0]:
+            bits |= (1 << int(b))
+        mask[s] = np.uint64(bits)
+        zk = float(z[s])
+        if zk not in cache:
+            cache[zk] = pdict_bounds(ms, zk)
+        pmin[s], pmax[s] = cache[zk]
+        consts[s, C_INV4PIDL2] = 1.0 / (4 * np.pi * dlum[s] ** 2)
+        if want_agn:
+            agn_branch[s] = hostmath.agnfrac_branch(nus[s], fluxes[s], z[s], hostmath.lumfactor(dlum[s]))
+        if ms.radio:
+            mode, j = hostmath.irsyn_constants(nus[s], fluxes[s], ms.bands, z[s])
+            if mode == 2:
+                raise ValueError("source %d: F_IR/F_syn == 2 exactly leaves prior_IR_SYNfraction "
+                                 "undefined in the reference (PRIORS_AGNfitter.py:244-254)" % s)
+            irsyn_mode[s], irsyn_j[s] = mode, j
+    return SourceSet(zi=zi, y=np.ascontiguousarray(fluxes), isig=np.ascontiguousarray(isig), mask=mask,
+                     pmin=pmin, pmax=pmax, consts=consts, agn_branch=agn_branch,
+                     irsyn_mode=irsyn_mode, irsyn_j=irsyn_j)

@@ -1,0 +1,308 @@
+"""
+TEST INFRASTRUCTURE.  Generates tests/golden/*.npz by running the UNMODIFIED reference
+functions (through oracle/ref_shim.py + oracle/ref_harness.py) on the real template and
+filter files under /root/reference.  Run in the build container only:
+
+    python -m oracle.make_golden            # writes tests/golden/k1_*.npz, k2_*.npz
+
+Each K1 file holds: the flattened ModelSet (agnfitter_b200.flatten arrays), the raw
+per-source rows (nus, fluxes, fluxerrs, z, dlum), the reference's P['min']/P['max'],
+walker positions, and the reference's outputs for them:
+    ref_lnp       PARAMETERSPACE.ln_probab
+    ref_ymodel    PARAMETERSPACE.ymodel
+    ref_rows      row index (key insertion order) of the keys pick_nD matched, per family
+    ref_lnprior   PARAMETERSPACE.ln_prior
+    ref_lnlike    PARAMETERSPACE.ln_likelihood
+    ref_mask      the x_valid index set of ln_likelihood as a bool vector
+Each K2 file holds templates (log nu, Fnu), filter curves, z values and the reference's
+DICTIONARIES.filtering_models band fluxes.
+
+Substitution stated everywhere: the galaxy libraries named by the example
+settings are absent from the mount; models/GALAXY/BC03_275seds.pickle is used through the
+'BC03' code path (grid E(B-V)) and through the free-E(B-V) variant of the same loader.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+from . import ref_shim, loaders, ref_harness as H
+from agnfitter_b200 import flatten, sources
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+warnings.filterwarnings("ignore")
+
+
+def walker_positions(rng, ms, pmin, pmax, n_uniform, n_ball, n_out, n_edge):
+    """Mixture used by every golden/parity test: uniform in the box, emcee-like
+    ball around mid-box (PARAMETERSPACE:263), out-of-box rows, and snapping edge cases
+    (exact grid values, midpoints between neighbouring grid values, exact bounds)."""
+    n_par = len(pmin)
+    blocks = [rng.uniform(pmin, pmax, size=(n_uniform, n_par))]
+    mid = 0.5 * (pmin + pmax)
+    blocks.append(mid + (2 * rng.uniform(size=(n_ball, n_par)) - 1) * 0.00001)
+    out = rng.uniform(pmin, pmax, size=(n_out, n_par))
+    for r in range(n_out):
+        j = rng.integers(n_par)
+        out[r, j] = pmax[j] + rng.uniform(1e-9, 3.0) if rng.uniform() < 0.5 else pmin[j] - rng.uniform(1e-9, 3.0)
+    blocks.append(out)
+    edge = rng.uniform(pmin, pmax, size=(n_edge, n_par))
+    col = 0
+    for f in ms.families:
+        if not f.fitted:
+            continue
+        for d in range(f.n_dim):
+            if f.par_types[d] == 'grid':
+                g = np.sort(f.grid[d])
+                for r in range(n_edge):
+                    kind = rng.integers(4)
+                    i = rng.integers(len(g))
+                    if kind == 0:
+                        edge[r, col] = g[i]
+                    elif kind == 1 and len(g) > 1:
+                        i = min(i, len(g) - 2)
+                        edge[r, col] = (g[i] + g[i + 1]) / 2
+                    elif kind == 2 and len(g) > 1:
+                        i = min(i, len(g) - 2)
+                        edge[r, col] = g[i] / 2 + g[i + 1] / 2
+                    else:
+                        edge[r, col] = pmin[col] if rng.uniform() < 0.5 else pmax[col]
+            col += 1
+    blocks.append(edge)
+    return np.concatenate(blocks, axis=0)
+
+
+def rows_from_keys(ms, keys):
+    out = np.zeros((len(keys), len(ms.families)), dtype=np.int32)
+    for fi, f in enumerate(ms.families):
+        pos = {k: t for t, k in enumerate(f.keys)}
+        for r, k in enumerate(keys):
+            kk = k[fi]
+            out[r, fi] = pos[tuple(kk) if isinstance(kk, tuple) else kk]
+    return out
+
+
+def synth_fluxes(rng, mods, models, data_nus, z, dlum, P, frac_ul=0.1, frac_missing=0.05):
+    """y = ymodel(truth)*(1+0.1 N), sigma = 0.1|y|; some bands -> upper limit / missing.
+    Returned in catalogue units of mJy so that the DATA transformation applies."""
+    truth = rng.uniform(P['min'], P['max'])
+    # keep the truth physically tame so that fluxes are finite and positive
+    y, _ = mods["PAR"].ymodel(data_nus, z, dlum, models, P, *tuple(truth))
+    y = np.abs(y) * (1 + 0.1 * rng.normal(size=len(y)))
+    y = np.abs(y) / 1e-26
+    err = 0.1 * np.abs(y)
+    u = rng.uniform(size=len(y))
+    err[u < frac_ul] = -99.
+    # bands the truth model does not reach (flux 0 or denormal-small) carry no datum
+    miss = ((u >= frac_ul) & (u < frac_ul + frac_missing)) | ~(y > 1e-12)
+    y[miss] = -99.
+    err[miss] = -99.
+    return y, err
+
+
+def run_case(name, settings, filterset, zs, catalog=None, galaxy_ebv="grid", galaxy_kw=None,
+             starburst_kw=None, n_pos=(400, 60, 40, 100), seed=1, nRADdata=None, nXRaysdata=None,
+             force_uv_detection=True):
+    mods = ref_shim.install()
+    rng = np.random.default_rng(seed)
+    allf = loaders.load_all_filters()
+    fd, fnames = loaders.make_filterdict(filterset, allf)
+    data_nus = loaders.data_nus_for(filterset)
+    n_b = len(fd[0])
+
+    if catalog is not None:
+        cat_names, cat_z, cat_fl, cat_fe = catalog
+        zs = list(cat_z)
+    S = len(zs)
+    dl = [float(loaders.z2Dlum(z)) for z in zs]
+
+    # raw catalogue rows -> DATA arrays
+    if catalog is not None:
+        # catalogue columns are in the filters' column order (SETTINGS:106-154 -> index 0 = GALEX_1500 ...);
+        # central wavelengths come from ALL_FILTERS_info.dat and are then sorted (DATA:89-96,180-183)
+        info_names = np.loadtxt(os.path.join(ref_shim.REF_ROOT, "models/FILTERS/ALL_FILTERS_info.dat"),
+                                delimiter="|", usecols=[1], skiprows=1, dtype=str)
+        info_nu = np.loadtxt(os.path.join(ref_shim.REF_ROOT, "models/FILTERS/ALL_FILTERS_info.dat"),
+                             delimiter="|", usecols=[3], skiprows=1)
+        col_order = list(reversed(loaders.FILTERSET_EXAMPLE49))   # column 0 = GALEX_1500
+        nus0 = np.array([info_nu[list(info_names).index(nm)] for nm in col_order])
+        rows = loaders.catalog_rows(cat_fl, cat_fe, nus0, np.array(zs), flux_unit_cgs=1e-26)
+    else:
+        rows = None
+
+    MDs, models_l, P_l, data_l = [], [], [], []
+    for s, z in enumerate(zs):
+        if rows is not None:
+            nR = int(rows["nRADdata"][s]) if nRADdata is None else nRADdata
+            nX = int(rows["nXRaysdata"][s]) if nXRaysdata is None else nXRaysdata
+        else:
+            nR = 0 if nRADdata is None else nRADdata
+            nX = 0 if nXRaysdata is None else nXRaysdata
+        MD = H.build_reference_dictionary(z, fd, settings, nRADdata=nR, nXRaysdata=nX,
+                                          galaxy_ebv=galaxy_ebv, galaxy_kw=galaxy_kw, starburst_kw=starburst_kw)
+        MDs.append(MD)
+        models_l.append(H.make_models(MD, settings))
+    # all sources of one case must share key structure (same nRAD/nXR class)
+    ms = flatten.modelset_from_modelsdicts(MDs, settings)
+
+    src_nus = np.empty((S, n_b))
+    src_fl = np.empty((S, n_b))
+    src_fe = np.empty((S, n_b))
+    for s, z in enumerate(zs):
+        if rows is not None:
+            src_nus[s], src_fl[s], src_fe[s] = rows["nus"][s], rows["fluxes"][s], rows["fluxerrs"][s]
+        else:
+            d0 = H.make_data(z, data_nus, np.ones(n_b), np.ones(n_b), dlum=dl[s])
+            P0 = mods["PAR"].Pdict(d0, models_l[s])
+            y, err = synth_fluxes(rng, mods, models_l[s], data_nus, z, dl[s], P0)
+            if force_uv_detection:
+                # prior_AGNfraction needs one positive flux with 14.3 < nu_rest < 15.3 (PRIORS:163-164)
+                r = data_nus + np.log10(1 + z)
+                win = np.nonzero((14.3 < r) & (r < 15.3))[0]
+                if len(win) and not np.any((y[win] > 0)):
+                    y[win[-1]] = abs(rng.normal(1.0, 0.1)) * 1e-3
+                    err[win[-1]] = 0.1 * y[win[-1]]
+            rr = loaders.catalog_rows(y[None, :], err[None, :], data_nus, np.array([z]), flux_unit_cgs=1e-26)
+            src_nus[s], src_fl[s], src_fe[s] = rr["nus"][0], rr["fluxes"][0], rr["fluxerrs"][0]
+        data_l.append(H.make_data(z, src_nus[s], src_fl[s], src_fe[s], dlum=dl[s]))
+        P_l.append(mods["PAR"].Pdict(data_l[s], models_l[s]))
+
+    n_par = len(P_l[0]['names'])
+    assert P_l[0]['names'] == ms.par_names, (P_l[0]['names'], ms.par_names)
+    pars_all, sid_all = [], []
+    ref = dict(lnp=[], ym=[], rows=[], lnprior=[], lnlike=[])
+    pmin = np.array([P['min'] for P in P_l], dtype=np.float64)
+    pmax = np.array([P['max'] for P in P_l], dtype=np.float64)
+    ref_mask = np.zeros((S, n_b), dtype=bool)
+    for s in range(S):
+        pars = walker_positions(rng, ms, pmin[s], pmax[s], *n_pos)
+        lnp, ym, keys, lpr, lll = H.reference_eval(pars, data_l[s], models_l[s], P_l[s])
+        pars_all.append(pars)
+        sid_all.append(np.full(len(pars), s, dtype=np.int32))
+        ref["lnp"].append(lnp)
+        ref["ym"].append(ym)
+        ref["rows"].append(rows_from_keys(ms, keys))
+        ref["lnprior"].append(lpr)
+        ref["lnlike"].append(lll)
+        # x_valid exactly as the reference evaluates it (PARAMETERSPACE:144-147)
+        x, y, z = data_l[s].nus, data_l[s].fluxes, data_l[s].z
+        if settings['XRAYS'] == 'Prior':
+            sel = (x < np.log10(10 ** (15.38) / (1 + z))) & (y > -99.e-23)
+        else:
+            sel = (x < np.log10(10 ** (15.38) / (1 + z))) | (x > np.log10(10 ** (16.685) / (1 + z))) & (y > -99.e-23)
+        ref_mask[s] = sel
+
+    arrs = flatten.modelset_to_arrays(ms, prefix="ms_")
+    arrs.update(dict(
+        src_z=np.array(zs, dtype=np.float64), src_dlum=np.array(dl), src_nus=src_nus, src_fluxes=src_fl,
+        src_fluxerrs=src_fe, ref_pmin=pmin, ref_pmax=pmax,
+        pars=np.concatenate(pars_all), source_id=np.concatenate(sid_all),
+        ref_lnp=np.concatenate(ref["lnp"]), ref_ymodel=np.concatenate(ref["ym"]),
+        ref_rows=np.concatenate(ref["rows"]), ref_lnprior=np.concatenate(ref["lnprior"]),
+        ref_lnlike=np.concatenate(ref["lnlike"]), ref_mask=ref_mask,
+        filter_names=np.array(fnames),
+    ))
+    path = os.path.join(OUT, "k1_%s.npz" % name)
+    np.savez_compressed(path, **arrs)
+    fin = np.isfinite(np.concatenate(ref["lnp"]))
+    print("%-22s S=%d n_b=%d n_par=%d rows=%d finite=%d  T=%s  -> %.2f MB" % (
+        name, S, n_b, n_par, len(arrs["pars"]), fin.sum(), [f.T for f in ms.families],
+        os.path.getsize(path) / 1e6))
+    return ms
+
+
+def k2_case(name, filterset, zs, seed=3):
+    """Reference filtering_models on a sample of every loadable family."""
+    mods = ref_shim.install()
+    MOD, DIC = mods["MOD"], mods["DIC"]
+    rng = np.random.default_rng(seed)
+    root = ref_shim.REF_ROOT + "/"
+    allf = loaders.load_all_filters()
+    fd, fnames = loaders.make_filterdict(filterset, allf)
+    bands = fd[0]
+    S = dict(H.DEFAULT_SETTINGS)
+    fams = {}
+    g4, *_ = loaders.galaxy_BC03(root, reddening_fn=MOD.GALAXYfunctions()[0],
+                                 age_slice=[0, 7, 13, 19, 24], tau_slice=[0, 5, 10])
+    fams["GA"] = [g4[k] for k in list(g4.keys())[::15]]
+    s4, *_ = MOD.STARBURST(root, S)
+    fams["SB_DH02"] = [s4[k] for k in list(s4.keys())[::9]]
+    s17, *_ = loaders.starburst_S17(root, tdust_slice=[0, 70, 149], fracpah_slice=[0, 30, 63])
+    fams["SB_S17"] = list(s17.values())
+    t4, *_ = MOD.TORUS(root, S)
+    fams["TO_S04"] = [t4[k] for k in list(t4.keys())[::6]]
+    b4, *_ = MOD.BBB(root, S, 0)
+    fams["BB_R06"] = [b4['0.0']]
+    Sx = dict(S, XRAYS=True)
+    bx, *_ = MOD.BBB(root, Sx, 2)
+    fams["BB_R06X"] = [bx[k] for k in list(bx.keys())[::20]]
+    Sr = dict(S, RADIO=True)
+    r4, *_ = MOD.AGN_RAD(root, Sr, 4)
+    fams["RAD4"] = [r4[k] for k in list(r4.keys())[::400]]
+    arrs = dict(bands=bands, z=np.array(zs, dtype=np.float64), filter_names=np.array(fnames),
+                family_names=np.array(list(fams.keys())))
+    lam_all = np.concatenate([np.asarray(fd[1][b][0]) for b in bands])
+    fac_all = np.concatenate([np.asarray(fd[2][b][0]) for b in bands])
+    off = np.cumsum([0] + [len(fd[1][b][0]) for b in bands])
+    arrs.update(filt_lambda=lam_all, filt_factor=fac_all, filt_offset=off.astype(np.int64))
+    n_entries = 0
+    for fname, tpl in fams.items():
+        nmax = max(len(t[0]) for t in tpl)
+        lognu = np.full((len(tpl), nmax), np.nan)
+        Fnu = np.full((len(tpl), nmax), np.nan)
+        nlen = np.zeros(len(tpl), dtype=np.int64)
+        out = np.empty((len(zs), len(tpl), len(bands)))
+        for i, (nu, F) in enumerate(tpl):
+            nu = np.asarray(nu, dtype=np.float64)
+            F = np.asarray(F, dtype=np.float64).reshape(-1)
+            nlen[i] = len(nu)
+            lognu[i, :len(nu)] = nu
+            Fnu[i, :len(nu)] = F
+            for zi, z in enumerate(zs):
+                _, f = DIC.filtering_models(nu, F, fd, z)
+                out[zi, i] = np.asarray(f).flatten()
+        arrs["%s_lognu" % fname] = lognu
+        arrs["%s_Fnu" % fname] = Fnu
+        arrs["%s_len" % fname] = nlen
+        arrs["%s_ref" % fname] = out
+        n_entries += out.size
+    path = os.path.join(OUT, "k2_%s.npz" % name)
+    np.savez_compressed(path, **arrs)
+    print("%-22s bands=%d z=%d entries=%d -> %.2f MB" % (name, len(bands), len(zs), n_entries,
+                                                        os.path.getsize(path) / 1e6))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    base = dict(H.DEFAULT_SETTINGS)
+    # A: the classic 10-parameter model set, default 18 bands, the two z of BASELINE configs[0]
+    run_case("classic18", base, loaders.FILTERSET_DEFAULT, [0.283, 1.58], n_pos=(900, 100, 60, 240), seed=11)
+    # B: example / brown2018 catalogues (49 bands), S17 starburst subset, galaxy subset
+    gk = dict(age_slice=[0, 6, 12, 18, 24], tau_slice=[0, 5, 10])
+    sk = dict(tdust_slice=range(0, 150, 15), fracpah_slice=range(0, 64, 8))
+    for cname in ("catalog_example", "brown2018_test"):
+        cat = loaders.read_ascii_catalog(os.path.join(ref_shim.REF_ROOT, "data", cname + ".txt"))
+        run_case("cat49_" + cname, dict(base, STARBURST='S17', TORUS='NK0'), loaders.FILTERSET_EXAMPLE49, None,
+                 catalog=cat, galaxy_kw=gk, starburst_kw=sk, n_pos=(300, 40, 30, 80), seed=12,
+                 nRADdata=0, nXRaysdata=0)
+    # C: free E(B-V)_gal + Restrictive energy balance + X-ray extended R06 (EBVbbb, alphaScat free)
+    run_case("freeebv_xray49", dict(base, STARBURST='S17', XRAYS=True, PRIOR_energy_balance='Restrictive'),
+             loaders.FILTERSET_EXAMPLE49, [0.129, 2.2], galaxy_ebv="free", galaxy_kw=gk, starburst_kw=sk,
+             n_pos=(400, 50, 30, 80), seed=13, nXRaysdata=1)
+    run_case("xray_gamma49", dict(base, XRAYS=True, PRIOR_energy_balance='None', turn_on_AGN=True),
+             loaders.FILTERSET_EXAMPLE49, [0.031024], galaxy_kw=gk, n_pos=(300, 40, 30, 80), seed=14, nXRaysdata=3)
+    # D: five components with radio (SN12 disk: no BB norm, /4 pi dlum^2 path) + IR/synchrotron prior
+    for nrad in (1, 2, 4):
+        run_case("radio%d_sn12_49" % nrad, dict(base, RADIO=True, BBB='SN12'), loaders.FILTERSET_EXAMPLE49,
+                 [0.129], galaxy_kw=gk, n_pos=(300, 40, 30, 80), seed=15 + nrad, nRADdata=nrad)
+    # AGN switched off (norm caps at -9.8), no AGN-fraction prior
+    run_case("agnoff18", dict(base, turn_on_AGN=False, PRIOR_AGNfraction=False), loaders.FILTERSET_DEFAULT,
+             [3.005], galaxy_kw=gk, n_pos=(300, 40, 30, 80), seed=21)
+    # K2
+    k2_case("default18", loaders.FILTERSET_DEFAULT, [0.0, 0.283, 1.58, 5.999])
+    k2_case("example49", loaders.FILTERSET_EXAMPLE49, [0.031024, 0.129, 2.2])
+
+
+if __name__ == "__main__":
+    main()

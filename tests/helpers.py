@@ -1,0 +1,50 @@
+"""Shared helpers for the parity tests (tests/ only)."""
+import os
+
+import numpy as np
+
+from agnfitter_b200 import flatten
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# north_star tolerance: ln-probability and band fluxes within 1e-10 relative in fp64
+RTOL = 1e-10
+
+
+def load_k1(name):
+    with np.load(os.path.join(GOLDEN, "k1_%s.npz" % name), allow_pickle=False) as z:
+        g = {k: z[k] for k in z.files}
+    ms = flatten.modelset_from_arrays(g, prefix="ms_")
+    return ms, g
+
+
+def load_k2(name):
+    with np.load(os.path.join(GOLDEN, "k2_%s.npz" % name), allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+def assert_close_with_specials(got, want, rtol=RTOL, what=""):
+    """Equal up to rtol where finite; identical placement of -inf/+inf/NaN."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    nan_w, nan_g = np.isnan(want), np.isnan(got)
+    assert np.array_equal(nan_w, nan_g), "%s: NaN placement differs at %s" % (what, np.nonzero(nan_w != nan_g)[0][:10])
+    inf_w = np.isinf(want)
+    assert np.array_equal(inf_w, np.isinf(got)), "%s: inf placement differs at %s" % (
+        what, np.nonzero(inf_w != np.isinf(got))[0][:10])
+    assert np.array_equal(np.sign(want[inf_w]), np.sign(got[inf_w])), "%s: inf sign differs" % what
+    fin = ~(nan_w | inf_w)
+    denom = np.maximum(np.abs(want[fin]), np.finfo(np.float64).tiny)
+    rel = np.abs(got[fin] - want[fin]) / denom
+    rel[want[fin] == got[fin]] = 0.0
+    worst = rel.max() if rel.size else 0.0
+    assert worst <= rtol, "%s: max relative error %.3e > %.1e (at %s)" % (what, worst, rtol, np.argmax(rel))
+    return worst
+
+
+def oracle_src(ms, g, s):
+    zpos = {float(v): i for i, v in enumerate(ms.z_grid)}
+    return dict(z=float(g["src_z"][s]), dlum=float(g["src_dlum"][s]), nus=g["src_nus"][s],
+                fluxes=g["src_fluxes"][s], fluxerrs=g["src_fluxerrs"][s],
+                pmin=g["ref_pmin"][s], pmax=g["ref_pmax"][s], zi=zpos[float(g["src_z"][s])])

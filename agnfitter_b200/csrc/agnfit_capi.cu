@@ -1,0 +1,566 @@
+// C ABI of libagnfit_b200.so (declared in include/agnfit_b200.h).  Owns the device-side copies of
+// the dictionary / per-source operands and launches K1 and K2.  No torch types anywhere.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/agnfit_b200.h"
+#include "k1_lnprob.cuh"
+#include "k2_dictbuild.cuh"
+
+using namespace agnf;
+
+struct agnf_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // bracket the last K1 kernel
+  cudaEvent_t ev2 = nullptr, ev3 = nullptr;     // bracket the last K2 contraction
+  bool k1_timed = false, k2_timed = false;
+  std::string err;
+  std::vector<void*> owned;                    // device allocations freed in destroy
+  int64_t launches = 0;
+
+  bool have_cfg = false;
+  K1Params k1{};
+  bool fam_set[AGNF_MAX_FAMILIES] = {false, false, false, false, false};
+  std::vector<double> h_grid;                  // staged grid values (host mirror, rebuilt per upload)
+  std::vector<int32_t> h_perm;
+  std::vector<int32_t> fam_grid_len = std::vector<int32_t>(AGNF_MAX_FAMILIES, 0);
+  std::vector<std::vector<double>> fam_grid = std::vector<std::vector<double>>(AGNF_MAX_FAMILIES);
+  std::vector<std::vector<int32_t>> fam_perm = std::vector<std::vector<int32_t>>(AGNF_MAX_FAMILIES);
+  bool grids_dirty = true;
+  void* d_grid = nullptr;
+  void* d_perm = nullptr;
+  bool have_z = false, have_src = false;
+
+  // host-variant staging
+  void* st_params = nullptr; size_t st_params_cap = 0;
+  void* st_sid = nullptr;    size_t st_sid_cap = 0;
+  void* st_out = nullptr;    size_t st_out_cap = 0;
+
+  // K2
+  K2Filters filt{};
+  bool have_filt = false;
+};
+
+static thread_local std::string g_create_err;
+
+namespace {
+
+int fail(agnf_ctx* ctx, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_err = buf;
+  return 1;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(ctx, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+int dev_alloc(agnf_ctx* ctx, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 8;
+  CUDA_TRY(ctx, cudaMalloc(p, bytes));
+  ctx->owned.push_back(*p);
+  return 0;
+}
+
+void dev_free(agnf_ctx* ctx, void* p) {
+  if (!p) return;
+  auto it = std::find(ctx->owned.begin(), ctx->owned.end(), p);
+  if (it != ctx->owned.end()) ctx->owned.erase(it);
+  cudaFree(p);
+}
+
+template <typename T>
+int upload(agnf_ctx* ctx, const T** dst, const T* src, size_t count) {
+  if (*dst) dev_free(ctx, const_cast<T*>(*dst));
+  void* p = nullptr;
+  if (dev_alloc(ctx, &p, count * sizeof(T))) return 1;
+  if (count) CUDA_TRY(ctx, cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *dst = static_cast<const T*>(p);
+  return 0;
+}
+
+int ensure(agnf_ctx* ctx, void** p, size_t* cap, size_t bytes) {
+  if (*cap >= bytes) return 0;
+  if (*p) dev_free(ctx, *p);
+  *cap = 0;
+  if (dev_alloc(ctx, p, bytes)) return 1;
+  *cap = bytes;
+  return 0;
+}
+
+int rebuild_grids(agnf_ctx* ctx) {
+  if (!ctx->grids_dirty) return 0;
+  ctx->h_grid.clear();
+  ctx->h_perm.clear();
+  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
+    if (!ctx->fam_set[f]) continue;
+    int off = (int)ctx->h_grid.size();
+    int local = 0;
+    FamDesc& F = ctx->k1.fam[f];
+    for (int d = 0; d < F.n_dim; ++d) {
+      F.dim[d].smem_off = off + local;
+      local += F.dim[d].size;
+    }
+    ctx->h_grid.insert(ctx->h_grid.end(), ctx->fam_grid[f].begin(), ctx->fam_grid[f].end());
+    ctx->h_perm.insert(ctx->h_perm.end(), ctx->fam_perm[f].begin(), ctx->fam_perm[f].end());
+  }
+  if (ctx->d_grid) dev_free(ctx, ctx->d_grid);
+  if (ctx->d_perm) dev_free(ctx, ctx->d_perm);
+  if (dev_alloc(ctx, &ctx->d_grid, ctx->h_grid.size() * sizeof(double))) return 1;
+  if (dev_alloc(ctx, &ctx->d_perm, ctx->h_perm.size() * sizeof(int32_t))) return 1;
+  if (!ctx->h_grid.empty()) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_grid, ctx->h_grid.data(), ctx->h_grid.size() * sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_perm, ctx->h_perm.data(), ctx->h_perm.size() * sizeof(int32_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors may be rebuilt later
+  }
+  ctx->k1.grid_sorted = static_cast<const double*>(ctx->d_grid);
+  ctx->k1.grid_perm = static_cast<const int32_t*>(ctx->d_perm);
+  ctx->k1.n_grid_vals = (int32_t)ctx->h_grid.size();
+  ctx->grids_dirty = false;
+  return 0;
+}
+
+int check_ready(agnf_ctx* ctx) {
+  if (!ctx->have_cfg) return fail(ctx, "agnf_modelset_config has not been called");
+  for (int f = 0; f < ctx->k1.cfg.n_fam; ++f)
+    if (!ctx->fam_set[f]) return fail(ctx, "family %d has not been uploaded", f);
+  if (!ctx->have_z) return fail(ctx, "agnf_zslices_upload has not been called");
+  if (!ctx->have_src) return fail(ctx, "agnf_sources_upload has not been called");
+  return rebuild_grids(ctx);
+}
+
+}  // namespace
+
+extern "C" {
+
+AGNF_API int agnf_version(void) { return AGNF_VERSION; }
+
+AGNF_API const char* agnf_last_error(const agnf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+AGNF_API int agnf_ctx_create(int device, agnf_ctx** out) {
+  if (!out) return fail(nullptr, "agnf_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, "no CUDA device available (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, "device %d out of range (have %d)", device, n);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, "device %d is sm_%d%d; this build only contains sm_100a code", device, prop.major,
+                prop.minor);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, "cudaSetDevice: %s", cudaGetErrorString(e));
+  agnf_ctx* ctx = new agnf_ctx();
+  ctx->device = device;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  cudaEventCreate(&ctx->ev2);
+  cudaEventCreate(&ctx->ev3);
+  *out = ctx;
+  return 0;
+}
+
+AGNF_API void agnf_ctx_destroy(agnf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (void* p : ctx->owned) cudaFree(p);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+  if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+AGNF_API int agnf_synchronize(agnf_ctx* ctx) {
+  if (!ctx) return 1;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+AGNF_API int64_t agnf_launch_count(const agnf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+AGNF_API int agnf_last_kernel_ms(agnf_ctx* ctx, int which, float* ms) {
+  if (!ctx || !ms) return 1;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (which == 1) {
+    if (!ctx->k1_timed) return fail(ctx, "no K1 launch has been timed yet");
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return 0;
+  }
+  if (which == 2) {
+    if (!ctx->k2_timed) return fail(ctx, "no K2 launch has been timed yet");
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev3));
+    CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev2, ctx->ev3));
+    return 0;
+  }
+  return fail(ctx, "agnf_last_kernel_ms: which must be 1 or 2");
+}
+
+// ------------------------------------------------------------------------------------------- K1
+
+AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg) {
+  if (!ctx || !cfg) return 1;
+  if (cfg->n_b < 1 || cfg->n_b > AGNF_MAX_BANDS) return fail(ctx, "n_b=%d outside [1,%d]", cfg->n_b, AGNF_MAX_BANDS);
+  if (cfg->n_par < 3 || cfg->n_par > AGNF_MAX_PARS) return fail(ctx, "n_par=%d outside [3,%d]", cfg->n_par, AGNF_MAX_PARS);
+  if (cfg->n_fam != 4 && cfg->n_fam != 5) return fail(ctx, "n_fam must be 4 or 5");
+  if ((cfg->n_fam == 5) != (cfg->radio != 0)) return fail(ctx, "n_fam == 5 iff radio");
+  if (cfg->n_z < 1) return fail(ctx, "n_z must be >= 1");
+  if (cfg->eb_mode < 0 || cfg->eb_mode > 2) return fail(ctx, "eb_mode must be 0, 1 or 2");
+  if (cfg->bb_mode < 0 || cfg->bb_mode > 3) return fail(ctx, "bb_mode must be 0..3");
+  ctx->k1.cfg = *cfg;
+  const int n_norm = 3 + (cfg->bbb_has_norm ? 1 : 0) + (cfg->radio ? 1 : 0);
+  ctx->k1.norm_offset = cfg->n_par - n_norm;
+  ctx->have_cfg = true;
+  return 0;
+}
+
+AGNF_API int agnf_family_upload(agnf_ctx* ctx, const agnf_family_desc* fd) {
+  if (!ctx || !fd) return 1;
+  if (!ctx->have_cfg) return fail(ctx, "call agnf_modelset_config first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int f = fd->fam;
+  if (f < 0 || f >= ctx->k1.cfg.n_fam) return fail(ctx, "family id %d out of range", f);
+  if (fd->n_dim < 0 || fd->n_dim > AGNF_MAX_DIMS) return fail(ctx, "family %d: n_dim=%d", f, fd->n_dim);
+  if (fd->T < 1 || !fd->table) return fail(ctx, "family %d: empty table", f);
+  FamDesc& F = ctx->k1.fam[f];
+  const agnf_config& cfg = ctx->k1.cfg;
+  F.T = fd->T;
+  F.n_dim = fd->n_dim;
+  F.par_offset = fd->par_offset;
+  if (fd->par_offset < 0 || fd->par_offset + fd->n_dim > ctx->k1.norm_offset)
+    return fail(ctx, "family %d: parameter block [%d,%d) overlaps the normalisations at %d", f, fd->par_offset,
+                fd->par_offset + fd->n_dim, ctx->k1.norm_offset);
+  ctx->fam_grid[f].clear();
+  ctx->fam_perm[f].clear();
+  int64_t max_row = 0;
+  int cursor = 0;
+  for (int d = 0; d < fd->n_dim; ++d) {
+    F.dim[d].is_grid = fd->dim_is_grid[d];
+    F.dim[d].size = fd->dim_size[d];
+    F.dim[d].stride = fd->dim_stride[d];
+    if (fd->dim_size[d] < 1) return fail(ctx, "family %d dim %d: size < 1", f, d);
+    for (int k = 0; k < fd->dim_size[d]; ++k) {
+      const double v = fd->grid_sorted[cursor + k];
+      if (k > 0 && !(v > fd->grid_sorted[cursor + k - 1]))
+        return fail(ctx, "family %d dim %d: grid values must be strictly ascending", f, d);
+      const int32_t pi = fd->grid_perm[cursor + k];
+      if (pi < 0 || pi >= fd->dim_size[d]) return fail(ctx, "family %d dim %d: bad permutation", f, d);
+      ctx->fam_grid[f].push_back(v);
+      ctx->fam_perm[f].push_back(pi);
+    }
+    if (fd->dim_is_grid[d]) max_row += (int64_t)(fd->dim_size[d] - 1) * fd->dim_stride[d];
+    cursor += fd->dim_size[d];
+  }
+  if (max_row >= fd->T) return fail(ctx, "family %d: strides address row %lld but T=%lld", f, (long long)max_row,
+                                    (long long)fd->T);
+  const size_t count = (size_t)cfg.n_z * (size_t)fd->T * (size_t)cfg.n_b;
+  if (fd->table_on_device) {
+    F.table = fd->table;
+  } else {
+    const double* old = nullptr;   // previous upload of this family (if any) stays owned until destroy
+    if (upload(ctx, &old, fd->table, count)) return 1;
+    F.table = old;
+  }
+  F.aux = nullptr;
+  if (fd->aux) {
+    const double* a = nullptr;
+    if (upload(ctx, &a, fd->aux, (size_t)fd->T)) return 1;
+    F.aux = a;
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->fam_set[f] = true;
+  ctx->grids_dirty = true;
+  return 0;
+}
+
+AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double* cbbb, const uint64_t* xray_bits,
+                        const int32_t* j1500, const double* omega) {
+  if (!ctx) return 1;
+  if (!ctx->have_cfg) return fail(ctx, "call agnf_modelset_config first");
+  if (!cgal || !cbbb || !xray_bits || !j1500 || !omega) return fail(ctx, "agnf_zslices_upload: NULL argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t nz = ctx->k1.cfg.n_z, nb = ctx->k1.cfg.n_b;
+  for (size_t i = 0; i < nz; ++i)
+    if (ctx->k1.cfg.prior_agnfrac && (j1500[i] < 0 || j1500[i] >= (int)nb))
+      return fail(ctx, "z-slice %zu: no band with 14.3 < log nu_rest < 15.3; prior_AGNfraction would raise "
+                       "IndexError in the reference (PRIORS_AGNfitter.py:166)", i);
+  if (upload(ctx, &ctx->k1.cgal, cgal, nz * nb)) return 1;
+  if (upload(ctx, &ctx->k1.cbbb, cbbb, nz * nb)) return 1;
+  if (upload(ctx, &ctx->k1.xray, xray_bits, nz)) return 1;
+  if (upload(ctx, &ctx->k1.j1500, j1500, nz)) return 1;
+  if (upload(ctx, &ctx->k1.omega, omega, nz * nb)) return 1;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->have_z = true;
+  return 0;
+}
+
+AGNF_API int agnf_sources_upload(agnf_ctx* ctx, int64_t S, const int32_t* zi, const double* y, const double* inv_sigma,
+                        const uint64_t* valid_bits, const double* pmin, const double* pmax,
+                        const double* consts, int32_t n_const, const int32_t* agn_branch,
+                        const int32_t* irsyn_mode, const int32_t* irsyn_j) {
+  if (!ctx) return 1;
+  if (!ctx->have_cfg) return fail(ctx, "call agnf_modelset_config first");
+  if (S < 1) return fail(ctx, "S must be >= 1");
+  if (!zi || !y || !inv_sigma || !valid_bits || !pmin || !pmax || !consts || !agn_branch || !irsyn_mode || !irsyn_j)
+    return fail(ctx, "agnf_sources_upload: NULL argument");
+  if (n_const < 1) return fail(ctx, "n_const must be >= 1");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t nb = ctx->k1.cfg.n_b, np = ctx->k1.cfg.n_par, s = (size_t)S;
+  for (size_t i = 0; i < s; ++i)
+    if (zi[i] < 0 || zi[i] >= ctx->k1.cfg.n_z) return fail(ctx, "source %zu: z-slice %d out of range", i, zi[i]);
+  if (upload(ctx, &ctx->k1.zi, zi, s)) return 1;
+  if (upload(ctx, &ctx->k1.y, y, s * nb)) return 1;
+  if (upload(ctx, &ctx->k1.isig, inv_sigma, s * nb)) return 1;
+  if (upload(ctx, &ctx->k1.valid, valid_bits, s)) return 1;
+  if (upload(ctx, &ctx->k1.pmin, pmin, s * np)) return 1;
+  if (upload(ctx, &ctx->k1.pmax, pmax, s * np)) return 1;
+  if (upload(ctx, &ctx->k1.consts, consts, s * (size_t)n_const)) return 1;
+  if (upload(ctx, &ctx->k1.agn_branch, agn_branch, s)) return 1;
+  if (upload(ctx, &ctx->k1.irsyn_mode, irsyn_mode, s)) return 1;
+  if (upload(ctx, &ctx->k1.irsyn_j, irsyn_j, s)) return 1;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->k1.n_const = n_const;
+  ctx->k1.S = S;
+  ctx->have_src = true;
+  return 0;
+}
+
+AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, const int32_t* d_source_id, int64_t n,
+                             double* d_lnp, int32_t* d_rows, double* d_ymodel, double* d_lnprior,
+                             double* d_lnlike, void* stream) {
+  if (!ctx) return 1;
+  if (n < 0) return fail(ctx, "n < 0");
+  if (n == 0) return 0;
+  if (!d_params || !d_source_id || !d_lnp) return fail(ctx, "agnf_lnprob_batch_device: NULL argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (check_ready(ctx)) return 1;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  K1Batch B{d_params, d_source_id, n, d_lnp, d_rows, d_ymodel, d_lnprior, d_lnlike};
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+  CUDA_TRY(ctx, launch_k1(ctx->k1, B, st));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+  ctx->k1_timed = true;
+  ctx->launches += 1;
+  return 0;
+}
+
+AGNF_API int agnf_lnprob_batch(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* lnp,
+                      int32_t* rows, double* ymodel, double* lnprior, double* lnlike) {
+  if (!ctx) return 1;
+  if (n < 0) return fail(ctx, "n < 0");
+  if (n == 0) return 0;
+  if (!params || !source_id || !lnp) return fail(ctx, "agnf_lnprob_batch: NULL argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (check_ready(ctx)) return 1;
+  const size_t nb = ctx->k1.cfg.n_b, np = ctx->k1.cfg.n_par, nf = ctx->k1.cfg.n_fam, N = (size_t)n;
+  if (ensure(ctx, &ctx->st_params, &ctx->st_params_cap, N * np * sizeof(double))) return 1;
+  if (ensure(ctx, &ctx->st_sid, &ctx->st_sid_cap, N * sizeof(int32_t))) return 1;
+  // output staging: lnp | lnprior | lnlike | ymodel | rows
+  size_t off_lnp = 0, off_pr = N * 8, off_ll = 2 * N * 8, off_ym = 3 * N * 8;
+  size_t off_rows = off_ym + (ymodel ? N * nb * 8 : 0);
+  size_t total = off_rows + (rows ? N * nf * 4 : 0);
+  if (ensure(ctx, &ctx->st_out, &ctx->st_out_cap, total)) return 1;
+  char* o = static_cast<char*>(ctx->st_out);
+  cudaStream_t st = ctx->stream;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->st_params, params, N * np * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->st_sid, source_id, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (agnf_lnprob_batch_device(ctx, static_cast<const double*>(ctx->st_params),
+                               static_cast<const int32_t*>(ctx->st_sid), n,
+                               reinterpret_cast<double*>(o + off_lnp),
+                               rows ? reinterpret_cast<int32_t*>(o + off_rows) : nullptr,
+                               ymodel ? reinterpret_cast<double*>(o + off_ym) : nullptr,
+                               lnprior ? reinterpret_cast<double*>(o + off_pr) : nullptr,
+                               lnlike ? reinterpret_cast<double*>(o + off_ll) : nullptr, st))
+    return 1;
+  CUDA_TRY(ctx, cudaMemcpyAsync(lnp, o + off_lnp, N * 8, cudaMemcpyDeviceToHost, st));
+  if (lnprior) CUDA_TRY(ctx, cudaMemcpyAsync(lnprior, o + off_pr, N * 8, cudaMemcpyDeviceToHost, st));
+  if (lnlike) CUDA_TRY(ctx, cudaMemcpyAsync(lnlike, o + off_ll, N * 8, cudaMemcpyDeviceToHost, st));
+  if (ymodel) CUDA_TRY(ctx, cudaMemcpyAsync(ymodel, o + off_ym, N * nb * 8, cudaMemcpyDeviceToHost, st));
+  if (rows) CUDA_TRY(ctx, cudaMemcpyAsync(rows, o + off_rows, N * nf * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- K2
+
+AGNF_API int agnf_filters_upload(agnf_ctx* ctx, int32_t n_b, const double* band_lambda_c, const int64_t* offset,
+                        const double* lambda_angstrom, const double* factor) {
+  if (!ctx) return 1;
+  if (n_b < 1 || n_b > AGNF_MAX_BANDS) return fail(ctx, "n_b=%d outside [1,%d]", n_b, AGNF_MAX_BANDS);
+  if (!band_lambda_c || !offset || !lambda_angstrom || !factor) return fail(ctx, "agnf_filters_upload: NULL argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int64_t N = offset[n_b];
+  std::vector<double> lam((size_t)N), wn((size_t)N), scale((size_t)n_b);
+  for (int b = 0; b < n_b; ++b) {
+    const int64_t o0 = offset[b], o1 = offset[b + 1];
+    const int64_t nk = o1 - o0;
+    if (nk < 2) return fail(ctx, "band %d has %lld samples; need >= 2 for a trapezoid", b, (long long)nk);
+    const double* x = lambda_angstrom + o0;
+    const double* T = factor + o0;
+    // trapz(T, x) = sum d_i (T_i + T_{i+1}) / 2 ; node weights w_i = (d_{i-1} + d_i) / 2
+    double den = 0.0;
+    std::vector<double> w((size_t)nk, 0.0);
+    for (int64_t i = 0; i + 1 < nk; ++i) {
+      const double d = x[i + 1] - x[i];
+      den += d * (T[i + 1] + T[i]) / 2.0;
+      w[(size_t)i] += d / 2.0;
+      w[(size_t)i + 1] += d / 2.0;
+    }
+    std::vector<int64_t> order((size_t)nk);
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t c) { return x[a] < x[c]; });
+    for (int64_t i = 0; i < nk; ++i) {
+      lam[(size_t)(o0 + i)] = x[order[(size_t)i]];
+      wn[(size_t)(o0 + i)] = w[(size_t)order[(size_t)i]] * T[order[(size_t)i]];
+    }
+    const double lc = band_lambda_c[b];
+    scale[(size_t)b] = (lc * lc) / 2.997e8 / 1.e10 / den;   // fluxlambda_2_fluxnu, DICTIONARIES:486-491
+  }
+  K2Filters& F = ctx->filt;
+  if (upload(ctx, &F.lam, lam.data(), (size_t)N)) return 1;
+  if (upload(ctx, &F.wn, wn.data(), (size_t)N)) return 1;
+  if (upload(ctx, &F.off, offset, (size_t)n_b + 1)) return 1;
+  if (upload(ctx, &F.scale, scale.data(), (size_t)n_b)) return 1;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  F.n_b = n_b;
+  F.n_samples = N;
+  ctx->have_filt = true;
+  return 0;
+}
+
+AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int32_t* perm, const double* Fnu, int64_t T,
+                    int32_t n_lam, const double* z, int32_t n_z, const int64_t* row_map, int64_t T_total,
+                    double* out, int32_t out_on_device) {
+  if (!ctx) return 1;
+  if (!ctx->have_filt) return fail(ctx, "call agnf_filters_upload first");
+  if (!lam_sorted || !perm || !Fnu || !z || !out) return fail(ctx, "agnf_dict_build: NULL argument");
+  if (T < 1 || n_lam < 1 || n_z < 1) return fail(ctx, "agnf_dict_build: empty problem");
+  if (!row_map) T_total = T;
+  if (T_total < T) return fail(ctx, "T_total < T");
+  for (int j = 1; j < n_lam; ++j)
+    if (!(lam_sorted[j] >= lam_sorted[j - 1])) return fail(ctx, "lam_sorted must be ascending");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n_b = ctx->filt.n_b;
+  K2Problem p;
+  p.filt = ctx->filt;
+  p.T = T;
+  p.n_lam = n_lam;
+  p.ldF = n_lam | 1;
+  p.n_z = n_z;
+  p.T_total = T_total;
+
+  void *d_lam = nullptr, *d_perm = nullptr, *d_F = nullptr, *d_Fs = nullptr, *d_z = nullptr, *d_jlo = nullptr,
+       *d_cnt = nullptr, *d_rmax = nullptr, *d_W = nullptr, *d_rowmap = nullptr, *d_out = nullptr;
+  auto cleanup = [&]() {
+    for (void* q : {d_lam, d_perm, d_F, d_Fs, d_z, d_jlo, d_cnt, d_rmax, d_W, d_rowmap}) dev_free(ctx, q);
+    if (!out_on_device) dev_free(ctx, d_out);
+  };
+#define K2_TRY(expr)                                                                                    \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess) {                                                                           \
+      cleanup();                                                                                        \
+      return fail(ctx, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);    \
+    }                                                                                                   \
+  } while (0)
+#define K2_ALLOC(ptr, bytes)                 \
+  do {                                       \
+    if (dev_alloc(ctx, &(ptr), (bytes))) {   \
+      cleanup();                             \
+      return 1;                              \
+    }                                        \
+  } while (0)
+
+  K2_ALLOC(d_lam, (size_t)n_lam * 8);
+  K2_ALLOC(d_perm, (size_t)n_lam * 4);
+  K2_ALLOC(d_F, (size_t)T * n_lam * 8);
+  K2_ALLOC(d_Fs, (size_t)T * p.ldF * 8);
+  K2_ALLOC(d_z, (size_t)n_z * 8);
+  K2_ALLOC(d_jlo, (size_t)n_z * n_b * 4);
+  K2_ALLOC(d_cnt, (size_t)n_z * n_b * 4);
+  K2_ALLOC(d_rmax, 4);
+  K2_TRY(cudaMemcpyAsync(d_lam, lam_sorted, (size_t)n_lam * 8, cudaMemcpyHostToDevice, st));
+  K2_TRY(cudaMemcpyAsync(d_perm, perm, (size_t)n_lam * 4, cudaMemcpyHostToDevice, st));
+  K2_TRY(cudaMemcpyAsync(d_F, Fnu, (size_t)T * n_lam * 8, cudaMemcpyHostToDevice, st));
+  K2_TRY(cudaMemcpyAsync(d_z, z, (size_t)n_z * 8, cudaMemcpyHostToDevice, st));
+  K2_TRY(cudaMemsetAsync(d_rmax, 0, 4, st));
+  if (row_map) {
+    for (int64_t t = 0; t < T; ++t)
+      if (row_map[t] < 0 || row_map[t] >= T_total) {
+        cleanup();
+        return fail(ctx, "row_map[%lld] out of range", (long long)t);
+      }
+    K2_ALLOC(d_rowmap, (size_t)T * 8);
+    K2_TRY(cudaMemcpyAsync(d_rowmap, row_map, (size_t)T * 8, cudaMemcpyHostToDevice, st));
+  }
+  p.lam0 = static_cast<const double*>(d_lam);
+  p.Fs = static_cast<const double*>(d_Fs);
+  p.z = static_cast<const double*>(d_z);
+  p.jlo = static_cast<int32_t*>(d_jlo);
+  p.cnt = static_cast<int32_t*>(d_cnt);
+  p.d_rmax = static_cast<int32_t*>(d_rmax);
+  p.row_map = static_cast<const int64_t*>(d_rowmap);
+
+  K2_TRY(launch_k2_permute(static_cast<const double*>(d_F), static_cast<const int32_t*>(d_perm),
+                           static_cast<double*>(d_Fs), T, n_lam, p.ldF, st));
+  K2_TRY(launch_k2_ranges(p, st));
+  int32_t rmax = 0;
+  K2_TRY(cudaMemcpyAsync(&rmax, d_rmax, 4, cudaMemcpyDeviceToHost, st));
+  K2_TRY(cudaStreamSynchronize(st));
+  if (rmax < 1) rmax = 1;
+  p.rmax = rmax;
+  K2_ALLOC(d_W, (size_t)n_z * n_b * rmax * 8);
+  p.W = static_cast<double*>(d_W);
+  K2_TRY(launch_k2_weights(p, st));
+  const size_t out_count = (size_t)n_z * (size_t)T_total * (size_t)n_b;
+  if (out_on_device) {
+    d_out = out;
+  } else {
+    K2_ALLOC(d_out, out_count * 8);
+    if (row_map) K2_TRY(cudaMemcpyAsync(d_out, out, out_count * 8, cudaMemcpyHostToDevice, st));  // keep other rows
+  }
+  p.out = static_cast<double*>(d_out);
+  K2_TRY(cudaEventRecord(ctx->ev2, st));
+  K2_TRY(launch_k2_contract(p, st));
+  K2_TRY(cudaEventRecord(ctx->ev3, st));
+  ctx->k2_timed = true;
+  ctx->launches += 4;
+  if (!out_on_device) K2_TRY(cudaMemcpyAsync(out, d_out, out_count * 8, cudaMemcpyDeviceToHost, st));
+  K2_TRY(cudaStreamSynchronize(st));
+  cleanup();
+  return 0;
+#undef K2_TRY
+#undef K2_ALLOC
+}
+
+}  // extern "C"

@@ -1,0 +1,325 @@
+// K1 — batched log-posterior kernel (see k1_lnprob.cuh for the mapping to the reference).
+#include "k1_lnprob.cuh"
+
+#include <cfloat>
+#include <climits>
+#include <cmath>
+
+namespace agnf {
+
+namespace {
+
+constexpr int K1_THREADS = 128;
+
+// First index (in first-appearance numbering) of the minimum of |g - p| over the distinct grid
+// values of one dimension.  `sv` is the ascending copy, `perm[k]` the first-appearance index of
+// sv[k].  Equivalent to np.abs(keys_float - p).argmin() mapped to the distinct-value list:
+//   * the minimisers of the rounded |g - p| form a contiguous run around p in sorted order
+//     (fp subtraction is monotone), so two neighbours + a tie walk find them all;
+//   * among minimisers numpy returns the earliest key, i.e. the smallest first-appearance index;
+//   * all-NaN -> index 0.
+__device__ __forceinline__ int snap_dim(const double* __restrict__ sv, const int32_t* __restrict__ perm,
+                                        int n, double p) {
+  if (p != p) return 0;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (sv[mid] <= p) lo = mid + 1; else hi = mid;
+  }
+  const int l = lo - 1, r = lo;  // sv[l] <= p < sv[r]
+  double best;
+  if (l < 0) best = fabs(sv[r] - p);
+  else if (r >= n) best = fabs(sv[l] - p);
+  else best = fmin(fabs(sv[l] - p), fabs(sv[r] - p));
+  int idx = INT_MAX;
+  for (int k = l; k >= 0; --k) {
+    if (fabs(sv[k] - p) == best) idx = min(idx, perm[k]); else break;
+  }
+  for (int k = r; k < n; ++k) {
+    if (fabs(sv[k] - p) == best) idx = min(idx, perm[k]); else break;
+  }
+  return idx;
+}
+
+// Gaussian_prior(mu, sigma, x) = log(1/(sqrt(2 pi) sigma)) - 0.5 (x-mu)^2 / sigma^2
+__device__ __forceinline__ double gaussian_prior(double mu, double sigma, double x) {
+  const double lognorm = log(1.0 / (sqrt(2.0 * 3.141592653589793) * sigma));
+  const double d = x - mu;
+  return lognorm - 0.5 * (d * d) / (sigma * sigma);
+}
+
+struct BandAcc {
+  double chi = 0.0;
+  double ga_j = 0.0, bb_j = 0.0;      // band j1500, after reddening and norm
+  double sb_ir = 0.0, syn_ir = 0.0;   // band j_IR
+  double ebA = 0.0, ebB = 0.0;        // energy-balance integrals (free E(B-V)_gal)
+};
+
+struct WalkerCtx {
+  double nGA, nSB, nTO, nBB, nRAD;
+  double cBB;        // 1 or 1/(4 pi dL^2) applied to the BBB row in the model sum
+  double ebv_gal, ebv_bbb, xfac;
+  uint64_t valid, xray;
+  int j1500, jir;
+};
+
+template <bool GA_FREE, int BB_MODE, bool RADIO>
+__device__ __forceinline__ double band_step(const agnf_config& cfg, const WalkerCtx& w, BandAcc& a, int b,
+                                            double dga, double dsb, double dto, double dbb, double drad,
+                                            double yb, double isb, double cg, double cb, double om,
+                                            bool eb_free) {
+  double rga = 1.0;
+  if (GA_FREE) rga = exp10(cg * w.ebv_gal);
+  const double ga_r = GA_FREE ? dga * rga : dga;
+  double bb_r = dbb;
+  if (BB_MODE != 0) {
+    if (BB_MODE >= 2 && ((w.xray >> b) & 1ull)) {
+      bb_r = dbb * w.xfac;
+    } else {
+      const double v = dbb * exp10(cb * w.ebv_bbb);
+      bb_r = (v != v) ? dbb : v;      // NaN -> unreddened (MODEL:1211)
+    }
+  }
+  double m = w.nSB * dsb + w.nBB * (bb_r * w.cBB) + w.nGA * ga_r + w.nTO * dto;
+  if (RADIO) m += w.nRAD * drad;
+  if ((w.valid >> b) & 1ull) {
+    const double r = (yb - m) * isb;
+    a.chi += r * r;
+  }
+  if (b == w.j1500) {
+    a.ga_j = ga_r * w.nGA;
+    a.bb_j = bb_r * w.nBB;
+  }
+  if (RADIO && b == w.jir) {
+    a.sb_ir = dsb * w.nSB;
+    a.syn_ir = drad * w.nRAD;
+  }
+  if (GA_FREE && eb_free) {
+    a.ebA += om * (dga * 3.826e33);
+    a.ebB += om * (((dga * 1e18) * rga) * 3.826e33);
+  }
+  return m;
+}
+
+template <bool GA_FREE, int BB_MODE, bool RADIO, bool VEC2>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_lnprob_kernel(const __grid_constant__ K1Params P, const K1Batch B) {
+  extern __shared__ double s_raw[];
+  double* s_grid = s_raw;
+  int32_t* s_perm = reinterpret_cast<int32_t*>(s_raw + P.n_grid_vals);
+  for (int i = threadIdx.x; i < P.n_grid_vals; i += blockDim.x) {
+    s_grid[i] = P.grid_sorted[i];
+    s_perm[i] = P.grid_perm[i];
+  }
+  __syncthreads();
+
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n) return;
+  const agnf_config& cfg = P.cfg;
+  const int n_b = cfg.n_b, n_par = cfg.n_par;
+  const int s = __ldg(B.source_id + i);
+  const double* __restrict__ p = B.params + i * n_par;
+
+  // ---- box prior -------------------------------------------------------------------------
+  bool inbox = true;
+  {
+    const double* __restrict__ pmin = P.pmin + (int64_t)s * n_par;
+    const double* __restrict__ pmax = P.pmax + (int64_t)s * n_par;
+    for (int c = 0; c < n_par; ++c) {
+      const double v = __ldg(p + c);
+      inbox = inbox && (__ldg(pmin + c) <= v) && (v <= __ldg(pmax + c));
+    }
+  }
+  const bool detail = (B.rows != nullptr) || (B.ymodel != nullptr) || (B.lnprior != nullptr) ||
+                      (B.lnlike != nullptr);
+  if (!inbox && !detail) {   // ymodel's value is discarded by the reference in this case
+    B.lnp[i] = -INFINITY;
+    return;
+  }
+
+  // ---- snap every family to its dictionary row ------------------------------------------------
+  const int zi = __ldg(P.zi + s);
+  const double* trow[AGNF_MAX_FAMILIES];
+  int64_t row[AGNF_MAX_FAMILIES];
+#pragma unroll
+  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
+    row[f] = 0;
+    trow[f] = nullptr;
+    if (f < cfg.n_fam) {
+      const FamDesc& F = P.fam[f];
+      int64_t r = 0;
+      for (int d = 0; d < F.n_dim; ++d) {
+        if (F.dim[d].is_grid) {
+          const int off = F.dim[d].smem_off;
+          const int idx = snap_dim(s_grid + off, s_perm + off, F.dim[d].size, __ldg(p + F.par_offset + d));
+          r += (int64_t)idx * F.dim[d].stride;
+        }
+      }
+      row[f] = r;
+      trow[f] = F.table + ((int64_t)zi * F.T + r) * n_b;
+    }
+  }
+  if (B.rows) {
+    for (int f = 0; f < cfg.n_fam; ++f) B.rows[i * cfg.n_fam + f] = (int32_t)row[f];
+  }
+
+  // ---- normalisations and free parameters ----------------------------------------------------
+  WalkerCtx w;
+  const int no = P.norm_offset;
+  const double GA = __ldg(p + no), SB = __ldg(p + no + 1), TO = __ldg(p + no + 2);
+  int k = 3;
+  double BB = 0.0, RAD = 0.0;
+  if (cfg.bbb_has_norm) BB = __ldg(p + no + k++);
+  if (RADIO) RAD = __ldg(p + no + k++);
+  const double inv4pidl2 = __ldg(P.consts + (int64_t)s * P.n_const + 0);
+  w.nGA = exp10(GA);
+  w.nSB = exp10(SB);
+  w.nTO = exp10(TO);
+  w.nBB = cfg.bbb_has_norm ? exp10(BB) : 1.0;
+  w.nRAD = RADIO ? exp10(RAD) : 0.0;
+  w.cBB = cfg.bbb_has_norm ? 1.0 : inv4pidl2;
+  w.ebv_gal = 0.0;
+  w.ebv_bbb = 0.0;
+  w.xfac = 1.0;
+  if (GA_FREE) w.ebv_gal = __ldg(p + P.fam[0].par_offset + P.fam[0].n_dim - 1);
+  if (BB_MODE == 1) w.ebv_bbb = __ldg(p + P.fam[3].par_offset + P.fam[3].n_dim - 1);
+  if (BB_MODE == 2) {
+    w.ebv_bbb = __ldg(p + P.fam[3].par_offset + P.fam[3].n_dim - 2);
+    w.xfac = exp10(__ldg(p + P.fam[3].par_offset + P.fam[3].n_dim - 1) / 0.3838);
+  }
+  if (BB_MODE == 3) {
+    w.ebv_bbb = __ldg(p + P.fam[3].par_offset + P.fam[3].n_dim - 3);
+    w.xfac = exp10(__ldg(p + P.fam[3].par_offset + P.fam[3].n_dim - 2) / 0.3838);
+  }
+  w.valid = __ldg(P.valid + s);
+  w.xray = __ldg(P.xray + zi);
+  w.j1500 = __ldg(P.j1500 + zi);
+  w.jir = RADIO ? __ldg(P.irsyn_j + s) : -1;
+  const bool eb_free = GA_FREE && cfg.eb_mode != 0;
+
+  // ---- band loop: gather, model, chi^2 -------------------------------------------------------
+  const double* __restrict__ tGA = trow[0];
+  const double* __restrict__ tSB = trow[1];
+  const double* __restrict__ tTO = trow[2];
+  const double* __restrict__ tBB = trow[3];
+  const double* __restrict__ tRAD = RADIO ? trow[4] : trow[0];
+  const double* __restrict__ ys = P.y + (int64_t)s * n_b;
+  const double* __restrict__ is = P.isig + (int64_t)s * n_b;
+  const double* __restrict__ cg = P.cgal + (int64_t)zi * n_b;
+  const double* __restrict__ cb = P.cbbb + (int64_t)zi * n_b;
+  const double* __restrict__ om = P.omega + (int64_t)zi * n_b;
+  double* ym = B.ymodel ? B.ymodel + i * n_b : nullptr;
+  BandAcc a;
+  if (VEC2) {
+    // n_b even: every row starts 16-byte aligned -> 128-bit loads, two bands per step
+    for (int b = 0; b < n_b; b += 2) {
+      const double2 dga = __ldg(reinterpret_cast<const double2*>(tGA + b));
+      const double2 dsb = __ldg(reinterpret_cast<const double2*>(tSB + b));
+      const double2 dto = __ldg(reinterpret_cast<const double2*>(tTO + b));
+      const double2 dbb = __ldg(reinterpret_cast<const double2*>(tBB + b));
+      double2 drad = make_double2(0.0, 0.0);
+      if (RADIO) drad = __ldg(reinterpret_cast<const double2*>(tRAD + b));
+      const double2 yb = __ldg(reinterpret_cast<const double2*>(ys + b));
+      const double2 ib = __ldg(reinterpret_cast<const double2*>(is + b));
+      double2 cgb = make_double2(0.0, 0.0), cbb = make_double2(0.0, 0.0), omb = make_double2(0.0, 0.0);
+      if (GA_FREE) {
+        cgb = __ldg(reinterpret_cast<const double2*>(cg + b));
+        omb = __ldg(reinterpret_cast<const double2*>(om + b));
+      }
+      if (BB_MODE != 0) cbb = __ldg(reinterpret_cast<const double2*>(cb + b));
+      const double m0 = band_step<GA_FREE, BB_MODE, RADIO>(cfg, w, a, b, dga.x, dsb.x, dto.x, dbb.x, drad.x,
+                                                          yb.x, ib.x, cgb.x, cbb.x, omb.x, eb_free);
+      const double m1 = band_step<GA_FREE, BB_MODE, RADIO>(cfg, w, a, b + 1, dga.y, dsb.y, dto.y, dbb.y, drad.y,
+                                                          yb.y, ib.y, cgb.y, cbb.y, omb.y, eb_free);
+      if (ym) {
+        ym[b] = m0;
+        ym[b + 1] = m1;
+      }
+    }
+  } else {
+    for (int b = 0; b < n_b; ++b) {
+      const double drad = RADIO ? __ldg(tRAD + b) : 0.0;
+      const double cgb = GA_FREE ? __ldg(cg + b) : 0.0;
+      const double omb = GA_FREE ? __ldg(om + b) : 0.0;
+      const double cbb = (BB_MODE != 0) ? __ldg(cb + b) : 0.0;
+      const double m = band_step<GA_FREE, BB_MODE, RADIO>(cfg, w, a, b, __ldg(tGA + b), __ldg(tSB + b),
+                                                         __ldg(tTO + b), __ldg(tBB + b), drad, __ldg(ys + b),
+                                                         __ldg(is + b), cgb, cbb, omb, eb_free);
+      if (ym) ym[b] = m;
+    }
+  }
+  const double lnlike = -0.5 * a.chi;
+
+  // ---- physical priors -------------------------------------------------------------------------
+  double prior = 0.0;
+  if (cfg.eb_mode != 0) {
+    double L_att;
+    if (GA_FREE) L_att = fabs((a.ebA - a.ebB) * w.nGA);
+    else L_att = __ldg(P.fam[0].aux + row[0]) * w.nGA;
+    const double L_sb = __ldg(P.fam[1].aux + row[1]) * w.nSB;
+    double pr;
+    if (L_sb < L_att) pr = -9999.0;
+    else if (L_sb >= L_att) pr = (cfg.eb_mode == 1) ? 0.0 : gaussian_prior(0.0, 0.1, log10(L_sb / L_att));
+    else pr = NAN;   // unordered: the reference has no branch for it
+    prior += pr;
+  }
+  if (cfg.prior_agnfrac) {
+    double bbj = a.bb_j;
+    if (BB == 0.0) bbj = bbj * inv4pidl2;          // decided by VALUE (PRIORS:177)
+    const double frac = log10(bbj / a.ga_j);
+    double pr;
+    if (__ldg(P.agn_branch + s) == 0) pr = gaussian_prior(-2.0, 2.0, frac);
+    else pr = (frac < 0.0) ? -9999.0 : gaussian_prior(2.0, 2.0, frac);
+    prior += pr + gaussian_prior(4.5, 1.5, GA);
+  }
+  if (RADIO) {
+    const int mode = __ldg(P.irsyn_mode + s);
+    if (mode != 0) {
+      const double f = log10(a.syn_ir / a.sb_ir);
+      prior += gaussian_prior(mode > 0 ? 2.0 : -2.0, 2.0, f);
+    }
+  }
+  const double lnprior = inbox ? prior : -INFINITY;
+  const bool fin = (lnprior - lnprior) == 0.0;     // isfinite
+  B.lnp[i] = fin ? lnprior + lnlike : -INFINITY;
+  if (B.lnprior) B.lnprior[i] = lnprior;
+  if (B.lnlike) B.lnlike[i] = lnlike;
+}
+
+template <bool GA_FREE, int BB_MODE, bool RADIO>
+cudaError_t launch_variant(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
+  const int64_t blocks = (B.n + K1_THREADS - 1) / K1_THREADS;
+  const size_t smem = (size_t)P.n_grid_vals * (sizeof(double) + sizeof(int32_t));
+  const bool vec2 = (P.cfg.n_b % 2) == 0;
+  if (vec2) {
+    auto kern = k1_lnprob_kernel<GA_FREE, BB_MODE, RADIO, true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)blocks, K1_THREADS, smem, stream>>>(P, B);
+  } else {
+    auto kern = k1_lnprob_kernel<GA_FREE, BB_MODE, RADIO, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)blocks, K1_THREADS, smem, stream>>>(P, B);
+  }
+  return cudaGetLastError();
+}
+
+template <bool GA_FREE, bool RADIO>
+cudaError_t launch_bb(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
+  switch (P.cfg.bb_mode) {
+    case 0: return launch_variant<GA_FREE, 0, RADIO>(P, B, stream);
+    case 1: return launch_variant<GA_FREE, 1, RADIO>(P, B, stream);
+    case 2: return launch_variant<GA_FREE, 2, RADIO>(P, B, stream);
+    default: return launch_variant<GA_FREE, 3, RADIO>(P, B, stream);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_k1(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
+  if (B.n <= 0) return cudaSuccess;
+  const bool gf = P.cfg.ga_free_ebv != 0, rad = P.cfg.radio != 0;
+  if (gf) return rad ? launch_bb<true, true>(P, B, stream) : launch_bb<true, false>(P, B, stream);
+  return rad ? launch_bb<false, true>(P, B, stream) : launch_bb<false, false>(P, B, stream);
+}
+
+}  // namespace agnf

@@ -41,7 +41,7 @@ class Family:
     fitted: bool                     # False: single fixed template, no entry in P (AGN_RAD '-99.9')
     grid: List[np.ndarray]           # per dim, first-appearance distinct values ('free' dims: 1 value)
     stride: np.ndarray               # [n_dim] int64
-    table: np.ndarray                # [n_z, T, n_b] float64
+    table: Optional[np.ndarray]      # [n_z, T, n_b] float64; None when the table lives only in HBM
     aux: Optional[np.ndarray] = None  # [T]
 
     @property
@@ -50,7 +50,7 @@ class Family:
 
     @property
     def T(self):
-        return self.table.shape[1]
+        return self.keys_float.shape[1]
 
     def sorted_grids(self):
         """(values ascending, original index) per dimension for the device binary search."""
@@ -300,7 +300,7 @@ def family_from_keys_float(name, par_names, par_types, keys_float, fitted, table
     keys = [tuple(keys_float[:, t]) for t in range(T)]
     return Family(name=name, par_names=list(par_names), par_types=list(par_types), keys=keys,
                   keys_float=keys_float, fitted=bool(fitted), grid=grid, stride=stride,
-                  table=np.ascontiguousarray(table, dtype=np.float64),
+                  table=None if table is None else np.ascontiguousarray(table, dtype=np.float64),
                   aux=None if aux is None else np.asarray(aux, dtype=np.float64))
 
 

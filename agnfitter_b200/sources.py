@@ -99,9 +99,17 @@ class SourceSet:
         return len(self.zi)
 
 
+def _bits(boolmat):
+    """[S, n_b] bool -> [S] uint64 with bit b = column b."""
+    n_b = boolmat.shape[1]
+    w = (np.uint64(1) << np.arange(n_b, dtype=np.uint64))
+    return (boolmat.astype(np.uint64) * w[None, :]).sum(axis=1, dtype=np.uint64)
+
+
 def make_sources(ms: ModelSet, z, dlum, nus, fluxes, fluxerrs, bounds_cache=None) -> SourceSet:
-    """z,dlum: [S]; nus/fluxes/fluxerrs: [S, n_b] (sorted by nu as DATA_all.PROPS leaves them).
-    Every source's z must be present in ms.z_grid (exact float match)."""
+    """z, dlum: [S]; nus/fluxes/fluxerrs: [S, n_b] (sorted by nu as DATA_all.PROPS leaves them).
+    Every source's z must be present in ms.z_grid (exact float match).  Vectorised over sources;
+    each expression is the per-source reference expression broadcast along axis 0."""
     z = np.atleast_1d(np.asarray(z, dtype=np.float64))
     dlum = np.atleast_1d(np.asarray(dlum, dtype=np.float64))
     nus = np.atleast_2d(np.asarray(nus, dtype=np.float64))
@@ -110,6 +118,8 @@ def make_sources(ms: ModelSet, z, dlum, nus, fluxes, fluxerrs, bounds_cache=None
     S, n_b = fluxes.shape
     if n_b != ms.n_b:
         raise ValueError("catalogue has %d bands, dictionary has %d" % (n_b, ms.n_b))
+    if nus.shape[0] == 1 and S > 1:
+        nus = np.broadcast_to(nus, (S, n_b))
     zpos = {float(v): i for i, v in enumerate(ms.z_grid)}
     try:
         zi = np.array([zpos[float(v)] for v in z], dtype=np.int32)
@@ -118,31 +128,49 @@ def make_sources(ms: ModelSet, z, dlum, nus, fluxes, fluxerrs, bounds_cache=None
 
     with np.errstate(divide="ignore"):
         isig = 1.0 / fluxerrs
-    mask = np.zeros(S, dtype=np.uint64)
+    zc = z[:, None]
+    # ln_likelihood's x_valid (PARAMETERSPACE:144-147); `a | b & c` == a | (b & c)
+    if ms.settings['XRAYS'] == 'Prior':
+        valid = (nus < np.log10(10 ** (15.38) / (1 + zc))) & (fluxes > -99.e-23)
+    else:
+        valid = (nus < np.log10(10 ** (15.38) / (1 + zc))) | (nus > np.log10(10 ** (16.685) / (1 + zc))) & (fluxes > -99.e-23)
+    mask = _bits(valid)
+
     n_par = ms.n_par
     pmin = np.empty((S, n_par))
     pmax = np.empty((S, n_par))
+    cache = {} if bounds_cache is None else bounds_cache
+    uz, inv = np.unique(z, return_inverse=True)
+    bmin = np.empty((len(uz), n_par))
+    bmax = np.empty((len(uz), n_par))
+    for k, zk in enumerate(uz):
+        zk = float(zk)
+        if zk not in cache:
+            cache[zk] = pdict_bounds(ms, zk)
+        bmin[k], bmax[k] = cache[zk]
+    pmin[:], pmax[:] = bmin[inv], bmax[inv]
+
     consts = np.zeros((S, C_NCONST))
+    consts[:, C_INV4PIDL2] = 1.0 / (4 * np.pi * dlum ** 2)
     agn_branch = np.zeros(S, dtype=np.int32)
     irsyn_mode = np.zeros(S, dtype=np.int32)
     irsyn_j = np.zeros(S, dtype=np.int32)
-    want_agn = ms.settings.get('PRIOR_AGNfraction') == True
-    xr = ms.settings['XRAYS']
-    cache = {} if bounds_cache is None else bounds_cache
-    for s in range(S):
-        v = hostmath.likelihood_mask(nus[s], fluxes[s], z[s], xr)
-        bits = 0
-        for b in np.nonzero(v)[0]:
-            bits |= (1 << int(b))
-        mask[s] = np.uint64(bits)
-        zk = float(z[s])
-        if zk not in cache:
-            cache[zk] = pdict_bounds(ms, zk)
-        pmin[s], pmax[s] = cache[zk]
-        consts[s, C_INV4PIDL2] = 1.0 / (4 * np.pi * dlum[s] ** 2)
-        if want_agn:
-            agn_branch[s] = hostmath.agnfrac_branch(nus[s], fluxes[s], z[s], hostmath.lumfactor(dlum[s]))
-        if ms.radio:
+    if ms.settings.get('PRIOR_AGNfraction') == True:
+        # PRIORS:163-164,169-172,182 — last positive flux with 14.3 < nu_rest < 15.3
+        r = nus + np.log10(1 + zc)
+        ok = (14.3 < r) & (r < 15.3) & (fluxes > 0)
+        if not ok.any(axis=1).all():
+            bad = int(np.nonzero(~ok.any(axis=1))[0][0])
+            raise IndexError("source %d has no positive flux with 14.3 < log nu_rest < 15.3; prior_AGNfraction "
+                             "raises IndexError in the reference (PRIORS_AGNfitter.py:164)" % bad)
+        last = n_b - 1 - np.argmax(ok[:, ::-1], axis=1)
+        d1500 = fluxes[np.arange(S), last]
+        lumf = 4. * np.pi * dlum ** 2.
+        abs_mag_data = 51.6 - 2.5 * np.log10(lumf * d1500)
+        characteristic_mag = -35.4 * (1 + z) ** 0.524 / (1 + (1 + z) ** 0.678)
+        agn_branch[:] = np.where(abs_mag_data > (characteristic_mag - 1.), 0, 1)
+    if ms.radio:
+        for s in range(S):
             mode, j = hostmath.irsyn_constants(nus[s], fluxes[s], ms.bands, z[s])
             if mode == 2:
                 raise ValueError("source %d: F_IR/F_syn == 2 exactly leaves prior_IR_SYNfraction "

@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""
+bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload ("config.workload"): C3 of SURVEY.md §8d — a synthetic catalogue of 100 000 sources x 100
+walkers per GPU, default 18-band set, classic 10-parameter model set (11 000 + 161 + 60 + 2
+templates), z ~ U(0.01, 6) rounded to 3 decimals; the dictionary for every distinct z of the shard
+is built on the GPU by K2 and stays in HBM; one step = one pass of the batched log-posterior (K1)
+over all 10^7 (source, walker) rows.  Sources are independent, so ranks hold independent shards
+(weak scaling, no data-path collective); the only collectives are the timing reductions.
+
+One JSON line on stdout (rank 0).  `value` = evals/s with inputs resident in HBM; `e2e` = the same
+through the host-buffer entry point (pinned host params -> H2D -> K1 -> D2H lnp) every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "walker-source log-posterior evals/s"
+UNIT = "evals/s"
+EVALS_PER_FIT = 100 * (2 * 12000 + 25000)     # example/SETTINGS_AGNfitter.py:265-268
+
+
+def k1_bytes_per_eval(n_comp, n_b, n_par, W):
+    """gathered rows + parameters + result, plus per-source vectors amortised over W."""
+    return 8 * (n_comp * n_b + n_par + 1) + 8 * 5 * n_b / W
+
+
+class ClockSampler(threading.Thread):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nm, v in zip(names, s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+_CPU_WORK = None     # (ModelSet, oracle sources, walker blocks): inherited by fork, never pickled
+
+
+def oracle_eval_sources(idx):
+    """Worker: the oracle port on the sources `idx` (each with its W walkers)."""
+    from oracle import agn_oracle as O
+    ms, srcs, pars_list = _CPU_WORK
+    n = 0
+    for i in idx:
+        O.ln_probab(ms, srcs[i], pars_list[i])
+        n += len(pars_list[i])
+    return n
+
+
+def cpu_port_throughput(ms_small, srcs, pars_list, cores, repeats=1):
+    """evals/s of the oracle port (vectorised over the walkers of a source), Pool over sources."""
+    import multiprocessing as mp
+    global _CPU_WORK
+    _CPU_WORK = (ms_small, srcs, pars_list)
+    chunks = [list(range(k, len(srcs), cores)) for k in range(cores)]
+    chunks = [c for c in chunks if c]
+    best = 0.0
+    if cores == 1:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            n = oracle_eval_sources(chunks[0])
+            best = max(best, n / (time.perf_counter() - t0))
+        return best
+    with mp.get_context("fork").Pool(len(chunks)) as pool:
+        pool.map(oracle_eval_sources, [c[:1] for c in chunks])          # warm the workers
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            n = sum(pool.map(oracle_eval_sources, chunks, chunksize=1))
+            best = max(best, n / (time.perf_counter() - t0))
+    return best
+
+
+def build_host_sample(ms, dev_tables, src_raw, sample_ids, pars, W):
+    """Small host-side ModelSet (only the sampled sources' z-slices) + oracle inputs."""
+    from agnfitter_b200.flatten import ModelSet, family_from_keys_float
+    zi = src_raw["zi"][sample_ids]
+    uz, inv = np.unique(zi, return_inverse=True)
+    small = ModelSet(settings=dict(ms.settings), bands=ms.bands, z_grid=ms.z_grid[uz])
+    import torch
+    idx = torch.as_tensor(uz.astype(np.int64), device=next(iter(dev_tables.values())).device)
+    for f in ms.families:
+        tab = dev_tables[f.name].index_select(0, idx).cpu().numpy()
+        small.families.append(family_from_keys_float(f.name, f.par_names, f.par_types, f.keys_float, f.fitted,
+                                                     tab, f.aux))
+    srcs, pl = [], []
+    for k, s in enumerate(sample_ids):
+        srcs.append(dict(z=float(src_raw["z"][s]), dlum=float(src_raw["dlum"][s]), nus=src_raw["nus"],
+                         fluxes=src_raw["fluxes"][s], fluxerrs=src_raw["fluxerrs"][s], pmin=src_raw["pmin"][s],
+                         pmax=src_raw["pmax"][s], zi=int(inv[k])))
+        pl.append(np.ascontiguousarray(pars[s * W:(s + 1) * W]))
+    return small, srcs, pl
+
+
+def make_workload(args, rank, device, need_gpu=True):
+    """Synthetic shard for this rank: dictionary (K2, on device), sources, walker positions."""
+    import torch
+    from agnfitter_b200 import synth, sources
+    from agnfitter_b200.engine import Engine, DictBuilder
+    t_setup = time.perf_counter()
+    fd = synth.synthetic_filterdict()
+    tpl = synth.synthetic_templates()
+    nus = np.asarray(fd[0])
+    S, W = args.sources, args.walkers
+    z, dlum, rng = synth.synthetic_catalog(None, S, seed=20260101 + rank)
+    z_grid = np.unique(z)
+    builder = DictBuilder(fd, device=device)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    ms, dev_tables = synth.build_modelset(tpl, fd, z_grid, builder, on_device=True)
+    torch.cuda.synchronize(device)
+    k2_wall = time.perf_counter() - t0
+    n_entries = len(z_grid) * sum(f.T for f in ms.families) * ms.n_b
+    eng = Engine(ms, device=device, ctx=builder.ctx, device_tables=dev_tables)
+    # fluxes from ymodel(truth) of every source, evaluated by K1 itself
+    dummy = sources.make_sources(ms, z, dlum, nus, np.ones((S, ms.n_b)), np.ones((S, ms.n_b)))
+    eng.set_sources(dummy)
+    truth = dummy.pmin + rng.uniform(size=dummy.pmin.shape) * (dummy.pmax - dummy.pmin)
+    _, _, ym, _, _ = eng.lnprob(truth, np.arange(S, dtype=np.int32), detail=True)
+    fl, fe = synth.catalog_fluxes(rng, ym, nus, z)
+    src = sources.make_sources(ms, z, dlum, nus, fl, fe)
+    eng.set_sources(src)
+    pars, sid = synth.walker_positions(rng, src.pmin, src.pmax, W, mode=args.positions, frac_out=0.01)
+    raw = dict(z=z, dlum=dlum, nus=nus, fluxes=fl, fluxerrs=fe, pmin=src.pmin, pmax=src.pmax, zi=src.zi)
+    info = dict(k2_wall_s=k2_wall, k2_entries=n_entries, n_z=len(z_grid), setup_s=time.perf_counter() - t_setup)
+    return eng, ms, dev_tables, raw, pars, sid, info
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng, ms, dev_tables, raw, pars, sid, info = make_workload(args, rank, local)
+    S, W, n = args.sources, args.walkers, len(pars)
+    n_b, n_par, n_comp = ms.n_b, ms.n_par, len(ms.families)
+    dev = torch.device("cuda", local)
+
+    # ---- device-resident operands for `value` ------------------------------------------------
+    h_pars = torch.from_numpy(pars).pin_memory()
+    h_sid = torch.from_numpy(sid).pin_memory()
+    d_pars = h_pars.to(dev, non_blocking=True)
+    d_sid = h_sid.to(dev, non_blocking=True)
+    d_lnp = torch.empty(n, dtype=torch.float64, device=dev)
+    h_lnp = torch.empty(n, dtype=torch.float64).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        eng.lnprob_device(d_pars, d_sid, d_lnp, stream_ptr=sp)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launch_count
+    per_launch = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launch_count - l0
+    # per-launch durations of the dominant kernel (events recorded by the library on the launching stream)
+    for _ in range(min(args.steps, 5)):
+        step_resident()
+        torch.cuda.synchronize(dev)
+        per_launch.append(eng.last_kernel_ms(1))
+    k1_ms = float(np.mean(per_launch))
+
+    # ---- end to end through the host-buffer entry point ----------------------------------------
+    np_pars, np_sid, np_lnp = h_pars.numpy(), h_sid.numpy(), h_lnp.numpy()
+    for _ in range(2):
+        eng.lnprob(np_pars, np_sid, out=np_lnp)
+    barrier()
+    l1 = eng.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.lnprob(np_pars, np_sid, out=np_lnp)        # synchronous: returns with lnp in host memory
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    launches += eng.launch_count - l1
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    check = float(np.nansum(np.where(np.isfinite(np_lnp), 1.0, 0.0)))
+
+    t_ms = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(n)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_total_max, e2e_ms_max = float(t_ms[0]), float(t_ms[1])
+    total_rows = float(cnt[0])
+    value = total_rows * args.steps / (ms_total_max * 1e-3)
+    e2e_value = total_rows * args.steps / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        bpe = k1_bytes_per_eval(n_comp, n_b, n_par, W)
+        peak, peak_src = measured_peak()
+        achieved = bpe * n / (k1_ms * 1e-3) / 1e9
+        cores = os.cpu_count() or 1
+        # CPU baseline: the oracle port on a bounded sample of the same workload
+        ns = min(args.cpu_sources, S)
+        sample_ids = np.linspace(0, S - 1, ns).astype(np.int64)
+        small, srcs, pl = build_host_sample(ms, dev_tables, raw, sample_ids, pars, W)
+        cpu_all = cpu_port_throughput(small, srcs, pl, cores)
+        cpu_one = cpu_port_throughput(small, srcs[:max(1, ns // cores)], pl[:max(1, ns // cores)], 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3: synthetic %d sources x %d walkers per GPU, 18-band default set, classic "
+                                   "10-parameter model (11000+161+60+2 templates), dictionary of %d z-slices in HBM"
+                                   % (S, W, info["n_z"]),
+                       "positions": args.positions + " in prior box + 1% out-of-box rows",
+                       "rows_per_step_per_gpu": n, "n_bands": n_b, "n_par": n_par,
+                       "l2_policy": "inputs larger than L2 (params %.0f MB + dictionary %.1f GB per GPU)" % (
+                           n * n_par * 8 / 1e6, info["k2_entries"] * 8 / 1e9),
+                       "parallelism": "sources sharded over %d GPU(s), no data-path collective" % world},
+            "sources_fitted_per_s": value / EVALS_PER_FIT,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * n_par * 8 + n * 4),
+                    "d2h_bytes_per_step": int(n * 8), "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k1_lnprob_kernel",
+                         "bytes_per_eval": bpe, "kernel_ms": k1_ms},
+            "cpu_baseline": {"value": cpu_all, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "oracle/agn_oracle.ln_probab on %d of the %d sources x %d walkers, vectorised "
+                                       "over a source's walkers, fork Pool over sources" % (ns, S, W),
+                             "one_core": cpu_one},
+            "dictionary_build": {"entries": int(info["k2_entries"]), "wall_s": info["k2_wall_s"],
+                                 "entries_per_s": info["k2_entries"] / info["k2_wall_s"]},
+            "clocks": sampler.summary(),
+            "finite_rows_last_step": check,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path.  The reference is Python and is not present
+    on the GPU box, so this arm times the oracle port (oracle/agn_oracle.py, pinned to the
+    reference by tests/golden) on all host cores, on bounded samples of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("the reference arm builds its synthetic dictionary sample with K2; needs the GPU box")
+    a2 = argparse.Namespace(**vars(args))
+    a2.sources = min(args.sources, 4000)         # the sample's dictionary; evaluated subset below
+    eng, ms, dev_tables, raw, pars, sid, info = make_workload(a2, 0, 0)
+    cores = os.cpu_count() or 1
+    ns = min(args.cpu_sources, a2.sources)
+    sample_ids = np.linspace(0, a2.sources - 1, ns).astype(np.int64)
+    small, srcs, pl = build_host_sample(ms, dev_tables, raw, sample_ids, pars, args.walkers)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_throughput(small, srcs[:cores], pl[:cores], cores)
+    vals = [cpu_port_throughput(small, srcs, pl, cores) for _ in range(args.steps)]
+    v = float(np.mean(vals))
+    n_step = ns * args.walkers
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": n_step / v * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 sample: %d sources x %d walkers per step of the same synthetic catalogue" % (
+            ns, args.walkers), "positions": args.positions},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "oracle port (NumPy, vectorised over a source's %d walkers), fork Pool over %d "
+                                   "sources on %d cores" % (args.walkers, ns, cores)},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sources", type=int, default=100000, help="sources per GPU")
+    ap.add_argument("--walkers", type=int, default=100)
+    ap.add_argument("--positions", default="uniform", choices=["uniform", "ball"])
+    ap.add_argument("--cpu-sources", type=int, default=384, help="sources in the CPU-baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,157 @@
+/*
+ * agnfit_b200 — C ABI of the B200-native AGNfitter hot path.
+ *
+ * The reference (GabrielaCR/AGNfitter) is pure Python and has no FFI; its plugin surface for
+ * this path is a set of Python callables.  Each entry point below names the
+ * reference callable it replaces (file:line relative to the AGNfitter tree); the ctypes binding
+ * a maintainer would add on the reference side is shown in INTEGRATION.md and implemented in
+ * agnfitter_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success, non-zero on error,
+ *     and never throws; agnf_last_error() returns a message for the last failure on that ctx
+ *     (or, for ctx == NULL, of the last failed agnf_ctx_create on this thread).
+ *   - the caller owns every buffer it passes; the library owns only what *_upload / *_build
+ *     allocate on the device and frees it in agnf_ctx_destroy.  No global state.
+ *   - one ctx per (process, device); create it AFTER fork (RUN_AGNfitter_multi.py:258 forks).
+ *   - "host" pointers are ordinary (ideally pinned) host memory; "_device" entry points take
+ *     device pointers and an optional cudaStream_t (as void*, NULL = the ctx's own stream).
+ *   - numeric results follow the reference: -inf outside the prior box or for a non-finite
+ *     prior (PARAMETERSPACE_AGNfitter.py:119-121,170-173), -9999 soft rejections
+ *     (PRIORS_AGNfitter.py:98,192), NaN propagation otherwise.
+ */
+#ifndef AGNFIT_B200_H
+#define AGNFIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AGNF_API __attribute__((visibility("default")))
+#else
+#define AGNF_API
+#endif
+
+#define AGNF_VERSION 1
+#define AGNF_MAX_FAMILIES 5   /* GA, SB, TO, BB, RAD — PARAMETERSPACE_AGNfitter.py:199 */
+#define AGNF_MAX_DIMS 4       /* most dimensions any template family has (MODEL_AGNfitter.py:163,498-510) */
+#define AGNF_MAX_BANDS 64     /* validity masks are 64-bit */
+#define AGNF_MAX_PARS 32
+
+typedef struct agnf_ctx agnf_ctx;
+
+AGNF_API int agnf_version(void);
+AGNF_API int agnf_ctx_create(int device, agnf_ctx** out);
+AGNF_API void agnf_ctx_destroy(agnf_ctx* ctx);
+AGNF_API const char* agnf_last_error(const agnf_ctx* ctx);
+/* blocks until everything queued on the ctx's stream has finished */
+AGNF_API int agnf_synchronize(agnf_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1 — batched log-posterior.  Replaces, for whole (source x walker) batches,
+ *   PARAMETERSPACE_AGNfitter.ln_probab   (PARAMETERSPACE_AGNfitter.py:153-173)
+ *     = ymodel (180-243) + ln_prior (109-124) -> PRIORS_AGNfitter.PRIORS (PRIORS_AGNfitter.py:7-75)
+ *       + ln_likelihood (127-150), with get_model.pick_nD / get_fluxes
+ *       (DICTIONARIES_AGNfitter.py:184-272) and the on-the-fly reddening laws
+ *       (MODEL_AGNfitter.py:1178-1255) inside.
+ * ------------------------------------------------------------------------------------------- */
+
+/* models.settings keys read on the path (PARAMETERSPACE:41-77,201-239; PRIORS:13-68) */
+typedef struct {
+  int32_t n_b;           /* bands                                                          */
+  int32_t n_z;           /* z-slices of the dictionary                                      */
+  int32_t n_par;         /* len(P['names'])                                                 */
+  int32_t n_fam;         /* 4, or 5 with RADIO                                              */
+  int32_t bbb_has_norm;  /* BBB in {R06, THB21}: BB is a fitted norm; else BB=0, /4 pi dL^2 */
+  int32_t radio;         /* settings['RADIO']                                               */
+  int32_t eb_mode;       /* PRIOR_energy_balance: 0 off, 1 'Flexible', 2 'Restrictive'      */
+  int32_t prior_agnfrac; /* PRIOR_AGNfraction (+ prior_stellar_mass)                        */
+  int32_t ga_free_ebv;   /* last GALAXY parameter is a free EBVgal (Calzetti on the fly)    */
+  int32_t bb_mode;       /* 0 all grid; 1 EBVbbb free; 2 EBVbbb,alphaScat free; 3 +Gamma grid */
+} agnf_config;
+
+AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg);
+
+/* One template family = one get_model object (DICTIONARIES_AGNfitter.py:172-182).
+ * Row order of `table` is the key insertion order of the reference's *Fdict. */
+typedef struct {
+  int32_t fam;                 /* 0 GA, 1 SB, 2 TO, 3 BB, 4 RAD                              */
+  int32_t n_dim;               /* fitted parameters of this family; 0 = one fixed template   */
+  int32_t par_offset;          /* first column of the family's block in a params row (P['idxs']) */
+  int32_t table_on_device;     /* `table` is a device pointer (e.g. written by agnf_dict_build) */
+  int64_t T;                   /* rows (distinct keys)                                       */
+  const int32_t* dim_is_grid;  /* [n_dim] 1 'grid' / 0 'free'                                */
+  const int32_t* dim_size;     /* [n_dim] distinct values ('free': 1)                        */
+  const int64_t* dim_stride;   /* [n_dim] row = sum idx_d * stride_d                         */
+  const double* grid_sorted;   /* concatenated over dims: distinct values, ascending         */
+  const int32_t* grid_perm;    /* same shape: first-appearance index of each sorted value    */
+  const double* table;         /* [n_z, T, n_b]                                              */
+  const double* aux;           /* [T] GALAXYatt_dict (GA, grid EBV) / STARBURST_LIRdict (SB); or NULL */
+} agnf_family_desc;
+
+AGNF_API int agnf_family_upload(agnf_ctx* ctx, const agnf_family_desc* fam);
+
+/* per-z-slice constants, all [n_z, n_b] / [n_z] host arrays (agnfitter_b200/sources.py:make_zslices) */
+AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double* cbbb, const uint64_t* xray_bits,
+                        const int32_t* j1500, const double* omega);
+
+/* per-source operands = the DATA object's fields (DATA_AGNfitter.py:357-369) after the
+ * walker-independent parts of ln_likelihood / Pdict / PRIORS have been evaluated on the host */
+AGNF_API int agnf_sources_upload(agnf_ctx* ctx, int64_t S, const int32_t* zi, const double* y, const double* inv_sigma,
+                        const uint64_t* valid_bits, const double* pmin, const double* pmax,
+                        const double* consts, int32_t n_const, const int32_t* agn_branch,
+                        const int32_t* irsyn_mode, const int32_t* irsyn_j);
+
+/* ln_probab for n rows.  params [n, n_par] row-major, source_id [n].  Outputs (any may be NULL
+ * except lnp): lnp [n]; rows [n, n_fam] snapped template row per family (pick_nD);
+ * ymodel [n, n_b] (PARAMETERSPACE.ymodel); lnprior [n]; lnlike [n].
+ * Host variant: copies in/out on the ctx stream and returns after the results are in the
+ * caller's buffers. */
+AGNF_API int agnf_lnprob_batch(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* lnp,
+                      int32_t* rows, double* ymodel, double* lnprior, double* lnlike);
+
+/* Device variant: all pointers are device pointers; asynchronous on `stream`. */
+AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, const int32_t* d_source_id, int64_t n,
+                             double* d_lnp, int32_t* d_rows, double* d_ymodel, double* d_lnprior,
+                             double* d_lnlike, void* stream);
+
+/* number of kernel launches this ctx has issued (bench.py's gpu_launches claim) */
+AGNF_API int64_t agnf_launch_count(const agnf_ctx* ctx);
+/* elapsed device time of the most recent K1 / K2 main kernel in ms (CUDA events on the launching stream) */
+AGNF_API int agnf_last_kernel_ms(agnf_ctx* ctx, int which /*1 = K1, 2 = K2 contraction*/, float* ms);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2 — dictionary build.  Replaces DICTIONARIES_AGNfitter.filtering_models
+ * (DICTIONARIES_AGNfitter.py:426-503) applied to every template of a family and every z
+ * (MODELSDICT.construct_dictionaryarray_filtered / build, DICTIONARIES_AGNfitter.py:78-154).
+ * ------------------------------------------------------------------------------------------- */
+
+/* filterdict = [central_nu_array, lambdas_dict, factors_dict] (FILTERS_AGNfitter.py:111-122),
+ * concatenated: band b (bands sorted by central nu) owns samples [offset[b], offset[b+1]) in the
+ * order stored in the filter file.  band_lambda_c[b] = nu2lambda_angstrom(central_nu_array[b])
+ * (DICTIONARIES_AGNfitter.py:464,498-503), evaluated by the caller with the same NumPy expression
+ * the reference uses so that no transcendental is re-derived on this side. */
+AGNF_API int agnf_filters_upload(agnf_ctx* ctx, int32_t n_b, const double* band_lambda_c, const int64_t* offset,
+                        const double* lambda_angstrom, const double* factor);
+
+/* filtering_models for T templates that share one frequency grid, at n_z redshifts.
+ *   lam_sorted [n_lam]  rest-frame wavelengths nu2lambda_angstrom(model_nus), ascending
+ *                       (caller: NumPy expression of DICTIONARIES:450,502 + stable argsort, as
+ *                       scipy interp1d does)
+ *   perm       [n_lam]  column of Fnu that holds the flux of lam_sorted[j]
+ *   Fnu        [T, n_lam] template F_nu in the template's stored order (host pointer)
+ *   z          [n_z]
+ *   out        [n_z, T_total, n_b]; template t writes row row_map[t] (NULL: identity, T_total = T).
+ * out is a host pointer (results copied back) or, with out_on_device = 1, a device pointer that
+ * can be handed to agnf_family_upload(table_on_device = 1) without leaving HBM. */
+AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int32_t* perm, const double* Fnu, int64_t T,
+                    int32_t n_lam, const double* z, int32_t n_z, const int64_t* row_map, int64_t T_total,
+                    double* out, int32_t out_on_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGNFIT_B200_H */

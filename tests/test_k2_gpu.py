@@ -1,0 +1,89 @@
+"""GPU: K2 (dictionary build) through the C ABI against the reference's filtering_models outputs
+(golden) and against the CPU oracle on synthetic templates.  Band fluxes within 1e-10 relative;
+entries the reference computes as exactly 0 (no spectral coverage) must be exactly 0."""
+import numpy as np
+import pytest
+
+from conftest import K2_CASES
+from helpers import load_k2, assert_close_with_specials
+from agnfitter_b200.engine import DictBuilder
+from agnfitter_b200 import synth
+from oracle import agn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _filterdict(g):
+    bands, off = g["bands"], g["filt_offset"]
+    ld = {b: [g["filt_lambda"][off[i]:off[i + 1]]] for i, b in enumerate(bands)}
+    fd = {b: [g["filt_factor"][off[i]:off[i + 1]]] for i, b in enumerate(bands)}
+    return [bands, ld, fd]
+
+
+@pytest.mark.parametrize("case", K2_CASES)
+def test_k2_matches_reference_golden(case):
+    g = load_k2(case)
+    builder = DictBuilder(_filterdict(g), device=0)
+    for fam in [str(x) for x in g["family_names"]]:
+        ref = g[fam + "_ref"]                       # [n_z, T, n_b]
+        tpl = {}
+        for i in range(ref.shape[1]):
+            n = int(g[fam + "_len"][i])
+            tpl[i] = (g[fam + "_lognu"][i, :n], g[fam + "_Fnu"][i, :n])
+        got = builder.build_family(tpl, g["z"])
+        assert got.shape == ref.shape
+        assert np.array_equal(got == 0.0, ref == 0.0), "%s: zero pattern (coverage) differs" % fam
+        assert_close_with_specials(got, ref, what=fam)
+        if fam in ("GA", "TO_S04"):
+            dev = builder.build_family(tpl, g["z"], on_device=True)
+            assert np.array_equal(dev.cpu().numpy(), got)
+
+
+def test_k2_filtering_models_signature():
+    g = load_k2("default18")
+    builder = DictBuilder(_filterdict(g), device=0)
+    bands, F = builder.filtering_models(g["BB_R06_lognu"][0], g["BB_R06_Fnu"][0], 0.283)
+    assert F.shape == (len(g["bands"]), 1) and np.array_equal(bands, g["bands"])
+    assert_close_with_specials(F[:, 0], g["BB_R06_ref"][1, 0], what="filtering_models")
+
+
+def test_k2_matches_oracle_on_synthetic_families():
+    fd = synth.synthetic_filterdict()
+    builder = DictBuilder(fd, device=0)
+    tpl = synth.synthetic_templates()
+    bands = fd[0]
+    lam = [np.asarray(fd[1][b][0]) for b in bands]
+    fac = [np.asarray(fd[2][b][0]) for b in bands]
+    z = np.array([0.0, 0.011, 0.5, 2.345, 5.999])
+    rng = np.random.default_rng(1)
+    for name in ("GA", "SB", "TO", "BB"):
+        keys = list(tpl[name]["F"].keys())
+        pick = [keys[i] for i in sorted(rng.choice(len(keys), size=min(len(keys), 24), replace=False))]
+        sub = {k: tpl[name]["F"][k] for k in pick}
+        got = builder.build_family(sub, z)
+        for zi, zz in enumerate(z):
+            for ti, k in enumerate(pick):
+                want = O.filtering_models(sub[k][0], sub[k][1], bands, lam, fac, float(zz))
+                assert np.array_equal(got[zi, ti] == 0.0, want == 0.0)
+                assert_close_with_specials(got[zi, ti], want, what="%s z=%g" % (name, zz))
+
+
+def test_k2_dense_zgrid_linearity_and_row_map():
+    """Size-independent properties on a dense z grid: linearity in the template flux, and ragged
+    families (two frequency grids) scatter into the right rows."""
+    fd = synth.synthetic_filterdict()
+    builder = DictBuilder(fd, device=0)
+    tpl = synth.synthetic_templates()
+    z = np.round(np.arange(0.0, 6.0, 0.01), 3)
+    to = tpl["TO"]["F"]
+    a = builder.build_family(to, z)
+    scaled = {k: (v[0], 3.0 * v[1]) for k, v in to.items()}
+    b = builder.build_family(scaled, z)
+    assert_close_with_specials(b, 3.0 * a, rtol=1e-14, what="linearity")
+    # ragged: every other template on a truncated grid
+    rag = {}
+    for i, (k, v) in enumerate(to.items()):
+        rag[k] = (v[0][:-5], v[1][:-5]) if i % 2 else v
+    c = builder.build_family(rag, z[:7])
+    full_sub = builder.build_family({k: v for i, (k, v) in enumerate(to.items()) if i % 2 == 0}, z[:7])
+    assert np.array_equal(c[:, 0::2], full_sub)

@@ -48,6 +48,8 @@ SIGNATURES = {
     "agnf_sources_upload": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_int32] + [C.c_void_p] * 3),
     "agnf_lnprob_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5),
     "agnf_lnprob_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6),
+    "agnf_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "agnf_debug_exp10": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "agnf_launch_count": (C.c_int64, [C.c_void_p]),
     "agnf_last_kernel_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "agnf_filters_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

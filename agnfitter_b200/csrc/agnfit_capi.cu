@@ -25,6 +25,7 @@ struct agnf_ctx {
   std::string err;
   std::vector<void*> owned;                    // device allocations freed in destroy
   int64_t launches = 0;
+  int k1_variant = 1;                          // 1: tiled kernel when the shape allows; 0: per-thread gather
 
   bool have_cfg = false;
   K1Params k1{};
@@ -225,6 +226,33 @@ AGNF_API int agnf_last_kernel_ms(agnf_ctx* ctx, int which, float* ms) {
   return fail(ctx, "agnf_last_kernel_ms: which must be 1 or 2");
 }
 
+AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return 1;
+  if (strcmp(name, "k1_variant") == 0) {
+    if (value != 0 && value != 1) return fail(ctx, "k1_variant must be 0 or 1");
+    ctx->k1_variant = (int)value;
+    return 0;
+  }
+  return fail(ctx, "unknown option '%s'", name);
+}
+
+AGNF_API int agnf_debug_exp10(agnf_ctx* ctx, const double* x, int64_t n, double* y) {
+  if (!ctx || !x || !y || n < 0) return 1;
+  if (n == 0) return 0;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  void *dx = nullptr, *dy = nullptr;
+  if (dev_alloc(ctx, &dx, (size_t)n * 8) || dev_alloc(ctx, &dy, (size_t)n * 8)) return 1;
+  cudaError_t e = cudaMemcpyAsync(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = launch_exp10_fast(static_cast<const double*>(dx), static_cast<double*>(dy), n, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, dx);
+  dev_free(ctx, dy);
+  if (e != cudaSuccess) return fail(ctx, "agnf_debug_exp10: %s", cudaGetErrorString(e));
+  ctx->launches += 1;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------- K1
 
 AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg) {
@@ -366,7 +394,8 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
   K1Batch B{d_params, d_source_id, n, d_lnp, d_rows, d_ymodel, d_lnprior, d_lnlike};
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-  CUDA_TRY(ctx, launch_k1(ctx->k1, B, st));
+  if (ctx->k1_variant == 1 && k1_tile_supported(ctx->k1)) CUDA_TRY(ctx, launch_k1_tile(ctx->k1, B, st));
+  else CUDA_TRY(ctx, launch_k1(ctx->k1, B, st));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
   ctx->k1_timed = true;
   ctx->launches += 1;

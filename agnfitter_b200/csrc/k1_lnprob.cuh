@@ -81,4 +81,9 @@ struct K1Batch {
 
 cudaError_t launch_k1(const K1Params& P, const K1Batch& B, cudaStream_t stream);
 
+// tiled variant (k1_tile.cu): same results, warp-cooperative cp.async staging of the template rows
+bool k1_tile_supported(const K1Params& P);
+cudaError_t launch_k1_tile(const K1Params& P, const K1Batch& B, cudaStream_t stream);
+cudaError_t launch_exp10_fast(const double* x, double* y, int64_t n, cudaStream_t stream);
+
 }  // namespace agnf

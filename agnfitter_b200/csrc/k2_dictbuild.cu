@@ -100,18 +100,23 @@ __global__ void k2_weights_kernel(K2Problem p) {
 // Banded contraction.  grid = (n_z, ceil(T / K2_TILE_T)); the z-slice's weights are staged in
 // shared memory and reused by the tile's templates; outputs are written band-fastest so a warp
 // stores contiguous rows of the [n_z, T, n_b] table.
+// W_SMEM = false: the weight rows are too long for shared memory (e.g. X-ray bands over the
+// 1000-point power-law tail of MODEL_AGNfitter.XRAYS) and are read through L1/L2 instead.
+template <bool W_SMEM>
 __global__ void __launch_bounds__(K2_THREADS) k2_contract_kernel(K2Problem p) {
   extern __shared__ double s_w[];
   const int n_b = p.filt.n_b;
   const int rmax = p.rmax;
-  const int rp = rmax | 1;                        // odd row pitch: spreads bands over banks
+  const int rp = W_SMEM ? (rmax | 1) : 0;         // odd row pitch: spreads bands over banks
   int32_t* s_jlo = reinterpret_cast<int32_t*>(s_w + (size_t)n_b * rp);
   int32_t* s_cnt = s_jlo + n_b;
   const int zi = blockIdx.x;
   const double* __restrict__ Wz = p.W + (int64_t)zi * n_b * rmax;
-  for (int i = threadIdx.x; i < n_b * rmax; i += blockDim.x) {
-    const int b = i / rmax, r = i - b * rmax;
-    s_w[b * rp + r] = __ldg(Wz + i);
+  if (W_SMEM) {
+    for (int i = threadIdx.x; i < n_b * rmax; i += blockDim.x) {
+      const int b = i / rmax, r = i - b * rmax;
+      s_w[b * rp + r] = __ldg(Wz + i);
+    }
   }
   for (int b = threadIdx.x; b < n_b; b += blockDim.x) {
     s_jlo[b] = __ldg(p.jlo + zi * n_b + b);
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_contract_kernel(K2Problem p) {
     const int64_t t = t0 + tt;
     if (t >= p.T) break;
     const double* __restrict__ F = p.Fs + t * p.ldF + s_jlo[b];
-    const double* w = s_w + b * rp;
+    const double* w = W_SMEM ? (s_w + b * rp) : (Wz + b * rmax);
     const int c = s_cnt[b];
     double acc = 0.0;
     for (int r = 0; r < c; ++r) acc = fma(w[r], __ldg(F + r), acc);
@@ -161,11 +166,19 @@ cudaError_t launch_k2_weights(const K2Problem& p, cudaStream_t stream) {
 cudaError_t launch_k2_contract(const K2Problem& p, cudaStream_t stream) {
   if (p.n_z == 0 || p.T == 0) return cudaSuccess;
   const int rp = p.rmax | 1;
-  const size_t smem = (size_t)p.filt.n_b * rp * sizeof(double) + 2 * (size_t)p.filt.n_b * sizeof(int32_t);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(k2_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t idx_bytes = 2 * (size_t)p.filt.n_b * sizeof(int32_t);
+  const size_t smem = (size_t)p.filt.n_b * rp * sizeof(double) + idx_bytes;
   dim3 grid((unsigned)p.n_z, (unsigned)((p.T + K2_TILE_T - 1) / K2_TILE_T));
-  k2_contract_kernel<<<grid, K2_THREADS, smem, stream>>>(p);
+  if (smem <= 96 * 1024) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k2_contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    k2_contract_kernel<true><<<grid, K2_THREADS, smem, stream>>>(p);
+  } else {
+    k2_contract_kernel<false><<<grid, K2_THREADS, idx_bytes, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 

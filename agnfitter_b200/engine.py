@@ -75,19 +75,22 @@ class Engine:
             self.ctx.check(self.lib.agnf_family_upload(self.ctx.h, C.byref(d)))
         zs = zslices if zslices is not None else make_zslices(ms)
         self.zslices = zs
-        self.ctx.check(self.lib.agnf_zslices_upload(
-            self.ctx.h, ptr(as_f64(zs.cgal)), ptr(as_f64(zs.cbbb)), ptr(as_u64(zs.xray)),
-            ptr(as_i32(zs.j1500)), ptr(as_f64(zs.omega))))
+        cgal, cbbb, xray, j1500, omega = (as_f64(zs.cgal), as_f64(zs.cbbb), as_u64(zs.xray), as_i32(zs.j1500),
+                                          as_f64(zs.omega))
+        self.ctx.check(self.lib.agnf_zslices_upload(self.ctx.h, ptr(cgal), ptr(cbbb), ptr(xray), ptr(j1500),
+                                                    ptr(omega)))
         self.S = 0
 
     # -- catalogue shard ---------------------------------------------------------------------
     def set_sources(self, src: SourceSet):
         if src.y.shape[1] != self.n_b or src.pmin.shape[1] != self.n_par:
             raise ValueError("SourceSet does not match the ModelSet")
+        zi, y, isig, mask = as_i32(src.zi), as_f64(src.y), as_f64(src.isig), as_u64(src.mask)
+        pmin, pmax, consts = as_f64(src.pmin), as_f64(src.pmax), as_f64(src.consts)
+        br, im, ij = as_i32(src.agn_branch), as_i32(src.irsyn_mode), as_i32(src.irsyn_j)
         self.ctx.check(self.lib.agnf_sources_upload(
-            self.ctx.h, src.S, ptr(as_i32(src.zi)), ptr(as_f64(src.y)), ptr(as_f64(src.isig)),
-            ptr(as_u64(src.mask)), ptr(as_f64(src.pmin)), ptr(as_f64(src.pmax)), ptr(as_f64(src.consts)),
-            C_NCONST, ptr(as_i32(src.agn_branch)), ptr(as_i32(src.irsyn_mode)), ptr(as_i32(src.irsyn_j))))
+            self.ctx.h, src.S, ptr(zi), ptr(y), ptr(isig), ptr(mask), ptr(pmin), ptr(pmax), ptr(consts),
+            C_NCONST, ptr(br), ptr(im), ptr(ij)))
         self.S = src.S
 
     # -- evaluation: host buffers in, host buffers out (the reference-facing path) -------------
@@ -126,6 +129,15 @@ class Engine:
             self.ctx.h, params_t.data_ptr(), sid_t.data_ptr(), n, lnp_t.data_ptr(),
             rows_t.data_ptr() if rows_t is not None else None,
             ymodel_t.data_ptr() if ymodel_t is not None else None, None, None, stream_ptr))
+
+    def set_option(self, name, value):
+        self.ctx.check(self.lib.agnf_set_option(self.ctx.h, name.encode(), int(value)))
+
+    def debug_exp10(self, x):
+        x = as_f64(x)
+        y = np.empty_like(x)
+        self.ctx.check(self.lib.agnf_debug_exp10(self.ctx.h, ptr(x), x.size, ptr(y)))
+        return y
 
     def synchronize(self):
         self.ctx.check(self.lib.agnf_synchronize(self.ctx.h))
@@ -166,10 +178,13 @@ class DictBuilder:
             fac.append(F[0])
             off.append(off[-1] + L.shape[1])
         self.n_b = len(self.bands)
-        band_lam_c = _C / (10 ** self.bands) * _ANG            # nu2lambda_angstrom(iband), DICTIONARIES:464
+        # NB every array handed to the C ABI is bound to a local first: ptr() of a temporary dangles
+        band_lam_c = as_f64(_C / (10 ** self.bands) * _ANG)    # nu2lambda_angstrom(iband), DICTIONARIES:464
+        off_a = as_i64(off)
+        lam_a = as_f64(np.concatenate(lam))
+        fac_a = as_f64(np.concatenate(fac))
         self.ctx.check(self.lib.agnf_filters_upload(
-            self.ctx.h, self.n_b, ptr(as_f64(band_lam_c)), ptr(as_i64(off)),
-            ptr(as_f64(np.concatenate(lam))), ptr(as_f64(np.concatenate(fac)))))
+            self.ctx.h, self.n_b, ptr(band_lam_c), ptr(off_a), ptr(lam_a), ptr(fac_a)))
         self.contract_ms = 0.0
 
     def build_family(self, templates, z_array, on_device=False):

@@ -150,6 +150,9 @@ def make_workload(args, rank, device, need_gpu=True):
     nus = np.asarray(fd[0])
     S, W = args.sources, args.walkers
     z, dlum, rng = synth.synthetic_catalog(None, S, seed=20260101 + rank)
+    if not args.no_sort_z:
+        order = np.argsort(z, kind="stable")       # host-side processing order of the shard
+        z, dlum = z[order], dlum[order]
     z_grid = np.unique(z)
     builder = DictBuilder(fd, device=device)
     torch.cuda.synchronize(device)
@@ -159,6 +162,7 @@ def make_workload(args, rank, device, need_gpu=True):
     k2_wall = time.perf_counter() - t0
     n_entries = len(z_grid) * sum(f.T for f in ms.families) * ms.n_b
     eng = Engine(ms, device=device, ctx=builder.ctx, device_tables=dev_tables)
+    eng.set_option("k1_variant", args.variant)
     # fluxes from ymodel(truth) of every source, evaluated by K1 itself
     dummy = sources.make_sources(ms, z, dlum, nus, np.ones((S, ms.n_b)), np.ones((S, ms.n_b)))
     eng.set_sources(dummy)
@@ -196,8 +200,10 @@ def run_ours(args):
     d_sid = h_sid.to(dev, non_blocking=True)
     d_lnp = torch.empty(n, dtype=torch.float64, device=dev)
     h_lnp = torch.empty(n, dtype=torch.float64).pin_memory()
-    stream = torch.cuda.current_stream(dev)
+    torch.cuda.synchronize(dev)
+    stream = torch.cuda.Stream(dev)          # a real stream: handle 0 would mean "the ctx's own stream" to the ABI
     sp = stream.cuda_stream
+    assert sp != 0
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -276,6 +282,8 @@ def run_ours(args):
                                    "10-parameter model (11000+161+60+2 templates), dictionary of %d z-slices in HBM"
                                    % (S, W, info["n_z"]),
                        "positions": args.positions + " in prior box + 1% out-of-box rows",
+                       "source_order": "random z" if args.no_sort_z else "sorted by z",
+                       "k1_variant": "tiled cp.async" if args.variant == 1 else "per-thread gather",
                        "rows_per_step_per_gpu": n, "n_bands": n_b, "n_par": n_par,
                        "l2_policy": "inputs larger than L2 (params %.0f MB + dictionary %.1f GB per GPU)" % (
                            n * n_par * 8 / 1e6, info["k2_entries"] * 8 / 1e9),
@@ -347,6 +355,10 @@ def main():
     ap.add_argument("--sources", type=int, default=100000, help="sources per GPU")
     ap.add_argument("--walkers", type=int, default=100)
     ap.add_argument("--positions", default="uniform", choices=["uniform", "ball"])
+    ap.add_argument("--variant", type=int, default=1, help="K1 kernel: 1 tiled (default), 0 per-thread gather")
+    ap.add_argument("--no-sort-z", action="store_true",
+                    help="keep the catalogue in random z order (default: the shard is processed in z order so "
+                         "that sources sharing a dictionary z-slice are adjacent)")
     ap.add_argument("--cpu-sources", type=int, default=384, help="sources in the CPU-baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -118,6 +118,12 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
                              double* d_lnp, int32_t* d_rows, double* d_ymodel, double* d_lnprior,
                              double* d_lnlike, void* stream);
 
+/* tuning knobs.  "k1_variant": 1 (default) = tiled K1 (warp-cooperative cp.async staging) whenever the
+ * band count has a compiled instantiation, 0 = per-thread gather K1 (any band count). */
+AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value);
+/* y[i] = 10^x[i] through the kernels' own exp10 routine (host pointers; unit-test hook) */
+AGNF_API int agnf_debug_exp10(agnf_ctx* ctx, const double* x, int64_t n, double* y);
+
 /* number of kernel launches this ctx has issued (bench.py's gpu_launches claim) */
 AGNF_API int64_t agnf_launch_count(const agnf_ctx* ctx);
 /* elapsed device time of the most recent K1 / K2 main kernel in ms (CUDA events on the launching stream) */

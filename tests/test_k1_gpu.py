@@ -14,17 +14,23 @@ from oracle import agn_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _engine(ms, g):
+def _engine(ms, g, variant=None):
     eng = Engine(ms, device=0)
+    if variant is not None:
+        eng.set_option("k1_variant", variant)
     src = sources.make_sources(ms, g["src_z"], g["src_dlum"], g["src_nus"], g["src_fluxes"], g["src_fluxerrs"])
     eng.set_sources(src)
     return eng, src
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("case", K1_CASES)
-def test_k1_matches_reference_golden(case):
+def test_k1_matches_reference_golden(case, variant):
+    """variant 1 = tiled kernel (used when the band count has an instantiation), 0 = per-thread gather."""
     ms, g = load_k1(case)
-    eng, _ = _engine(ms, g)
+    if variant == 1 and ms.n_b != 18:
+        pytest.skip("tiled K1 is instantiated for 18 bands; other band counts run the per-thread kernel")
+    eng, _ = _engine(ms, g, variant)
     lnp, rows, ym, lpr, lll = eng.lnprob(g["pars"], g["source_id"], detail=True)
     assert np.array_equal(rows, g["ref_rows"]), "template indices must be bit-exact"
     assert_close_with_specials(ym, g["ref_ymodel"], what="ymodel")
@@ -120,3 +126,37 @@ def test_k1_empty_and_errors():
         eng.lnprob(np.zeros((3, ms.n_par + 1)))
     with pytest.raises(IndexError):
         eng.lnprob(np.zeros((3, ms.n_par)), np.array([0, 1, 7], dtype=np.int32))
+
+
+def test_k1_variants_agree_and_tail_handling():
+    """Both kernels on batches whose size is not a multiple of the warp / CTA size."""
+    ms, g = load_k1("classic18")
+    rng = np.random.default_rng(3)
+    outs = {}
+    for variant in (0, 1):
+        eng, src = _engine(ms, g, variant)
+        res = []
+        for n in (1, 31, 33, 127, 129, 1000, 4097):
+            r2 = np.random.default_rng(n)
+            sid = r2.integers(src.S, size=n).astype(np.int32)
+            pars = src.pmin[sid] + r2.uniform(size=(n, ms.n_par)) * (src.pmax[sid] - src.pmin[sid])
+            res.append(eng.lnprob(pars, sid, detail=True))
+        outs[variant] = res
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a[1], b[1])                      # rows
+        for k in (0, 2, 3, 4):
+            assert_close_with_specials(b[k], a[k], rtol=1e-12, what="variant output %d" % k)
+
+
+def test_exp10_fast_accuracy():
+    """The kernels' own 10**x (table + degree-6 polynomial) against NumPy, incl. special values."""
+    ms, g = load_k1("agnoff18")
+    eng, _ = _engine(ms, g)
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-40, 40, 200000), rng.uniform(-299, 299, 50000), rng.uniform(-1e-3, 1e-3, 1000),
+                        np.array([0.0, -0.0, 1.0, -1.0, 10.0, -10.0, 299.999, -299.999, 300.0, -300.0, 308.0,
+                                  -320.0, 400.0, -400.0, np.inf, -np.inf, np.nan])])
+    y = eng.debug_exp10(x)
+    with np.errstate(all="ignore"):
+        want = 10.0 ** x
+    assert_close_with_specials(y, want, rtol=2e-15, what="exp10_fast")

@@ -32,7 +32,7 @@ class agnf_family_desc(C.Structure):
                 ("table_on_device", C.c_int32), ("T", C.c_int64),
                 ("dim_is_grid", C.c_void_p), ("dim_size", C.c_void_p), ("dim_stride", C.c_void_p),
                 ("grid_sorted", C.c_void_p), ("grid_perm", C.c_void_p), ("table", C.c_void_p),
-                ("aux", C.c_void_p)]
+                ("aux", C.c_void_p), ("table_pitch", C.c_int32), ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/agnfit_b200.h declares
@@ -49,12 +49,13 @@ SIGNATURES = {
     "agnf_lnprob_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5),
     "agnf_lnprob_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6),
     "agnf_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "agnf_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "agnf_debug_exp10": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "agnf_launch_count": (C.c_int64, [C.c_void_p]),
     "agnf_last_kernel_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "agnf_filters_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnf_dict_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
-                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32]),
 }
 
 _lib = None

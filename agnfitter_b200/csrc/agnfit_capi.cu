@@ -1,6 +1,8 @@
 // C ABI of libagnfit_b200.so (declared in include/agnfit_b200.h).  Owns the device-side copies of
 // the dictionary / per-source operands and launches K1 and K2.  No torch types anywhere.
 #include <algorithm>
+#include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -25,13 +27,15 @@ struct agnf_ctx {
   std::string err;
   std::vector<void*> owned;                    // device allocations freed in destroy
   int64_t launches = 0;
-  int k1_variant = 1;                          // 1: tiled kernel when the shape allows; 0: per-thread gather
+  int k1_variant = 1;                          // 1: cooperative kernel when its preconditions hold; 0: per-thread
+  int last_k1_kernel = -1;                     // which kernel the last K1 launch used
 
   bool have_cfg = false;
   K1Params k1{};
   bool fam_set[AGNF_MAX_FAMILIES] = {false, false, false, false, false};
   std::vector<double> h_grid;                  // staged grid values (host mirror, rebuilt per upload)
   std::vector<int32_t> h_perm;
+  void* d_stage = nullptr;
   std::vector<int32_t> fam_grid_len = std::vector<int32_t>(AGNF_MAX_FAMILIES, 0);
   std::vector<std::vector<double>> fam_grid = std::vector<std::vector<double>>(AGNF_MAX_FAMILIES);
   std::vector<std::vector<int32_t>> fam_perm = std::vector<std::vector<int32_t>>(AGNF_MAX_FAMILIES);
@@ -96,6 +100,20 @@ int upload(agnf_ctx* ctx, const T** dst, const T* src, size_t count) {
   return 0;
 }
 
+// [rows, n_b] host array -> [rows, nbp] device array, pad columns zero
+int upload_padded(agnf_ctx* ctx, const double** dst, const double* src, size_t rows, int n_b, int nbp) {
+  if (*dst) dev_free(ctx, const_cast<double*>(*dst));
+  void* p = nullptr;
+  if (dev_alloc(ctx, &p, rows * (size_t)nbp * 8)) return 1;
+  if (rows) {
+    if (nbp != n_b) CUDA_TRY(ctx, cudaMemsetAsync(p, 0, rows * (size_t)nbp * 8, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(p, (size_t)nbp * 8, src, (size_t)n_b * 8, (size_t)n_b * 8, rows,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+  }
+  *dst = static_cast<const double*>(p);
+  return 0;
+}
+
 int ensure(agnf_ctx* ctx, void** p, size_t* cap, size_t bytes) {
   if (*cap >= bytes) return 0;
   if (*p) dev_free(ctx, *p);
@@ -109,32 +127,105 @@ int rebuild_grids(agnf_ctx* ctx) {
   if (!ctx->grids_dirty) return 0;
   ctx->h_grid.clear();
   ctx->h_perm.clear();
+  std::vector<double> ext;          // sentinel-extended sorted grids
+  std::vector<int32_t> eperm;
+  std::vector<uint16_t> lut;
   for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
     if (!ctx->fam_set[f]) continue;
     int off = (int)ctx->h_grid.size();
     int local = 0;
     FamDesc& F = ctx->k1.fam[f];
     for (int d = 0; d < F.n_dim; ++d) {
-      F.dim[d].smem_off = off + local;
-      local += F.dim[d].size;
+      DimDesc& D = F.dim[d];
+      D.smem_off = off + local;
+      const double* sv = ctx->fam_grid[f].data() + local;
+      const int32_t* pv = ctx->fam_perm[f].data() + local;
+      const int n = D.size;
+      D.ext_off = (int)ext.size();
+      ext.push_back(-INFINITY);
+      eperm.push_back(INT32_MAX);
+      for (int k = 0; k < n; ++k) {
+        ext.push_back(sv[k]);
+        eperm.push_back(pv[k]);
+      }
+      ext.push_back(INFINITY);
+      eperm.push_back(INT32_MAX);
+      // Cell table for the snap (k1_common.cuh::snap_dim_lut).  The table path is exact only if, for
+      // |p| <= big, two grid values can never give the same rounded |g - p| unless they bracket p:
+      // with M = max |g| and big = 1e6 M, |g - p| < 2e6 M, whose ulp (< 5e-10 M) must stay below the
+      // smallest spacing; we ask for spacing >= 1e-6 M.  Each cell may hold at most 2 grid values
+      // (the kernel makes 2 up-steps); otherwise the cell count doubles, up to 4096.
+      D.lut_off = (int)lut.size();
+      D.lut_m = 0;
+      D.lut_lo = D.lut_inv = D.lut_big = 0.0;
+      if (D.is_grid && n > 1 && n < 60000 && std::isfinite(sv[0]) && std::isfinite(sv[n - 1])) {
+        const double M = std::max(std::fabs(sv[0]), std::fabs(sv[n - 1]));
+        double min_gap = INFINITY;
+        for (int k = 1; k < n; ++k) min_gap = std::min(min_gap, sv[k] - sv[k - 1]);
+        const double span = sv[n - 1] - sv[0];
+        if (min_gap >= 1e-6 * M && std::isfinite(span) && span > 0.0) {
+          int m = 16;
+          while (m < 4 * n && m < 4096) m *= 2;
+          for (; m <= 4096; m *= 2) {
+            std::vector<uint16_t> cand((size_t)m);
+            bool ok = true;
+            int l = 0;                               // sv index of the last value <= left edge
+            for (int c = 0; c < m && ok; ++c) {
+              const double left = sv[0] + span * ((double)c / (double)m);
+              const double right = sv[0] + span * ((double)(c + 1) / (double)m);
+              while (l + 1 < n && sv[l + 1] <= left) ++l;
+              int le = l;
+              while (le + 1 < n && sv[le + 1] <= right) ++le;
+              if (le - l > 2) ok = false;
+              cand[(size_t)c] = (uint16_t)(l + 1);   // ext indexing
+            }
+            if (ok) {
+              D.lut_m = m;
+              D.lut_lo = sv[0];
+              D.lut_inv = (double)m / span;
+              D.lut_big = 1e6 * M;
+              lut.insert(lut.end(), cand.begin(), cand.end());
+              break;
+            }
+          }
+        }
+      }
+      local += D.size;
     }
     ctx->h_grid.insert(ctx->h_grid.end(), ctx->fam_grid[f].begin(), ctx->fam_grid[f].end());
     ctx->h_perm.insert(ctx->h_perm.end(), ctx->fam_perm[f].begin(), ctx->fam_perm[f].end());
   }
+  // blob for the cooperative kernel
+  auto pad16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  const size_t off_grid = 0, off_perm = off_grid + pad16(ext.size() * 8),
+               off_lut = off_perm + pad16(eperm.size() * 4), total = off_lut + pad16(lut.size() * 2);
+  std::vector<unsigned char> blob(total + 16, 0);
+  if (!ext.empty()) memcpy(blob.data() + off_grid, ext.data(), ext.size() * 8);
+  if (!eperm.empty()) memcpy(blob.data() + off_perm, eperm.data(), eperm.size() * 4);
+  if (!lut.empty()) memcpy(blob.data() + off_lut, lut.data(), lut.size() * 2);
+
   if (ctx->d_grid) dev_free(ctx, ctx->d_grid);
   if (ctx->d_perm) dev_free(ctx, ctx->d_perm);
+  if (ctx->d_stage) dev_free(ctx, ctx->d_stage);
   if (dev_alloc(ctx, &ctx->d_grid, ctx->h_grid.size() * sizeof(double))) return 1;
   if (dev_alloc(ctx, &ctx->d_perm, ctx->h_perm.size() * sizeof(int32_t))) return 1;
+  if (dev_alloc(ctx, &ctx->d_stage, total)) return 1;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage, blob.data(), total, cudaMemcpyHostToDevice, ctx->stream));
   if (!ctx->h_grid.empty()) {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_grid, ctx->h_grid.data(), ctx->h_grid.size() * sizeof(double),
                                   cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_perm, ctx->h_perm.data(), ctx->h_perm.size() * sizeof(int32_t),
                                   cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors may be rebuilt later
   }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));     // host vectors go out of scope / may be rebuilt
   ctx->k1.grid_sorted = static_cast<const double*>(ctx->d_grid);
   ctx->k1.grid_perm = static_cast<const int32_t*>(ctx->d_perm);
   ctx->k1.n_grid_vals = (int32_t)ctx->h_grid.size();
+  ctx->k1.stage = static_cast<const unsigned char*>(ctx->d_stage);
+  ctx->k1.stage_bytes = (int32_t)total;
+  ctx->k1.stage_off_grid = (int32_t)off_grid;
+  ctx->k1.stage_off_perm = (int32_t)off_perm;
+  ctx->k1.stage_off_lut = (int32_t)off_lut;
   ctx->grids_dirty = false;
   return 0;
 }
@@ -229,11 +320,20 @@ AGNF_API int agnf_last_kernel_ms(agnf_ctx* ctx, int which, float* ms) {
 AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return 1;
   if (strcmp(name, "k1_variant") == 0) {
-    if (value != 0 && value != 1) return fail(ctx, "k1_variant must be 0 or 1");
+    if (value != 0 && value != 1) return fail(ctx, "k1_variant must be 0 (per-thread) or 1 (cooperative)");
     ctx->k1_variant = (int)value;
     return 0;
   }
   return fail(ctx, "unknown option '%s'", name);
+}
+
+AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
+  if (!ctx || !name || !value) return 1;
+  if (strcmp(name, "k1_variant") == 0) *value = ctx->k1_variant;
+  else if (strcmp(name, "k1_last_kernel") == 0) *value = ctx->last_k1_kernel;
+  else if (strcmp(name, "band_pitch") == 0) *value = ctx->have_cfg ? ctx->k1.nbp : 0;
+  else return fail(ctx, "unknown option '%s'", name);
+  return 0;
 }
 
 AGNF_API int agnf_debug_exp10(agnf_ctx* ctx, const double* x, int64_t n, double* y) {
@@ -267,6 +367,11 @@ AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg) {
   ctx->k1.cfg = *cfg;
   const int n_norm = 3 + (cfg->bbb_has_norm ? 1 : 0) + (cfg->radio ? 1 : 0);
   ctx->k1.norm_offset = cfg->n_par - n_norm;
+  ctx->k1.nbp = (cfg->n_b + 1) & ~1;
+  // log(1 / (sqrt(2 pi) sigma)) as PRIORS_AGNfitter.py:429 writes it, in host libm
+  ctx->k1.lognorm_s2 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 2.0));
+  ctx->k1.lognorm_s15 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 1.5));
+  ctx->k1.lognorm_s01 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 0.1));
   ctx->have_cfg = true;
   return 0;
 }
@@ -310,13 +415,18 @@ AGNF_API int agnf_family_upload(agnf_ctx* ctx, const agnf_family_desc* fd) {
   }
   if (max_row >= fd->T) return fail(ctx, "family %d: strides address row %lld but T=%lld", f, (long long)max_row,
                                     (long long)fd->T);
-  const size_t count = (size_t)cfg.n_z * (size_t)fd->T * (size_t)cfg.n_b;
   if (fd->table_on_device) {
+    const int pitch = fd->table_pitch > 0 ? fd->table_pitch : cfg.n_b;
+    if (pitch < cfg.n_b) return fail(ctx, "family %d: table_pitch %d < n_b %d", f, pitch, cfg.n_b);
     F.table = fd->table;
+    F.pitch = pitch;
   } else {
+    if (fd->table_pitch > 0 && fd->table_pitch != cfg.n_b)
+      return fail(ctx, "family %d: host tables must be dense (table_pitch 0 or n_b)", f);
     const double* old = nullptr;   // previous upload of this family (if any) stays owned until destroy
-    if (upload(ctx, &old, fd->table, count)) return 1;
+    if (upload_padded(ctx, &old, fd->table, (size_t)cfg.n_z * (size_t)fd->T, cfg.n_b, ctx->k1.nbp)) return 1;
     F.table = old;
+    F.pitch = ctx->k1.nbp;
   }
   F.aux = nullptr;
   if (fd->aux) {
@@ -341,11 +451,11 @@ AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double
     if (ctx->k1.cfg.prior_agnfrac && (j1500[i] < 0 || j1500[i] >= (int)nb))
       return fail(ctx, "z-slice %zu: no band with 14.3 < log nu_rest < 15.3; prior_AGNfraction would raise "
                        "IndexError in the reference (PRIORS_AGNfitter.py:166)", i);
-  if (upload(ctx, &ctx->k1.cgal, cgal, nz * nb)) return 1;
-  if (upload(ctx, &ctx->k1.cbbb, cbbb, nz * nb)) return 1;
+  if (upload_padded(ctx, &ctx->k1.cgal, cgal, nz, (int)nb, ctx->k1.nbp)) return 1;
+  if (upload_padded(ctx, &ctx->k1.cbbb, cbbb, nz, (int)nb, ctx->k1.nbp)) return 1;
   if (upload(ctx, &ctx->k1.xray, xray_bits, nz)) return 1;
   if (upload(ctx, &ctx->k1.j1500, j1500, nz)) return 1;
-  if (upload(ctx, &ctx->k1.omega, omega, nz * nb)) return 1;
+  if (upload_padded(ctx, &ctx->k1.omega, omega, nz, (int)nb, ctx->k1.nbp)) return 1;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->have_z = true;
   return 0;
@@ -366,11 +476,17 @@ AGNF_API int agnf_sources_upload(agnf_ctx* ctx, int64_t S, const int32_t* zi, co
   for (size_t i = 0; i < s; ++i)
     if (zi[i] < 0 || zi[i] >= ctx->k1.cfg.n_z) return fail(ctx, "source %zu: z-slice %d out of range", i, zi[i]);
   if (upload(ctx, &ctx->k1.zi, zi, s)) return 1;
-  if (upload(ctx, &ctx->k1.y, y, s * nb)) return 1;
-  if (upload(ctx, &ctx->k1.isig, inv_sigma, s * nb)) return 1;
+  if (upload_padded(ctx, &ctx->k1.y, y, s, (int)nb, ctx->k1.nbp)) return 1;
+  if (upload_padded(ctx, &ctx->k1.isig, inv_sigma, s, (int)nb, ctx->k1.nbp)) return 1;
   if (upload(ctx, &ctx->k1.valid, valid_bits, s)) return 1;
   if (upload(ctx, &ctx->k1.pmin, pmin, s * np)) return 1;
   if (upload(ctx, &ctx->k1.pmax, pmax, s * np)) return 1;
+  {
+    std::vector<double2> box(s * np);
+    for (size_t i = 0; i < s * np; ++i) box[i] = make_double2(pmin[i], pmax[i]);
+    if (upload(ctx, &ctx->k1.pbox, box.data(), s * np)) return 1;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // `box` dies at the end of this scope
+  }
   if (upload(ctx, &ctx->k1.consts, consts, s * (size_t)n_const)) return 1;
   if (upload(ctx, &ctx->k1.agn_branch, agn_branch, s)) return 1;
   if (upload(ctx, &ctx->k1.irsyn_mode, irsyn_mode, s)) return 1;
@@ -394,8 +510,14 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
   K1Batch B{d_params, d_source_id, n, d_lnp, d_rows, d_ymodel, d_lnprior, d_lnlike};
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-  if (ctx->k1_variant == 1 && k1_tile_supported(ctx->k1)) CUDA_TRY(ctx, launch_k1_tile(ctx->k1, B, st));
-  else CUDA_TRY(ctx, launch_k1(ctx->k1, B, st));
+  const char* why = nullptr;
+  if (ctx->k1_variant == 1 && k1_coop_supported(ctx->k1, B, &why)) {
+    CUDA_TRY(ctx, launch_k1_coop(ctx->k1, B, st));
+    ctx->last_k1_kernel = 1;
+  } else {
+    CUDA_TRY(ctx, launch_k1(ctx->k1, B, st));
+    ctx->last_k1_kernel = 0;
+  }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
   ctx->k1_timed = true;
   ctx->launches += 1;
@@ -488,13 +610,16 @@ AGNF_API int agnf_filters_upload(agnf_ctx* ctx, int32_t n_b, const double* band_
 
 AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int32_t* perm, const double* Fnu, int64_t T,
                     int32_t n_lam, const double* z, int32_t n_z, const int64_t* row_map, int64_t T_total,
-                    double* out, int32_t out_on_device) {
+                    double* out, int32_t out_on_device, int32_t out_pitch) {
   if (!ctx) return 1;
   if (!ctx->have_filt) return fail(ctx, "call agnf_filters_upload first");
   if (!lam_sorted || !perm || !Fnu || !z || !out) return fail(ctx, "agnf_dict_build: NULL argument");
   if (T < 1 || n_lam < 1 || n_z < 1) return fail(ctx, "agnf_dict_build: empty problem");
   if (!row_map) T_total = T;
   if (T_total < T) return fail(ctx, "T_total < T");
+  if (out_pitch == 0) out_pitch = ctx->filt.n_b;
+  if (out_pitch < ctx->filt.n_b) return fail(ctx, "out_pitch %d < n_b %d", out_pitch, ctx->filt.n_b);
+  if (!out_on_device && out_pitch != ctx->filt.n_b) return fail(ctx, "host outputs must be dense (out_pitch 0 or n_b)");
   for (int j = 1; j < n_lam; ++j)
     if (!(lam_sorted[j] >= lam_sorted[j - 1])) return fail(ctx, "lam_sorted must be ascending");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -507,6 +632,7 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   p.ldF = n_lam | 1;
   p.n_z = n_z;
   p.T_total = T_total;
+  p.out_pitch = out_pitch;
 
   void *d_lam = nullptr, *d_perm = nullptr, *d_F = nullptr, *d_Fs = nullptr, *d_z = nullptr, *d_jlo = nullptr,
        *d_cnt = nullptr, *d_rmax = nullptr, *d_W = nullptr, *d_rowmap = nullptr, *d_out = nullptr;

@@ -1,0 +1,118 @@
+// Device helpers shared by the K1 kernels (k1_lnprob.cu, k1_coop.cu).
+#pragma once
+#include <climits>
+#include <cmath>
+#include <cstdint>
+
+namespace agnf {
+
+// 2^(j/64), j = 0..63
+__constant__ double c_exp2_tab[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138, 1.0556451783605572,
+    1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841, 1.1143867425958924,
+    1.1265216186082418, 1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687, 1.241857812073484,
+    1.255380757024691, 1.2690509571917332, 1.2828700160787783, 1.2968395546510096, 1.3109612115247644,
+    1.3252366431597413, 1.339667524053303, 1.3542555469368927, 1.3690024229745905, 1.383909881963832,
+    1.3989796725383112, 1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384, 1.5422108254079407,
+    1.559004400237837, 1.5759808451078865, 1.593142151342267, 1.6104903319492543, 1.6280274218573478,
+    1.645755478153965, 1.6636765803267364, 1.681792830507429, 1.7001063537185235, 1.718619298122478,
+    1.7373338352737062, 1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656, 1.9152065613971474,
+    1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+
+static __device__ __noinline__ double exp10_slow(double x) { return exp10(x); }
+
+// 10^x for |x| < 300 to ~4e-16 relative: x = k*log10(2)/64 + r, |r| <= log10(2)/128;
+// 10^x = 2^(k>>6) * 2^((k&63)/64) * exp(r ln 10), the last factor by a degree-5 polynomial
+// (next term < 4e-17).  Anything else (NaN, inf, huge) goes to the library exp10.
+// `tab` is a shared-memory copy of c_exp2_tab (lanes index it divergently).
+__device__ __forceinline__ double exp10_fast(double x, const double* __restrict__ tab) {
+  if (!(fabs(x) < 300.0)) return exp10_slow(x);
+  const double magic = 6755399441055744.0;                 // 1.5 * 2^52: round-to-nearest-int trick
+  const double t = fma(x, 212.60339807279118, magic);      // 64 * log2(10)
+  const int k = __double2loint(t);
+  const double kf = t - magic;
+  double r = fma(kf, -0.004703593680460472, x);            // Cody-Waite: log10(2)/64 = C1 + C2, kf*C1 exact
+  r = fma(kf, -1.7892345153159123e-12, r);
+  double p = 0.5393829291955814;
+  p = fma(p, r, 1.171255148912267);
+  p = fma(p, r, 2.034678592293476);
+  p = fma(p, r, 2.650949055239199);
+  p = fma(p, r, 2.302585092994046);
+  p = fma(p, r, 1.0);
+  const double v = tab[k & 63] * p;
+  return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+}
+
+// Given l = last index with sv[l] <= p (or -1), return the first-appearance index of the minimum
+// of |g - p| over the distinct grid values of one dimension == np.abs(keys_float - p).argmin()
+// (DICTIONARIES_AGNfitter.py:204) mapped to the distinct-value list:
+//   * the minimisers of the rounded |g - p| form a contiguous run around p in sorted order
+//     (fp subtraction is monotone), so the two neighbours + a tie walk find them all;
+//   * among minimisers numpy returns the earliest key, i.e. the smallest first-appearance index.
+__device__ __forceinline__ int snap_resolve(const double* __restrict__ sv, const int32_t* __restrict__ perm,
+                                            int n, double p, int l) {
+  const int r = l + 1;
+  double best;
+  if (l < 0) best = fabs(sv[r] - p);
+  else if (r >= n) best = fabs(sv[l] - p);
+  else best = fmin(fabs(sv[l] - p), fabs(sv[r] - p));
+  int idx = INT_MAX;
+  for (int k = l; k >= 0; --k) {
+    if (fabs(sv[k] - p) == best) idx = min(idx, perm[k]); else break;
+  }
+  for (int k = r; k < n; ++k) {
+    if (fabs(sv[k] - p) == best) idx = min(idx, perm[k]); else break;
+  }
+  return idx;
+}
+
+// Binary-search snap (all-NaN -> index 0, like np.argmin of an all-NaN array).
+__device__ __forceinline__ int snap_dim(const double* __restrict__ sv, const int32_t* __restrict__ perm,
+                                        int n, double p) {
+  if (p != p) return 0;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (sv[mid] <= p) lo = mid + 1; else hi = mid;
+  }
+  return snap_resolve(sv, perm, n, p, lo - 1);
+}
+
+// Same result through a cell table.  `ext` / `eperm` are the sorted values and their first-appearance
+// indices with a sentinel on either side: ext[0] = -inf, ext[1..n] = sv[0..n-1], ext[n+1] = +inf.
+// lut[c] is a guess for l (ext indexing) at the left edge of cell c of a uniform partition of
+// [sv[0], sv[n-1]]; three predicated steps correct it and an explicit bracket test
+// ext[l] <= p < ext[l+1] decides whether the guess path may answer.  It may only when the minimum can
+// tie between the two bracketing values and nowhere else: the host sets `big` so that for
+// |p| <= big the spacing of the grid exceeds the rounding granularity of |g - p| (agnfit_capi.cu).
+// Everything else (NaN, +-inf, huge |p|, a failed bracket) takes the binary search.
+__device__ __forceinline__ int snap_dim_lut(const double* __restrict__ ext, const int32_t* __restrict__ eperm,
+                                            int n, double p, const uint16_t* __restrict__ lut, int m,
+                                            double lo, double inv, double big) {
+  if (fabs(p) <= big) {
+    const double t = fmin(fmax((p - lo) * inv, 0.0), (double)(m - 1));
+    int l = lut[__double2int_rz(t)];
+    if (ext[l] > p) --l;
+    if (ext[l + 1] <= p) ++l;
+    if (ext[l + 1] <= p) ++l;
+    const double a = ext[l], b = ext[l + 1];
+    if (a <= p && p < b) {
+      const double da = fabs(a - p), db = fabs(b - p);
+      const int ia = eperm[l], ib = eperm[l + 1];
+      return da < db ? ia : (db < da ? ib : min(ia, ib));
+    }
+  }
+  return snap_dim(ext + 1, eperm + 1, n, p);
+}
+
+// Gaussian_prior(mu, sigma, x) = log(1/(sqrt(2 pi) sigma)) - 0.5 (x-mu)^2 / sigma^2 (PRIORS_AGNfitter.py:428-430);
+// lognorm is evaluated once on the host (libm), inv_var = 1/sigma^2.
+__device__ __forceinline__ double gaussian_prior(double lognorm, double inv_var, double mu, double x) {
+  const double d = x - mu;
+  return lognorm - 0.5 * (d * d) * inv_var;
+}
+
+}  // namespace agnf

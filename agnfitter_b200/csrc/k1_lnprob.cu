@@ -1,52 +1,14 @@
 // K1 — batched log-posterior kernel (see k1_lnprob.cuh for the mapping to the reference).
 #include "k1_lnprob.cuh"
+#include "k1_common.cuh"
 
 #include <cfloat>
-#include <climits>
-#include <cmath>
 
 namespace agnf {
 
 namespace {
 
 constexpr int K1_THREADS = 128;
-
-// First index (in first-appearance numbering) of the minimum of |g - p| over the distinct grid
-// values of one dimension.  `sv` is the ascending copy, `perm[k]` the first-appearance index of
-// sv[k].  Equivalent to np.abs(keys_float - p).argmin() mapped to the distinct-value list:
-//   * the minimisers of the rounded |g - p| form a contiguous run around p in sorted order
-//     (fp subtraction is monotone), so two neighbours + a tie walk find them all;
-//   * among minimisers numpy returns the earliest key, i.e. the smallest first-appearance index;
-//   * all-NaN -> index 0.
-__device__ __forceinline__ int snap_dim(const double* __restrict__ sv, const int32_t* __restrict__ perm,
-                                        int n, double p) {
-  if (p != p) return 0;
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (sv[mid] <= p) lo = mid + 1; else hi = mid;
-  }
-  const int l = lo - 1, r = lo;  // sv[l] <= p < sv[r]
-  double best;
-  if (l < 0) best = fabs(sv[r] - p);
-  else if (r >= n) best = fabs(sv[l] - p);
-  else best = fmin(fabs(sv[l] - p), fabs(sv[r] - p));
-  int idx = INT_MAX;
-  for (int k = l; k >= 0; --k) {
-    if (fabs(sv[k] - p) == best) idx = min(idx, perm[k]); else break;
-  }
-  for (int k = r; k < n; ++k) {
-    if (fabs(sv[k] - p) == best) idx = min(idx, perm[k]); else break;
-  }
-  return idx;
-}
-
-// Gaussian_prior(mu, sigma, x) = log(1/(sqrt(2 pi) sigma)) - 0.5 (x-mu)^2 / sigma^2
-__device__ __forceinline__ double gaussian_prior(double mu, double sigma, double x) {
-  const double lognorm = log(1.0 / (sqrt(2.0 * 3.141592653589793) * sigma));
-  const double d = x - mu;
-  return lognorm - 0.5 * (d * d) / (sigma * sigma);
-}
 
 struct BandAcc {
   double chi = 0.0;
@@ -101,7 +63,7 @@ __device__ __forceinline__ double band_step(const agnf_config& cfg, const Walker
   return m;
 }
 
-template <bool GA_FREE, int BB_MODE, bool RADIO, bool VEC2>
+template <bool GA_FREE, int BB_MODE, bool RADIO>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_lnprob_kernel(const __grid_constant__ K1Params P, const K1Batch B) {
   extern __shared__ double s_raw[];
@@ -156,7 +118,7 @@ k1_lnprob_kernel(const __grid_constant__ K1Params P, const K1Batch B) {
         }
       }
       row[f] = r;
-      trow[f] = F.table + ((int64_t)zi * F.T + r) * n_b;
+      trow[f] = F.table + ((int64_t)zi * F.T + r) * F.pitch;
     }
   }
   if (B.rows) {
@@ -203,40 +165,14 @@ k1_lnprob_kernel(const __grid_constant__ K1Params P, const K1Batch B) {
   const double* __restrict__ tTO = trow[2];
   const double* __restrict__ tBB = trow[3];
   const double* __restrict__ tRAD = RADIO ? trow[4] : trow[0];
-  const double* __restrict__ ys = P.y + (int64_t)s * n_b;
-  const double* __restrict__ is = P.isig + (int64_t)s * n_b;
-  const double* __restrict__ cg = P.cgal + (int64_t)zi * n_b;
-  const double* __restrict__ cb = P.cbbb + (int64_t)zi * n_b;
-  const double* __restrict__ om = P.omega + (int64_t)zi * n_b;
+  const double* __restrict__ ys = P.y + (int64_t)s * P.nbp;
+  const double* __restrict__ is = P.isig + (int64_t)s * P.nbp;
+  const double* __restrict__ cg = P.cgal + (int64_t)zi * P.nbp;
+  const double* __restrict__ cb = P.cbbb + (int64_t)zi * P.nbp;
+  const double* __restrict__ om = P.omega + (int64_t)zi * P.nbp;
   double* ym = B.ymodel ? B.ymodel + i * n_b : nullptr;
   BandAcc a;
-  if (VEC2) {
-    // n_b even: every row starts 16-byte aligned -> 128-bit loads, two bands per step
-    for (int b = 0; b < n_b; b += 2) {
-      const double2 dga = __ldg(reinterpret_cast<const double2*>(tGA + b));
-      const double2 dsb = __ldg(reinterpret_cast<const double2*>(tSB + b));
-      const double2 dto = __ldg(reinterpret_cast<const double2*>(tTO + b));
-      const double2 dbb = __ldg(reinterpret_cast<const double2*>(tBB + b));
-      double2 drad = make_double2(0.0, 0.0);
-      if (RADIO) drad = __ldg(reinterpret_cast<const double2*>(tRAD + b));
-      const double2 yb = __ldg(reinterpret_cast<const double2*>(ys + b));
-      const double2 ib = __ldg(reinterpret_cast<const double2*>(is + b));
-      double2 cgb = make_double2(0.0, 0.0), cbb = make_double2(0.0, 0.0), omb = make_double2(0.0, 0.0);
-      if (GA_FREE) {
-        cgb = __ldg(reinterpret_cast<const double2*>(cg + b));
-        omb = __ldg(reinterpret_cast<const double2*>(om + b));
-      }
-      if (BB_MODE != 0) cbb = __ldg(reinterpret_cast<const double2*>(cb + b));
-      const double m0 = band_step<GA_FREE, BB_MODE, RADIO>(cfg, w, a, b, dga.x, dsb.x, dto.x, dbb.x, drad.x,
-                                                          yb.x, ib.x, cgb.x, cbb.x, omb.x, eb_free);
-      const double m1 = band_step<GA_FREE, BB_MODE, RADIO>(cfg, w, a, b + 1, dga.y, dsb.y, dto.y, dbb.y, drad.y,
-                                                          yb.y, ib.y, cgb.y, cbb.y, omb.y, eb_free);
-      if (ym) {
-        ym[b] = m0;
-        ym[b + 1] = m1;
-      }
-    }
-  } else {
+  {
     for (int b = 0; b < n_b; ++b) {
       const double drad = RADIO ? __ldg(tRAD + b) : 0.0;
       const double cgb = GA_FREE ? __ldg(cg + b) : 0.0;
@@ -259,7 +195,7 @@ k1_lnprob_kernel(const __grid_constant__ K1Params P, const K1Batch B) {
     const double L_sb = __ldg(P.fam[1].aux + row[1]) * w.nSB;
     double pr;
     if (L_sb < L_att) pr = -9999.0;
-    else if (L_sb >= L_att) pr = (cfg.eb_mode == 1) ? 0.0 : gaussian_prior(0.0, 0.1, log10(L_sb / L_att));
+    else if (L_sb >= L_att) pr = (cfg.eb_mode == 1) ? 0.0 : gaussian_prior(P.lognorm_s01, 100.0, 0.0, log10(L_sb / L_att));
     else pr = NAN;   // unordered: the reference has no branch for it
     prior += pr;
   }
@@ -268,15 +204,15 @@ k1_lnprob_kernel(const __grid_constant__ K1Params P, const K1Batch B) {
     if (BB == 0.0) bbj = bbj * inv4pidl2;          // decided by VALUE (PRIORS:177)
     const double frac = log10(bbj / a.ga_j);
     double pr;
-    if (__ldg(P.agn_branch + s) == 0) pr = gaussian_prior(-2.0, 2.0, frac);
-    else pr = (frac < 0.0) ? -9999.0 : gaussian_prior(2.0, 2.0, frac);
-    prior += pr + gaussian_prior(4.5, 1.5, GA);
+    if (__ldg(P.agn_branch + s) == 0) pr = gaussian_prior(P.lognorm_s2, 0.25, -2.0, frac);
+    else pr = (frac < 0.0) ? -9999.0 : gaussian_prior(P.lognorm_s2, 0.25, 2.0, frac);
+    prior += pr + gaussian_prior(P.lognorm_s15, 1.0 / 2.25, 4.5, GA);
   }
   if (RADIO) {
     const int mode = __ldg(P.irsyn_mode + s);
     if (mode != 0) {
       const double f = log10(a.syn_ir / a.sb_ir);
-      prior += gaussian_prior(mode > 0 ? 2.0 : -2.0, 2.0, f);
+      prior += gaussian_prior(P.lognorm_s2, 0.25, mode > 0 ? 2.0 : -2.0, f);
     }
   }
   const double lnprior = inbox ? prior : -INFINITY;
@@ -290,16 +226,12 @@ template <bool GA_FREE, int BB_MODE, bool RADIO>
 cudaError_t launch_variant(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
   const int64_t blocks = (B.n + K1_THREADS - 1) / K1_THREADS;
   const size_t smem = (size_t)P.n_grid_vals * (sizeof(double) + sizeof(int32_t));
-  const bool vec2 = (P.cfg.n_b % 2) == 0;
-  if (vec2) {
-    auto kern = k1_lnprob_kernel<GA_FREE, BB_MODE, RADIO, true>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)blocks, K1_THREADS, smem, stream>>>(P, B);
-  } else {
-    auto kern = k1_lnprob_kernel<GA_FREE, BB_MODE, RADIO, false>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)blocks, K1_THREADS, smem, stream>>>(P, B);
+  auto kern = k1_lnprob_kernel<GA_FREE, BB_MODE, RADIO>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
   }
+  kern<<<(unsigned)blocks, K1_THREADS, smem, stream>>>(P, B);
   return cudaGetLastError();
 }
 

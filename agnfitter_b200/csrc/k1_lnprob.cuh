@@ -1,10 +1,15 @@
 // K1 — batched (source x walker) log-posterior for sm_100a.
 //
-// One thread evaluates one row of `params` end to end (snap -> gather -> normalise -> chi^2 ->
-// priors).  Rows of one source are contiguous in a batch, so the per-source vectors (y, 1/sigma,
-// reddening coefficients, bounds) are warp-uniform broadcast loads and the z-slice of the
-// dictionary a warp touches stays hot in L1/L2; the per-walker template rows are 8*n_b-byte
-// contiguous gathers.  All arithmetic is fp64.
+// Two kernels produce the same results (rows bit-identical, floating point to ~1e-15):
+//   k1_coop.cu    the production kernel.  A warp owns 32 consecutive rows of `params`.  The
+//                 per-evaluation scalar work (box test, snapping, normalisations, priors) runs
+//                 thread-per-row; the band work (gather, reddening, model sum, chi^2) runs
+//                 lane-per-16-byte-chunk over the warp's 32 x n_b tile so that every template
+//                 row is fetched by consecutive lanes with 128-bit loads (2 L1 wavefronts per
+//                 row instead of 9); the two layouts meet in per-warp shared memory.
+//   k1_lnprob.cu  one thread per row end to end; no alignment or size requirements.  Used when
+//                 the cooperative kernel's preconditions do not hold, and as a cross-check.
+// All arithmetic is fp64.
 //
 // What each step mirrors in the reference (paths relative to AGNfitter/functions):
 //   box test            PARAMETERSPACE_AGNfitter.py:119-121
@@ -25,40 +30,57 @@ namespace agnf {
 struct DimDesc {
   int32_t is_grid;
   int32_t size;
-  int32_t smem_off;   // offset (in values) of this dimension inside the staged grid arrays
-  int32_t pad;
+  int32_t smem_off;   // offset (in values) of this dimension inside grid_sorted / grid_perm
+  int32_t ext_off;    // offset of this dimension's -inf sentinel inside the sentinel-extended arrays
+  int32_t lut_off;    // offset (in entries) of this dimension's cell table
+  int32_t lut_m;      // cells; 0: no table for this dimension (binary search)
   int64_t stride;
+  double lut_lo;      // left edge of cell 0
+  double lut_inv;     // cells per unit
+  double lut_big;     // the table path answers only for |p| <= lut_big (k1_common.cuh::snap_dim_lut)
 };
 
 struct FamDesc {
-  const double* table;  // [n_z, T, n_b]
+  const double* table;  // [n_z, T, pitch]; columns n_b..pitch-1 are zero
   const double* aux;    // [T] or nullptr
   int64_t T;
   int32_t n_dim;
   int32_t par_offset;
+  int32_t pitch;        // row pitch of `table` in doubles (>= n_b)
+  int32_t pad;
   DimDesc dim[AGNF_MAX_DIMS];
 };
 
 struct K1Params {
   agnf_config cfg;
   FamDesc fam[AGNF_MAX_FAMILIES];
-  int32_t n_grid_vals;        // total staged grid values
+  int32_t n_grid_vals;        // total grid values
   int32_t norm_offset;        // column of GA in a params row
-  const double* grid_sorted;  // [n_grid_vals]
+  int32_t nbp;                // pitch of every library-owned per-band array: n_b rounded up to even
+  int32_t pad0;
+  const double* grid_sorted;  // [n_grid_vals]  (per-thread kernel)
   const int32_t* grid_perm;   // [n_grid_vals]
-  // z-slices
-  const double* cgal;         // [n_z, n_b]  -0.4 k_Calzetti
-  const double* cbbb;         // [n_z, n_b]  -0.4 k_Prevot
+  // cooperative kernel: one blob a CTA pulls into shared memory with a single bulk copy:
+  //   sentinel-extended grid doubles | their first-appearance indices int32 | cell tables uint16,
+  //   each padded to 16 bytes
+  const unsigned char* stage;
+  int32_t stage_bytes, stage_off_grid, stage_off_perm, stage_off_lut;
+  // Gaussian_prior constants, evaluated on the host: log(1/(sqrt(2 pi) sigma)) for sigma = 2, 1.5, 0.1
+  double lognorm_s2, lognorm_s15, lognorm_s01;
+  // z-slices (pad columns are zero)
+  const double* cgal;         // [n_z, nbp]  -0.4 k_Calzetti
+  const double* cbbb;         // [n_z, nbp]  -0.4 k_Prevot
   const uint64_t* xray;       // [n_z]
   const int32_t* j1500;       // [n_z]
-  const double* omega;        // [n_z, n_b]
-  // sources
+  const double* omega;        // [n_z, nbp]
+  // sources (pad columns are zero)
   const int32_t* zi;          // [S]
-  const double* y;            // [S, n_b]
-  const double* isig;         // [S, n_b]
+  const double* y;            // [S, nbp]
+  const double* isig;         // [S, nbp]
   const uint64_t* valid;      // [S]
   const double* pmin;         // [S, n_par]
   const double* pmax;         // [S, n_par]
+  const double2* pbox;        // [S, n_par] (min, max) pairs
   const double* consts;       // [S, n_const]
   int32_t n_const;
   int32_t pad;
@@ -81,9 +103,9 @@ struct K1Batch {
 
 cudaError_t launch_k1(const K1Params& P, const K1Batch& B, cudaStream_t stream);
 
-// tiled variant (k1_tile.cu): same results, warp-cooperative cp.async staging of the template rows
-bool k1_tile_supported(const K1Params& P);
-cudaError_t launch_k1_tile(const K1Params& P, const K1Batch& B, cudaStream_t stream);
+// cooperative kernel (k1_coop.cu); `why` receives a static string when unsupported
+bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why);
+cudaError_t launch_k1_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream);
 cudaError_t launch_exp10_fast(const double* x, double* y, int64_t n, cudaStream_t stream);
 
 }  // namespace agnf

@@ -124,18 +124,24 @@ __global__ void __launch_bounds__(K2_THREADS) k2_contract_kernel(K2Problem p) {
   }
   __syncthreads();
   const int64_t t0 = (int64_t)blockIdx.y * K2_TILE_T;
-  const int n_out = K2_TILE_T * n_b;
+  const int pitch = p.out_pitch;
+  const int n_out = K2_TILE_T * pitch;
   for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
-    const int tt = o / n_b, b = o - tt * n_b;
+    const int tt = o / pitch, b = o - tt * pitch;
     const int64_t t = t0 + tt;
     if (t >= p.T) break;
+    if (b >= n_b) {                 // pad column
+      const int64_t prow = p.row_map ? __ldg(p.row_map + t) : t;
+      p.out[((int64_t)zi * p.T_total + prow) * pitch + b] = 0.0;
+      continue;
+    }
     const double* __restrict__ F = p.Fs + t * p.ldF + s_jlo[b];
     const double* w = W_SMEM ? (s_w + b * rp) : (Wz + b * rmax);
     const int c = s_cnt[b];
     double acc = 0.0;
     for (int r = 0; r < c; ++r) acc = fma(w[r], __ldg(F + r), acc);
     const int64_t row = p.row_map ? __ldg(p.row_map + t) : t;
-    p.out[((int64_t)zi * p.T_total + row) * n_b + b] = acc;
+    p.out[((int64_t)zi * p.T_total + row) * pitch + b] = acc;
   }
 }
 

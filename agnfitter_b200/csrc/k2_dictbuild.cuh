@@ -51,7 +51,8 @@ struct K2Problem {
   double* W = nullptr;              // [n_z, n_b, rmax]
   const int64_t* row_map = nullptr; // [T] or nullptr
   int64_t T_total = 0;
-  double* out = nullptr;            // [n_z, T_total, n_b]
+  int32_t out_pitch = 0;            // row pitch of out in doubles (>= n_b); pad columns are written as 0
+  double* out = nullptr;            // [n_z, T_total, out_pitch]
 };
 
 cudaError_t launch_k2_permute(const double* Fnu, const int32_t* perm, double* Fs, int64_t T, int32_t n_lam,

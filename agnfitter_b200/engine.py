@@ -53,11 +53,13 @@ class Engine:
             gs = as_f64(np.concatenate([s[0] for s in sg])) if sg else as_f64([])
             gp = as_i32(np.concatenate([s[1] for s in sg])) if sg else as_i32([])
             dev = device_tables.get(f.name) if device_tables else None
+            pitch = 0
             if dev is not None:
-                if tuple(dev.shape) != (ms.n_z, f.T, ms.n_b) or not dev.is_contiguous() or str(dev.dtype) != "torch.float64":
-                    raise ValueError("device table for %s must be contiguous float64 [n_z, T, n_b]" % f.name)
+                if (dev.dim() != 3 or tuple(dev.shape[:2]) != (ms.n_z, f.T) or dev.shape[2] < ms.n_b
+                        or not dev.is_contiguous() or str(dev.dtype) != "torch.float64"):
+                    raise ValueError("device table for %s must be contiguous float64 [n_z, T, pitch >= n_b]" % f.name)
                 self._keep.append(dev)
-                table_ptr, on_dev = dev.data_ptr(), 1
+                table_ptr, on_dev, pitch = dev.data_ptr(), 1, int(dev.shape[2])
             else:
                 if f.table is None:
                     raise ValueError("family %s has no host table and no device table was given" % f.name)
@@ -71,7 +73,8 @@ class Engine:
                 raise ValueError("energy-balance prior needs STARBURST_LIR")
             d = _lib.agnf_family_desc(fam=fi, n_dim=n_dim, par_offset=idxs[fi], table_on_device=on_dev, T=f.T,
                                       dim_is_grid=ptr(is_grid), dim_size=ptr(size), dim_stride=ptr(stride),
-                                      grid_sorted=ptr(gs), grid_perm=ptr(gp), table=table_ptr, aux=ptr(aux))
+                                      grid_sorted=ptr(gs), grid_perm=ptr(gp), table=table_ptr, aux=ptr(aux),
+                                      table_pitch=pitch, reserved=0)
             self.ctx.check(self.lib.agnf_family_upload(self.ctx.h, C.byref(d)))
         zs = zslices if zslices is not None else make_zslices(ms)
         self.zslices = zs
@@ -133,6 +136,11 @@ class Engine:
     def set_option(self, name, value):
         self.ctx.check(self.lib.agnf_set_option(self.ctx.h, name.encode(), int(value)))
 
+    def get_option(self, name):
+        v = C.c_int64()
+        self.ctx.check(self.lib.agnf_get_option(self.ctx.h, name.encode(), C.byref(v)))
+        return int(v.value)
+
     def debug_exp10(self, x):
         x = as_f64(x)
         y = np.empty_like(x)
@@ -189,15 +197,18 @@ class DictBuilder:
 
     def build_family(self, templates, z_array, on_device=False):
         """templates: the reference's `*Fdict_4plot` ({key: (log10 nu, Fnu)}, insertion-ordered).
-        Returns the band-flux table [n_z, T, n_b] in key order — a NumPy array, or with
-        on_device=True a torch CUDA tensor that never leaves HBM."""
+        Returns the band-flux table in key order: a NumPy array [n_z, T, n_b], or with on_device=True
+        a torch CUDA tensor [n_z, T, pitch] (pitch = n_b rounded up to even, pad column zero) that
+        never leaves HBM."""
         keys = list(templates.keys())
         T_total = len(keys)
         z = as_f64(np.atleast_1d(z_array))
         n_z = len(z)
+        pitch = self.n_b
         if on_device:
             import torch
-            out_t = torch.empty((n_z, T_total, self.n_b), dtype=torch.float64,
+            pitch = (self.n_b + 1) & ~1          # even pitch: rows stay 16-byte aligned for the cooperative K1
+            out_t = torch.empty((n_z, T_total, pitch), dtype=torch.float64,
                                 device="cuda:%d" % self.ctx.device)
             out_ptr = out_t.data_ptr()
         else:
@@ -222,7 +233,7 @@ class DictBuilder:
             row_map = None if identity else as_i64(members)
             self.ctx.check(self.lib.agnf_dict_build(
                 self.ctx.h, ptr(lam_sorted), ptr(perm), ptr(F), len(members), n_lam, ptr(z), n_z,
-                ptr(row_map), T_total, out_ptr, 1 if on_device else 0))
+                ptr(row_map), T_total, out_ptr, 1 if on_device else 0, pitch))
             ms = C.c_float()
             self.ctx.check(self.lib.agnf_last_kernel_ms(self.ctx.h, 2, C.byref(ms)))
             self.contract_ms += float(ms.value)

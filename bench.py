@@ -127,7 +127,7 @@ def build_host_sample(ms, dev_tables, src_raw, sample_ids, pars, W):
     import torch
     idx = torch.as_tensor(uz.astype(np.int64), device=next(iter(dev_tables.values())).device)
     for f in ms.families:
-        tab = dev_tables[f.name].index_select(0, idx).cpu().numpy()
+        tab = np.ascontiguousarray(dev_tables[f.name].index_select(0, idx)[..., :ms.n_b].cpu().numpy())
         small.families.append(family_from_keys_float(f.name, f.par_names, f.par_types, f.keys_float, f.fitted,
                                                      tab, f.aux))
     srcs, pl = [], []
@@ -283,7 +283,7 @@ def run_ours(args):
                                    % (S, W, info["n_z"]),
                        "positions": args.positions + " in prior box + 1% out-of-box rows",
                        "source_order": "random z" if args.no_sort_z else "sorted by z",
-                       "k1_variant": "tiled cp.async" if args.variant == 1 else "per-thread gather",
+                       "k1_variant": "cooperative (k1_coop_kernel)" if eng.get_option("k1_last_kernel") == 1 else "per-thread (k1_lnprob_kernel)",
                        "rows_per_step_per_gpu": n, "n_bands": n_b, "n_par": n_par,
                        "l2_policy": "inputs larger than L2 (params %.0f MB + dictionary %.1f GB per GPU)" % (
                            n * n_par * 8 / 1e6, info["k2_entries"] * 8 / 1e9),
@@ -293,7 +293,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(n * 8), "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k1_lnprob_kernel",
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "k1_coop_kernel" if eng.get_option("k1_last_kernel") == 1 else "k1_lnprob_kernel",
                          "bytes_per_eval": bpe, "kernel_ms": k1_ms},
             "cpu_baseline": {"value": cpu_all, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "oracle/agn_oracle.ln_probab on %d of the %d sources x %d walkers, vectorised "
@@ -355,7 +356,7 @@ def main():
     ap.add_argument("--sources", type=int, default=100000, help="sources per GPU")
     ap.add_argument("--walkers", type=int, default=100)
     ap.add_argument("--positions", default="uniform", choices=["uniform", "ball"])
-    ap.add_argument("--variant", type=int, default=1, help="K1 kernel: 1 tiled (default), 0 per-thread gather")
+    ap.add_argument("--variant", type=int, default=1, help="K1 kernel: 1 cooperative (default), 0 per-thread")
     ap.add_argument("--no-sort-z", action="store_true",
                     help="keep the catalogue in random z order (default: the shard is processed in z order so "
                          "that sources sharing a dictionary z-slice are adjacent)")

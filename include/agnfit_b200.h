@@ -88,8 +88,11 @@ typedef struct {
   const int64_t* dim_stride;   /* [n_dim] row = sum idx_d * stride_d                         */
   const double* grid_sorted;   /* concatenated over dims: distinct values, ascending         */
   const int32_t* grid_perm;    /* same shape: first-appearance index of each sorted value    */
-  const double* table;         /* [n_z, T, n_b]                                              */
+  const double* table;         /* [n_z, T, n_b] host, or [n_z, T, table_pitch] device          */
   const double* aux;           /* [T] GALAXYatt_dict (GA, grid EBV) / STARBURST_LIRdict (SB); or NULL */
+  int32_t table_pitch;         /* device tables: row pitch in doubles (0 = n_b).  An even pitch with  */
+  int32_t reserved;            /* zeroed pad columns (agnf_dict_build writes them) keeps rows 16-byte  */
+                               /* aligned, which the cooperative K1 kernel needs.                      */
 } agnf_family_desc;
 
 AGNF_API int agnf_family_upload(agnf_ctx* ctx, const agnf_family_desc* fam);
@@ -118,9 +121,12 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
                              double* d_lnp, int32_t* d_rows, double* d_ymodel, double* d_lnprior,
                              double* d_lnlike, void* stream);
 
-/* tuning knobs.  "k1_variant": 1 (default) = tiled K1 (warp-cooperative cp.async staging) whenever the
- * band count has a compiled instantiation, 0 = per-thread gather K1 (any band count). */
+/* tuning knobs.  "k1_variant": 1 (default) = cooperative K1 kernel whenever its preconditions hold
+ * (16-byte aligned params and tables, even table pitch), 0 = per-thread K1 kernel (no preconditions).
+ * agnf_get_option also answers "k1_last_kernel" (which kernel the last K1 launch ran: 1 / 0, -1 none)
+ * and "band_pitch" (n_b rounded up to even: the pitch to ask agnf_dict_build for). */
 AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value);
+AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value);
 /* y[i] = 10^x[i] through the kernels' own exp10 routine (host pointers; unit-test hook) */
 AGNF_API int agnf_debug_exp10(agnf_ctx* ctx, const double* x, int64_t n, double* y);
 
@@ -150,12 +156,13 @@ AGNF_API int agnf_filters_upload(agnf_ctx* ctx, int32_t n_b, const double* band_
  *   perm       [n_lam]  column of Fnu that holds the flux of lam_sorted[j]
  *   Fnu        [T, n_lam] template F_nu in the template's stored order (host pointer)
  *   z          [n_z]
- *   out        [n_z, T_total, n_b]; template t writes row row_map[t] (NULL: identity, T_total = T).
- * out is a host pointer (results copied back) or, with out_on_device = 1, a device pointer that
- * can be handed to agnf_family_upload(table_on_device = 1) without leaving HBM. */
+ *   out        [n_z, T_total, out_pitch]; template t writes row row_map[t] (NULL: identity, T_total = T);
+ *              out_pitch 0 = n_b; columns n_b..out_pitch-1 are written as 0.
+ * out is a host pointer (dense, results copied back) or, with out_on_device = 1, a device pointer that
+ * can be handed to agnf_family_upload(table_on_device = 1, table_pitch = out_pitch) without leaving HBM. */
 AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int32_t* perm, const double* Fnu, int64_t T,
                     int32_t n_lam, const double* z, int32_t n_z, const int64_t* row_map, int64_t T_total,
-                    double* out, int32_t out_on_device);
+                    double* out, int32_t out_on_device, int32_t out_pitch);
 
 #ifdef __cplusplus
 }

@@ -26,12 +26,11 @@ def _engine(ms, g, variant=None):
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("case", K1_CASES)
 def test_k1_matches_reference_golden(case, variant):
-    """variant 1 = tiled kernel (used when the band count has an instantiation), 0 = per-thread gather."""
+    """variant 1 = cooperative kernel (production), 0 = per-thread kernel (fallback / cross-check)."""
     ms, g = load_k1(case)
-    if variant == 1 and ms.n_b != 18:
-        pytest.skip("tiled K1 is instantiated for 18 bands; other band counts run the per-thread kernel")
     eng, _ = _engine(ms, g, variant)
     lnp, rows, ym, lpr, lll = eng.lnprob(g["pars"], g["source_id"], detail=True)
+    assert eng.get_option("k1_last_kernel") == variant, "the requested kernel must be the one that ran"
     assert np.array_equal(rows, g["ref_rows"]), "template indices must be bit-exact"
     assert_close_with_specials(ym, g["ref_ymodel"], what="ymodel")
     assert_close_with_specials(lll, g["ref_lnlike"], what="ln_likelihood")
@@ -136,7 +135,7 @@ def test_k1_variants_agree_and_tail_handling():
     for variant in (0, 1):
         eng, src = _engine(ms, g, variant)
         res = []
-        for n in (1, 31, 33, 127, 129, 1000, 4097):
+        for n in (1, 31, 33, 127, 129, 255, 257, 1000, 4097):
             r2 = np.random.default_rng(n)
             sid = r2.integers(src.S, size=n).astype(np.int32)
             pars = src.pmin[sid] + r2.uniform(size=(n, ms.n_par)) * (src.pmax[sid] - src.pmin[sid])
@@ -149,7 +148,7 @@ def test_k1_variants_agree_and_tail_handling():
 
 
 def test_exp10_fast_accuracy():
-    """The kernels' own 10**x (table + degree-6 polynomial) against NumPy, incl. special values."""
+    """The cooperative kernel's own 10**x (table + degree-6 polynomial) against NumPy, incl. special values."""
     ms, g = load_k1("agnoff18")
     eng, _ = _engine(ms, g)
     rng = np.random.default_rng(1)

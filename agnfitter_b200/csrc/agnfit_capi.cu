@@ -192,6 +192,21 @@ int rebuild_grids(agnf_ctx* ctx) {
       }
       local += D.size;
     }
+    F.n_snap = 0;
+    for (int d = 0; d < F.n_dim; ++d) {
+      const DimDesc& D = F.dim[d];
+      if (!D.is_grid || D.size < 2) continue;
+      SnapTask& T = F.snap[F.n_snap++];
+      T.col = F.par_offset + d;
+      T.n = D.size;
+      T.ext_off = D.ext_off;
+      T.lut_off = D.lut_off;
+      T.lut_mmax = D.lut_m > 0 ? D.lut_m - 1 : -1;
+      T.stride = (int32_t)D.stride;
+      T.lo = D.lut_lo;
+      T.inv = D.lut_inv;
+      T.big = D.lut_big;
+    }
     ctx->h_grid.insert(ctx->h_grid.end(), ctx->fam_grid[f].begin(), ctx->fam_grid[f].end());
     ctx->h_perm.insert(ctx->h_perm.end(), ctx->fam_perm[f].begin(), ctx->fam_perm[f].end());
   }
@@ -453,6 +468,17 @@ AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double
                        "IndexError in the reference (PRIORS_AGNfitter.py:166)", i);
   if (upload_padded(ctx, &ctx->k1.cgal, cgal, nz, (int)nb, ctx->k1.nbp)) return 1;
   if (upload_padded(ctx, &ctx->k1.cbbb, cbbb, nz, (int)nb, ctx->k1.nbp)) return 1;
+  {
+    const double k64 = 212.60339807279118;      // 64 log2(10)
+    std::vector<double> a(nz * nb), b(nz * nb);
+    for (size_t i = 0; i < nz * nb; ++i) {
+      a[i] = cgal[i] * k64;
+      b[i] = cbbb[i] * k64;
+    }
+    if (upload_padded(ctx, &ctx->k1.cgal64, a.data(), nz, (int)nb, ctx->k1.nbp)) return 1;
+    if (upload_padded(ctx, &ctx->k1.cbbb64, b.data(), nz, (int)nb, ctx->k1.nbp)) return 1;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   if (upload(ctx, &ctx->k1.xray, xray_bits, nz)) return 1;
   if (upload(ctx, &ctx->k1.j1500, j1500, nz)) return 1;
   if (upload_padded(ctx, &ctx->k1.omega, omega, nz, (int)nb, ctx->k1.nbp)) return 1;

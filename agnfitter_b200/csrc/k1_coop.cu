@@ -2,10 +2,11 @@
 //
 // A warp owns 32 consecutive rows of `params` (= 32 evaluations).
 //
-//   phase 1  thread-per-evaluation.  The warp's params block is contiguous in global memory and is
-//            staged with 16-byte cp.async; each thread then box-tests its row, snaps every family
-//            (cell table + guarded walk, k1_common.cuh), evaluates the normalisations 10^x and
-//            leaves a 10- or 14-double record in shared memory.
+//   phase 1  thread-per-evaluation.  One 1-D bulk copy (TMA unit, mbarrier completion) per CTA brings
+//            the snapping grids and cell tables into shared memory, one per warp brings that warp's
+//            contiguous params rows.  Each thread box-tests its row, snaps every family (cell table +
+//            bracket test, k1_common.cuh), evaluates the normalisations 10^x, leaves a 10- or
+//            14-double record in shared memory and prefetches its galaxy-template row into L2.
 //   phase 2  lane-per-chunk.  The 32 x nbp tile of band values is cut into 16-byte chunks
 //            (2 bands); chunk c = e * nbp/2 + k goes to lane c % 32 of iteration c / 32, so the
 //            nbp/2 iterations keep all 32 lanes busy and consecutive lanes read consecutive
@@ -19,7 +20,7 @@
 //            re-reads the two band values prior_AGNfraction needs (L1 hits), evaluates the
 //            priors and writes lnP.
 //
-// Only __syncwarp() separates the phases; the CTA synchronises once, after staging the grids.
+// Only __syncwarp() separates the phases; the CTA synchronises once, to publish the mbarriers.
 #include "k1_lnprob.cuh"
 #include "k1_common.cuh"
 
@@ -64,33 +65,118 @@ CoopPlan make_plan(const K1Params& P) {
   return c;
 }
 
-// ---- mbarrier + bulk copy (TMA unit, 1-D) -------------------------------------------------------
+// ---- shared memory through 32-bit shared-window addresses (no generic -> shared conversions) ------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
+  return v;
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ double2 lds_v2f64(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ int4 lds_v4s32(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u16(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+}
+
+// ---- mbarrier + bulk copy (TMA unit, 1-D) -------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   for (int spin = 0; !ok; ++spin) {
     asm volatile(
         "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     if (spin > (1 << 24)) __trap();      // a lost copy must not hang the device
   }
 }
 
-template <bool GA_FREE, int BB_MODE, bool RADIO>
+// ---- 2^(t/64): the reddening factors 10^(c E) with c pre-scaled by 64 log2(10) on the host ----------
+// coefficients (ln 2 / 64)^n / n!, n = 1..5, in constant memory so the DFMAs take them as operands
+__constant__ double c_p64[5] = {0.010830424696249145, 5.86490495505617e-05, 2.1173137155464776e-07,
+                                5.732851688640402e-10, 1.2417843701716925e-12};
+
+// t = k + r, k integer, |r| <= 1/2: 2^(t/64) = 2^(k>>6) * tab[k&63] * exp(r ln2/64); the degree-5
+// polynomial's first neglected term is < 4e-17.  |t| >= 64000 (or NaN) goes to the library.
+static __device__ __noinline__ double pow2_64_slow(double t) { return exp2(t * 0.015625); }
+
+__device__ __forceinline__ double pow2_64(double t, uint32_t tab_s) {
+  if (!(fabs(t) < 64000.0)) return pow2_64_slow(t);
+  const double magic = 6755399441055744.0;                 // 1.5 * 2^52
+  const double km = t + magic;
+  const int k = __double2loint(km);
+  const double r = t - (km - magic);
+  double p = c_p64[4];
+  p = fma(p, r, c_p64[3]);
+  p = fma(p, r, c_p64[2]);
+  p = fma(p, r, c_p64[1]);
+  p = fma(p, r, c_p64[0]);
+  p = fma(p, r, 1.0);
+  const double v = lds_f64(tab_s + ((k << 3) & 0x1f8)) * p;
+  return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+}
+
+// snap through the cell table; see k1_common.cuh::snap_dim_lut for the argument (same steps, shared
+// window addresses, task constants from the kernel parameter bank)
+__device__ __forceinline__ int snap_task(const SnapTask& T, double p, uint32_t ext_s, uint32_t eperm_s, uint32_t lut_s,
+                                         const double* ext_g, const int32_t* eperm_g) {
+  if (T.lut_mmax >= 0) {
+    const int c = min(max(__double2int_rz((p - T.lo) * T.inv), 0), T.lut_mmax);
+    int l = (int)lds_u16(lut_s + 2u * (unsigned)(T.lut_off + c));
+    const uint32_t base = ext_s + 8u * (unsigned)T.ext_off;
+    if (lds_f64(base + 8u * l) > p) --l;
+    if (lds_f64(base + 8u * l + 8u) <= p) ++l;
+    if (lds_f64(base + 8u * l + 8u) <= p) ++l;
+    const double a = lds_f64(base + 8u * l), b = lds_f64(base + 8u * l + 8u);
+    if (a <= p && p < b && fabs(p) <= T.big) {
+      const uint32_t pb = eperm_s + 4u * (unsigned)(T.ext_off + l);
+      const int ia = lds_s32(pb), ib = lds_s32(pb + 4u);
+      const double da = fabs(a - p), db = fabs(b - p);
+      return da < db ? ia : (db < da ? ib : min(ia, ib));
+    }
+  }
+  return snap_dim(ext_g + T.ext_off + 1, eperm_g + T.ext_off + 1, T.n, p);
+}
+
+// CPR_T: chunks per row as a compile-time constant (fully unrolled band phase), or 0 = runtime
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
 __global__ void __launch_bounds__(KC_THREADS, 3)
 k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPlan C) {
   constexpr bool EXT = GA_FREE || RADIO || BB_MODE >= 2;
@@ -99,38 +185,38 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   const agnf_config& cfg = P.cfg;
   const int n_par = cfg.n_par, n_b = cfg.n_b, nbp = P.nbp;
   const bool eb_free = GA_FREE && cfg.eb_mode != 0;
-  double* s_tab = reinterpret_cast<double*>(smem_raw);                        // 64
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tab + 64);                  // [0] blob, [1 + w] warp w
-  unsigned char* s_stage = reinterpret_cast<unsigned char*>(s_bar + 16);
-  const double* s_ext = reinterpret_cast<const double*>(s_stage + P.stage_off_grid);
-  const int32_t* s_eperm = reinterpret_cast<const int32_t*>(s_stage + P.stage_off_perm);
-  const uint16_t* s_lut = reinterpret_cast<const uint16_t*>(s_stage + P.stage_off_lut);
-  double* s_warp = reinterpret_cast<double*>(s_stage + C.stage_pad);
-
+  const int CPR = CPR_T ? CPR_T : C.cpr;
+  const int CPRP = CPR | 1;
+  // shared-window addresses
+  const uint32_t tab_s = smem_u32(smem_raw);                 // 64 doubles
+  const uint32_t bar_s = tab_s + 64 * 8;                     // [0] blob, [1 + w] warp w
+  const uint32_t stage_s = bar_s + 16 * 8;
+  const uint32_t ext_s = stage_s + P.stage_off_grid, eperm_s = stage_s + P.stage_off_perm,
+                 lut_s = stage_s + P.stage_off_lut;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* scal = s_warp + (size_t)warp * C.per_warp;
-  double* part = scal + 32 * STRIDE;
+  const uint32_t scal_s = stage_s + C.stage_pad + (unsigned)warp * (unsigned)C.per_warp * 8u;
+  const uint32_t part_s = scal_s + 32 * STRIDE * 8;
+  const unsigned char* stage_generic = smem_raw + 64 * 8 + 16 * 8;
+
   const int64_t row0 = ((int64_t)blockIdx.x * KC_WARPS + warp) * 32;
   const int rows_here = (int)max((int64_t)0, min((int64_t)32, B.n - row0));
   const int n_dbl = rows_here * n_par;
   const uint32_t par_bytes = (uint32_t)(n_dbl >> 1) * 16u;
 
   if (threadIdx.x == 0) {
-    for (int w = 0; w <= KC_WARPS; ++w) mbar_init(s_bar + w, 1);
+    for (int w = 0; w <= KC_WARPS; ++w) mbar_init(bar_s + 8u * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (threadIdx.x < 64) s_tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+  if (threadIdx.x < 64) sts_f64(tab_s + 8u * threadIdx.x, c_exp2_tab[threadIdx.x]);
   __syncthreads();
   // one bulk copy brings the grids + cell tables; one per warp brings that warp's params rows
-  if (threadIdx.x == 0) {
-    if (P.stage_bytes > 0) {
-      mbar_expect_tx(s_bar, (uint32_t)P.stage_bytes);
-      bulk_g2s(s_stage, P.stage, (uint32_t)P.stage_bytes, s_bar);
-    }
+  if (threadIdx.x == 0 && P.stage_bytes > 0) {
+    mbar_expect_tx(bar_s, (uint32_t)P.stage_bytes);
+    bulk_g2s(stage_s, P.stage, (uint32_t)P.stage_bytes, bar_s);
   }
   if (lane == 0 && par_bytes > 0) {
-    mbar_expect_tx(s_bar + 1 + warp, par_bytes);
-    bulk_g2s(part, B.params + row0 * n_par, par_bytes, s_bar + 1 + warp);   // row0*n_par*8 is a multiple of 256
+    mbar_expect_tx(bar_s + 8u + 8u * warp, par_bytes);
+    bulk_g2s(part_s, B.params + row0 * n_par, par_bytes, bar_s + 8u + 8u * warp);   // 256-byte aligned source
   }
   if (rows_here == 0) return;
   const bool live = lane < rows_here;
@@ -142,22 +228,24 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   const int zi = __ldg(P.zi + s);
   const uint64_t valid = __ldg(P.valid + s);
   const double inv4pidl2 = __ldg(P.consts + (int64_t)s * P.n_const);
-  if ((n_dbl & 1) && lane == 0) part[n_dbl - 1] = __ldg(B.params + row0 * n_par + n_dbl - 1);
-  if (par_bytes > 0) mbar_wait(s_bar + 1 + warp, 0);
+  if ((n_dbl & 1) && lane == 0) sts_f64(part_s + 8u * (n_dbl - 1), __ldg(B.params + row0 * n_par + n_dbl - 1));
+  if (par_bytes > 0) mbar_wait(bar_s + 8u + 8u * warp, 0);
   __syncwarp();
-  const double* __restrict__ p = part + my * n_par;
+  const uint32_t p_s = part_s + 8u * (unsigned)(my * n_par);
 
   bool inbox = true;
   {
     const double2* __restrict__ box = P.pbox + (int64_t)s * n_par;
     for (int c = 0; c < n_par; ++c) {
-      const double v = p[c];
+      const double v = lds_f64(p_s + 8u * c);
       const double2 mm = __ldg(box + c);
       inbox = inbox && (mm.x <= v) && (v <= mm.y);
     }
   }
 
-  if (P.stage_bytes > 0) mbar_wait(s_bar, 0);
+  if (P.stage_bytes > 0) mbar_wait(bar_s, 0);
+  const double* ext_g = reinterpret_cast<const double*>(stage_generic + P.stage_off_grid);
+  const int32_t* eperm_g = reinterpret_cast<const int32_t*>(stage_generic + P.stage_off_perm);
   int row[AGNF_MAX_FAMILIES], grow[AGNF_MAX_FAMILIES];
 #pragma unroll
   for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
@@ -165,63 +253,64 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     grow[f] = 0;
     if (f < (RADIO ? 5 : 4)) {
       const FamDesc& F = P.fam[f];
-      int64_t r = 0;
-      for (int d = 0; d < F.n_dim; ++d) {
-        const DimDesc& D = F.dim[d];
-        if (D.is_grid && D.size > 1) {
-          const double pv = p[F.par_offset + d];
-          int idx;
-          if (D.lut_m > 0)
-            idx = snap_dim_lut(s_ext + D.ext_off, s_eperm + D.ext_off, D.size, pv, s_lut + D.lut_off, D.lut_m,
-                               D.lut_lo, D.lut_inv, D.lut_big);
-          else
-            idx = snap_dim(s_ext + D.ext_off + 1, s_eperm + D.ext_off + 1, D.size, pv);
-          r += (int64_t)idx * D.stride;
-        }
+      int r = 0;
+      for (int t = 0; t < F.n_snap; ++t) {
+        const SnapTask& T = F.snap[t];
+        r += snap_task(T, lds_f64(p_s + 8u * T.col), ext_s, eperm_s, lut_s, ext_g, eperm_g) * T.stride;
       }
-      row[f] = (int)r;
-      grow[f] = (int)((int64_t)zi * F.T + r);
+      row[f] = r;
+      grow[f] = zi * (int)F.T + r;
     }
+  }
+  // start the only DRAM-bound gather early: this evaluation's galaxy row -> L2
+  {
+    const char* ga = reinterpret_cast<const char*>(P.fam[0].table + (int64_t)grow[0] * P.fam[0].pitch);
+    prefetch_l2(ga);
+    prefetch_l2(ga + 8 * n_b - 8);
   }
 
   const int no = P.norm_offset;
-  const double GA = p[no], SB = p[no + 1], TO = p[no + 2];
+  const double GA = lds_f64(p_s + 8u * no), SB = lds_f64(p_s + 8u * no + 8u), TO = lds_f64(p_s + 8u * no + 16u);
   int kk = 3;
   double BB = 0.0, RAD = 0.0;
-  if (cfg.bbb_has_norm) BB = p[no + kk++];
-  if (RADIO) RAD = p[no + kk++];
+  if (cfg.bbb_has_norm) BB = lds_f64(p_s + 8u * (no + kk++));
+  if (RADIO) RAD = lds_f64(p_s + 8u * (no + kk++));
   double ebv_gal = 0.0, ebv_bbb = 0.0, alpha = 0.0;
-  if (GA_FREE) ebv_gal = p[P.fam[0].par_offset + P.fam[0].n_dim - 1];
-  if (BB_MODE == 1) ebv_bbb = p[P.fam[3].par_offset + P.fam[3].n_dim - 1];
+  if (GA_FREE) ebv_gal = lds_f64(p_s + 8u * (P.fam[0].par_offset + P.fam[0].n_dim - 1));
+  if (BB_MODE == 1) ebv_bbb = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 1));
   if (BB_MODE == 2) {
-    ebv_bbb = p[P.fam[3].par_offset + P.fam[3].n_dim - 2];
-    alpha = p[P.fam[3].par_offset + P.fam[3].n_dim - 1];
+    ebv_bbb = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 2));
+    alpha = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 1));
   }
   if (BB_MODE == 3) {
-    ebv_bbb = p[P.fam[3].par_offset + P.fam[3].n_dim - 3];
-    alpha = p[P.fam[3].par_offset + P.fam[3].n_dim - 2];
+    ebv_bbb = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 3));
+    alpha = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 2));
   }
+  const double* s_tab = reinterpret_cast<const double*>(smem_raw);
   const double nGA = exp10_fast(GA, s_tab), nSB = exp10_fast(SB, s_tab), nTO = exp10_fast(TO, s_tab);
   const double nBB = cfg.bbb_has_norm ? exp10_fast(BB, s_tab) : 1.0;
   const double nRAD = RADIO ? exp10_fast(RAD, s_tab) : 0.0;
   const double cBB = cfg.bbb_has_norm ? 1.0 : inv4pidl2;
   const double xfac = (BB_MODE >= 2) ? exp10_fast(alpha / 0.3838, s_tab) : 1.0;
-  const int CPR = C.cpr, CPRP = C.cprp;
   {
-    double* rec = scal + lane * STRIDE;
-    *reinterpret_cast<int4*>(rec) =
-        make_int4(grow[0] * (P.fam[0].pitch >> 1), grow[1] * (P.fam[1].pitch >> 1),
-                  grow[2] * (P.fam[2].pitch >> 1), grow[3] * (P.fam[3].pitch >> 1));
-    *reinterpret_cast<double2*>(rec + 2) = make_double2(nGA, nSB);
-    *reinterpret_cast<double2*>(rec + 4) = make_double2(nTO, nBB * cBB);
-    *reinterpret_cast<double2*>(rec + 6) = make_double2(ebv_bbb, xfac);
-    *reinterpret_cast<ulonglong2*>(rec + 8) = make_ulonglong2(
-        (unsigned long long)(unsigned)(s * CPR) | ((unsigned long long)(unsigned)(zi * CPR) << 32), valid);
+    const uint32_t rec = scal_s + (unsigned)lane * (STRIDE * 8);
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};\n" ::"r"(rec), "r"(grow[0] * (P.fam[0].pitch >> 1)),
+                 "r"(grow[1] * (P.fam[1].pitch >> 1)), "r"(grow[2] * (P.fam[2].pitch >> 1)),
+                 "r"(grow[3] * (P.fam[3].pitch >> 1))
+                 : "memory");
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(rec + 16), "d"(nGA), "d"(nSB) : "memory");
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(rec + 32), "d"(nTO), "d"(nBB * cBB) : "memory");
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(rec + 48), "d"(ebv_bbb), "d"(xfac) : "memory");
+    asm volatile("st.shared.v2.u64 [%0], {%1, %2};\n" ::"r"(rec + 64),
+                 "l"((unsigned long long)(unsigned)(s * CPR) | ((unsigned long long)(unsigned)(zi * CPR) << 32)),
+                 "l"((unsigned long long)valid)
+                 : "memory");
     if (EXT) {
-      *reinterpret_cast<double2*>(rec + 10) = make_double2(ebv_gal, nRAD);
-      *reinterpret_cast<ulonglong2*>(rec + 12) = make_ulonglong2(
-          (unsigned long long)(unsigned)(RADIO ? grow[4] * (P.fam[4].pitch >> 1) : 0),
-          BB_MODE >= 2 ? __ldg(P.xray + zi) : 0ull);
+      asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(rec + 80), "d"(ebv_gal), "d"(nRAD) : "memory");
+      asm volatile("st.shared.v2.u64 [%0], {%1, %2};\n" ::"r"(rec + 96),
+                   "l"((unsigned long long)(unsigned)(RADIO ? grow[4] * (P.fam[4].pitch >> 1) : 0)),
+                   "l"((unsigned long long)(BB_MODE >= 2 ? __ldg(P.xray + zi) : 0ull))
+                   : "memory");
     }
   }
   if (B.rows && live) {
@@ -238,60 +327,57 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     const double2* __restrict__ tRAD = reinterpret_cast<const double2*>(P.fam[RADIO ? 4 : 0].table);
     const double2* __restrict__ y2 = reinterpret_cast<const double2*>(P.y);
     const double2* __restrict__ i2 = reinterpret_cast<const double2*>(P.isig);
-    const double2* __restrict__ cb2 = reinterpret_cast<const double2*>(P.cbbb);
-    const double2* __restrict__ cg2 = reinterpret_cast<const double2*>(P.cgal);
+    const double2* __restrict__ cb2 = reinterpret_cast<const double2*>(P.cbbb64);
+    const double2* __restrict__ cg2 = reinterpret_cast<const double2*>(P.cgal64);
     const double2* __restrict__ om2 = reinterpret_cast<const double2*>(P.omega);
     int e = lane / CPR;
     int k = lane - e * CPR;
     const int de = 32 / CPR, dk = 32 - de * CPR;
-#pragma unroll 3
+#pragma unroll
     for (int it = 0; it < CPR; ++it) {
-      const double* rec = scal + e * STRIDE;
-      const int4 g = *reinterpret_cast<const int4*>(rec);
-      const double2 n01 = *reinterpret_cast<const double2*>(rec + 2);
-      const double2 n23 = *reinterpret_cast<const double2*>(rec + 4);
-      const ulonglong2 sv = *reinterpret_cast<const ulonglong2*>(rec + 8);
-      const unsigned qs = (unsigned)(sv.x & 0xffffffffull), qz = (unsigned)(sv.x >> 32);
+      const uint32_t rec = scal_s + (unsigned)e * (STRIDE * 8);
+      const int4 g = lds_v4s32(rec);
+      const double2 n01 = lds_v2f64(rec + 16);
+      const double2 n23 = lds_v2f64(rec + 32);
+      const int4 sv = lds_v4s32(rec + 64);                  // {s*CPR, zi*CPR, valid lo, valid hi}
       const double2 dga = __ldg(tGA + (unsigned)(g.x + k));
       const double2 dsb = __ldg(tSB + (unsigned)(g.y + k));
       const double2 dto = __ldg(tTO + (unsigned)(g.z + k));
       const double2 dbb = __ldg(tBB + (unsigned)(g.w + k));
-      const double2 yv = __ldg(y2 + (qs + k));
-      const double2 iv = __ldg(i2 + (qs + k));
+      const double2 yv = __ldg(y2 + (unsigned)(sv.x + k));
+      const double2 iv = __ldg(i2 + (unsigned)(sv.x + k));
       double2 drad = make_double2(0.0, 0.0);
       double c_ebvgal = 0.0, c_nrad = 0.0;
       if (GA_FREE || RADIO) {
-        const double2 x = *reinterpret_cast<const double2*>(rec + 10);
+        const double2 x = lds_v2f64(rec + 80);
         c_ebvgal = x.x;
         c_nrad = x.y;
       }
-      if (RADIO) {
-        const int gr = *reinterpret_cast<const int*>(rec + 12);
-        drad = __ldg(tRAD + (unsigned)(gr + k));
-      }
+      if (RADIO) drad = __ldg(tRAD + (unsigned)(lds_s32(rec + 96) + k));
       double bb0 = dbb.x, bb1 = dbb.y;
       if (BB_MODE != 0) {
-        const double2 eb = *reinterpret_cast<const double2*>(rec + 6);
-        const double2 cb = __ldg(cb2 + (qz + k));
-        const double w0 = dbb.x * exp10_fast(cb.x * eb.x, s_tab);
-        const double w1 = dbb.y * exp10_fast(cb.y * eb.x, s_tab);
+        const double2 eb = lds_v2f64(rec + 48);
+        const double2 cb = __ldg(cb2 + (unsigned)(sv.y + k));
+        const double w0 = dbb.x * pow2_64(cb.x * eb.x, tab_s);
+        const double w1 = dbb.y * pow2_64(cb.y * eb.x, tab_s);
         bb0 = (w0 != w0) ? dbb.x : w0;                        // NaN -> unreddened (MODEL:1211)
         bb1 = (w1 != w1) ? dbb.y : w1;
         if (BB_MODE >= 2) {
-          const unsigned xr = (unsigned)(*reinterpret_cast<const unsigned long long*>(rec + 13) >> (2 * k));
+          const unsigned xr = (unsigned)(lds_u64(rec + 104) >> (2 * k));
           if (xr & 1u) bb0 = dbb.x * eb.y;
           if (xr & 2u) bb1 = dbb.y * eb.y;
         }
       }
       double ga0 = dga.x, ga1 = dga.y;
       if (GA_FREE) {
-        const double2 cg = __ldg(cg2 + (qz + k));
-        const double rg0 = exp10_fast(cg.x * c_ebvgal, s_tab), rg1 = exp10_fast(cg.y * c_ebvgal, s_tab);
+        const double2 cg = __ldg(cg2 + (unsigned)(sv.y + k));
+        const double rg0 = pow2_64(cg.x * c_ebvgal, tab_s), rg1 = pow2_64(cg.y * c_ebvgal, tab_s);
         if (eb_free) {
-          const double2 om = __ldg(om2 + (qz + k));
-          part[32 * CPRP + e * CPRP + k] = om.x * (dga.x * 3.826e33) + om.y * (dga.y * 3.826e33);
-          part[64 * CPRP + e * CPRP + k] =
-              om.x * (((dga.x * 1e18) * rg0) * 3.826e33) + om.y * (((dga.y * 1e18) * rg1) * 3.826e33);
+          const double2 om = __ldg(om2 + (unsigned)(sv.y + k));
+          sts_f64(part_s + 8u * (unsigned)(32 * CPRP + e * CPRP + k),
+                  om.x * (dga.x * 3.826e33) + om.y * (dga.y * 3.826e33));
+          sts_f64(part_s + 8u * (unsigned)(64 * CPRP + e * CPRP + k),
+                  om.x * (((dga.x * 1e18) * rg0) * 3.826e33) + om.y * (((dga.y * 1e18) * rg1) * 3.826e33));
         }
         ga0 = dga.x * rg0;
         ga1 = dga.y * rg1;
@@ -302,10 +388,11 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
         m0 += c_nrad * drad.x;
         m1 += c_nrad * drad.y;
       }
-      const unsigned vb = (unsigned)(sv.y >> (2 * k));
+      const unsigned long long vmask = ((unsigned long long)(unsigned)sv.w << 32) | (unsigned)sv.z;
+      const unsigned vb = (unsigned)(vmask >> (2 * k));
       const double r0 = (yv.x - m0) * iv.x, r1 = (yv.y - m1) * iv.y;
       const double c0 = (vb & 1u) ? r0 * r0 : 0.0;
-      part[e * CPRP + k] = (vb & 2u) ? fma(r1, r1, c0) : c0;
+      sts_f64(part_s + 8u * (unsigned)(e * CPRP + k), (vb & 2u) ? fma(r1, r1, c0) : c0);
       if (B.ymodel && row0 + e < B.n) {
         double* ym = B.ymodel + (row0 + e) * n_b + 2 * k;
         ym[0] = m0;
@@ -325,11 +412,12 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   if (!live) return;
   double chi = 0.0, ebA = 0.0, ebB = 0.0;
   {
-    const double* mine = part + lane * CPRP;
-    for (int k = 0; k < CPR; ++k) chi += mine[k];
+    const uint32_t mine = part_s + 8u * (unsigned)(lane * CPRP);
+#pragma unroll
+    for (int k = 0; k < CPR; ++k) chi += lds_f64(mine + 8u * k);
     if (eb_free) {
-      for (int k = 0; k < CPR; ++k) ebA += mine[32 * CPRP + k];
-      for (int k = 0; k < CPR; ++k) ebB += mine[64 * CPRP + k];
+      for (int k = 0; k < CPR; ++k) ebA += lds_f64(mine + 8u * (32 * CPRP + k));
+      for (int k = 0; k < CPR; ++k) ebB += lds_f64(mine + 8u * (64 * CPRP + k));
     }
   }
   const double lnlike = -0.5 * chi;
@@ -350,14 +438,14 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   if (cfg.prior_agnfrac) {
     const int j = __ldg(P.j1500 + zi);
     double ga_r = __ldg(P.fam[0].table + (int64_t)grow[0] * P.fam[0].pitch + j);
-    if (GA_FREE) ga_r = ga_r * exp10_fast(__ldg(P.cgal + (int64_t)zi * nbp + j) * ebv_gal, s_tab);
+    if (GA_FREE) ga_r = ga_r * pow2_64(__ldg(P.cgal64 + (int64_t)zi * nbp + j) * ebv_gal, tab_s);
     const double dbb = __ldg(P.fam[3].table + (int64_t)grow[3] * P.fam[3].pitch + j);
     double bb_r = dbb;
     if (BB_MODE != 0) {
       if (BB_MODE >= 2 && ((__ldg(P.xray + zi) >> j) & 1ull)) {
         bb_r = dbb * xfac;
       } else {
-        const double w = dbb * exp10_fast(__ldg(P.cbbb + (int64_t)zi * nbp + j) * ebv_bbb, s_tab);
+        const double w = dbb * pow2_64(__ldg(P.cbbb64 + (int64_t)zi * nbp + j) * ebv_bbb, tab_s);
         bb_r = (w != w) ? dbb : w;
       }
     }
@@ -385,9 +473,9 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   if (B.lnlike) B.lnlike[i] = lnlike;
 }
 
-template <bool GA_FREE, int BB_MODE, bool RADIO>
-cudaError_t launch_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
-  auto kern = k1_coop_kernel<GA_FREE, BB_MODE, RADIO>;
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
+cudaError_t launch_coop_cpr(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
+  auto kern = k1_coop_kernel<GA_FREE, BB_MODE, RADIO, CPR_T>;
   const CoopPlan C = make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P);
   static int attr_bytes[64] = {0};   // per instantiation and device
   int dev = 0;
@@ -400,6 +488,16 @@ cudaError_t launch_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream
   const int64_t blocks = (B.n + KC_THREADS - 1) / KC_THREADS;
   kern<<<(unsigned)blocks, KC_THREADS, (size_t)C.smem_bytes, stream>>>(P, B, C);
   return cudaGetLastError();
+}
+
+// the default 18-band set has a fully unrolled instantiation; every other band count runs the
+// runtime-trip-count instantiation
+template <bool GA_FREE, int BB_MODE, bool RADIO>
+cudaError_t launch_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
+  switch (P.nbp / 2) {
+    case 9: return launch_coop_cpr<GA_FREE, BB_MODE, RADIO, 9>(P, B, stream);
+    default: return launch_coop_cpr<GA_FREE, BB_MODE, RADIO, 0>(P, B, stream);
+  }
 }
 
 template <bool GA_FREE, bool RADIO>

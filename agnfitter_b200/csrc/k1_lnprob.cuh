@@ -40,6 +40,17 @@ struct DimDesc {
   double lut_big;     // the table path answers only for |p| <= lut_big (k1_common.cuh::snap_dim_lut)
 };
 
+// one snapped dimension of a family, as the cooperative kernel wants it (grid dims with > 1 value only)
+struct SnapTask {
+  int32_t col;        // column of the parameter in a params row
+  int32_t n;          // grid values
+  int32_t ext_off;    // see DimDesc
+  int32_t lut_off;
+  int32_t lut_mmax;   // cells - 1; -1: no table (binary search)
+  int32_t stride;     // rows per grid step
+  double lo, inv, big;
+};
+
 struct FamDesc {
   const double* table;  // [n_z, T, pitch]; columns n_b..pitch-1 are zero
   const double* aux;    // [T] or nullptr
@@ -47,8 +58,9 @@ struct FamDesc {
   int32_t n_dim;
   int32_t par_offset;
   int32_t pitch;        // row pitch of `table` in doubles (>= n_b)
-  int32_t pad;
+  int32_t n_snap;
   DimDesc dim[AGNF_MAX_DIMS];
+  SnapTask snap[AGNF_MAX_DIMS];
 };
 
 struct K1Params {
@@ -70,6 +82,8 @@ struct K1Params {
   // z-slices (pad columns are zero)
   const double* cgal;         // [n_z, nbp]  -0.4 k_Calzetti
   const double* cbbb;         // [n_z, nbp]  -0.4 k_Prevot
+  const double* cgal64;       // cgal * 64 log2(10): the cooperative kernel evaluates 10^(c E) as 2^(c64 E / 64)
+  const double* cbbb64;       // cbbb * 64 log2(10)
   const uint64_t* xray;       // [n_z]
   const int32_t* j1500;       // [n_z]
   const double* omega;        // [n_z, nbp]

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libagnfit_b200.so")
+# AGNFIT_B200_LIB: alternative build of the same library (kernel-tuning experiments only)
+LIB_PATH = os.environ.get("AGNFIT_B200_LIB") or os.path.join(_HERE, "csrc", "libagnfit_b200.so")
 
 AGNF_MAX_FAMILIES = 5
 AGNF_MAX_DIMS = 4

@@ -21,6 +21,9 @@ using namespace agnf;
 struct agnf_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // host-variant pipeline: H2D / K1 / D2H of successive chunks overlap
+  cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
+  int64_t pipeline_rows = 1 << 20;              // chunk size of the host-variant pipeline (0: one shot)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // bracket the last K1 kernel
   cudaEvent_t ev2 = nullptr, ev3 = nullptr;     // bracket the last K2 contraction
   bool k1_timed = false, k2_timed = false;
@@ -284,6 +287,10 @@ AGNF_API int agnf_ctx_create(int device, agnf_ctx** out) {
     delete ctx;
     return fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
+  for (int i = 0; i < 3; ++i) {
+    cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming);
+  }
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
   cudaEventCreate(&ctx->ev2);
@@ -297,6 +304,11 @@ AGNF_API void agnf_ctx_destroy(agnf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->owned) cudaFree(p);
+  for (int i = 0; i < 3; ++i) {
+    if (ctx->pipe[i]) cudaStreamSynchronize(ctx->pipe[i]);
+    if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
+    if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
+  }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -339,6 +351,11 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     ctx->k1_variant = (int)value;
     return 0;
   }
+  if (strcmp(name, "pipeline_rows") == 0) {
+    if (value < 0) return fail(ctx, "pipeline_rows must be >= 0");
+    ctx->pipeline_rows = value;
+    return 0;
+  }
   return fail(ctx, "unknown option '%s'", name);
 }
 
@@ -347,6 +364,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   if (strcmp(name, "k1_variant") == 0) *value = ctx->k1_variant;
   else if (strcmp(name, "k1_last_kernel") == 0) *value = ctx->last_k1_kernel;
   else if (strcmp(name, "band_pitch") == 0) *value = ctx->have_cfg ? ctx->k1.nbp : 0;
+  else if (strcmp(name, "pipeline_rows") == 0) *value = ctx->pipeline_rows;
   else return fail(ctx, "unknown option '%s'", name);
   return 0;
 }
@@ -568,6 +586,29 @@ AGNF_API int agnf_lnprob_batch(agnf_ctx* ctx, const double* params, const int32_
   if (ensure(ctx, &ctx->st_out, &ctx->st_out_cap, total)) return 1;
   char* o = static_cast<char*>(ctx->st_out);
   cudaStream_t st = ctx->stream;
+  const bool plain = !rows && !ymodel && !lnprior && !lnlike;
+  if (plain && ctx->pipeline_rows > 0 && n > ctx->pipeline_rows) {
+    // Production shape (lnp only): cut the batch into chunks and rotate them over three streams, so
+    // that chunk c's upload, chunk c-1's kernel and chunk c-2's download run at the same time.  Chunk
+    // boundaries are multiples of 256 rows: every chunk's params block stays 16-byte aligned and CTA
+    // tiles never straddle chunks, so results are bit-identical to the one-shot path.
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));             // uploads queued on the ctx stream are visible
+    const int64_t chunk = (ctx->pipeline_rows + 255) & ~(int64_t)255;
+    int k = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk, ++k) {
+      const int64_t m = std::min(chunk, n - r0);
+      cudaStream_t ps = ctx->pipe[k % 3];
+      double* dp = static_cast<double*>(ctx->st_params) + r0 * np;
+      int32_t* ds = static_cast<int32_t*>(ctx->st_sid) + r0;
+      double* dl = reinterpret_cast<double*>(o + off_lnp) + r0;
+      CUDA_TRY(ctx, cudaMemcpyAsync(dp, params + r0 * np, (size_t)m * np * 8, cudaMemcpyHostToDevice, ps));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ds, source_id + r0, (size_t)m * 4, cudaMemcpyHostToDevice, ps));
+      if (agnf_lnprob_batch_device(ctx, dp, ds, m, dl, nullptr, nullptr, nullptr, nullptr, ps)) return 1;
+      CUDA_TRY(ctx, cudaMemcpyAsync(lnp + r0, dl, (size_t)m * 8, cudaMemcpyDeviceToHost, ps));
+    }
+    for (int i = 0; i < 3; ++i) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+    return 0;
+  }
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->st_params, params, N * np * sizeof(double), cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->st_sid, source_id, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   if (agnf_lnprob_batch_device(ctx, static_cast<const double*>(ctx->st_params),

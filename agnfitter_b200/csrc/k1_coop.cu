@@ -28,7 +28,13 @@ namespace agnf {
 
 namespace {
 
-constexpr int KC_THREADS = 256;
+#ifndef KC_THREADS_DEF
+#define KC_THREADS_DEF 256
+#endif
+#ifndef KC_MINBLOCKS
+#define KC_MINBLOCKS 3
+#endif
+constexpr int KC_THREADS = KC_THREADS_DEF;
 constexpr int KC_WARPS = KC_THREADS / 32;
 
 // hand-off record of one evaluation, in doubles (q = chunk index = element offset / 2):
@@ -177,7 +183,7 @@ __device__ __forceinline__ int snap_task(const SnapTask& T, double p, uint32_t e
 
 // CPR_T: chunks per row as a compile-time constant (fully unrolled band phase), or 0 = runtime
 template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
-__global__ void __launch_bounds__(KC_THREADS, 3)
+__global__ void __launch_bounds__(KC_THREADS, KC_MINBLOCKS)
 k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPlan C) {
   constexpr bool EXT = GA_FREE || RADIO || BB_MODE >= 2;
   constexpr int STRIDE = Rec<EXT>::STRIDE;

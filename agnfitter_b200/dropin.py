@@ -1,0 +1,137 @@
+"""
+Reference-facing mirror of the hot path: the callables AGNfitter's samplers and driver bind to,
+with the reference's names, argument order and return conventions, backed by the sm_100a kernels.
+
+    reference callable (AGNfitter/functions)                              here
+    -------------------------------------------------------------------   -----------------------------
+    PARAMETERSPACE_AGNfitter.ln_probab(pars, data, models, P)   :153-173   Posterior.ln_probab
+    ... called per walker by emcee.EnsembleSampler         MCMC:114        Posterior.ln_probab_batch (vectorize=True)
+    my_posterior(params[n, ndim])                          MCMC:56-62      Posterior.my_posterior
+    my_params_transform(cube[n, ndim])                     MCMC:64-72      Posterior.my_params_transform
+    PARAMETERSPACE_AGNfitter.ymodel(nus, z, dlum, models, P, *par) :180-243  Posterior.ymodel
+    DICTIONARIES_AGNfitter.filtering_models(nus, F, filterdict, z) :426-478  engine.DictBuilder.filtering_models
+    MODELSDICT.construct_dictionaryarray_filtered / build  DIC:78-154      fill_modelsdict
+
+`data`, `models`, `P` are the reference's own objects (DATA_AGNfitter.DATA, MODEL_AGNfitter.MODELS,
+PARAMETERSPACE_AGNfitter.Pdict): nothing in RUN_AGNfitter_multi.py or the settings files changes.
+There is no CPU fallback: constructing a Posterior without an sm_100 device raises.
+"""
+import numpy as np
+
+from . import sources as _sources
+from .engine import Engine, DictBuilder
+from .flatten import modelset_from_modelsdicts, ModelSet
+
+
+def params_transform(cube, pmin, pmax):
+    """my_params_transform (MCMC_AGNfitter.py:64-72) without the Python loops:
+    params[i, k] = (P.max[k] - P.min[k]) * cube[i, k] + P.min[k], same operation order."""
+    cube = np.asarray(cube, dtype=np.float64)
+    pmin = np.asarray(pmin, dtype=np.float64)
+    pmax = np.asarray(pmax, dtype=np.float64)
+    return (pmax - pmin) * cube + pmin
+
+
+def check_P(ms: ModelSet, P, pmin, pmax):
+    """The parameter table the caller built with the reference's Pdict must describe the same
+    parameter vector the kernel unpacks (names, order, bounds)."""
+    if list(P['names']) != list(ms.par_names):
+        raise ValueError("P['names'] = %s but the dictionary describes %s" % (list(P['names']), ms.par_names))
+    if not (np.array_equal(np.asarray(P['min'], dtype=np.float64), pmin)
+            and np.array_equal(np.asarray(P['max'], dtype=np.float64), pmax)):
+        raise ValueError("P['min']/P['max'] differ from the bounds Pdict gives for this dictionary and redshift")
+
+
+class Posterior:
+    """ln_probab for ONE source, bound to the reference's (data, models, P) triple.
+
+        post = Posterior(data, models, P)
+        sampler = emcee.EnsembleSampler(nwalkers, npar, post.ln_probab_batch, vectorize=True)
+        # or, unchanged call sites:  emcee.EnsembleSampler(nwalkers, npar, post.ln_probab, args=[data, models, P])
+    """
+
+    def __init__(self, data, models, P, device=0, ctx=None):
+        md = models.dict_modelfluxes                     # the MODELSDICT instance (MODEL_AGNfitter.py:1483-1490)
+        self.ms = modelset_from_modelsdicts([md], models.settings)
+        if float(md.z) != float(data.z):
+            raise ValueError("the dictionary was built for z=%r, the source is at z=%r" % (md.z, data.z))
+        self.engine = Engine(self.ms, device=device, ctx=ctx)
+        nus = np.asarray(data.nus, dtype=np.float64)
+        self.src = _sources.make_sources(self.ms, [float(data.z)], [float(data.dlum)], nus[None, :],
+                                         np.asarray(data.fluxes, dtype=np.float64)[None, :],
+                                         np.asarray(data.fluxerrs, dtype=np.float64)[None, :])
+        check_P(self.ms, P, self.src.pmin[0], self.src.pmax[0])
+        self.engine.set_sources(self.src)
+        self.P = P
+        self.n_par = self.ms.n_par
+        self.bands = self.ms.bands
+
+    # ---- emcee ---------------------------------------------------------------------------------
+    def ln_probab(self, pars, data=None, models=None, P=None):
+        """Same signature and return type as the reference: one walker -> Python float."""
+        return float(self.engine.lnprob(np.asarray(pars, dtype=np.float64)[None, :])[0])
+
+    def ln_probab_batch(self, params):
+        """[n, n_par] -> [n]: the log_prob_fn of emcee.EnsembleSampler(..., vectorize=True)."""
+        return self.engine.lnprob(params)
+
+    # ---- ultranest -----------------------------------------------------------------------------
+    def my_posterior(self, params):
+        return self.engine.lnprob(params)
+
+    def my_params_transform(self, cube):
+        return params_transform(cube, self.P['min'], self.P['max'])
+
+    # ---- plots / post-processing -----------------------------------------------------------------
+    def ymodel(self, data_nus=None, z=None, dlum=None, models=None, P=None, *par):
+        """-> (lum[n_b], bands) like PARAMETERSPACE_AGNfitter.ymodel."""
+        _, _, ym, _, _ = self.engine.lnprob(np.asarray(par, dtype=np.float64)[None, :], detail=True)
+        return ym[0], self.bands
+
+
+class CatalogPosterior:
+    """ln_probab for a whole catalogue shard: rows of `params` carry a source index.  This is the
+    entry point a batched multi-source sampler uses (SURVEY.md §8b `ln_probab_batch`)."""
+
+    def __init__(self, ms: ModelSet, z, dlum, nus, fluxes, fluxerrs, device=0, ctx=None, device_tables=None):
+        self.ms = ms
+        self.engine = Engine(ms, device=device, ctx=ctx, device_tables=device_tables)
+        self.src = _sources.make_sources(ms, z, dlum, nus, fluxes, fluxerrs)
+        self.engine.set_sources(self.src)
+
+    @property
+    def pmin(self):
+        return self.src.pmin
+
+    @property
+    def pmax(self):
+        return self.src.pmax
+
+    def ln_probab_batch(self, params, source_id):
+        return self.engine.lnprob(params, source_id)
+
+    def my_params_transform(self, cube, source_id):
+        sid = np.asarray(source_id)
+        return params_transform(cube, self.src.pmin[sid], self.src.pmax[sid])
+
+
+# ---------------------------------------------------------------------------------------------
+_FAMILY_ATTR = (("GALAXY", "GALAXYFdict"), ("STARBURST", "STARBURSTFdict"), ("BBB", "BBBFdict"),
+                ("TORUS", "TORUSFdict"), ("AGN_RAD", "AGN_RADFdict"))
+
+
+def fill_modelsdict(md, builder: DictBuilder, z, templates_4plot):
+    """The filtering loop of MODELSDICT.construct_dictionaryarray_filtered
+    (DICTIONARIES_AGNfitter.py:92-128) on the GPU: for every family in `templates_4plot`
+    ({'GALAXY': {key: (log nu, Fnu)}, 'STARBURST': ..., 'BBB': ..., 'TORUS': ..., ['AGN_RAD': ...]},
+    i.e. the reference's `*Fdict_4plot` dicts) set `md.<FAMILY>Fdict = {key: (bands, Fnu[n_b])}`
+    with the reference's key order, and keep the `_4plot` dicts on `md` as the reference does."""
+    for fam, attr in _FAMILY_ATTR:
+        if fam not in templates_4plot:
+            continue
+        tpl = templates_4plot[fam]
+        tab = builder.build_family(tpl, [z])[0]
+        setattr(md, attr, {k: (builder.bands, tab[i]) for i, k in enumerate(tpl.keys())})
+        setattr(md, attr + "_4plot", tpl)
+    md.z = z
+    return md

@@ -39,6 +39,8 @@ def k1_bytes_per_eval(n_comp, n_b, n_par, W):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock, power and throttle reasons DURING the timed region, through NVML (sub-millisecond per
+    sample; the timed region of a default run is tens of milliseconds), nvidia-smi as a fallback."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -46,32 +48,78 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.stop_flag = False
+        self.how = "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except ValueError:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            self.nv = None
+            self.how = "nvidia-smi"
+
+    def _nvml_sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for nm, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                        ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                        ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                        ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _smi_sample(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        s = [x.strip() for x in out.split(",")]
+        if len(s) >= 8:
+            self.sm.append(float(s[1]))
+            self.mx.append(float(s[2]))
+            for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[4:8]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(nm)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nv is not None:
+                    self._nvml_sample()
+                else:
+                    self._smi_sample()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.002 if self.nv is not None else 0.1)
 
     def summary(self):
-        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
-        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            for nm, v in zip(names, s[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
+
+
+def ncu_traffic(kernel, rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` over `rows` rows, from the
+    committed ncu --set full capture (profiles/k1_traffic.json, written by tools/ncu_summary.py);
+    None when no capture of this launch shape is on file."""
+    p = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    for rec in json.load(open(p)):
+        if rec.get("kernel") == kernel and int(rec.get("rows", -1)) == int(rows):
+            return float(rec["dram_bytes"])
+    return None
 
 
 def measured_peak():
@@ -266,6 +314,7 @@ def run_ours(args):
     if rank == 0:
         bpe = k1_bytes_per_eval(n_comp, n_b, n_par, W)
         peak, peak_src = measured_peak()
+        kname = "k1_coop_kernel" if eng.get_option("k1_last_kernel") == 1 else "k1_lnprob_kernel"
         achieved = bpe * n / (k1_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
         # CPU baseline: the oracle port on a bounded sample of the same workload
@@ -290,11 +339,13 @@ def run_ours(args):
                        "parallelism": "sources sharded over %d GPU(s), no data-path collective" % world},
             "sources_fitted_per_s": value / EVALS_PER_FIT,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * n_par * 8 + n * 4),
-                    "d2h_bytes_per_step": int(n * 8), "ms_per_step": e2e_ms_max / args.steps},
+                    "d2h_bytes_per_step": int(n * 8), "ms_per_step": e2e_ms_max / args.steps,
+                    "api": "agnf_lnprob_batch (host buffers; %d-row chunks pipelined over 3 streams)"
+                           % eng.get_option("pipeline_rows")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "kernel": "k1_coop_kernel" if eng.get_option("k1_last_kernel") == 1 else "k1_lnprob_kernel",
+                         "traffic": ncu_traffic(kname, n), "peak_source": peak_src, "kernel": kname,
+                         "algorithmic_bytes_per_launch": bpe * n,
                          "bytes_per_eval": bpe, "kernel_ms": k1_ms},
             "cpu_baseline": {"value": cpu_all, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "oracle/agn_oracle.ln_probab on %d of the %d sources x %d walkers, vectorised "

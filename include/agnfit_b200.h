@@ -124,7 +124,9 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
 /* tuning knobs.  "k1_variant": 1 (default) = cooperative K1 kernel whenever its preconditions hold
  * (16-byte aligned params and tables, even table pitch), 0 = per-thread K1 kernel (no preconditions).
  * agnf_get_option also answers "k1_last_kernel" (which kernel the last K1 launch ran: 1 / 0, -1 none)
- * and "band_pitch" (n_b rounded up to even: the pitch to ask agnf_dict_build for). */
+ * and "band_pitch" (n_b rounded up to even: the pitch to ask agnf_dict_build for).
+ * "pipeline_rows" (default 2^20): agnf_lnprob_batch with only lnp requested cuts batches larger than
+ * this into chunks whose upload / kernel / download overlap on three streams; 0 = one shot. */
 AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value);
 AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value);
 /* y[i] = 10^x[i] through the kernels' own exp10 routine (host pointers; unit-test hook) */

@@ -388,8 +388,14 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 1), "ms_per_step": n_step / v * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C3 sample: %d sources x %d walkers per step of the same synthetic catalogue" % (
-            ns, args.walkers), "positions": args.positions},
+        "config": {"workload": "C3: synthetic %d sources x %d walkers per GPU, 18-band default set, classic "
+                               "10-parameter model (11000+161+60+2 templates)" % (args.sources, args.walkers),
+                   "positions": args.positions + " in prior box + 1% out-of-box rows",
+                   "sample": "each step evaluates %d of the sources x %d walkers (bounded sample of the workload; "
+                             "the sample's dictionary z-slices were built with K2, outside the timed region)"
+                             % (ns, args.walkers),
+                   "n_bands": ms.n_b, "n_par": ms.n_par,
+                   "parallelism": "host cores of rank 0 only (%d); other ranks idle" % cores},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "oracle port (NumPy, vectorised over a source's %d walkers), fork Pool over %d "
                                    "sources on %d cores" % (args.walkers, ns, cores)},

@@ -702,9 +702,11 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   p.out_pitch = out_pitch;
 
   void *d_lam = nullptr, *d_perm = nullptr, *d_F = nullptr, *d_Fs = nullptr, *d_z = nullptr, *d_jlo = nullptr,
-       *d_cnt = nullptr, *d_rmax = nullptr, *d_W = nullptr, *d_rowmap = nullptr, *d_out = nullptr;
+       *d_cnt = nullptr, *d_rmax = nullptr, *d_W = nullptr, *d_rowmap = nullptr, *d_out = nullptr, *d_woff = nullptr,
+       *d_bandof = nullptr;
   auto cleanup = [&]() {
-    for (void* q : {d_lam, d_perm, d_F, d_Fs, d_z, d_jlo, d_cnt, d_rmax, d_W, d_rowmap}) dev_free(ctx, q);
+    for (void* q : {d_lam, d_perm, d_F, d_Fs, d_z, d_jlo, d_cnt, d_rmax, d_W, d_rowmap, d_woff, d_bandof})
+      dev_free(ctx, q);
     if (!out_on_device) dev_free(ctx, d_out);
   };
 #define K2_TRY(expr)                                                                                    \
@@ -726,16 +728,18 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   K2_ALLOC(d_lam, (size_t)n_lam * 8);
   K2_ALLOC(d_perm, (size_t)n_lam * 4);
   K2_ALLOC(d_F, (size_t)T * n_lam * 8);
-  K2_ALLOC(d_Fs, (size_t)T * p.ldF * 8);
+  const int64_t T_pad = (T + 31) & ~(int64_t)31;          // whole 32-template tiles for the tiled contraction
+  K2_ALLOC(d_Fs, (size_t)T_pad * p.ldF * 8);
+  K2_TRY(cudaMemsetAsync(d_Fs, 0, (size_t)T_pad * p.ldF * 8, st));
   K2_ALLOC(d_z, (size_t)n_z * 8);
   K2_ALLOC(d_jlo, (size_t)n_z * n_b * 4);
   K2_ALLOC(d_cnt, (size_t)n_z * n_b * 4);
-  K2_ALLOC(d_rmax, 4);
+  K2_ALLOC(d_rmax, (size_t)n_b * 4);
   K2_TRY(cudaMemcpyAsync(d_lam, lam_sorted, (size_t)n_lam * 8, cudaMemcpyHostToDevice, st));
   K2_TRY(cudaMemcpyAsync(d_perm, perm, (size_t)n_lam * 4, cudaMemcpyHostToDevice, st));
   K2_TRY(cudaMemcpyAsync(d_F, Fnu, (size_t)T * n_lam * 8, cudaMemcpyHostToDevice, st));
   K2_TRY(cudaMemcpyAsync(d_z, z, (size_t)n_z * 8, cudaMemcpyHostToDevice, st));
-  K2_TRY(cudaMemsetAsync(d_rmax, 0, 4, st));
+  K2_TRY(cudaMemsetAsync(d_rmax, 0, (size_t)n_b * 4, st));
   if (row_map) {
     for (int64_t t = 0; t < T; ++t)
       if (row_map[t] < 0 || row_map[t] >= T_total) {
@@ -750,18 +754,30 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   p.z = static_cast<const double*>(d_z);
   p.jlo = static_cast<int32_t*>(d_jlo);
   p.cnt = static_cast<int32_t*>(d_cnt);
-  p.d_rmax = static_cast<int32_t*>(d_rmax);
+  p.d_rmaxb = static_cast<int32_t*>(d_rmax);
   p.row_map = static_cast<const int64_t*>(d_rowmap);
 
   K2_TRY(launch_k2_permute(static_cast<const double*>(d_F), static_cast<const int32_t*>(d_perm),
                            static_cast<double*>(d_Fs), T, n_lam, p.ldF, st));
   K2_TRY(launch_k2_ranges(p, st));
-  int32_t rmax = 0;
-  K2_TRY(cudaMemcpyAsync(&rmax, d_rmax, 4, cudaMemcpyDeviceToHost, st));
+  // compact weight layout: band b owns max_z cnt[z][b] slots of every z-slice
+  std::vector<int32_t> rmaxb((size_t)n_b), woff((size_t)n_b + 1, 0);
+  K2_TRY(cudaMemcpyAsync(rmaxb.data(), d_rmax, (size_t)n_b * 4, cudaMemcpyDeviceToHost, st));
   K2_TRY(cudaStreamSynchronize(st));
-  if (rmax < 1) rmax = 1;
-  p.rmax = rmax;
-  K2_ALLOC(d_W, (size_t)n_z * n_b * rmax * 8);
+  for (int b = 0; b < n_b; ++b) woff[(size_t)b + 1] = woff[(size_t)b] + std::max(rmaxb[(size_t)b], 1);
+  const int32_t wstride = (woff[(size_t)n_b] + 1) & ~1;       // even: a z-slice of weights is a 16-byte multiple
+  std::vector<int32_t> band_of((size_t)wstride, -1);
+  for (int b = 0; b < n_b; ++b)
+    for (int32_t k = woff[(size_t)b]; k < woff[(size_t)b + 1]; ++k) band_of[(size_t)k] = b;
+  K2_ALLOC(d_woff, ((size_t)n_b + 1) * 4);
+  K2_ALLOC(d_bandof, (size_t)wstride * 4);
+  K2_TRY(cudaMemcpyAsync(d_woff, woff.data(), ((size_t)n_b + 1) * 4, cudaMemcpyHostToDevice, st));
+  K2_TRY(cudaMemcpyAsync(d_bandof, band_of.data(), (size_t)wstride * 4, cudaMemcpyHostToDevice, st));
+  p.wstride = wstride;
+  p.woff = static_cast<const int32_t*>(d_woff);
+  p.band_of = static_cast<const int32_t*>(d_bandof);
+  p.tile_ok = 1;
+  K2_ALLOC(d_W, (size_t)n_z * wstride * 8);
   p.W = static_cast<double*>(d_W);
   K2_TRY(launch_k2_weights(p, st));
   const size_t out_count = (size_t)n_z * (size_t)T_total * (size_t)n_b;

@@ -53,20 +53,22 @@ __global__ void k2_ranges_kernel(K2Problem p) {
   }
   p.jlo[idx] = jl;
   p.cnt[idx] = c;
-  atomicMax(p.d_rmax, c);
+  atomicMax(p.d_rmaxb + b, c);
 }
 
-// One thread per (z, band, r): the weight of template sample j = j_lo + r in band b at redshift z.
+// One thread per (z, slot): the weight of template sample j = j_lo + r in band b at redshift z.
 __global__ void k2_weights_kernel(K2Problem p) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_b = p.filt.n_b;
-  const int64_t total = (int64_t)p.n_z * n_b * p.rmax;
+  const int64_t total = (int64_t)p.n_z * p.wstride;
   if (idx >= total) return;
-  const int r = (int)(idx % p.rmax);
-  const int zb = (int)(idx / p.rmax);
-  const int zi = zb / n_b, b = zb - zi * n_b;
+  const int slot = (int)(idx % p.wstride);
+  const int zi = (int)(idx / p.wstride);
+  const int b = __ldg(p.band_of + slot);
   double w = 0.0;
-  if (r < __ldg(p.cnt + zb)) {
+  const int r = b >= 0 ? slot - __ldg(p.woff + b) : 0;
+  const int zb = zi * n_b + (b >= 0 ? b : 0);
+  if (b >= 0 && r < __ldg(p.cnt + zb)) {
     const int j = __ldg(p.jlo + zb) + r;
     const int n = p.n_lam;
     const double zp1 = __dadd_rn(1.0, __ldg(p.z + zi));
@@ -106,17 +108,13 @@ template <bool W_SMEM>
 __global__ void __launch_bounds__(K2_THREADS) k2_contract_kernel(K2Problem p) {
   extern __shared__ double s_w[];
   const int n_b = p.filt.n_b;
-  const int rmax = p.rmax;
-  const int rp = W_SMEM ? (rmax | 1) : 0;         // odd row pitch: spreads bands over banks
-  int32_t* s_jlo = reinterpret_cast<int32_t*>(s_w + (size_t)n_b * rp);
+  const int ws = p.wstride;
+  int32_t* s_jlo = reinterpret_cast<int32_t*>(s_w + (W_SMEM ? ws : 0));
   int32_t* s_cnt = s_jlo + n_b;
   const int zi = blockIdx.x;
-  const double* __restrict__ Wz = p.W + (int64_t)zi * n_b * rmax;
+  const double* __restrict__ Wz = p.W + (int64_t)zi * ws;
   if (W_SMEM) {
-    for (int i = threadIdx.x; i < n_b * rmax; i += blockDim.x) {
-      const int b = i / rmax, r = i - b * rmax;
-      s_w[b * rp + r] = __ldg(Wz + i);
-    }
+    for (int i = threadIdx.x; i < ws; i += blockDim.x) s_w[i] = __ldg(Wz + i);
   }
   for (int b = threadIdx.x; b < n_b; b += blockDim.x) {
     s_jlo[b] = __ldg(p.jlo + zi * n_b + b);
@@ -136,13 +134,185 @@ __global__ void __launch_bounds__(K2_THREADS) k2_contract_kernel(K2Problem p) {
       continue;
     }
     const double* __restrict__ F = p.Fs + t * p.ldF + s_jlo[b];
-    const double* w = W_SMEM ? (s_w + b * rp) : (Wz + b * rmax);
+    const double* w = (W_SMEM ? s_w : Wz) + __ldg(p.woff + b);
     const int c = s_cnt[b];
     double acc = 0.0;
     for (int r = 0; r < c; ++r) acc = fma(w[r], __ldg(F + r), acc);
     const int64_t row = p.row_map ? __ldg(p.row_map + t) : t;
     p.out[((int64_t)zi * p.T_total + row) * pitch + b] = acc;
   }
+}
+
+
+// ---- tiled contraction --------------------------------------------------------------------------
+// k2_contract_kernel re-reads the family's whole template block from L2 once per z-slice (C3: 36 MB x
+// 5 991 slices).  Here a CTA keeps a tile of TT templates in shared memory (one bulk copy through the TMA
+// unit) and walks a chunk of z-slices: per slice the weight rows arrive by a second, double-buffered
+// bulk copy, every thread forms its (template, band) dot products from shared memory, the tile of
+// results is transposed through shared memory and leaves with coalesced stores.  Template traffic
+// drops by the chunk length, weight traffic by TT.
+constexpr int K2T_THREADS = 512;
+
+__device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k2_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void k2_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void k2_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void k2_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (int spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1 << 24)) __trap();
+  }
+}
+
+struct K2TilePlan {
+  int32_t tt;          // templates per tile (power of two, <= 32)
+  int32_t zb;          // z-slices per batch (one weight copy, one synchronisation pair)
+  int32_t zc;          // z-slices per CTA (multiple of zb)
+  int32_t opitch;      // pitch of a result tile in shared memory (out_pitch + 1: conflict-free transposition)
+  int32_t off_w, off_o, off_bar, smem_bytes;   // byte offsets inside dynamic shared memory
+};
+
+template <int TT>
+__global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_tile_kernel(K2Problem p, K2TilePlan c) {
+  extern __shared__ __align__(16) unsigned char k2_smem[];
+  double* Fs_s = reinterpret_cast<double*>(k2_smem);                        // [tt][ldF]
+  double* W_s = reinterpret_cast<double*>(k2_smem + c.off_w);               // [2][zb * wstride]
+  double* O_s = reinterpret_cast<double*>(k2_smem + c.off_o);               // [zb][tt][opitch]
+  const uint32_t bar = k2_smem_u32(k2_smem + c.off_bar);                    // [0] template tile, [1], [2] weights
+  const int n_b = p.filt.n_b, ws = p.wstride, ldF = p.ldF, pitch = p.out_pitch, ZB = c.zb;
+  constexpr int TASKS_PER_PASS = K2T_THREADS / TT;       // (slice, band) pairs the CTA covers per pass
+  const int tt_of_thread = threadIdx.x % TT;
+  const int64_t t0 = (int64_t)blockIdx.y * TT;
+  const int nt = (int)min((int64_t)TT, p.T - t0);
+  const int z0 = blockIdx.x * c.zc;
+  const int nz = min(c.zc, p.n_z - z0);
+  const int n_batches = (nz + ZB - 1) / ZB;
+  if (threadIdx.x == 0) {
+    k2_mbar_init(bar, 1);
+    k2_mbar_init(bar + 8, 1);
+    k2_mbar_init(bar + 16, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < ZB * TT * c.opitch; i += K2T_THREADS) O_s[i] = 0.0;   // pad columns stay zero
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t fbytes = (uint32_t)TT * (uint32_t)ldF * 8u;        // Fs is padded to whole tiles with zero rows
+    k2_mbar_expect_tx(bar, fbytes);
+    k2_bulk_g2s(k2_smem_u32(Fs_s), p.Fs + t0 * ldF, fbytes, bar);
+    const uint32_t wb = (uint32_t)min(ZB, nz) * (uint32_t)ws * 8u;
+    k2_mbar_expect_tx(bar + 8, wb);
+    k2_bulk_g2s(k2_smem_u32(W_s), p.W + (int64_t)z0 * ws, wb, bar + 8);
+  }
+  k2_mbar_wait(bar, 0);
+  for (int ib = 0; ib < n_batches; ++ib) {
+    const int buf = ib & 1;
+    const int zfirst = z0 + ib * ZB;
+    const int nzb = min(ZB, z0 + nz - zfirst);
+    if (threadIdx.x == 0 && ib + 1 < n_batches) {   // the other buffer was last read before the previous __syncthreads
+      const int znext = zfirst + ZB;
+      const uint32_t wb = (uint32_t)min(ZB, z0 + nz - znext) * (uint32_t)ws * 8u;
+      k2_mbar_expect_tx(bar + 8 + 8 * (buf ^ 1), wb);
+      k2_bulk_g2s(k2_smem_u32(W_s + (size_t)(buf ^ 1) * ZB * ws), p.W + (int64_t)znext * ws, wb,
+                  bar + 8 + 8 * (buf ^ 1));
+    }
+    k2_mbar_wait(bar + 8 + 8 * buf, (ib >> 1) & 1);
+    const double* __restrict__ Wb = W_s + (size_t)buf * ZB * ws;
+    // one (slice, band) pair per warp pass (TT = 32): the weight reads are broadcasts, the template
+    // reads are conflict-free across the 32 templates (odd ldF); four accumulators break the FMA chain
+    // no integer division in the loops: (slice, band) and (row, column) advance incrementally
+    {
+      const int n_task = nzb * n_b;
+      int task = threadIdx.x / TT;
+      int zl = task / n_b, b = task - zl * n_b;
+      const int tt = tt_of_thread;
+      for (; task < n_task; task += TASKS_PER_PASS) {
+        const int zb_idx = (zfirst + zl) * n_b + b;
+        const double* __restrict__ F = Fs_s + tt * ldF + __ldg(p.jlo + zb_idx);
+        const double* __restrict__ w = Wb + zl * ws + __ldg(p.woff + b);
+        const int cnum = __ldg(p.cnt + zb_idx);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int r = 0;
+        for (; r + 4 <= cnum; r += 4) {
+          a0 = fma(w[r], F[r], a0);
+          a1 = fma(w[r + 1], F[r + 1], a1);
+          a2 = fma(w[r + 2], F[r + 2], a2);
+          a3 = fma(w[r + 3], F[r + 3], a3);
+        }
+        for (; r < cnum; ++r) a0 = fma(w[r], F[r], a0);
+        O_s[(zl * TT + tt) * c.opitch + b] = (a0 + a1) + (a2 + a3);
+        b += TASKS_PER_PASS;
+        while (b >= n_b) {
+          b -= n_b;
+          ++zl;
+        }
+      }
+    }
+    __syncthreads();
+    {
+      // the nt x pitch results of a slice are contiguous in global memory when rows are not remapped
+      const int per_z = nt * pitch;
+      const int d_tt = K2T_THREADS / pitch, d_col = K2T_THREADS - d_tt * pitch;
+      for (int zl = 0; zl < nzb; ++zl) {
+        int tt = threadIdx.x / pitch, col = threadIdx.x - tt * pitch;
+        double* __restrict__ dst = p.out + ((int64_t)(zfirst + zl) * p.T_total) * pitch;
+        for (int i = threadIdx.x; i < per_z; i += K2T_THREADS) {
+          const int64_t row = p.row_map ? __ldg(p.row_map + t0 + tt) : t0 + tt;
+          dst[row * pitch + col] = O_s[(zl * TT + tt) * c.opitch + col];
+          tt += d_tt;
+          col += d_col;
+          if (col >= pitch) {
+            col -= pitch;
+            ++tt;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+bool k2_tile_plan(const K2Problem& p, K2TilePlan* c) {
+  if ((p.wstride & 1) || p.wstride < 2) return false;              // bulk copies move 16-byte multiples
+  const int opitch = p.out_pitch + 1;
+  for (int tt = 32; tt >= 2; tt >>= 1) {
+    for (int zb = 4; zb >= 1; zb >>= 1) {
+      const size_t f = (size_t)tt * p.ldF * 8;
+      const size_t off_w = (f + 15) & ~(size_t)15;
+      const size_t off_o = off_w + 2 * (size_t)zb * p.wstride * 8;
+      const size_t off_bar = (off_o + (size_t)zb * tt * opitch * 8 + 15) & ~(size_t)15;
+      const size_t total = off_bar + 32;
+      if (total > 200 * 1024) continue;
+      c->tt = tt;
+      c->zb = zb;
+      c->opitch = opitch;
+      c->off_w = (int32_t)off_w;
+      c->off_o = (int32_t)off_o;
+      c->off_bar = (int32_t)off_bar;
+      c->smem_bytes = (int32_t)total;
+      const int64_t tiles = (p.T + tt - 1) / tt;
+      // enough CTAs for ~4 waves of 148 SMs, at most 64 slices per CTA, whole batches
+      int64_t zc = (p.n_z * tiles) / (4 * 148);
+      if (zc > 64) zc = 64;
+      zc = (zc / zb) * zb;
+      if (zc < zb) zc = zb;
+      c->zc = (int32_t)zc;
+      return true;
+    }
+  }
+  return false;
 }
 
 }  // namespace
@@ -163,7 +333,7 @@ cudaError_t launch_k2_ranges(const K2Problem& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_k2_weights(const K2Problem& p, cudaStream_t stream) {
-  const int64_t total = (int64_t)p.n_z * p.filt.n_b * p.rmax;
+  const int64_t total = (int64_t)p.n_z * p.wstride;
   if (total == 0) return cudaSuccess;
   k2_weights_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
   return cudaGetLastError();
@@ -171,9 +341,25 @@ cudaError_t launch_k2_weights(const K2Problem& p, cudaStream_t stream) {
 
 cudaError_t launch_k2_contract(const K2Problem& p, cudaStream_t stream) {
   if (p.n_z == 0 || p.T == 0) return cudaSuccess;
-  const int rp = p.rmax | 1;
+  K2TilePlan c;
+  if (p.tile_ok && k2_tile_plan(p, &c)) {
+    dim3 grid((unsigned)((p.n_z + c.zc - 1) / c.zc), (unsigned)((p.T + c.tt - 1) / c.tt));
+    auto go = [&](auto kern) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
+      if (e != cudaSuccess) return e;
+      kern<<<grid, K2T_THREADS, (size_t)c.smem_bytes, stream>>>(p, c);
+      return cudaGetLastError();
+    };
+    switch (c.tt) {
+      case 32: return go(k2_contract_tile_kernel<32>);
+      case 16: return go(k2_contract_tile_kernel<16>);
+      case 8: return go(k2_contract_tile_kernel<8>);
+      case 4: return go(k2_contract_tile_kernel<4>);
+      default: return go(k2_contract_tile_kernel<2>);
+    }
+  }
   const size_t idx_bytes = 2 * (size_t)p.filt.n_b * sizeof(int32_t);
-  const size_t smem = (size_t)p.filt.n_b * rp * sizeof(double) + idx_bytes;
+  const size_t smem = (size_t)p.wstride * sizeof(double) + idx_bytes;
   dim3 grid((unsigned)p.n_z, (unsigned)((p.T + K2_TILE_T - 1) / K2_TILE_T));
   if (smem <= 96 * 1024) {
     if (smem > 48 * 1024) {

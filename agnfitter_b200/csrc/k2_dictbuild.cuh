@@ -17,9 +17,12 @@
 //     out[z][t][b] = sum_r W[z][b][r] * F_nu[t][j_lo[z][b] + r]
 // i.e. the dense contraction (templates x lambda) . (lambda x bands) of the north star, stored
 // banded.  Three kernels:
-//   k2_ranges    j_lo / cnt per (z, band) and the global max cnt        (integer work, bit-exact)
-//   k2_weights   W[z][b][r]: two binary searches + a short sequential sum per entry
-//   k2_contract  the banded contraction; writes the [n_z, T, n_b] table K1 gathers from
+//   k2_ranges    j_lo / cnt per (z, band) and the per-band max cnt       (integer work, bit-exact)
+//   k2_weights   W[z][woff[b] + r]: two binary searches + a short sequential sum per entry; band b owns
+//                rmax_b = max_z cnt[z][b] slots per z-slice (compact: no padding to the widest band)
+//   k2_contract  the banded contraction; writes the [n_z, T, pitch] table K1 gathers from.  The tiled
+//                kernel keeps 32 templates in shared memory across a chunk of z-slices; the per-slice
+//                kernel is the fallback when a slice of weights does not fit (X-ray power-law tails)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -44,11 +47,14 @@ struct K2Problem {
   int32_t ldF = 0;
   const double* z = nullptr;        // [n_z]
   int32_t n_z = 0;
-  int32_t rmax = 0;                 // W row length (>= max cnt)
+  int32_t wstride = 0;              // weights per z-slice (even): sum of the per-band slot counts
   int32_t* jlo = nullptr;           // [n_z, n_b]
   int32_t* cnt = nullptr;           // [n_z, n_b]
-  int32_t* d_rmax = nullptr;        // [1]
-  double* W = nullptr;              // [n_z, n_b, rmax]
+  int32_t* d_rmaxb = nullptr;       // [n_b] max over z of cnt (written by k2_ranges)
+  const int32_t* woff = nullptr;    // [n_b + 1] first slot of each band inside a z-slice of W
+  const int32_t* band_of = nullptr; // [wstride] band that owns a slot (-1: padding)
+  double* W = nullptr;              // [n_z, wstride]
+  int32_t tile_ok = 0;              // Fs is zero-padded to a multiple of 32 rows: the tiled contraction may be used
   const int64_t* row_map = nullptr; // [T] or nullptr
   int64_t T_total = 0;
   int32_t out_pitch = 0;            // row pitch of out in doubles (>= n_b); pad columns are written as 0

@@ -57,6 +57,13 @@ SIGNATURES = {
     "agnf_filters_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnf_dict_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32]),
+    "agnf_ens_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_double, C.c_int32]),
+    "agnf_ens_set_positions": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "agnf_ens_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
+    "agnf_ens_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agnf_ens_best": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agnf_ens_reset_stats": (C.c_int, [C.c_void_p]),
+    "agnf_ens_percentiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

@@ -15,6 +15,7 @@
 #include "../../include/agnfit_b200.h"
 #include "k1_lnprob.cuh"
 #include "k2_dictbuild.cuh"
+#include "k3_ensemble.cuh"
 
 using namespace agnf;
 
@@ -55,6 +56,16 @@ struct agnf_ctx {
   // K2
   K2Filters filt{};
   bool have_filt = false;
+
+  // K3 ensemble (allocated by agnf_ens_create)
+  bool have_ens = false;
+  K3State ens{};
+  K3Scratch ens_sc{};
+  K3Hist ens_hist{};
+  double* ens_best_pos = nullptr;
+  double* ens_best_lnp = nullptr;
+  int64_t ens_step = 0;              // stretch-move steps taken since agnf_ens_create (Philox counter)
+  int64_t ens_hist_samples = 0;
 };
 
 static thread_local std::string g_create_err;
@@ -799,6 +810,180 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   return 0;
 #undef K2_TRY
 #undef K2_ALLOC
+}
+
+// ------------------------------------------------------------------------------------------- K3
+
+AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, double a, int32_t n_bins) {
+  if (!ctx) return 1;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (check_ready(ctx)) return 1;
+  if (walkers < 2 || (walkers & 1)) return fail(ctx, "walkers must be even and >= 2 (two half-ensembles)");
+  if (!(a > 1.0)) return fail(ctx, "stretch scale a must be > 1");
+  if (n_bins < 0) return fail(ctx, "n_bins < 0");
+  if (ctx->have_ens) {
+    for (void* q : {(void*)ctx->ens.pos, (void*)ctx->ens.lnp, (void*)ctx->ens.n_acc, (void*)ctx->ens_sc.prop,
+                    (void*)ctx->ens_sc.prop_lnp, (void*)ctx->ens_sc.factor, (void*)ctx->ens_sc.lnu,
+                    (void*)ctx->ens_sc.sid, (void*)ctx->ens_hist.hist, (void*)ctx->ens_best_pos,
+                    (void*)ctx->ens_best_lnp})
+      dev_free(ctx, q);
+    ctx->have_ens = false;
+  }
+  const int64_t S = ctx->k1.S;
+  const int np = ctx->k1.cfg.n_par, H = walkers / 2;
+  K3State& st = ctx->ens;
+  st.S = S;
+  st.W = walkers;
+  st.n_par = np;
+  st.seed = seed;
+  st.a = a;
+  void* p = nullptr;
+#define ENS_ALLOC(dst, type, count)                             \
+  do {                                                          \
+    if (dev_alloc(ctx, &p, (size_t)(count) * sizeof(type))) return 1; \
+    dst = static_cast<type*>(p);                                \
+  } while (0)
+  ENS_ALLOC(st.pos, double, S * walkers * np);
+  ENS_ALLOC(st.lnp, double, S * walkers);
+  ENS_ALLOC(st.n_acc, int32_t, S * walkers);
+  ENS_ALLOC(ctx->ens_sc.prop, double, S * H * np);
+  ENS_ALLOC(ctx->ens_sc.prop_lnp, double, S * H);
+  ENS_ALLOC(ctx->ens_sc.factor, double, S * H);
+  ENS_ALLOC(ctx->ens_sc.lnu, double, S * H);
+  ENS_ALLOC(ctx->ens_sc.sid, int32_t, S * walkers);       // [S*W] for the initial evaluation, [S*H] prefix per half-step
+  ENS_ALLOC(ctx->ens_best_pos, double, S * np);
+  ENS_ALLOC(ctx->ens_best_lnp, double, S);
+  ctx->ens_hist.hist = nullptr;
+  ctx->ens_hist.n_bins = n_bins;
+  ctx->ens_hist.pbox = ctx->k1.pbox;
+  if (n_bins > 0) {
+    ENS_ALLOC(ctx->ens_hist.hist, uint32_t, S * np * n_bins);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->ens_hist.hist, 0, (size_t)S * np * n_bins * 4, ctx->stream));
+  }
+#undef ENS_ALLOC
+  CUDA_TRY(ctx, cudaMemsetAsync(st.n_acc, 0, (size_t)S * walkers * 4, ctx->stream));
+  ctx->ens_step = 0;
+  ctx->ens_hist_samples = 0;
+  ctx->have_ens = true;
+  return 0;
+}
+
+AGNF_API int agnf_ens_set_positions(agnf_ctx* ctx, const double* pos) {
+  if (!ctx || !pos) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  K3State& st = ctx->ens;
+  cudaStream_t s = ctx->stream;
+  const int64_t n = st.S * st.W;
+  CUDA_TRY(ctx, cudaMemcpyAsync(st.pos, pos, (size_t)n * st.n_par * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(ctx, launch_k3_fill_sid(ctx->ens_sc.sid, st.S, st.W, s));
+  if (agnf_lnprob_batch_device(ctx, st.pos, ctx->ens_sc.sid, n, st.lnp, nullptr, nullptr, nullptr, nullptr, s)) return 1;
+  CUDA_TRY(ctx, launch_k3_fill_sid(ctx->ens_sc.sid, st.S, st.W / 2, s));
+  std::vector<double> ninf((size_t)st.S, -INFINITY);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ens_best_lnp, ninf.data(), (size_t)st.S * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(ctx, launch_k3_best(st, ctx->ens_best_pos, ctx->ens_best_lnp, s));
+  CUDA_TRY(ctx, cudaMemsetAsync(st.n_acc, 0, (size_t)n * 4, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  ctx->launches += 4;
+  return 0;
+}
+
+AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, int32_t track_best) {
+  if (!ctx) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  if (n_steps < 0) return fail(ctx, "n_steps < 0");
+  if (hist_every > 0 && !ctx->ens_hist.hist) return fail(ctx, "the ensemble was created without histograms");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  K3State& st = ctx->ens;
+  cudaStream_t s = ctx->stream;
+  const int64_t nh = st.S * (st.W / 2);
+  for (int64_t it = 0; it < n_steps; ++it) {
+    for (int half = 0; half < 2; ++half) {
+      CUDA_TRY(ctx, launch_k3_propose(st, ctx->ens_sc, ctx->ens_step, half, s));
+      if (agnf_lnprob_batch_device(ctx, ctx->ens_sc.prop, ctx->ens_sc.sid, nh, ctx->ens_sc.prop_lnp, nullptr, nullptr,
+                                   nullptr, nullptr, s))
+        return 1;
+      CUDA_TRY(ctx, launch_k3_accept(st, ctx->ens_sc, half, s));
+      ctx->launches += 2;
+    }
+    ++ctx->ens_step;
+    if (track_best) {
+      CUDA_TRY(ctx, launch_k3_best(st, ctx->ens_best_pos, ctx->ens_best_lnp, s));
+      ctx->launches += 1;
+    }
+    if (hist_every > 0 && (ctx->ens_step % hist_every) == 0) {
+      CUDA_TRY(ctx, launch_k3_hist(st, ctx->ens_hist, s));
+      ctx->ens_hist_samples += st.W;
+      ctx->launches += 1;
+    }
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return 0;
+}
+
+AGNF_API int agnf_ens_get(agnf_ctx* ctx, double* pos, double* lnp, int32_t* n_acc) {
+  if (!ctx) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  K3State& st = ctx->ens;
+  const size_t n = (size_t)st.S * st.W;
+  if (pos) CUDA_TRY(ctx, cudaMemcpyAsync(pos, st.pos, n * st.n_par * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (lnp) CUDA_TRY(ctx, cudaMemcpyAsync(lnp, st.lnp, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_acc) CUDA_TRY(ctx, cudaMemcpyAsync(n_acc, st.n_acc, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+AGNF_API int agnf_ens_best(agnf_ctx* ctx, double* best_pos, double* best_lnp) {
+  if (!ctx) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  K3State& st = ctx->ens;
+  if (best_pos)
+    CUDA_TRY(ctx, cudaMemcpyAsync(best_pos, ctx->ens_best_pos, (size_t)st.S * st.n_par * 8, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+  if (best_lnp)
+    CUDA_TRY(ctx, cudaMemcpyAsync(best_lnp, ctx->ens_best_lnp, (size_t)st.S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+AGNF_API int agnf_ens_reset_stats(agnf_ctx* ctx) {
+  if (!ctx) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  K3State& st = ctx->ens;
+  CUDA_TRY(ctx, cudaMemsetAsync(st.n_acc, 0, (size_t)st.S * st.W * 4, ctx->stream));
+  if (ctx->ens_hist.hist)
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->ens_hist.hist, 0, (size_t)st.S * st.n_par * ctx->ens_hist.n_bins * 4, ctx->stream));
+  ctx->ens_hist_samples = 0;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, double* out) {
+  if (!ctx || !q || !out) return 1;
+  if (!ctx->have_ens || !ctx->ens_hist.hist) return fail(ctx, "the ensemble has no histograms");
+  if (n_q < 1 || n_q > 64) return fail(ctx, "n_q outside [1, 64]");
+  for (int k = 0; k < n_q; ++k)
+    if (!(q[k] >= 0.0 && q[k] <= 100.0) || (k > 0 && q[k] < q[k - 1]))
+      return fail(ctx, "percentiles must be ascending values in [0, 100]");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  K3State& st = ctx->ens;
+  void *dq = nullptr, *dout = nullptr;
+  const size_t n_out = (size_t)st.S * st.n_par * n_q;
+  if (dev_alloc(ctx, &dq, (size_t)n_q * 8) || dev_alloc(ctx, &dout, n_out * 8)) return 1;
+  cudaError_t e = cudaMemcpyAsync(dq, q, (size_t)n_q * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+    e = launch_k3_percentiles(ctx->ens_hist, st.S, st.n_par, static_cast<const double*>(dq), n_q,
+                              static_cast<double*>(dout), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, dq);
+  dev_free(ctx, dout);
+  if (e != cudaSuccess) return fail(ctx, "agnf_ens_percentiles: %s", cudaGetErrorString(e));
+  ctx->launches += 1;
+  return 0;
 }
 
 }  // extern "C"

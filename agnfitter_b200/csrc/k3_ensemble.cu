@@ -1,0 +1,184 @@
+// K3 — ensemble step kernels (see k3_ensemble.cuh).
+#include "k3_ensemble.cuh"
+
+#include <cmath>
+
+namespace agnf {
+
+namespace {
+
+constexpr int K3_THREADS = 256;
+
+// Philox4x32-10 (Salmon et al. 2011), counter (c0..c3), key (k0, k1)
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+__global__ void k3_fill_sid_kernel(int32_t* __restrict__ sid, int64_t S, int32_t half) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S * half) sid[i] = (int32_t)(i / half);
+}
+
+// one thread per (source, walker of the active half)
+__global__ void __launch_bounds__(K3_THREADS) k3_propose_kernel(K3State st, K3Scratch sc, int64_t step, int half) {
+  const int H = st.W / 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st.S * H) return;
+  const int64_t s = i / H;
+  const int k = (int)(i - s * H);
+  uint32_t x[4];
+  philox4x32_10((uint32_t)step, (uint32_t)half, (uint32_t)s, (uint32_t)k, (uint32_t)st.seed, (uint32_t)(st.seed >> 32),
+                x);
+  const double u1 = (double)((((uint64_t)x[0] << 32) | x[1]) >> 11) * 1.1102230246251565e-16;   // 2^-53
+  const int j = (int)(((uint64_t)x[2] * (uint64_t)H) >> 32);
+  const double u3 = ((double)x[3] + 0.5) * 2.3283064365386963e-10;                            // 2^-32
+  // zz = ((a - 1) u1 + 1)^2 / a, every operation rounded on its own (bit-identical to NumPy)
+  const double t = __dadd_rn(__dmul_rn(st.a - 1.0, u1), 1.0);
+  const double zz = __ddiv_rn(__dmul_rn(t, t), st.a);
+  const int np = st.n_par;
+  const double* __restrict__ xk = st.pos + ((s * st.W) + (half ? H : 0) + k) * np;       // walker being moved
+  const double* __restrict__ cj = st.pos + ((s * st.W) + (half ? 0 : H) + j) * np;       // partner, other half
+  double* __restrict__ q = sc.prop + i * np;
+  for (int c = 0; c < np; ++c) {
+    const double cc = cj[c];
+    q[c] = __dsub_rn(cc, __dmul_rn(__dsub_rn(cc, xk[c]), zz));
+  }
+  sc.factor[i] = (double)(np - 1) * log(zz);
+  sc.lnu[i] = log(u3);
+}
+
+__global__ void __launch_bounds__(K3_THREADS) k3_accept_kernel(K3State st, K3Scratch sc, int half) {
+  const int H = st.W / 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st.S * H) return;
+  const int64_t s = i / H;
+  const int k = (int)(i - s * H);
+  const int64_t w = s * st.W + (half ? H : 0) + k;
+  const double newl = sc.prop_lnp[i];
+  const double lnpdiff = sc.factor[i] + newl - st.lnp[w];
+  if (lnpdiff > sc.lnu[i]) {          // false for NaN and for -inf proposals
+    const int np = st.n_par;
+    const double* __restrict__ q = sc.prop + i * np;
+    double* __restrict__ x = st.pos + w * np;
+    for (int c = 0; c < np; ++c) x[c] = q[c];
+    st.lnp[w] = newl;
+    st.n_acc[w] += 1;
+  }
+}
+
+// one thread per (source, walker, parameter)
+__global__ void __launch_bounds__(K3_THREADS) k3_hist_kernel(K3State st, K3Hist h) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = st.S * st.W * st.n_par;
+  if (i >= total) return;
+  const int c = (int)(i % st.n_par);
+  const int64_t s = i / ((int64_t)st.W * st.n_par);
+  const double2 mm = h.pbox[s * st.n_par + c];
+  const double v = st.pos[i];
+  const double f = (v - mm.x) / (mm.y - mm.x) * (double)h.n_bins;
+  int b = (int)f;
+  b = max(0, min(h.n_bins - 1, b));
+  if (v == v) atomicAdd(h.hist + (s * st.n_par + c) * h.n_bins + b, 1u);
+}
+
+// one thread per (source, parameter)
+__global__ void __launch_bounds__(K3_THREADS) k3_percentiles_kernel(K3Hist h, int64_t S, int32_t n_par,
+                                                                     const double* __restrict__ q, int32_t n_q,
+                                                                     double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * n_par) return;
+  const uint32_t* __restrict__ hh = h.hist + i * h.n_bins;
+  const double2 mm = h.pbox[i];
+  uint64_t total = 0;
+  for (int b = 0; b < h.n_bins; ++b) total += hh[b];
+  const double width = (mm.y - mm.x) / (double)h.n_bins;
+  int b = 0;
+  uint64_t cum = 0;              // samples in bins < b
+  for (int k = 0; k < n_q; ++k) {    // q ascending
+    double val = NAN;
+    if (total > 0) {
+      const double target = q[k] * 0.01 * (double)total;
+      while (b < h.n_bins - 1 && (double)(cum + hh[b]) < target) {
+        cum += hh[b];
+        ++b;
+      }
+      const double inbin = hh[b] > 0 ? (target - (double)cum) / (double)hh[b] : 0.5;
+      val = mm.x + ((double)b + fmin(fmax(inbin, 0.0), 1.0)) * width;
+    }
+    out[i * n_q + k] = val;
+  }
+}
+
+// one thread per source: walker with the largest lnp; keeps the stored best (initialised to -inf) if larger
+__global__ void __launch_bounds__(K3_THREADS) k3_best_kernel(K3State st, double* __restrict__ best_pos,
+                                                              double* __restrict__ best_lnp) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= st.S) return;
+  double best = best_lnp[s];
+  int arg = -1;
+  for (int k = 0; k < st.W; ++k) {
+    const double v = st.lnp[s * st.W + k];
+    if (v > best) {
+      best = v;
+      arg = k;
+    }
+  }
+  if (arg >= 0) {
+    best_lnp[s] = best;
+    for (int c = 0; c < st.n_par; ++c) best_pos[s * st.n_par + c] = st.pos[(s * st.W + arg) * st.n_par + c];
+  }
+}
+
+inline unsigned blocks_for(int64_t n) { return (unsigned)((n + K3_THREADS - 1) / K3_THREADS); }
+
+}  // namespace
+
+cudaError_t launch_k3_fill_sid(int32_t* sid, int64_t S, int32_t half, cudaStream_t stream) {
+  if (S * half <= 0) return cudaSuccess;
+  k3_fill_sid_kernel<<<blocks_for(S * half), K3_THREADS, 0, stream>>>(sid, S, half);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k3_propose(const K3State& st, const K3Scratch& sc, int64_t step, int half, cudaStream_t stream) {
+  k3_propose_kernel<<<blocks_for(st.S * (st.W / 2)), K3_THREADS, 0, stream>>>(st, sc, step, half);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k3_accept(const K3State& st, const K3Scratch& sc, int half, cudaStream_t stream) {
+  k3_accept_kernel<<<blocks_for(st.S * (st.W / 2)), K3_THREADS, 0, stream>>>(st, sc, half);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k3_hist(const K3State& st, const K3Hist& h, cudaStream_t stream) {
+  k3_hist_kernel<<<blocks_for(st.S * st.W * st.n_par), K3_THREADS, 0, stream>>>(st, h);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k3_percentiles(const K3Hist& h, int64_t S, int32_t n_par, const double* q, int32_t n_q,
+                                  double* out, cudaStream_t stream) {
+  k3_percentiles_kernel<<<blocks_for(S * n_par), K3_THREADS, 0, stream>>>(h, S, n_par, q, n_q, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k3_best(const K3State& st, double* best_pos, double* best_lnp, cudaStream_t stream) {
+  k3_best_kernel<<<blocks_for(st.S), K3_THREADS, 0, stream>>>(st, best_pos, best_lnp);
+  return cudaGetLastError();
+}
+
+}  // namespace agnf

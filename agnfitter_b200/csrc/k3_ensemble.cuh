@@ -1,0 +1,56 @@
+// K3 — GPU-resident affine-invariant ensemble step for many sources in lock-step.
+//
+// The reference hands one source at a time to emcee (MCMC_AGNfitter.py:114-135): a stretch move offers
+// only W/2 independent evaluations per step, far too few for a B200.  Here S sources advance together:
+// per half-step, k3_propose draws the stretch factors and partners of all S * W/2 walkers and writes
+// their proposals as one params batch, K1 evaluates it, k3_accept applies emcee's acceptance rule.
+// Walker positions and log-probabilities never leave HBM.
+//
+// Move (Goodman & Weare 2010 as implemented by emcee's StretchMove/RedBlueMove with a = 2):
+//     zz = ((a - 1) u1 + 1)^2 / a            j = floor(u2 * W/2)          (partner in the other half)
+//     q  = c_j - (c_j - x_k) * zz            accept iff (n_par - 1) ln zz + lnp(q) - lnp(x_k) > ln u3
+// The halves are the fixed first/second half of the ensemble (emcee's `randomize_split=False`).
+// u1, u2, u3 come from Philox4x32-10 keyed by (seed) with counter (step, half, source, walker), so the
+// stream is reproducible on the CPU (oracle/ensemble_oracle.py) bit for bit.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace agnf {
+
+struct K3State {
+  double* pos;        // [S, W, n_par]
+  double* lnp;        // [S, W]
+  int32_t* n_acc;     // [S, W] accepted proposals
+  int64_t S;
+  int32_t W, n_par;
+  uint64_t seed;
+  double a;           // stretch scale (emcee default 2.0)
+};
+
+struct K3Scratch {
+  double* prop;       // [S * W/2, n_par] proposals of the current half-step
+  double* prop_lnp;   // [S * W/2]
+  double* factor;     // [S * W/2] (n_par - 1) ln zz
+  double* lnu;        // [S * W/2] ln u3
+  int32_t* sid;       // [S * W/2] source of each proposal row
+};
+
+// histogram accumulation for on-device percentiles: hist [S, n_par, n_bins] uint32 over [pmin, pmax]
+struct K3Hist {
+  uint32_t* hist;
+  const double2* pbox;   // [S, n_par] (min, max)
+  int32_t n_bins;
+};
+
+cudaError_t launch_k3_fill_sid(int32_t* sid, int64_t S, int32_t half, cudaStream_t stream);
+cudaError_t launch_k3_propose(const K3State& st, const K3Scratch& sc, int64_t step, int half, cudaStream_t stream);
+cudaError_t launch_k3_accept(const K3State& st, const K3Scratch& sc, int half, cudaStream_t stream);
+cudaError_t launch_k3_hist(const K3State& st, const K3Hist& h, cudaStream_t stream);
+// percentiles (linear interpolation inside the bin) of every (source, parameter): out [S, n_par, n_q]
+cudaError_t launch_k3_percentiles(const K3Hist& h, int64_t S, int32_t n_par, const double* q, int32_t n_q,
+                                  double* out, cudaStream_t stream);
+// best (max lnp) walker of every source: best_pos [S, n_par], best_lnp [S]
+cudaError_t launch_k3_best(const K3State& st, double* best_pos, double* best_lnp, cudaStream_t stream);
+
+}  // namespace agnf

@@ -166,6 +166,36 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
                     int32_t n_lam, const double* z, int32_t n_z, const int64_t* row_map, int64_t T_total,
                     double* out, int32_t out_on_device, int32_t out_pitch);
 
+/* ---------------------------------------------------------------------------------------------
+ * K3 — GPU-resident ensemble sampler for every uploaded source in lock-step.
+ * Replaces, for whole catalogue shards, the emcee loop of MCMC_AGNfitter.main
+ * (MCMC_AGNfitter.py:114-135,156-189): sampler.sample() -> stretch move -> ln_probab per walker.
+ * Move = emcee's StretchMove (a = 2 by default) on the fixed first/second half-ensembles; random
+ * numbers are Philox4x32-10 with counter (step, half, source, walker) and key `seed`, so a CPU
+ * implementation reproduces the chain (oracle/ensemble_oracle.py).  Positions, log-probabilities and
+ * the percentile histograms stay in HBM; only summaries come back.
+ * ------------------------------------------------------------------------------------------- */
+
+/* allocate the state for the S sources currently uploaded, `walkers` (even) walkers each.
+ * n_bins > 0 also allocates per-(source, parameter) histograms over [P.min, P.max] for agnf_ens_percentiles. */
+AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, double a, int32_t n_bins);
+/* pos [S, walkers, n_par] (host): initial positions (PARAMETERSPACE_AGNfitter.get_initial_positions /
+ * get_best_position, :251-294); evaluates their ln_probab; clears the acceptance counters and the running best. */
+AGNF_API int agnf_ens_set_positions(agnf_ctx* ctx, const double* pos);
+/* n_steps full stretch-move steps (2 half-steps each = 2 K1 launches).  hist_every > 0: every hist_every-th
+ * step adds all walker positions to the histograms (the reference thins its chain the same way,
+ * PLOTandWRITE_AGNfitter.py:471-492).  track_best: keep the best (position, lnP) seen per source
+ * (what get_best_position reads back from the burn-in file). */
+AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, int32_t track_best);
+/* current state to host buffers (any may be NULL): pos [S, W, n_par], lnp [S, W], n_acc [S, W] */
+AGNF_API int agnf_ens_get(agnf_ctx* ctx, double* pos, double* lnp, int32_t* n_acc);
+AGNF_API int agnf_ens_best(agnf_ctx* ctx, double* best_pos, double* best_lnp);   /* [S, n_par], [S] */
+/* zero the acceptance counters and histograms (after burn-in: sampler.reset(), MCMC_AGNfitter.py:178) */
+AGNF_API int agnf_ens_reset_stats(agnf_ctx* ctx);
+/* q [n_q] ascending percentiles in [0, 100] (the reference reports 2.5/16/50/84/97.5,
+ * PLOTandWRITE_AGNfitter.py:152-173); out [S, n_par, n_q]; resolution = (P.max - P.min) / n_bins. */
+AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,44 @@
+"""CPU: the ensemble oracle's building blocks — Philox known answers and the stretch-move algebra."""
+import numpy as np
+
+from oracle import ensemble_oracle as E
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors: philox4x32 10 rounds."""
+    def run(c, k):
+        return [int(v) for v in E.philox4x32_10(*[np.uint32(x) for x in c], k[0], k[1])]
+    assert run((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert run((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert run((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_draw_ranges_and_independence():
+    u1, j, lnu = E.draws(step=3, half=1, S=50, H=40, seed=1234567890123)
+    assert u1.shape == (50, 40) and np.all((u1 >= 0) & (u1 < 1))
+    assert np.all((j >= 0) & (j < 40)) and np.all(np.isfinite(lnu)) and np.all(lnu < 0)
+    u1b, jb, _ = E.draws(step=4, half=1, S=50, H=40, seed=1234567890123)
+    assert not np.array_equal(u1, u1b) and abs(np.corrcoef(u1.ravel(), u1b.ravel())[0, 1]) < 0.1
+    assert abs(u1.mean() - 0.5) < 0.03 and abs(j.mean() - 19.5) < 1.5
+
+
+def test_stretch_move_samples_a_gaussian():
+    """Detailed balance in practice: the oracle step samples N(mu, sigma^2) in 3-D."""
+    rng = np.random.default_rng(0)
+    S, W, n = 4, 40, 3
+    mu, sig = np.array([1.0, -2.0, 0.5]), np.array([0.5, 2.0, 1.0])
+    lnprob = lambda q: -0.5 * (((q - mu) / sig) ** 2).sum(axis=-1)
+    pos = rng.normal(size=(S, W, n))
+    lnp = lnprob(pos)
+    acc = np.zeros((S, W), dtype=np.int64)
+    keep = []
+    for it in range(1500):
+        E.step(pos, lnp, acc, lnprob, it, seed=42)
+        if it >= 300 and it % 5 == 0:
+            keep.append(pos.copy())
+    x = np.concatenate(keep, axis=1).reshape(-1, n)
+    assert np.allclose(x.mean(axis=0), mu, atol=0.08 * sig.max())
+    assert np.allclose(x.std(axis=0), sig, rtol=0.06)
+    frac = acc.mean() / 1500
+    assert 0.3 < frac < 0.8

@@ -1,0 +1,143 @@
+"""GPU: the ensemble sampler (K3 + K1) against the CPU oracle step for step — same Philox stream, same
+proposals bit for bit, same accept decisions — and its on-device percentile reduction; then the
+reference's burn-in / production schedule on the example catalogue's two sources."""
+import numpy as np
+import pytest
+
+from helpers import load_k1, oracle_src
+from agnfitter_b200 import sources
+from agnfitter_b200.engine import Engine
+from agnfitter_b200.ensemble import EnsembleSampler, REFERENCE_PERCENTILES
+from oracle import agn_oracle as O
+from oracle import ensemble_oracle as E
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_histogram_quantiles(got, samples, width, q=REFERENCE_PERCENTILES):
+    """got [n_par, n_q] are q-quantiles of samples [N, n_par] up to the histogram's resolution: the
+    empirical CDF brackets q within one bin either side (np.percentile interpolates across gaps between
+    order statistics, a histogram cannot, so values are compared through the CDF, not directly)."""
+    n = samples.shape[0]
+    for p in range(samples.shape[1]):
+        x = np.sort(samples[:, p])
+        for k, qq in enumerate(q):
+            lo = np.searchsorted(x, got[p, k] - 1.01 * width[p], side="left") / n     # P(x < got - w)
+            hi = np.searchsorted(x, got[p, k] + 1.01 * width[p], side="right") / n    # P(x <= got + w)
+            assert lo <= qq / 100 + 1.0 / n and hi >= qq / 100 - 1.0 / n, (p, qq, got[p, k], lo, hi)
+
+
+def _setup(case):
+    ms, g = load_k1(case)
+    eng = Engine(ms, device=0)
+    src = sources.make_sources(ms, g["src_z"], g["src_dlum"], g["src_nus"], g["src_fluxes"], g["src_fluxerrs"])
+    eng.set_sources(src)
+    osrc = [oracle_src(ms, g, s) for s in range(src.S)]
+
+    def lnprob(q):                                   # q [S, H, n_par] -> [S, H], CPU oracle
+        return np.stack([O.ln_probab(ms, osrc[s], q[s]) for s in range(src.S)])
+    return ms, eng, src, lnprob
+
+
+@pytest.mark.parametrize("case", ["classic18", "cat49_catalog_example"])
+def test_ensemble_matches_oracle_step_for_step(case):
+    ms, eng, src, lnprob = _setup(case)
+    W, seed, n_steps = 24, 20260101, 40
+    rng = np.random.default_rng(5)
+    pos0 = src.pmin[:, None, :] + rng.uniform(size=(src.S, W, ms.n_par)) * (src.pmax - src.pmin)[:, None, :]
+    pos0[:, : W // 3] = EnsembleSampler.initial_positions(src.pmin, src.pmax, W, rng)[:, : W // 3]
+    ens = EnsembleSampler(eng, W, seed=seed, n_bins=0)
+    ens.set_positions(pos0)
+    gpos, glnp, gacc = ens.state()
+    opos, olnp, oacc = pos0.copy(), lnprob(pos0), np.zeros((src.S, W), dtype=np.int64)
+    assert np.array_equal(gpos, pos0)
+    fin = np.isfinite(olnp)
+    assert np.array_equal(np.isfinite(glnp), fin) and np.allclose(glnp[fin], olnp[fin], rtol=1e-10, atol=0)
+    for it in range(n_steps):
+        ens.run(1)
+        E.step(opos, olnp, oacc, lnprob, it, seed)
+        gpos, glnp, gacc = ens.state()
+        assert np.array_equal(gacc, oacc), "accept decisions differ at step %d" % it
+        assert np.array_equal(gpos, opos), "positions differ at step %d" % it       # proposals are bit-identical
+        fin = np.isfinite(olnp)
+        assert np.allclose(glnp[fin], olnp[fin], rtol=1e-10, atol=0)
+    assert oacc.sum() > 0, "the test must exercise accepted moves"
+
+
+def test_ensemble_percentiles_and_best():
+    ms, eng, src, _ = _setup("classic18")
+    W, n_bins = 40, 2048
+    rng = np.random.default_rng(11)
+    ens = EnsembleSampler(eng, W, seed=7, n_bins=n_bins)
+    ens.set_positions(EnsembleSampler.initial_positions(src.pmin, src.pmax, W, rng))
+    ens.run(200, track_best=True)
+    ens.reset_stats()
+    chain, best = [], -np.inf
+    for it in range(120):
+        ens.run(1, hist_every=1, track_best=True)
+        chain.append(ens.state()[0])
+    chain = np.stack(chain, axis=1)                              # [S, steps, W, n_par]
+    got = ens.percentiles()
+    width = (src.pmax - src.pmin) / n_bins
+    for s in range(src.S):
+        assert_histogram_quantiles(got[s], chain[s].reshape(-1, ms.n_par), width[s])
+    bp, bl = ens.best()
+    pos, lnp, acc = ens.state()
+    assert np.all(bl >= lnp.max(axis=1))
+    back = eng.lnprob(bp, np.arange(src.S, dtype=np.int32))
+    assert np.array_equal(back, bl), "best position and best lnP must belong together"
+    assert acc.sum() > 0
+
+
+def test_reference_schedule_on_example_catalogue():
+    """Burn-in sets restarted from the best sample, reset, production (MCMC_AGNfitter.py:122-135): the GPU
+    run and the oracle run with the same seeds give the same posterior percentiles."""
+    ms, eng, src, lnprob = _setup("cat49_catalog_example")
+    mc = dict(Nwalkers=20, Nburnsets=2, Nburn=25, Nmcmc=60, Nthin=2)
+    seed, n_bins = 99, 4096
+    ens = EnsembleSampler(eng, mc['Nwalkers'], seed=seed, n_bins=n_bins)
+    out = ens.run_reference_schedule(mc, src.pmin, src.pmax, np.random.default_rng(3))
+
+    # the same schedule on the CPU oracle
+    rng = np.random.default_rng(3)
+    W = mc['Nwalkers']
+    pos = EnsembleSampler.initial_positions(src.pmin, src.pmax, W, rng)
+    step = 0
+    best_l = np.full(src.S, -np.inf)
+    best_p = np.zeros((src.S, ms.n_par))
+
+    def track(pos, lnp):
+        k = lnp.argmax(axis=1)
+        v = lnp[np.arange(src.S), k]
+        up = v > best_l
+        best_l[up] = v[up]
+        best_p[up] = pos[np.arange(src.S), k][up]
+
+    for _ in range(mc['Nburnsets']):
+        lnp = lnprob(pos)
+        best_l[:] = -np.inf
+        track(pos, lnp)
+        acc = np.zeros((src.S, W), dtype=np.int64)
+        for _ in range(mc['Nburn']):
+            E.step(pos, lnp, acc, lnprob, step, seed)
+            step += 1
+            track(pos, lnp)
+        pos = EnsembleSampler.ball_around(best_p, W, rng)
+    lnp = lnprob(pos)
+    best_l[:] = -np.inf
+    track(pos, lnp)
+    acc = np.zeros((src.S, W), dtype=np.int64)
+    kept = []
+    for _ in range(mc['Nmcmc']):
+        E.step(pos, lnp, acc, lnprob, step, seed)
+        step += 1
+        track(pos, lnp)
+        if step % mc['Nthin'] == 0:
+            kept.append(pos.copy())
+    chain = np.stack(kept, axis=1)
+    width = (src.pmax - src.pmin) / n_bins
+    for s in range(src.S):
+        assert_histogram_quantiles(out['percentiles'][s], chain[s].reshape(-1, ms.n_par), width[s])
+    assert np.allclose(out['best_lnp'], best_l, rtol=1e-10)
+    assert np.array_equal(out['best_pos'], best_p)
+    assert np.allclose(out['acceptance'], acc.mean(axis=1) / mc['Nmcmc'])

@@ -284,6 +284,25 @@ def run_ours(args):
         per_launch.append(eng.last_kernel_ms(1))
     k1_ms = float(np.mean(per_launch))
 
+    # ---- the sampler loop the evaluations are for: S sources x W walkers, stretch moves on the GPU -----
+    ens_info = None
+    if args.ensemble_steps > 0:
+        from agnfitter_b200.ensemble import EnsembleSampler
+        ens = EnsembleSampler(eng, W, seed=20260101 + rank, n_bins=0)
+        ens.set_positions(pars.reshape(S, W, n_par))
+        ens.run(2)                                            # warm-up
+        barrier()
+        l_e = eng.launch_count
+        t0 = time.perf_counter()
+        ens.run(args.ensemble_steps)                          # synchronises the ctx stream before returning
+        ens_s = time.perf_counter() - t0
+        ens_launches = eng.launch_count - l_e
+        _, _, acc = ens.state()
+        ens_info = dict(steps=args.ensemble_steps, s_per_step=ens_s / args.ensemble_steps,
+                        evals_per_s=S * W * args.ensemble_steps / ens_s, launches=int(ens_launches),
+                        acceptance=float(acc.mean() / (args.ensemble_steps + 2)))
+        del ens
+
     # ---- end to end through the host-buffer entry point ----------------------------------------
     np_pars, np_sid, np_lnp = h_pars.numpy(), h_sid.numpy(), h_lnp.numpy()
     for _ in range(2):
@@ -301,12 +320,13 @@ def run_ours(args):
     sampler.join(timeout=2)
     check = float(np.nansum(np.where(np.isfinite(np_lnp), 1.0, 0.0)))
 
-    t_ms = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    ens_ms = (ens_info["s_per_step"] * 1e3) if ens_info else 0.0
+    t_ms = torch.tensor([ms_total, e2e_s * 1e3, ens_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(n)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total_max, e2e_ms_max = float(t_ms[0]), float(t_ms[1])
+    ms_total_max, e2e_ms_max, ens_ms_max = float(t_ms[0]), float(t_ms[1]), float(t_ms[2])
     total_rows = float(cnt[0])
     value = total_rows * args.steps / (ms_total_max * 1e-3)
     e2e_value = total_rows * args.steps / (e2e_ms_max * 1e-3)
@@ -351,6 +371,13 @@ def run_ours(args):
                              "sample": "oracle/agn_oracle.ln_probab on %d of the %d sources x %d walkers, vectorised "
                                        "over a source's walkers, fork Pool over sources" % (ns, S, W),
                              "one_core": cpu_one},
+            "ensemble": None if not ens_info else {
+                "what": "agnf_ens_run: lock-step stretch moves for every source of the shard, walkers resident in "
+                        "HBM (2 x [propose + K1 + accept] per step)",
+                "steps": ens_info["steps"], "ms_per_step": ens_ms_max,
+                "evals_per_s": total_rows / (ens_ms_max * 1e-3),
+                "sources_fitted_per_s": total_rows / (ens_ms_max * 1e-3) / EVALS_PER_FIT,
+                "mean_acceptance": ens_info["acceptance"], "launches": ens_info["launches"]},
             "dictionary_build": {"entries": int(info["k2_entries"]), "wall_s": info["k2_wall_s"],
                                  "entries_per_s": info["k2_entries"] / info["k2_wall_s"]},
             "clocks": sampler.summary(),
@@ -418,6 +445,8 @@ def main():
                     help="keep the catalogue in random z order (default: the shard is processed in z order so "
                          "that sources sharing a dictionary z-slice are adjacent)")
     ap.add_argument("--cpu-sources", type=int, default=384, help="sources in the CPU-baseline sample")
+    ap.add_argument("--ensemble-steps", type=int, default=10,
+                    help="also time this many lock-step stretch-move steps of the GPU-resident sampler (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

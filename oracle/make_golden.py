@@ -273,7 +273,68 @@ def k2_case(name, filterset, zs, seed=3):
                                                         os.path.getsize(path) / 1e6))
 
 
+def k2_write(name, fd, fnames, zs, fams, DIC):
+    """Run the reference's filtering_models over `fams` ({name: [(log nu, Fnu), ...]}) and store inputs + outputs."""
+    bands = fd[0]
+    arrs = dict(bands=bands, z=np.array(zs, dtype=np.float64), filter_names=np.array(fnames),
+                family_names=np.array(list(fams.keys())))
+    lam_all = np.concatenate([np.asarray(fd[1][b][0]) for b in bands])
+    fac_all = np.concatenate([np.asarray(fd[2][b][0]) for b in bands])
+    off = np.cumsum([0] + [len(fd[1][b][0]) for b in bands])
+    arrs.update(filt_lambda=lam_all, filt_factor=fac_all, filt_offset=off.astype(np.int64))
+    n_entries = 0
+    for fname, tpl in fams.items():
+        nmax = max(len(t[0]) for t in tpl)
+        lognu = np.full((len(tpl), nmax), np.nan)
+        Fnu = np.full((len(tpl), nmax), np.nan)
+        nlen = np.zeros(len(tpl), dtype=np.int64)
+        out = np.empty((len(zs), len(tpl), len(bands)))
+        for i, (nu, F) in enumerate(tpl):
+            nu = np.asarray(nu, dtype=np.float64)
+            F = np.asarray(F, dtype=np.float64).reshape(-1)
+            nlen[i] = len(nu)
+            lognu[i, :len(nu)] = nu
+            Fnu[i, :len(nu)] = F
+            for zi, z in enumerate(zs):
+                _, f = DIC.filtering_models(nu, F, fd, z)
+                out[zi, i] = np.asarray(f).flatten()
+        arrs["%s_lognu" % fname] = lognu
+        arrs["%s_Fnu" % fname] = Fnu
+        arrs["%s_len" % fname] = nlen
+        arrs["%s_ref" % fname] = out
+        n_entries += out.size
+    path = os.path.join(OUT, "k2_%s.npz" % name)
+    np.savez_compressed(path, **arrs)
+    print("%-22s bands=%d z=%d entries=%d -> %.2f MB" % (name, len(bands), len(zs), n_entries,
+                                                        os.path.getsize(path) / 1e6))
+
+
+def k2_families_case(name, filterset, zs):
+    """The remaining template families of SURVEY §8a-T, loaded by the reference's OWN loaders
+    (MODEL_AGNfitter.TORUS / BBB under the import shims): every torus option and the SN12 / KD18 discs."""
+    mods = ref_shim.install()
+    MOD, DIC = mods["MOD"], mods["DIC"]
+    root = ref_shim.REF_ROOT + "/"
+    fd, fnames = loaders.make_filterdict(filterset, loaders.load_all_filters())
+    S = dict(H.DEFAULT_SETTINGS)
+    fams = {}
+    for opt, n_keep in (("NK0", 5), ("NK0_2P", 6), ("NK0_3P", 8), ("SKIRTOR_1P", 5), ("SKIRTOR_2P", 6),
+                        ("SKIRTOR_3P", 8), ("CAT3D_3P", 8)):
+        d4, *_ = MOD.TORUS(root, dict(S, TORUS=opt))
+        keys = list(d4.keys())
+        fams["TO_" + opt] = [d4[k] for k in keys[::max(1, len(keys) // n_keep)][:n_keep]]
+    for opt, n_keep in (("SN12", 8), ("KD18", 8)):
+        d4, *_ = MOD.BBB(root, dict(S, BBB=opt), 0)
+        keys = list(d4.keys())
+        fams["BB_" + opt] = [d4[k] for k in keys[::max(1, len(keys) // n_keep)][:n_keep]]
+    k2_write(name, fd, fnames, zs, fams, DIC)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "families":
+        os.makedirs(OUT, exist_ok=True)
+        k2_families_case("families18", loaders.FILTERSET_DEFAULT, [0.05, 1.0, 3.3])
+        return
     os.makedirs(OUT, exist_ok=True)
     base = dict(H.DEFAULT_SETTINGS)
     # A: the classic 10-parameter model set, default 18 bands, the two z of BASELINE configs[0]
@@ -302,6 +363,7 @@ def main():
     # K2
     k2_case("default18", loaders.FILTERSET_DEFAULT, [0.0, 0.283, 1.58, 5.999])
     k2_case("example49", loaders.FILTERSET_EXAMPLE49, [0.031024, 0.129, 2.2])
+    k2_families_case("families18", loaders.FILTERSET_DEFAULT, [0.05, 1.0, 3.3])
 
 
 if __name__ == "__main__":

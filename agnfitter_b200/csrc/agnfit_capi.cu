@@ -65,6 +65,7 @@ struct agnf_ctx {
   double* ens_best_pos = nullptr;
   double* ens_best_lnp = nullptr;
   int64_t ens_step = 0;              // stretch-move steps taken since agnf_ens_create (Philox counter)
+  int ens_fused = 1;                 // 1: one fused K1 launch per half-step; 0: propose / K1 / accept kernels
   int64_t ens_hist_samples = 0;
 };
 
@@ -362,6 +363,11 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     ctx->k1_variant = (int)value;
     return 0;
   }
+  if (strcmp(name, "ens_fused") == 0) {
+    if (value != 0 && value != 1) return fail(ctx, "ens_fused must be 0 or 1");
+    ctx->ens_fused = (int)value;
+    return 0;
+  }
   if (strcmp(name, "pipeline_rows") == 0) {
     if (value < 0) return fail(ctx, "pipeline_rows must be >= 0");
     ctx->pipeline_rows = value;
@@ -376,6 +382,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "k1_last_kernel") == 0) *value = ctx->last_k1_kernel;
   else if (strcmp(name, "band_pitch") == 0) *value = ctx->have_cfg ? ctx->k1.nbp : 0;
   else if (strcmp(name, "pipeline_rows") == 0) *value = ctx->pipeline_rows;
+  else if (strcmp(name, "ens_fused") == 0) *value = ctx->ens_fused;
   else return fail(ctx, "unknown option '%s'", name);
   return 0;
 }
@@ -897,8 +904,28 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
   K3State& st = ctx->ens;
   cudaStream_t s = ctx->stream;
   const int64_t nh = st.S * (st.W / 2);
+  // fused launch (propose -> ln_probab -> accept inside the cooperative K1 kernel) when its preconditions hold
+  K1Batch FB{nullptr, nullptr, nh, nullptr, nullptr, nullptr, nullptr, nullptr};
+  FB.ens.pos = st.pos;
+  FB.ens.lnp = st.lnp;
+  FB.ens.n_acc = st.n_acc;
+  FB.ens.W = st.W;
+  FB.ens.seed = st.seed;
+  FB.ens.a = st.a;
+  const bool fused = ctx->k1_variant == 1 && ctx->ens_fused && k1_coop_supported(ctx->k1, FB, nullptr);
   for (int64_t it = 0; it < n_steps; ++it) {
     for (int half = 0; half < 2; ++half) {
+      if (fused) {
+        FB.ens.half = half;
+        FB.ens.step = ctx->ens_step;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, s));
+        CUDA_TRY(ctx, launch_k1_coop(ctx->k1, FB, s));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, s));
+        ctx->k1_timed = true;
+        ctx->last_k1_kernel = 1;
+        ctx->launches += 1;
+        continue;
+      }
       CUDA_TRY(ctx, launch_k3_propose(st, ctx->ens_sc, ctx->ens_step, half, s));
       if (agnf_lnprob_batch_device(ctx, ctx->ens_sc.prop, ctx->ens_sc.sid, nh, ctx->ens_sc.prop_lnp, nullptr, nullptr,
                                    nullptr, nullptr, s))

@@ -23,6 +23,7 @@
 // Only __syncwarp() separates the phases; the CTA synchronises once, to publish the mbarriers.
 #include "k1_lnprob.cuh"
 #include "k1_common.cuh"
+#include "k3_common.cuh"
 
 namespace agnf {
 
@@ -53,12 +54,13 @@ struct Rec {
 struct CoopPlan {
   int32_t stage_pad;      // bytes reserved for the staged blob (16-byte multiple)
   int32_t cpr, cprp;      // chunks per row; partial-sum pitch (odd)
-  int32_t per_warp;       // doubles per warp: 32 records + max(params block, partial planes)
+  int32_t per_warp;       // doubles per warp: 32 records + max(params block, partial planes) [+ proposals]
+  int32_t q_off;          // doubles from the partial-sum area to the proposal rows (ensemble mode), else 0
   int32_t smem_bytes;
 };
 
 template <bool EXT>
-CoopPlan make_plan(const K1Params& P) {
+CoopPlan make_plan(const K1Params& P, bool ens) {
   CoopPlan c;
   const bool eb_free = P.cfg.ga_free_ebv != 0 && P.cfg.eb_mode != 0;
   c.stage_pad = (P.stage_bytes + 15) & ~15;
@@ -66,7 +68,9 @@ CoopPlan make_plan(const K1Params& P) {
   c.cprp = c.cpr | 1;
   const int a = 32 * c.cprp * (eb_free ? 3 : 1), b = 32 * P.cfg.n_par;
   const int part = ((a > b ? a : b) + 1) & ~1;
-  c.per_warp = 32 * Rec<EXT>::STRIDE + part;
+  // ensemble mode keeps the proposal rows until the acceptance test: they cannot share the partial-sum area
+  c.q_off = ens ? part : 0;
+  c.per_warp = 32 * Rec<EXT>::STRIDE + part + (ens ? ((32 * P.cfg.n_par + 1) & ~1) : 0);
   c.smem_bytes = 64 * 8 /*exp2 table*/ + 16 * 8 /*mbarriers*/ + c.stage_pad + KC_WARPS * c.per_warp * 8;
   return c;
 }
@@ -182,7 +186,8 @@ __device__ __forceinline__ int snap_task(const SnapTask& T, double p, uint32_t e
 }
 
 // CPR_T: chunks per row as a compile-time constant (fully unrolled band phase), or 0 = runtime
-template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
+// ENS: fused stretch-move launch (propose -> ln_probab -> accept), see K1Ensemble
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS>
 __global__ void __launch_bounds__(KC_THREADS, KC_MINBLOCKS)
 k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPlan C) {
   constexpr bool EXT = GA_FREE || RADIO || BB_MODE >= 2;
@@ -206,8 +211,9 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
 
   const int64_t row0 = ((int64_t)blockIdx.x * KC_WARPS + warp) * 32;
   const int rows_here = (int)max((int64_t)0, min((int64_t)32, B.n - row0));
+  const uint32_t q_s = part_s + 8u * (unsigned)C.q_off;        // params / proposal rows of the warp
   const int n_dbl = rows_here * n_par;
-  const uint32_t par_bytes = (uint32_t)(n_dbl >> 1) * 16u;
+  const uint32_t par_bytes = ENS ? 0u : (uint32_t)(n_dbl >> 1) * 16u;
 
   if (threadIdx.x == 0) {
     for (int w = 0; w <= KC_WARPS; ++w) mbar_init(bar_s + 8u * w, 1);
@@ -222,7 +228,7 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   }
   if (lane == 0 && par_bytes > 0) {
     mbar_expect_tx(bar_s + 8u + 8u * warp, par_bytes);
-    bulk_g2s(part_s, B.params + row0 * n_par, par_bytes, bar_s + 8u + 8u * warp);   // 256-byte aligned source
+    bulk_g2s(q_s, B.params + row0 * n_par, par_bytes, bar_s + 8u + 8u * warp);   // 256-byte aligned source
   }
   if (rows_here == 0) return;
   const bool live = lane < rows_here;
@@ -230,14 +236,55 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   const int64_t i = row0 + my;
 
   // ================================ phase 1: thread per evaluation =================================
-  const int s = __ldg(B.source_id + i);
+  int s;
+  int64_t wrow = 0;                 // ensemble mode: this walker's row in pos / lnp / n_acc
+  double ens_factor = 0.0, ens_lnu = 0.0;
+  if (ENS) {
+    // the proposal is drawn here instead of being read: q = c_j - (c_j - x_k) zz (k3_common.cuh)
+    const int H = B.ens.W >> 1;
+    const int64_t src = i / H;
+    const int kw = (int)(i - src * H);
+    const StretchDraw d = stretch_draw(B.ens.seed, B.ens.a, B.ens.step, B.ens.half, src, kw, H);
+    s = (int)src;
+    wrow = src * B.ens.W + (B.ens.half ? H : 0) + kw;
+    // Both rows are fetched by the whole warp: element e of the flat [32][n_par] block goes to lane e % 32,
+    // so consecutive lanes read consecutive coordinates of one walker (a per-thread row read would touch 32
+    // different lines per load).  x_k lands in the proposal area, c_j in the (still unused) partial-sum area.
+    const int my_w = (int)wrow;
+    const int my_c = (int)(src * B.ens.W + (B.ens.half ? 0 : H) + d.j);
+    {
+      const int d_row = 32 / n_par, d_col = 32 - d_row * n_par;
+      int row = lane / n_par, col = lane - row * n_par;
+      for (int r = 0; r < n_par; ++r) {
+        const int wr = __shfl_sync(0xffffffffu, my_w, row), cr = __shfl_sync(0xffffffffu, my_c, row);
+        const unsigned e = (unsigned)(r * 32 + lane);
+        sts_f64(q_s + 8u * e, B.ens.pos[(int64_t)wr * n_par + col]);
+        sts_f64(part_s + 8u * e, B.ens.pos[(int64_t)cr * n_par + col]);
+        row += d_row;
+        col += d_col;
+        if (col >= n_par) {
+          col -= n_par;
+          ++row;
+        }
+      }
+    }
+    __syncwarp();
+    for (int c = 0; c < n_par; ++c) {
+      const unsigned o = 8u * (unsigned)(lane * n_par + c);
+      sts_f64(q_s + o, stretch_coord(lds_f64(part_s + o), lds_f64(q_s + o), d.zz));
+    }
+    ens_factor = (double)(n_par - 1) * log(d.zz);
+    ens_lnu = d.lnu;
+  } else {
+    s = __ldg(B.source_id + i);
+    if ((n_dbl & 1) && lane == 0) sts_f64(q_s + 8u * (n_dbl - 1), __ldg(B.params + row0 * n_par + n_dbl - 1));
+    if (par_bytes > 0) mbar_wait(bar_s + 8u + 8u * warp, 0);
+  }
   const int zi = __ldg(P.zi + s);
   const uint64_t valid = __ldg(P.valid + s);
   const double inv4pidl2 = __ldg(P.consts + (int64_t)s * P.n_const);
-  if ((n_dbl & 1) && lane == 0) sts_f64(part_s + 8u * (n_dbl - 1), __ldg(B.params + row0 * n_par + n_dbl - 1));
-  if (par_bytes > 0) mbar_wait(bar_s + 8u + 8u * warp, 0);
   __syncwarp();
-  const uint32_t p_s = part_s + 8u * (unsigned)(my * n_par);
+  const uint32_t p_s = q_s + 8u * (unsigned)(my * n_par);
 
   bool inbox = true;
   {
@@ -415,7 +462,7 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   __syncwarp();
 
   // ================================ phase 3: thread per evaluation =================================
-  if (!live) return;
+  if (!live && !ENS) return;          // ensemble mode keeps tail lanes for the cooperative write-back
   double chi = 0.0, ebA = 0.0, ebB = 0.0;
   {
     const uint32_t mine = part_s + 8u * (unsigned)(lane * CPRP);
@@ -474,15 +521,44 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   }
   const double lnprior = inbox ? prior : -INFINITY;
   const bool fin = (lnprior - lnprior) == 0.0;     // isfinite
-  B.lnp[i] = fin ? lnprior + lnlike : -INFINITY;
+  const double lnp_new = fin ? lnprior + lnlike : -INFINITY;
+  if (ENS) {
+    // emcee's acceptance rule, in place: only this thread touches walker `wrow` during the launch, and the
+    // partners it read belong to the other (frozen) half
+    const double lnpdiff = ens_factor + lnp_new - B.ens.lnp[wrow];
+    const bool accept = live && (lnpdiff > ens_lnu);          // false for NaN and for -inf proposals
+    if (accept) {
+      B.ens.lnp[wrow] = lnp_new;
+      B.ens.n_acc[wrow] += 1;
+    }
+    // accepted rows go back to `pos` the way they came: consecutive lanes store consecutive coordinates
+    const unsigned acc_mask = __ballot_sync(0xffffffffu, accept);
+    if (acc_mask) {
+      const int my_w = (int)wrow;
+      const int d_row = 32 / n_par, d_col = 32 - d_row * n_par;
+      int row = lane / n_par, col = lane - row * n_par;
+      for (int r = 0; r < n_par; ++r) {
+        const int wr = __shfl_sync(0xffffffffu, my_w, row);
+        if ((acc_mask >> row) & 1u) B.ens.pos[(int64_t)wr * n_par + col] = lds_f64(q_s + 8u * (unsigned)(r * 32 + lane));
+        row += d_row;
+        col += d_col;
+        if (col >= n_par) {
+          col -= n_par;
+          ++row;
+        }
+      }
+    }
+    return;
+  }
+  B.lnp[i] = lnp_new;
   if (B.lnprior) B.lnprior[i] = lnprior;
   if (B.lnlike) B.lnlike[i] = lnlike;
 }
 
-template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
-cudaError_t launch_coop_cpr(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
-  auto kern = k1_coop_kernel<GA_FREE, BB_MODE, RADIO, CPR_T>;
-  const CoopPlan C = make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P);
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS>
+cudaError_t launch_coop_ens(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
+  auto kern = k1_coop_kernel<GA_FREE, BB_MODE, RADIO, CPR_T, ENS>;
+  const CoopPlan C = make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, B.ens.pos != nullptr);
   static int attr_bytes[64] = {0};   // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -494,6 +570,19 @@ cudaError_t launch_coop_cpr(const K1Params& P, const K1Batch& B, cudaStream_t st
   const int64_t blocks = (B.n + KC_THREADS - 1) / KC_THREADS;
   kern<<<(unsigned)blocks, KC_THREADS, (size_t)C.smem_bytes, stream>>>(P, B, C);
   return cudaGetLastError();
+}
+
+// This file is compiled twice: k1_coop.o holds the ordinary instantiations, k1_coop_ens.cu (which
+// defines K1_COOP_ENS_TU and includes this file) the fused stretch-move ones, so the halves build in parallel.
+#ifdef K1_COOP_ENS_TU
+constexpr bool TU_ENS = true;
+#else
+constexpr bool TU_ENS = false;
+#endif
+
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
+cudaError_t launch_coop_cpr(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
+  return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS>(P, B, stream);
 }
 
 // the default 18-band set has a fully unrolled instantiation; every other band count runs the
@@ -516,18 +605,23 @@ cudaError_t launch_coop_bb(const K1Params& P, const K1Batch& B, cudaStream_t str
   }
 }
 
-size_t coop_smem_bytes(const K1Params& P) {
+#ifndef K1_COOP_ENS_TU
+size_t coop_smem_bytes(const K1Params& P, bool ens) {
   const bool ext = P.cfg.ga_free_ebv != 0 || P.cfg.radio != 0 || P.cfg.bb_mode >= 2;
-  return (size_t)(ext ? make_plan<true>(P) : make_plan<false>(P)).smem_bytes;
+  return (size_t)(ext ? make_plan<true>(P, ens) : make_plan<false>(P, ens)).smem_bytes;
 }
+
+#endif
 
 }  // namespace
 
+#ifndef K1_COOP_ENS_TU
 bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why) {
   const char* w = nullptr;
   if (P.nbp & 1) w = "band pitch is odd";
-  else if (reinterpret_cast<uintptr_t>(B.params) & 15) w = "params is not 16-byte aligned";
-  else if (coop_smem_bytes(P) > 200 * 1024) w = "grids + per-warp tiles exceed shared memory";
+  else if (!B.ens.pos && (reinterpret_cast<uintptr_t>(B.params) & 15)) w = "params is not 16-byte aligned";
+  else if (coop_smem_bytes(P, B.ens.pos != nullptr) > 200 * 1024) w = "grids + per-warp tiles exceed shared memory";
+  else if (B.ens.pos && P.S * (int64_t)B.ens.W >= (int64_t)INT32_MAX) w = "too many walkers for 32-bit row indices";
   else if (P.S * (int64_t)(P.nbp / 2) >= (int64_t)INT32_MAX) w = "too many sources for 32-bit chunk offsets";
   else {
     for (int f = 0; f < P.cfg.n_fam && !w; ++f) {
@@ -541,8 +635,11 @@ bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why) {
   return w == nullptr;
 }
 
+cudaError_t launch_k1_coop_ens(const K1Params& P, const K1Batch& B, cudaStream_t stream);   // k1_coop_ens.o
+
 cudaError_t launch_k1_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
   if (B.n <= 0) return cudaSuccess;
+  if (B.ens.pos) return launch_k1_coop_ens(P, B, stream);
   const bool gf = P.cfg.ga_free_ebv != 0, rad = P.cfg.radio != 0;
   if (gf) return rad ? launch_coop_bb<true, true>(P, B, stream) : launch_coop_bb<true, false>(P, B, stream);
   return rad ? launch_coop_bb<false, true>(P, B, stream) : launch_coop_bb<false, false>(P, B, stream);
@@ -562,5 +659,15 @@ cudaError_t launch_exp10_fast(const double* x, double* y, int64_t n, cudaStream_
   exp10_fast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, y, n);
   return cudaGetLastError();
 }
+
+#else   // K1_COOP_ENS_TU
+
+cudaError_t launch_k1_coop_ens(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
+  const bool gf = P.cfg.ga_free_ebv != 0, rad = P.cfg.radio != 0;
+  if (gf) return rad ? launch_coop_bb<true, true>(P, B, stream) : launch_coop_bb<true, false>(P, B, stream);
+  return rad ? launch_coop_bb<false, true>(P, B, stream) : launch_coop_bb<false, false>(P, B, stream);
+}
+
+#endif  // K1_COOP_ENS_TU
 
 }  // namespace agnf

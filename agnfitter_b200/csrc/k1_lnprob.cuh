@@ -104,15 +104,29 @@ struct K1Params {
   int64_t S;
 };
 
+// Ensemble mode of the cooperative kernel: row i = (source i / H, walker i % H of the active half);
+// the kernel draws the stretch-move proposal from the walker state itself, evaluates it and applies the
+// acceptance rule in place (see k3_ensemble.cuh).  `pos == nullptr`: ordinary batch.
+struct K1Ensemble {
+  double* pos = nullptr;      // [S, W, n_par]
+  double* lnp = nullptr;      // [S, W]
+  int32_t* n_acc = nullptr;   // [S, W]
+  int32_t W = 0, half = 0;
+  int64_t step = 0;
+  uint64_t seed = 0;
+  double a = 2.0;
+};
+
 struct K1Batch {
-  const double* params;       // [n, n_par]
-  const int32_t* source_id;   // [n]
+  const double* params;       // [n, n_par]  (ignored in ensemble mode)
+  const int32_t* source_id;   // [n]         (ignored in ensemble mode)
   int64_t n;
   double* lnp;                // [n]
   int32_t* rows;              // [n, n_fam] or nullptr
   double* ymodel;             // [n, n_b]   or nullptr
   double* lnprior;            // [n]        or nullptr
   double* lnlike;             // [n]        or nullptr
+  K1Ensemble ens;
 };
 
 cudaError_t launch_k1(const K1Params& P, const K1Batch& B, cudaStream_t stream);

@@ -1,0 +1,56 @@
+// Stretch-move arithmetic shared by k3_ensemble.cu (stand-alone propose kernel) and k1_coop.cu (the
+// fused propose -> ln_probab -> accept launch).  See k3_ensemble.cuh for the move and its RNG.
+#pragma once
+#include <cstdint>
+
+namespace agnf {
+
+// Philox4x32-10 (Salmon et al. 2011), counter (c0..c3), key (k0, k1)
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+struct StretchDraw {
+  double zz;       // stretch factor
+  int j;           // partner index inside the other half
+  double lnu;      // ln u3 of the acceptance test
+};
+
+// draws of walker k (of the active half) of source s at (step, half); H = walkers per half
+__device__ __forceinline__ StretchDraw stretch_draw(uint64_t seed, double a, int64_t step, int half, int64_t s, int k,
+                                                    int H) {
+  uint32_t x[4];
+  philox4x32_10((uint32_t)step, (uint32_t)half, (uint32_t)s, (uint32_t)k, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+  const double u1 = (double)((((uint64_t)x[0] << 32) | x[1]) >> 11) * 1.1102230246251565e-16;   // 2^-53
+  const double u3 = ((double)x[3] + 0.5) * 2.3283064365386963e-10;                            // 2^-32
+  // zz = ((a - 1) u1 + 1)^2 / a, every operation rounded on its own (bit-identical to NumPy)
+  const double t = __dadd_rn(__dmul_rn(a - 1.0, u1), 1.0);
+  StretchDraw d;
+  d.zz = __ddiv_rn(__dmul_rn(t, t), a);
+  d.j = (int)(((uint64_t)x[2] * (uint64_t)H) >> 32);
+  d.lnu = log(u3);
+  return d;
+}
+
+// q = c - (c - x) * zz, no contraction
+__device__ __forceinline__ double stretch_coord(double c, double x, double zz) {
+  return __dsub_rn(c, __dmul_rn(__dsub_rn(c, x), zz));
+}
+
+}  // namespace agnf

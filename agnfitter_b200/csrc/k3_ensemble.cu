@@ -1,5 +1,6 @@
 // K3 — ensemble step kernels (see k3_ensemble.cuh).
 #include "k3_ensemble.cuh"
+#include "k3_common.cuh"
 
 #include <cmath>
 
@@ -8,27 +9,6 @@ namespace agnf {
 namespace {
 
 constexpr int K3_THREADS = 256;
-
-// Philox4x32-10 (Salmon et al. 2011), counter (c0..c3), key (k0, k1)
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t out[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0;
-    c1 = lo1;
-    c2 = n2;
-    c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  out[0] = c0;
-  out[1] = c1;
-  out[2] = c2;
-  out[3] = c3;
-}
 
 __global__ void k3_fill_sid_kernel(int32_t* __restrict__ sid, int64_t S, int32_t half) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -42,25 +22,16 @@ __global__ void __launch_bounds__(K3_THREADS) k3_propose_kernel(K3State st, K3Sc
   if (i >= st.S * H) return;
   const int64_t s = i / H;
   const int k = (int)(i - s * H);
-  uint32_t x[4];
-  philox4x32_10((uint32_t)step, (uint32_t)half, (uint32_t)s, (uint32_t)k, (uint32_t)st.seed, (uint32_t)(st.seed >> 32),
-                x);
-  const double u1 = (double)((((uint64_t)x[0] << 32) | x[1]) >> 11) * 1.1102230246251565e-16;   // 2^-53
-  const int j = (int)(((uint64_t)x[2] * (uint64_t)H) >> 32);
-  const double u3 = ((double)x[3] + 0.5) * 2.3283064365386963e-10;                            // 2^-32
-  // zz = ((a - 1) u1 + 1)^2 / a, every operation rounded on its own (bit-identical to NumPy)
-  const double t = __dadd_rn(__dmul_rn(st.a - 1.0, u1), 1.0);
-  const double zz = __ddiv_rn(__dmul_rn(t, t), st.a);
+  const StretchDraw d = stretch_draw(st.seed, st.a, step, half, s, k, H);
+  const double zz = d.zz;
+  const int j = d.j;
   const int np = st.n_par;
   const double* __restrict__ xk = st.pos + ((s * st.W) + (half ? H : 0) + k) * np;       // walker being moved
   const double* __restrict__ cj = st.pos + ((s * st.W) + (half ? 0 : H) + j) * np;       // partner, other half
   double* __restrict__ q = sc.prop + i * np;
-  for (int c = 0; c < np; ++c) {
-    const double cc = cj[c];
-    q[c] = __dsub_rn(cc, __dmul_rn(__dsub_rn(cc, xk[c]), zz));
-  }
+  for (int c = 0; c < np; ++c) q[c] = stretch_coord(cj[c], xk[c], zz);
   sc.factor[i] = (double)(np - 1) * log(zz);
-  sc.lnu[i] = log(u3);
+  sc.lnu[i] = d.lnu;
 }
 
 __global__ void __launch_bounds__(K3_THREADS) k3_accept_kernel(K3State st, K3Scratch sc, int half) {

@@ -373,7 +373,7 @@ def run_ours(args):
                              "one_core": cpu_one},
             "ensemble": None if not ens_info else {
                 "what": "agnf_ens_run: lock-step stretch moves for every source of the shard, walkers resident in "
-                        "HBM (2 x [propose + K1 + accept] per step)",
+                        "HBM; one fused launch per half-step (propose -> ln_probab -> accept inside k1_coop_kernel)",
                 "steps": ens_info["steps"], "ms_per_step": ens_ms_max,
                 "evals_per_s": total_rows / (ens_ms_max * 1e-3),
                 "sources_fitted_per_s": total_rows / (ens_ms_max * 1e-3) / EVALS_PER_FIT,

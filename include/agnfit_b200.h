@@ -126,7 +126,10 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
  * agnf_get_option also answers "k1_last_kernel" (which kernel the last K1 launch ran: 1 / 0, -1 none)
  * and "band_pitch" (n_b rounded up to even: the pitch to ask agnf_dict_build for).
  * "pipeline_rows" (default 2^20): agnf_lnprob_batch with only lnp requested cuts batches larger than
- * this into chunks whose upload / kernel / download overlap on three streams; 0 = one shot. */
+ * this into chunks whose upload / kernel / download overlap on three streams; 0 = one shot.
+ * "ens_fused" (default 1): agnf_ens_run issues one fused launch per half-step (the cooperative K1 kernel
+ * draws the proposal, evaluates it and applies the acceptance rule in place); 0 = separate propose / K1 /
+ * accept kernels (same chain, bit for bit). */
 AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value);
 AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value);
 /* y[i] = 10^x[i] through the kernels' own exp10 routine (host pointers; unit-test hook) */

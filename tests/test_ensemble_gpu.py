@@ -39,9 +39,12 @@ def _setup(case):
     return ms, eng, src, lnprob
 
 
+@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("case", ["classic18", "cat49_catalog_example"])
-def test_ensemble_matches_oracle_step_for_step(case):
+def test_ensemble_matches_oracle_step_for_step(case, fused):
+    """fused = 1: one K1 launch per half-step draws, evaluates and accepts; 0: propose / K1 / accept kernels."""
     ms, eng, src, lnprob = _setup(case)
+    eng.set_option("ens_fused", fused)
     W, seed, n_steps = 24, 20260101, 40
     rng = np.random.default_rng(5)
     pos0 = src.pmin[:, None, :] + rng.uniform(size=(src.S, W, ms.n_par)) * (src.pmax - src.pmin)[:, None, :]

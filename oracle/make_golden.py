@@ -357,6 +357,11 @@ def main():
     for nrad in (1, 2, 4):
         run_case("radio%d_sn12_49" % nrad, dict(base, RADIO=True, BBB='SN12'), loaders.FILTERSET_EXAMPLE49,
                  [0.129], galaxy_kw=gk, n_pos=(300, 40, 30, 80), seed=15 + nrad, nRADdata=nrad)
+    # C4 of BASELINE.json: radio-to-X-ray full model — five components, X-ray extended R06 (EBVbbb and alphaScat
+    # free, Gamma grid), 3 000-key synchrotron family, 18 parameters
+    run_case("radio_xray49", dict(base, RADIO=True, XRAYS=True, STARBURST='S17', TORUS='SKIRTOR_2P'),
+             loaders.FILTERSET_EXAMPLE49, [0.129, 1.234], galaxy_kw=gk, starburst_kw=sk,
+             n_pos=(300, 40, 30, 80), seed=31, nRADdata=4, nXRaysdata=3)
     # AGN switched off (norm caps at -9.8), no AGN-fraction prior
     run_case("agnoff18", dict(base, turn_on_AGN=False, PRIOR_AGNfraction=False), loaders.FILTERSET_DEFAULT,
              [3.005], galaxy_kw=gk, n_pos=(300, 40, 30, 80), seed=21)

@@ -108,7 +108,9 @@ AGNF_API int agnf_sources_upload(agnf_ctx* ctx, int64_t S, const int32_t* zi, co
                         const double* consts, int32_t n_const, const int32_t* agn_branch,
                         const int32_t* irsyn_mode, const int32_t* irsyn_j);
 
-/* ln_probab for n rows.  params [n, n_par] row-major, source_id [n].  Outputs (any may be NULL
+/* ln_probab for n rows.  params [n, n_par] row-major, source_id [n] with 0 <= source_id < S (the caller's
+ * contract; agnfitter_b200.engine checks it).  Rows of one source should be adjacent and sources ordered by
+ * z-slice: the kernels are correct for any order, fastest for that one.  Outputs (any may be NULL
  * except lnp): lnp [n]; rows [n, n_fam] snapped template row per family (pick_nD);
  * ymodel [n, n_b] (PARAMETERSPACE.ymodel); lnprior [n]; lnlike [n].
  * Host variant: copies in/out on the ctx stream and returns after the results are in the

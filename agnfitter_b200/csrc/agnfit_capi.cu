@@ -505,7 +505,7 @@ AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double
   if (upload_padded(ctx, &ctx->k1.cgal, cgal, nz, (int)nb, ctx->k1.nbp)) return 1;
   if (upload_padded(ctx, &ctx->k1.cbbb, cbbb, nz, (int)nb, ctx->k1.nbp)) return 1;
   {
-    const double k64 = 212.60339807279118;      // 64 log2(10)
+    const double k64 = (double)AGNF_POW2_DENOM * 3.321928094887362;      // D log2(10)
     std::vector<double> a(nz * nb), b(nz * nb);
     for (size_t i = 0; i < nz * nb; ++i) {
       a[i] = cgal[i] * k64;

@@ -6,7 +6,7 @@
 
 namespace agnf {
 
-// 2^(j/64), j = 0..63
+// 2^(j/64), j = 0..63 (the cooperative kernel stages every (64/D)-th entry, see AGNF_POW2_DENOM)
 __constant__ double c_exp2_tab[64] = {
     1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138, 1.0556451783605572,
     1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841, 1.1143867425958924,
@@ -21,30 +21,6 @@ __constant__ double c_exp2_tab[64] = {
     1.7373338352737062, 1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
     1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656, 1.9152065613971474,
     1.9360617934922943, 1.9571441241754002, 1.978456026387951};
-
-static __device__ __noinline__ double exp10_slow(double x) { return exp10(x); }
-
-// 10^x for |x| < 300 to ~4e-16 relative: x = k*log10(2)/64 + r, |r| <= log10(2)/128;
-// 10^x = 2^(k>>6) * 2^((k&63)/64) * exp(r ln 10), the last factor by a degree-5 polynomial
-// (next term < 4e-17).  Anything else (NaN, inf, huge) goes to the library exp10.
-// `tab` is a shared-memory copy of c_exp2_tab (lanes index it divergently).
-__device__ __forceinline__ double exp10_fast(double x, const double* __restrict__ tab) {
-  if (!(fabs(x) < 300.0)) return exp10_slow(x);
-  const double magic = 6755399441055744.0;                 // 1.5 * 2^52: round-to-nearest-int trick
-  const double t = fma(x, 212.60339807279118, magic);      // 64 * log2(10)
-  const int k = __double2loint(t);
-  const double kf = t - magic;
-  double r = fma(kf, -0.004703593680460472, x);            // Cody-Waite: log10(2)/64 = C1 + C2, kf*C1 exact
-  r = fma(kf, -1.7892345153159123e-12, r);
-  double p = 0.5393829291955814;
-  p = fma(p, r, 1.171255148912267);
-  p = fma(p, r, 2.034678592293476);
-  p = fma(p, r, 2.650949055239199);
-  p = fma(p, r, 2.302585092994046);
-  p = fma(p, r, 1.0);
-  const double v = tab[k & 63] * p;
-  return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
-}
 
 // Given l = last index with sv[l] <= p (or -1), return the first-appearance index of the minimum
 // of |g - p| over the distinct grid values of one dimension == np.abs(keys_float - p).argmin()

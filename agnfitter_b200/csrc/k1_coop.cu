@@ -138,30 +138,44 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// ---- 2^(t/64): the reddening factors 10^(c E) with c pre-scaled by 64 log2(10) on the host ----------
-// coefficients (ln 2 / 64)^n / n!, n = 1..5, in constant memory so the DFMAs take them as operands
-__constant__ double c_p64[5] = {0.010830424696249145, 5.86490495505617e-05, 2.1173137155464776e-07,
-                                5.732851688640402e-10, 1.2417843701716925e-12};
+// ---- 2^(t/D): the factors 10^(c E) with c pre-scaled by D log2(10) on the host (D = AGNF_POW2_DENOM) ----
+// t = k + r, k integer, |r| <= 1/2: 2^(t/D) = 2^(k/D) * exp(r ln2/D); 2^(k/D) = 2^(k div D) * tab[k mod D].
+// Polynomial coefficients (ln 2 / D)^n / n! sit in constant memory so the DFMAs take them as operands;
+// the first neglected term is < 4e-17 (D = 64, degree 5) / 2e-18 (D = 16, degree 7).
+#if AGNF_POW2_DENOM == 64
+constexpr int P2_DEG = 5, P2_SHIFT = 6;
+__constant__ double c_p2[5] = {0.010830424696249145, 5.86490495505617e-05, 2.1173137155464776e-07,
+                               5.732851688640402e-10, 1.2417843701716925e-12};
+#elif AGNF_POW2_DENOM == 16
+constexpr int P2_DEG = 7, P2_SHIFT = 4;
+__constant__ double c_p2[7] = {0.04332169878499658, 0.0009383847928089872, 1.3550807779497457e-05,
+                               1.467610032291943e-07, 1.2715871950558131e-09, 9.181219573844438e-12,
+                               5.682086126528621e-14};
+#else
+#error "AGNF_POW2_DENOM must be 16 or 64"
+#endif
+constexpr double P2_LOG2_10_D = (double)AGNF_POW2_DENOM * 3.321928094887362;   // D log2(10)
 
-// t = k + r, k integer, |r| <= 1/2: 2^(t/64) = 2^(k>>6) * tab[k&63] * exp(r ln2/64); the degree-5
-// polynomial's first neglected term is < 4e-17.  |t| >= 64000 (or NaN) goes to the library.
-static __device__ __noinline__ double pow2_64_slow(double t) { return exp2(t * 0.015625); }
+// |t| >= 1000 D (or NaN) goes to the library
+static __device__ __noinline__ double pow2_64_slow(double t) { return exp2(t * (1.0 / AGNF_POW2_DENOM)); }
 
 __device__ __forceinline__ double pow2_64(double t, uint32_t tab_s) {
-  if (!(fabs(t) < 64000.0)) return pow2_64_slow(t);
+  if (!(fabs(t) < 1000.0 * AGNF_POW2_DENOM)) return pow2_64_slow(t);
   const double magic = 6755399441055744.0;                 // 1.5 * 2^52
   const double km = t + magic;
   const int k = __double2loint(km);
   const double r = t - (km - magic);
-  double p = c_p64[4];
-  p = fma(p, r, c_p64[3]);
-  p = fma(p, r, c_p64[2]);
-  p = fma(p, r, c_p64[1]);
-  p = fma(p, r, c_p64[0]);
+  double p = c_p2[P2_DEG - 1];
+#pragma unroll
+  for (int n = P2_DEG - 2; n >= 0; --n) p = fma(p, r, c_p2[n]);
   p = fma(p, r, 1.0);
-  const double v = lds_f64(tab_s + ((k << 3) & 0x1f8)) * p;
-  return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+  const double v = lds_f64(tab_s + ((k << 3) & (8 * AGNF_POW2_DENOM - 8))) * p;
+  return __hiloint2double(__double2hiint(v) + ((k >> P2_SHIFT) << 20), __double2loint(v));
 }
+
+// 10^x for the normalisations through the same routine (|x| <= 10 in the prior box: relative error
+// <= |x| D log2(10) 2^-53 ln2 / D ~ 2.6e-15)
+__device__ __forceinline__ double pow10_via2(double x, uint32_t tab_s) { return pow2_64(x * P2_LOG2_10_D, tab_s); }
 
 // snap through the cell table; see k1_common.cuh::snap_dim_lut for the argument (same steps, shared
 // window addresses, task constants from the kernel parameter bank)
@@ -219,7 +233,8 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     for (int w = 0; w <= KC_WARPS; ++w) mbar_init(bar_s + 8u * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (threadIdx.x < 64) sts_f64(tab_s + 8u * threadIdx.x, c_exp2_tab[threadIdx.x]);
+  if (threadIdx.x < AGNF_POW2_DENOM)
+    sts_f64(tab_s + 8u * threadIdx.x, c_exp2_tab[threadIdx.x * (64 / AGNF_POW2_DENOM)]);
   __syncthreads();
   // one bulk copy brings the grids + cell tables; one per warp brings that warp's params rows
   if (threadIdx.x == 0 && P.stage_bytes > 0) {
@@ -289,7 +304,15 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   bool inbox = true;
   {
     const double2* __restrict__ box = P.pbox + (int64_t)s * n_par;
-    for (int c = 0; c < n_par; ++c) {
+    int c = 0;
+    if ((n_par & 1) == 0) {          // even row length: rows are 16-byte aligned -> conflict-free 128-bit reads
+      for (; c < n_par; c += 2) {
+        const double2 v = lds_v2f64(p_s + 8u * c);
+        const double2 m0 = __ldg(box + c), m1 = __ldg(box + c + 1);
+        inbox = inbox && (m0.x <= v.x) && (v.x <= m0.y) && (m1.x <= v.y) && (v.y <= m1.y);
+      }
+    }
+    for (; c < n_par; ++c) {
       const double v = lds_f64(p_s + 8u * c);
       const double2 mm = __ldg(box + c);
       inbox = inbox && (mm.x <= v) && (v <= mm.y);
@@ -339,12 +362,11 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     ebv_bbb = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 3));
     alpha = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 2));
   }
-  const double* s_tab = reinterpret_cast<const double*>(smem_raw);
-  const double nGA = exp10_fast(GA, s_tab), nSB = exp10_fast(SB, s_tab), nTO = exp10_fast(TO, s_tab);
-  const double nBB = cfg.bbb_has_norm ? exp10_fast(BB, s_tab) : 1.0;
-  const double nRAD = RADIO ? exp10_fast(RAD, s_tab) : 0.0;
+  const double nGA = pow10_via2(GA, tab_s), nSB = pow10_via2(SB, tab_s), nTO = pow10_via2(TO, tab_s);
+  const double nBB = cfg.bbb_has_norm ? pow10_via2(BB, tab_s) : 1.0;
+  const double nRAD = RADIO ? pow10_via2(RAD, tab_s) : 0.0;
   const double cBB = cfg.bbb_has_norm ? 1.0 : inv4pidl2;
-  const double xfac = (BB_MODE >= 2) ? exp10_fast(alpha / 0.3838, s_tab) : 1.0;
+  const double xfac = (BB_MODE >= 2) ? pow10_via2(alpha / 0.3838, tab_s) : 1.0;
   {
     const uint32_t rec = scal_s + (unsigned)lane * (STRIDE * 8);
     asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};\n" ::"r"(rec), "r"(grow[0] * (P.fam[0].pitch >> 1)),
@@ -645,13 +667,13 @@ cudaError_t launch_k1_coop(const K1Params& P, const K1Batch& B, cudaStream_t str
   return rad ? launch_coop_bb<false, true>(P, B, stream) : launch_coop_bb<false, false>(P, B, stream);
 }
 
-// 10^x through the kernels' own exp10_fast (debug / unit test hook)
+// 10^x through the kernel's own routine (debug / unit test hook)
 __global__ void exp10_fast_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n) {
-  __shared__ double tab[64];
-  if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+  __shared__ __align__(16) double tab[AGNF_POW2_DENOM];
+  if (threadIdx.x < AGNF_POW2_DENOM) tab[threadIdx.x] = c_exp2_tab[threadIdx.x * (64 / AGNF_POW2_DENOM)];
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = exp10_fast(x[i], tab);
+  if (i < n) y[i] = pow10_via2(x[i], smem_u32(tab));
 }
 
 cudaError_t launch_exp10_fast(const double* x, double* y, int64_t n, cudaStream_t stream) {

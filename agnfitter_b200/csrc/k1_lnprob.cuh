@@ -25,6 +25,13 @@
 #include <cuda_runtime.h>
 #include "../../include/agnfit_b200.h"
 
+// The cooperative kernel evaluates 10^(c E) as 2^(c' E / D) with c' = c * D log2(10) pre-scaled on the host and a
+// D-entry table of 2^(j/D).  D = 16: the table is 128 bytes = one shared-memory row, so divergent lookups
+// never bank-conflict (degree-7 polynomial); D = 64: degree 5, conflicts ~2x the ideal wavefronts.
+#ifndef AGNF_POW2_DENOM
+#define AGNF_POW2_DENOM 16
+#endif
+
 namespace agnf {
 
 struct DimDesc {
@@ -82,8 +89,8 @@ struct K1Params {
   // z-slices (pad columns are zero)
   const double* cgal;         // [n_z, nbp]  -0.4 k_Calzetti
   const double* cbbb;         // [n_z, nbp]  -0.4 k_Prevot
-  const double* cgal64;       // cgal * 64 log2(10): the cooperative kernel evaluates 10^(c E) as 2^(c64 E / 64)
-  const double* cbbb64;       // cbbb * 64 log2(10)
+  const double* cgal64;       // cgal * D log2(10), D = AGNF_POW2_DENOM (see above)
+  const double* cbbb64;       // cbbb * D log2(10)
   const uint64_t* xray;       // [n_z]
   const int32_t* j1500;       // [n_z]
   const double* omega;        // [n_z, nbp]

@@ -148,14 +148,22 @@ def test_k1_variants_agree_and_tail_handling():
 
 
 def test_exp10_fast_accuracy():
-    """The cooperative kernel's own 10**x (table + degree-6 polynomial) against NumPy, incl. special values."""
+    """The cooperative kernel's own 10**x (2^(x D log2 10 / D): D-entry table + polynomial) against NumPy, incl.
+    special values.  The argument scaling costs |x| * 3.3 ulp of relative accuracy; inside the prior box
+    (|x| <= 10) that is 4e-15, three orders below what 1e-10 on ln_probab needs."""
     ms, g = load_k1("agnoff18")
     eng, _ = _engine(ms, g)
     rng = np.random.default_rng(1)
-    x = np.concatenate([rng.uniform(-40, 40, 200000), rng.uniform(-299, 299, 50000), rng.uniform(-1e-3, 1e-3, 1000),
+    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-40, 40, 100000), rng.uniform(-299, 299, 50000),
+                        rng.uniform(-1e-3, 1e-3, 1000),
                         np.array([0.0, -0.0, 1.0, -1.0, 10.0, -10.0, 299.999, -299.999, 300.0, -300.0, 308.0,
                                   -320.0, 400.0, -400.0, np.inf, -np.inf, np.nan])])
     y = eng.debug_exp10(x)
     with np.errstate(all="ignore"):
         want = 10.0 ** x
-    assert_close_with_specials(y, want, rtol=2e-15, what="exp10_fast")
+    assert np.array_equal(np.isnan(y), np.isnan(want)) and np.array_equal(np.isinf(y), np.isinf(want))
+    fin = np.isfinite(want) & (want > 1e-300)
+    rel = np.abs(y[fin] - want[fin]) / want[fin]
+    bound = 4e-16 * (1.0 + 3.4 * np.abs(x[fin]))
+    assert np.all(rel <= bound), (rel / bound).max()
+    assert np.all(rel[np.abs(x[fin]) <= 10] <= 1.5e-14)

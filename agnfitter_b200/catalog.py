@@ -1,0 +1,103 @@
+"""
+Whole-catalogue fitting: the multi-source, multi-GPU counterpart of RUN_AGNfitter_multiprocessing
+(RUN_AGNfitter_multi.py:246-270).  The reference maps `RUN_AGNfitter_onesource_independent` over catalogue
+rows with a process pool; every worker builds its source's dictionary (DICTIONARIES_AGNfitter.py:139-154),
+runs the sampler (MCMC_AGNfitter.py:98-135) and writes its own files.  Here every rank (one process per GPU)
+
+  1. takes a contiguous block of the z-sorted catalogue (shard.shard_catalog — a dictionary z-slice is never
+     split between ranks),
+  2. builds the dictionary for the distinct redshifts of its block on its GPU (K2) and keeps it in HBM,
+  3. runs the reference's burn-in / production schedule for all its sources in lock-step (K3 + K1),
+  4. reduces the thinned production chain to the reference's five percentiles on the device,
+
+and the only exchange is one gather of the fixed-size per-source summaries to rank 0 (NCCL on the GPUs, gloo
+in the CPU tests).  No collective touches the evaluation path.
+"""
+import numpy as np
+
+from . import shard as _shard
+from . import sources as _sources
+from .engine import Engine, DictBuilder
+from .ensemble import EnsembleSampler, REFERENCE_PERCENTILES
+from .flatten import ModelSet, family_from_keys_float
+
+FAMILY_OF = (("GA", "GALAXY"), ("SB", "STARBURST"), ("TO", "TORUS"), ("BB", "BBB"), ("RAD", "AGN_RAD"))
+
+
+def build_modelset_on_device(templates, filterdict, z_grid, settings, builder):
+    """templates: {'GALAXY': dict(F={key: (log nu, Fnu)}, names=[...], types=[...], aux={key: value} | None), ...}
+    — the reference's `*Fdict_4plot` dicts with their parameter names / types (the loaders' return values,
+    MODEL_AGNfitter.py:69-1147) and, where the priors need them, GALAXYatt_dict / STARBURST_LIRdict.
+    Returns (ModelSet without host tables, {family: CUDA tensor [n_z, T, pitch]})."""
+    ms = ModelSet(settings=dict(settings), bands=np.asarray(filterdict[0], dtype=np.float64),
+                  z_grid=np.asarray(z_grid, dtype=np.float64))
+    dev = {}
+    for short, long_name in FAMILY_OF:
+        if long_name not in templates:
+            continue
+        fam = templates[long_name]
+        keys = list(fam["F"].keys())
+        kf = np.array(keys).T.astype(float)
+        if kf.ndim == 1:
+            kf = kf[None, :]
+        fitted = not (short == "RAD" and keys == ['-99.9'])
+        tab = builder.build_family(fam["F"], z_grid, on_device=True)
+        aux = None if fam.get("aux") is None else np.array([float(fam["aux"][k]) for k in keys])
+        if short == "GA" and 'free' in fam["types"]:
+            aux = None
+        ms.families.append(family_from_keys_float(short, fam["names"], fam["types"], kf, fitted, None, aux))
+        dev[short] = tab
+    return ms, dev
+
+
+def summary_columns(n_par, n_q=len(REFERENCE_PERCENTILES)):
+    """Layout of one summary row."""
+    return ["source_index", "z"] + ["p%d_q%d" % (p, q) for p in range(n_par) for q in range(n_q)] + \
+           ["best_%d" % p for p in range(n_par)] + ["best_lnp", "acceptance"]
+
+
+def fit_catalog(templates, filterdict, settings, z, dlum, nus, fluxes, fluxerrs, mc, seed=0, n_bins=1024,
+                rank=0, world=1, device=0):
+    """Fit every source of the catalogue this rank owns and gather the summaries.
+
+    z, dlum [S]; nus [n_b] or [S, n_b]; fluxes, fluxerrs [S, n_b] in the reference's DATA conventions
+    (DATA_AGNfitter.py:145-193 already applied).  mc: MCMC_settings() dict (Nwalkers, Nburnsets, Nburn, Nmcmc,
+    Nthin).  Returns on rank 0 an array [S_total, len(summary_columns)] ordered by z (None on other ranks)."""
+    import torch
+    z = np.asarray(z, dtype=np.float64)
+    order, lo, hi = _shard.shard_catalog(z, rank, world)
+    mine = order[lo:hi]
+    nus = np.asarray(nus, dtype=np.float64)
+    rows = None
+    n_par = None
+    if len(mine):
+        zs = z[mine]
+        builder = DictBuilder(filterdict, device=device)
+        ms, dev = build_modelset_on_device(templates, filterdict, np.unique(zs), settings, builder)
+        eng = Engine(ms, device=device, ctx=builder.ctx, device_tables=dev)
+        src = _sources.make_sources(ms, zs, np.asarray(dlum, dtype=np.float64)[mine],
+                                    nus if nus.ndim == 1 else nus[mine],
+                                    np.asarray(fluxes, dtype=np.float64)[mine],
+                                    np.asarray(fluxerrs, dtype=np.float64)[mine])
+        eng.set_sources(src)
+        n_par = ms.n_par
+        # random numbers are keyed by the source's position in the z-sorted catalogue, not by the shard:
+        # the fit of a source does not depend on the number of GPUs
+        ens = EnsembleSampler(eng, int(mc['Nwalkers']), seed=int(seed), n_bins=n_bins, source_offset=lo)
+        rngs = [np.random.default_rng([int(seed), lo + i]) for i in range(len(mine))]
+        out = ens.run_reference_schedule(mc, src.pmin, src.pmax, rngs)
+        rows = np.concatenate([mine[:, None].astype(np.float64), zs[:, None],
+                               out["percentiles"].reshape(len(mine), -1), out["best_pos"],
+                               out["best_lnp"][:, None], out["acceptance"][:, None]], axis=1)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dev_t = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        # ranks with no sources still take part in the gather; they learn the row width from the others
+        width = torch.tensor([0 if rows is None else rows.shape[1]], dtype=torch.int64, device=dev_t)
+        dist.all_reduce(width, op=dist.ReduceOp.MAX)
+        w = int(width.item())
+        local = torch.zeros((0, w), dtype=torch.float64, device=dev_t) if rows is None else \
+            torch.from_numpy(np.ascontiguousarray(rows)).to(dev_t)
+        got = _shard.gather_summaries(local)
+        return None if got is None else got.cpu().numpy()
+    return rows

@@ -66,6 +66,7 @@ struct agnf_ctx {
   double* ens_best_lnp = nullptr;
   int64_t ens_step = 0;              // stretch-move steps taken since agnf_ens_create (Philox counter)
   int ens_fused = 1;                 // 1: one fused K1 launch per half-step; 0: propose / K1 / accept kernels
+  int64_t ens_src_offset = 0;        // catalogue row of the shard's first source (Philox counter)
   int64_t ens_hist_samples = 0;
 };
 
@@ -363,6 +364,12 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     ctx->k1_variant = (int)value;
     return 0;
   }
+  if (strcmp(name, "ens_source_offset") == 0) {
+    if (value < 0) return fail(ctx, "ens_source_offset must be >= 0");
+    ctx->ens_src_offset = value;
+    if (ctx->have_ens) ctx->ens.src_offset = value;
+    return 0;
+  }
   if (strcmp(name, "ens_fused") == 0) {
     if (value != 0 && value != 1) return fail(ctx, "ens_fused must be 0 or 1");
     ctx->ens_fused = (int)value;
@@ -383,6 +390,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "band_pitch") == 0) *value = ctx->have_cfg ? ctx->k1.nbp : 0;
   else if (strcmp(name, "pipeline_rows") == 0) *value = ctx->pipeline_rows;
   else if (strcmp(name, "ens_fused") == 0) *value = ctx->ens_fused;
+  else if (strcmp(name, "ens_source_offset") == 0) *value = ctx->ens_src_offset;
   else return fail(ctx, "unknown option '%s'", name);
   return 0;
 }
@@ -844,6 +852,7 @@ AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, doub
   st.n_par = np;
   st.seed = seed;
   st.a = a;
+  st.src_offset = ctx->ens_src_offset;
   void* p = nullptr;
 #define ENS_ALLOC(dst, type, count)                             \
   do {                                                          \
@@ -912,6 +921,7 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
   FB.ens.W = st.W;
   FB.ens.seed = st.seed;
   FB.ens.a = st.a;
+  FB.ens.src_offset = st.src_offset;
   const bool fused = ctx->k1_variant == 1 && ctx->ens_fused && k1_coop_supported(ctx->k1, FB, nullptr);
   for (int64_t it = 0; it < n_steps; ++it) {
     for (int half = 0; half < 2; ++half) {

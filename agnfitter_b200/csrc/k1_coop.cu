@@ -259,7 +259,7 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     const int H = B.ens.W >> 1;
     const int64_t src = i / H;
     const int kw = (int)(i - src * H);
-    const StretchDraw d = stretch_draw(B.ens.seed, B.ens.a, B.ens.step, B.ens.half, src, kw, H);
+    const StretchDraw d = stretch_draw(B.ens.seed, B.ens.a, B.ens.step, B.ens.half, src + B.ens.src_offset, kw, H);
     s = (int)src;
     wrow = src * B.ens.W + (B.ens.half ? H : 0) + kw;
     // Both rows are fetched by the whole warp: element e of the flat [32][n_par] block goes to lane e % 32,

@@ -122,6 +122,7 @@ struct K1Ensemble {
   int64_t step = 0;
   uint64_t seed = 0;
   double a = 2.0;
+  int64_t src_offset = 0;     // see K3State
 };
 
 struct K1Batch {

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_propose_kernel(K3State st, K3Sc
   if (i >= st.S * H) return;
   const int64_t s = i / H;
   const int k = (int)(i - s * H);
-  const StretchDraw d = stretch_draw(st.seed, st.a, step, half, s, k, H);
+  const StretchDraw d = stretch_draw(st.seed, st.a, step, half, s + st.src_offset, k, H);
   const double zz = d.zz;
   const int j = d.j;
   const int np = st.n_par;

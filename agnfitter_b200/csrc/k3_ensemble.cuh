@@ -26,6 +26,8 @@ struct K3State {
   int32_t W, n_par;
   uint64_t seed;
   double a;           // stretch scale (emcee default 2.0)
+  int64_t src_offset; // added to the local source index in the Philox counter: a shard that starts at catalogue
+                      // row `src_offset` draws exactly what a single-GPU run draws for those sources
 };
 
 struct K3Scratch {

@@ -17,15 +17,18 @@ REFERENCE_PERCENTILES = (2.5, 16.0, 50.0, 84.0, 97.5)
 
 
 class EnsembleSampler:
-    def __init__(self, engine, walkers, seed=0, a=2.0, n_bins=1024):
+    def __init__(self, engine, walkers, seed=0, a=2.0, n_bins=1024, source_offset=0):
         """engine: an Engine with sources uploaded.  walkers: even.  n_bins: histogram resolution of the
-        on-device percentiles ((P.max - P.min) / n_bins per parameter); 0 = no histograms."""
+        on-device percentiles ((P.max - P.min) / n_bins per parameter); 0 = no histograms.  source_offset:
+        catalogue row of the first uploaded source (enters the random-number counter: a shard draws what a
+        single-GPU run draws for the same sources)."""
         self.engine = engine
         self.ctx, self.lib = engine.ctx, engine.lib
         self.S, self.W, self.n_par = engine.S, int(walkers), engine.n_par
         if self.S < 1:
             raise ValueError("upload sources first (Engine.set_sources)")
         self.n_bins = int(n_bins)
+        self.ctx.check(self.lib.agnf_set_option(self.ctx.h, b"ens_source_offset", int(source_offset)))
         self.ctx.check(self.lib.agnf_ens_create(self.ctx.h, self.W, int(seed) & (2 ** 64 - 1), float(a), self.n_bins))
 
     # -- positions --------------------------------------------------------------------------------
@@ -77,16 +80,29 @@ class EnsembleSampler:
 
     # -- the reference's schedule -----------------------------------------------------------------
     def run_reference_schedule(self, mc, pmin, pmax, rng):
-        """mc: the dict of MCMC_settings() (Nwalkers, Nburnsets, Nburn, Nmcmc, Nthin).  Returns a
-        summary dict: percentiles [S, n_par, 5] of the thinned production chain, best position / lnP,
-        mean acceptance fraction per source."""
+        """mc: the dict of MCMC_settings() (Nwalkers, Nburnsets, Nburn, Nmcmc, Nthin).  rng: a NumPy
+        Generator, or a list of S Generators (one per source: the initial balls then do not depend on
+        which other sources share the shard).  Returns a summary dict: percentiles [S, n_par, 5] of the
+        thinned production chain, best position / lnP, mean acceptance fraction per source."""
         if int(mc['Nwalkers']) != self.W:
             raise ValueError("mc['Nwalkers'] != walkers")
-        self.set_positions(self.initial_positions(pmin, pmax, self.W, rng))
+        per_source = isinstance(rng, (list, tuple))
+
+        def initial():
+            if not per_source:
+                return self.initial_positions(pmin, pmax, self.W, rng)
+            return np.concatenate([self.initial_positions(pmin[s], pmax[s], self.W, rng[s]) for s in range(self.S)])
+
+        def ball(best_pos):
+            if not per_source:
+                return self.ball_around(best_pos, self.W, rng)
+            return np.concatenate([self.ball_around(best_pos[s], self.W, rng[s]) for s in range(self.S)])
+
+        self.set_positions(initial())
         for _ in range(int(mc['Nburnsets'])):
             self.run(int(mc['Nburn']), track_best=True)
             best_pos, _ = self.best()
-            self.set_positions(self.ball_around(best_pos, self.W, rng))
+            self.set_positions(ball(best_pos))
         self.reset_stats()
         n = int(mc['Nmcmc'])
         self.run(n, hist_every=int(mc.get('Nthin', 1)) if self.n_bins else 0, track_best=True)

@@ -131,7 +131,10 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
  * this into chunks whose upload / kernel / download overlap on three streams; 0 = one shot.
  * "ens_fused" (default 1): agnf_ens_run issues one fused launch per half-step (the cooperative K1 kernel
  * draws the proposal, evaluates it and applies the acceptance rule in place); 0 = separate propose / K1 /
- * accept kernels (same chain, bit for bit). */
+ * accept kernels (same chain, bit for bit).
+ * "ens_source_offset" (default 0): catalogue row of the first uploaded source; it is added to the source index
+ * in the sampler's Philox counter, so a shard of a catalogue draws what a single-GPU run draws for the same
+ * sources (results do not depend on how the catalogue is split over GPUs). */
 AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value);
 AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value);
 /* y[i] = 10^x[i] through the kernels' own exp10 routine (host pointers; unit-test hook) */

@@ -38,9 +38,10 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def draws(step, half, S, H, seed):
-    """(u1 [S,H] in [0,1), j [S,H] in [0,H), ln u3 [S,H]) of one half-step."""
-    s = np.arange(S, dtype=np.uint32)[:, None]
+def draws(step, half, S, H, seed, src_offset=0):
+    """(u1 [S,H] in [0,1), j [S,H] in [0,H), ln u3 [S,H]) of one half-step; the sources are catalogue rows
+    src_offset .. src_offset + S - 1."""
+    s = (np.arange(S, dtype=np.int64) + int(src_offset)).astype(np.uint32)[:, None]
     k = np.arange(H, dtype=np.uint32)[None, :]
     seed = int(seed) & (2 ** 64 - 1)
     x0, x1, x2, x3 = philox4x32_10(np.uint32(step), np.uint32(half), s, k, seed & 0xFFFFFFFF, seed >> 32)
@@ -51,11 +52,11 @@ def draws(step, half, S, H, seed):
     return u1, j, np.log(u3)
 
 
-def proposals(pos, step, half, seed, a=2.0):
+def proposals(pos, step, half, seed, a=2.0, src_offset=0):
     """pos [S, W, n_par] -> (q [S, H, n_par], factor [S, H], ln u3 [S, H]) for one half-step."""
     S, W, n_par = pos.shape
     H = W // 2
-    u1, j, lnu = draws(step, half, S, H, seed)
+    u1, j, lnu = draws(step, half, S, H, seed, src_offset)
     t = (a - 1.0) * u1 + 1.0
     zz = (t * t) / a
     mine = pos[:, H:] if half else pos[:, :H]
@@ -65,12 +66,12 @@ def proposals(pos, step, half, seed, a=2.0):
     return q, (n_par - 1) * np.log(zz), lnu
 
 
-def step(pos, lnp, n_acc, lnprob_fn, step_idx, seed, a=2.0):
+def step(pos, lnp, n_acc, lnprob_fn, step_idx, seed, a=2.0, src_offset=0):
     """One full stretch-move step in place.  lnprob_fn(q [S, H, n_par]) -> [S, H]."""
     S, W, n_par = pos.shape
     H = W // 2
     for half in (0, 1):
-        q, factor, lnu = proposals(pos, step_idx, half, seed, a)
+        q, factor, lnu = proposals(pos, step_idx, half, seed, a, src_offset)
         new = lnprob_fn(q)
         sl = slice(H, W) if half else slice(0, H)
         with np.errstate(invalid="ignore"):

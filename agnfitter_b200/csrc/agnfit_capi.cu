@@ -31,7 +31,8 @@ struct agnf_ctx {
   std::string err;
   std::vector<void*> owned;                    // device allocations freed in destroy
   int64_t launches = 0;
-  int k1_variant = 1;                          // 1: cooperative kernel when its preconditions hold; 0: per-thread
+  int k1_variant = 1;                          // 1: cooperative kernel when supported and profitable; 2: whenever
+                                               // supported; 0: per-thread kernel
   int last_k1_kernel = -1;                     // which kernel the last K1 launch used
 
   bool have_cfg = false;
@@ -360,7 +361,7 @@ AGNF_API int agnf_last_kernel_ms(agnf_ctx* ctx, int which, float* ms) {
 AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return 1;
   if (strcmp(name, "k1_variant") == 0) {
-    if (value != 0 && value != 1) return fail(ctx, "k1_variant must be 0 (per-thread) or 1 (cooperative)");
+    if (value < 0 || value > 2) return fail(ctx, "k1_variant must be 0 (per-thread), 1 (automatic) or 2 (cooperative)");
     ctx->k1_variant = (int)value;
     return 0;
   }
@@ -581,7 +582,8 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
   K1Batch B{d_params, d_source_id, n, d_lnp, d_rows, d_ymodel, d_lnprior, d_lnlike};
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
   const char* why = nullptr;
-  if (ctx->k1_variant == 1 && k1_coop_supported(ctx->k1, B, &why)) {
+  if (ctx->k1_variant != 0 && k1_coop_supported(ctx->k1, B, &why) &&
+      (ctx->k1_variant == 2 || k1_coop_profitable(ctx->k1, B))) {
     CUDA_TRY(ctx, launch_k1_coop(ctx->k1, B, st));
     ctx->last_k1_kernel = 1;
   } else {
@@ -922,7 +924,8 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
   FB.ens.seed = st.seed;
   FB.ens.a = st.a;
   FB.ens.src_offset = st.src_offset;
-  const bool fused = ctx->k1_variant == 1 && ctx->ens_fused && k1_coop_supported(ctx->k1, FB, nullptr);
+  const bool fused = ctx->k1_variant != 0 && ctx->ens_fused && k1_coop_supported(ctx->k1, FB, nullptr) &&
+                     (ctx->k1_variant == 2 || k1_coop_profitable(ctx->k1, FB));
   for (int64_t it = 0; it < n_steps; ++it) {
     for (int half = 0; half < 2; ++half) {
       if (fused) {

@@ -638,6 +638,13 @@ size_t coop_smem_bytes(const K1Params& P, bool ens) {
 }  // namespace
 
 #ifndef K1_COOP_ENS_TU
+bool k1_coop_profitable(const K1Params& P, const K1Batch& B) {
+  // The kernel hides its latencies with resident warps; when the per-warp tiles are so large that only one
+  // CTA fits an SM (free E(B-V) galaxies with the energy-balance prior on ~50 bands: three partial-sum planes),
+  // the per-thread kernel is the faster one (measured 2x on the freeebv_xray49 case).
+  return 2 * coop_smem_bytes(P, B.ens.pos != nullptr) <= 220 * 1024;
+}
+
 bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why) {
   const char* w = nullptr;
   if (P.nbp & 1) w = "band pitch is odd";

@@ -141,6 +141,7 @@ cudaError_t launch_k1(const K1Params& P, const K1Batch& B, cudaStream_t stream);
 
 // cooperative kernel (k1_coop.cu); `why` receives a static string when unsupported
 bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why);
+bool k1_coop_profitable(const K1Params& P, const K1Batch& B);   // false: the per-thread kernel is expected to win
 cudaError_t launch_k1_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream);
 cudaError_t launch_exp10_fast(const double* x, double* y, int64_t n, cudaStream_t stream);
 

@@ -123,8 +123,9 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
                              double* d_lnp, int32_t* d_rows, double* d_ymodel, double* d_lnprior,
                              double* d_lnlike, void* stream);
 
-/* tuning knobs.  "k1_variant": 1 (default) = cooperative K1 kernel whenever its preconditions hold
- * (16-byte aligned params and tables, even table pitch), 0 = per-thread K1 kernel (no preconditions).
+/* tuning knobs.  "k1_variant": 1 (default) = cooperative K1 kernel when its preconditions hold (16-byte
+ * aligned params and tables, even table pitch) and two CTAs fit an SM, else the per-thread kernel;
+ * 2 = cooperative whenever the preconditions hold; 0 = per-thread K1 kernel (no preconditions).
  * agnf_get_option also answers "k1_last_kernel" (which kernel the last K1 launch ran: 1 / 0, -1 none)
  * and "band_pitch" (n_b rounded up to even: the pitch to ask agnf_dict_build for).
  * "pipeline_rows" (default 2^20): agnf_lnprob_batch with only lnp requested cuts batches larger than

@@ -20,6 +20,21 @@ DEFAULT18_NK = [512, 512, 512, 128, 421, 370, 427, 505, 200, 169, 5205, 116, 198
 DEFAULT18_SPAN = [0.778, 0.778, 0.778, 0.253, 0.264, 0.173, 0.158, 0.148, 0.121, 0.134, 0.173, 0.097, 0.132,
                   0.136, 0.127, 0.182, 0.155, 0.251]
 
+# the 49-band set of example/SETTINGS_AGNfitter.py (radio to X-ray), same three quantities per curve
+EXAMPLE49_NU = [9.145694, 9.698535, 10.175657, 11.774163, 11.932734, 12.079841, 12.246828, 12.460938, 12.629178,
+                13.105391, 13.129294, 13.385592, 13.585464, 13.720665, 13.811172, 13.825887, 13.927985, 13.947874,
+                14.141412, 14.260066, 14.379951, 14.49291, 14.511204, 14.524307, 14.538192, 14.59011, 14.599052,
+                14.601643, 14.677783, 14.683271, 14.685333, 14.74192, 14.783841, 14.789474, 14.802849, 14.837293,
+                14.894014, 14.925019, 14.935101, 14.935668, 15.051964, 15.114285, 15.123116, 15.158924, 15.295975,
+                17.264134, 17.562297, 17.891176, 18.220277]
+EXAMPLE49_NK = [1000, 1000, 1000, 512, 512, 512, 3560, 1428, 405, 128, 2559, 2559, 421, 370, 548, 427, 505, 398, 200,
+                169, 5205, 201, 24, 141, 153, 22, 167, 89, 22, 178, 75, 1282, 26, 172, 89, 1282, 31, 47, 35, 1282, 1282,
+                23, 1282, 1282, 14, 1001, 1001, 1001, 1001]
+EXAMPLE49_SPAN = [0.269, 0.269, 0.269, 0.778, 0.778, 0.778, 0.421, 0.292, 0.342, 0.253, 1.052, 1.052, 0.264, 0.173,
+                  0.5, 0.158, 0.148, 0.41, 0.121, 0.134, 0.173, 0.087, 0.107, 0.162, 0.076, 0.118, 0.096, 0.128, 0.147,
+                  0.125, 0.128, 0.7, 0.22, 0.157, 0.206, 0.7, 0.085, 0.142, 0.108, 0.7, 0.7, 0.251, 0.7, 0.7, 0.131,
+                  0.301, 0.301, 0.352, 0.426]
+
 CLASSIC_SETTINGS = dict(
     path='models/', modelset='modelsv1', GALAXY='BC03', STARBURST='DH02_CE01', BBB='R06', TORUS='S04',
     XRAYS=False, RADIO=False, Blazar='None', PRIOR_energy_balance='Flexible', PRIOR_AGNfraction=True,
@@ -28,10 +43,12 @@ CLASSIC_SETTINGS = dict(
 _C = 2.997e8
 
 
-def synthetic_filterdict(nus=DEFAULT18_NU, nks=DEFAULT18_NK, spans=DEFAULT18_SPAN, decreasing=(0, 1, 2)):
+def synthetic_filterdict(nus=DEFAULT18_NU, nks=DEFAULT18_NK, spans=DEFAULT18_SPAN, decreasing=(0, 1, 2), which=None):
     """[central_nu_array, lambdas_dict, factors_dict] in the reference's container shapes
     (FILTERS_AGNfitter.py:111-122).  Curves listed in `decreasing` store lambda descending, like the
-    SPIRE curves of ALL_FILTERS do."""
+    SPIRE curves of ALL_FILTERS do.  which='example49' selects the 49-band example set's geometry."""
+    if which == "example49":
+        nus, nks, spans, decreasing = EXAMPLE49_NU, EXAMPLE49_NK, EXAMPLE49_SPAN, (3, 4, 5)
     lambdas_dict, factors_dict = {}, {}
     for i, (nu, nk, span) in enumerate(zip(nus, nks, spans)):
         lam_c = _C / 10 ** nu * 1e10

@@ -166,6 +166,24 @@ def cpu_port_throughput(ms_small, srcs, pars_list, cores, repeats=1):
     return best
 
 
+def cpu_dictionary_throughput(n_templates=400, bands=18):
+    """Dictionary entries/s of the oracle port of filtering_models (one core) on a sample of the same synthetic
+    templates / filters: the CPU figure beside K2's."""
+    from agnfitter_b200 import synth
+    from oracle import agn_oracle as O
+    fd = synth.synthetic_filterdict(which="example49" if bands == 49 else None)
+    tpl = synth.synthetic_templates()["GA"]["F"]
+    b = fd[0]
+    lam = [np.asarray(fd[1][x][0]) for x in b]
+    fac = [np.asarray(fd[2][x][0]) for x in b]
+    keys = list(tpl.keys())[:: max(1, len(tpl) // n_templates)][:n_templates]
+    t0 = time.perf_counter()
+    for i, k in enumerate(keys):
+        O.filtering_models(tpl[k][0], tpl[k][1], b, lam, fac, 0.5 + 0.001 * i)
+    dt = time.perf_counter() - t0
+    return len(keys) * len(b) / dt, len(keys)
+
+
 def build_host_sample(ms, dev_tables, src_raw, sample_ids, pars, W):
     """Small host-side ModelSet (only the sampled sources' z-slices) + oracle inputs."""
     from agnfitter_b200.flatten import ModelSet, family_from_keys_float
@@ -193,7 +211,7 @@ def make_workload(args, rank, device, need_gpu=True):
     from agnfitter_b200 import synth, sources
     from agnfitter_b200.engine import Engine, DictBuilder
     t_setup = time.perf_counter()
-    fd = synth.synthetic_filterdict()
+    fd = synth.synthetic_filterdict(which="example49" if args.bands == 49 else None)
     tpl = synth.synthetic_templates()
     nus = np.asarray(fd[0])
     S, W = args.sources, args.walkers
@@ -341,15 +359,17 @@ def run_ours(args):
         ns = min(args.cpu_sources, S)
         sample_ids = np.linspace(0, S - 1, ns).astype(np.int64)
         small, srcs, pl = build_host_sample(ms, dev_tables, raw, sample_ids, pars, W)
+        k2_cpu, k2_cpu_n = cpu_dictionary_throughput(bands=n_b)
         cpu_all = cpu_port_throughput(small, srcs, pl, cores)
         cpu_one = cpu_port_throughput(small, srcs[:max(1, ns // cores)], pl[:max(1, ns // cores)], 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3: synthetic %d sources x %d walkers per GPU, 18-band default set, classic "
+            "config": {"workload": "C3: synthetic %d sources x %d walkers per GPU, %s, classic "
                                    "10-parameter model (11000+161+60+2 templates), dictionary of %d z-slices in HBM"
-                                   % (S, W, info["n_z"]),
+                                   % (S, W, "18-band default set" if n_b == 18 else "%d-band example set" % n_b,
+                                      info["n_z"]),
                        "positions": args.positions + " in prior box + 1% out-of-box rows",
                        "source_order": "random z" if args.no_sort_z else "sorted by z",
                        "k1_variant": "cooperative (k1_coop_kernel)" if eng.get_option("k1_last_kernel") == 1 else "per-thread (k1_lnprob_kernel)",
@@ -383,7 +403,11 @@ def run_ours(args):
                 "sources_fitted_per_s": total_rows / (ens_ms_max * 1e-3) / EVALS_PER_FIT,
                 "mean_acceptance": ens_info["acceptance"], "launches": ens_info["launches"]},
             "dictionary_build": {"entries": int(info["k2_entries"]), "wall_s": info["k2_wall_s"],
-                                 "entries_per_s": info["k2_entries"] / info["k2_wall_s"]},
+                                 "entries_per_s": info["k2_entries"] / info["k2_wall_s"],
+                                 "what": "K2 over every family and every distinct z of the shard, tables left in HBM; "
+                                         "wall time incl. host preparation and uploads",
+                                 "cpu_entries_per_s_one_core": k2_cpu,
+                                 "cpu_sample": "oracle filtering_models on %d galaxy templates x %d bands" % (k2_cpu_n, n_b)},
             "clocks": sampler.summary(),
             "finite_rows_last_step": check,
         }
@@ -449,6 +473,9 @@ def main():
                     help="keep the catalogue in random z order (default: the shard is processed in z order so "
                          "that sources sharing a dictionary z-slice are adjacent)")
     ap.add_argument("--cpu-sources", type=int, default=384, help="sources in the CPU-baseline sample")
+    ap.add_argument("--bands", type=int, default=18, choices=[18, 49],
+                    help="18: the default band set (the workload BASELINE.json names); 49: the example settings' "
+                         "radio-to-X-ray set (C1/C2 shape at catalogue scale)")
     ap.add_argument("--ensemble-steps", type=int, default=10,
                     help="also time this many lock-step stretch-move steps of the GPU-resident sampler (0: skip)")
     args = ap.parse_args()

@@ -792,7 +792,8 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   std::vector<int32_t> rmaxb((size_t)n_b), woff((size_t)n_b + 1, 0);
   K2_TRY(cudaMemcpyAsync(rmaxb.data(), d_rmax, (size_t)n_b * 4, cudaMemcpyDeviceToHost, st));
   K2_TRY(cudaStreamSynchronize(st));
-  for (int b = 0; b < n_b; ++b) woff[(size_t)b + 1] = woff[(size_t)b] + std::max(rmaxb[(size_t)b], 1);
+  for (int b = 0; b < n_b; ++b)     // even slot counts: every band's weight row starts 16-byte aligned
+    woff[(size_t)b + 1] = woff[(size_t)b] + ((std::max(rmaxb[(size_t)b], 1) + 1) & ~1);
   const int32_t wstride = (woff[(size_t)n_b] + 1) & ~1;       // even: a z-slice of weights is a 16-byte multiple
   std::vector<int32_t> band_of((size_t)wstride, -1);
   for (int b = 0; b < n_b; ++b)

@@ -181,7 +181,8 @@ struct K2TilePlan {
   int32_t tt;          // templates per tile (power of two, <= 32)
   int32_t zb;          // z-slices per batch (one weight copy, one synchronisation pair)
   int32_t zc;          // z-slices per CTA (multiple of zb)
-  int32_t opitch;      // pitch of a result tile in shared memory (out_pitch + 1: conflict-free transposition)
+  int32_t opitch;      // pitch of a result tile in shared memory: out_pitch (bulk store) or out_pitch + 1
+  int32_t bulk_store;  // rows are not remapped and out_pitch is even: slices leave by bulk stores
   int32_t off_w, off_o, off_bar, smem_bytes;   // byte offsets inside dynamic shared memory
 };
 
@@ -243,15 +244,22 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_tile_kernel(K2Prob
         const double* __restrict__ F = Fs_s + tt * ldF + __ldg(p.jlo + zb_idx);
         const double* __restrict__ w = Wb + zl * ws + __ldg(p.woff + b);
         const int cnum = __ldg(p.cnt + zb_idx);
+        // weights: 128-bit broadcast reads (woff and wstride are even: the row is 16-byte aligned); slots
+        // beyond cnt hold 0 by construction, but the template samples beyond the band's window are NOT
+        // read (a non-finite sample there must not leak into this band): the tail is predicated
+        const double2* __restrict__ w2 = reinterpret_cast<const double2*>(w);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int r = 0;
         for (; r + 4 <= cnum; r += 4) {
-          a0 = fma(w[r], F[r], a0);
-          a1 = fma(w[r + 1], F[r + 1], a1);
-          a2 = fma(w[r + 2], F[r + 2], a2);
-          a3 = fma(w[r + 3], F[r + 3], a3);
+          const double2 wa = w2[r >> 1], wb = w2[(r >> 1) + 1];
+          a0 = fma(wa.x, F[r], a0);
+          a1 = fma(wa.y, F[r + 1], a1);
+          a2 = fma(wb.x, F[r + 2], a2);
+          a3 = fma(wb.y, F[r + 3], a3);
         }
-        for (; r < cnum; ++r) a0 = fma(w[r], F[r], a0);
+        if (r < cnum) a0 = fma(w[r], F[r], a0);
+        if (r + 1 < cnum) a1 = fma(w[r + 1], F[r + 1], a1);
+        if (r + 2 < cnum) a2 = fma(w[r + 2], F[r + 2], a2);
         O_s[(zl * TT + tt) * c.opitch + b] = (a0 + a1) + (a2 + a3);
         b += TASKS_PER_PASS;
         while (b >= n_b) {
@@ -261,8 +269,22 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_tile_kernel(K2Prob
       }
     }
     __syncthreads();
-    {
-      // the nt x pitch results of a slice are contiguous in global memory when rows are not remapped
+    if (c.bulk_store) {
+      // the nt x pitch results of a slice are one contiguous block of `out`: with an unpadded tile
+      // (c.opitch == pitch) each slice leaves with a single bulk store (shared -> global through the TMA unit)
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes -> async proxy
+        for (int zl = 0; zl < nzb; ++zl) {
+          double* dst = p.out + ((int64_t)(zfirst + zl) * p.T_total + t0) * pitch;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst),
+                       "r"(k2_smem_u32(O_s + (size_t)zl * TT * c.opitch)), "r"((uint32_t)(nt * pitch * 8))
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");    // the tile may be overwritten
+      }
+    } else {
+      // remapped rows (ragged families) or an odd pitch (dense host output): element-wise coalesced stores
       const int per_z = nt * pitch;
       const int d_tt = K2T_THREADS / pitch, d_col = K2T_THREADS - d_tt * pitch;
       for (int zl = 0; zl < nzb; ++zl) {
@@ -286,7 +308,10 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_tile_kernel(K2Prob
 
 bool k2_tile_plan(const K2Problem& p, K2TilePlan* c) {
   if ((p.wstride & 1) || p.wstride < 2) return false;              // bulk copies move 16-byte multiples
-  const int opitch = p.out_pitch + 1;
+  // a dense tile for the bulk store (two-way bank conflicts on the 18 x 32 result writes are cheaper than a
+  // store loop); the padded, conflict-free pitch only when rows are remapped
+  const bool bulk = !p.row_map && (p.out_pitch % 2 == 0) && (reinterpret_cast<uintptr_t>(p.out) % 16 == 0);
+  const int opitch = bulk ? p.out_pitch : p.out_pitch + 1;
   for (int tt = 32; tt >= 2; tt >>= 1) {
     for (int zb = 4; zb >= 1; zb >>= 1) {
       const size_t f = (size_t)tt * p.ldF * 8;
@@ -297,6 +322,7 @@ bool k2_tile_plan(const K2Problem& p, K2TilePlan* c) {
       if (total > 200 * 1024) continue;
       c->tt = tt;
       c->zb = zb;
+      c->bulk_store = bulk ? 1 : 0;
       c->opitch = opitch;
       c->off_w = (int32_t)off_w;
       c->off_o = (int32_t)off_o;

@@ -731,9 +731,9 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
 
   void *d_lam = nullptr, *d_perm = nullptr, *d_F = nullptr, *d_Fs = nullptr, *d_z = nullptr, *d_jlo = nullptr,
        *d_cnt = nullptr, *d_rmax = nullptr, *d_W = nullptr, *d_rowmap = nullptr, *d_out = nullptr, *d_woff = nullptr,
-       *d_bandof = nullptr;
+       *d_bandof = nullptr, *d_border = nullptr;
   auto cleanup = [&]() {
-    for (void* q : {d_lam, d_perm, d_F, d_Fs, d_z, d_jlo, d_cnt, d_rmax, d_W, d_rowmap, d_woff, d_bandof})
+    for (void* q : {d_lam, d_perm, d_F, d_Fs, d_z, d_jlo, d_cnt, d_rmax, d_W, d_rowmap, d_woff, d_bandof, d_border})
       dev_free(ctx, q);
     if (!out_on_device) dev_free(ctx, d_out);
   };
@@ -802,6 +802,13 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   K2_ALLOC(d_bandof, (size_t)wstride * 4);
   K2_TRY(cudaMemcpyAsync(d_woff, woff.data(), ((size_t)n_b + 1) * 4, cudaMemcpyHostToDevice, st));
   K2_TRY(cudaMemcpyAsync(d_bandof, band_of.data(), (size_t)wstride * 4, cudaMemcpyHostToDevice, st));
+  std::vector<int32_t> border((size_t)n_b);
+  std::iota(border.begin(), border.end(), 0);
+  std::stable_sort(border.begin(), border.end(),
+                   [&](int32_t x, int32_t y) { return rmaxb[(size_t)x] > rmaxb[(size_t)y]; });
+  K2_ALLOC(d_border, (size_t)n_b * 4);
+  K2_TRY(cudaMemcpyAsync(d_border, border.data(), (size_t)n_b * 4, cudaMemcpyHostToDevice, st));
+  p.band_order = static_cast<const int32_t*>(d_border);
   p.wstride = wstride;
   p.woff = static_cast<const int32_t*>(d_woff);
   p.band_of = static_cast<const int32_t*>(d_bandof);

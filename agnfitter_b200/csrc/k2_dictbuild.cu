@@ -233,13 +233,19 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_tile_kernel(K2Prob
     const double* __restrict__ Wb = W_s + (size_t)buf * ZB * ws;
     // one (slice, band) pair per warp pass (TT = 32): the weight reads are broadcasts, the template
     // reads are conflict-free across the 32 templates (odd ldF); four accumulators break the FMA chain
-    // no integer division in the loops: (slice, band) and (row, column) advance incrementally
+    // Work units = (band, slice) pairs, listed longest band first (band_order) with the slices of a band
+    // adjacent, and dealt to the warps in snake order (pass 0: warp 0..15, pass 1: warp 15..0, ...): the
+    // three far-infrared bands see ~75 template samples, most optical bands ~15, and a plain round-robin
+    // leaves most warps idle behind the two or three that drew the long bands.
     {
       const int n_task = nzb * n_b;
-      int task = threadIdx.x / TT;
-      int zl = task / n_b, b = task - zl * n_b;
       const int tt = tt_of_thread;
-      for (; task < n_task; task += TASKS_PER_PASS) {
+      const int g = threadIdx.x / TT;                       // this thread's unit slot inside a pass
+      for (int pass = 0, base = 0; base < n_task; ++pass, base += TASKS_PER_PASS) {
+        const int task = base + ((pass & 1) ? (TASKS_PER_PASS - 1 - g) : g);
+        if (task >= n_task) continue;
+        const int rank = task / nzb, zl = task - rank * nzb;
+        const int b = __ldg(p.band_order + rank);
         const int zb_idx = (zfirst + zl) * n_b + b;
         const double* __restrict__ F = Fs_s + tt * ldF + __ldg(p.jlo + zb_idx);
         const double* __restrict__ w = Wb + zl * ws + __ldg(p.woff + b);
@@ -261,11 +267,6 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_tile_kernel(K2Prob
         if (r + 1 < cnum) a1 = fma(w[r + 1], F[r + 1], a1);
         if (r + 2 < cnum) a2 = fma(w[r + 2], F[r + 2], a2);
         O_s[(zl * TT + tt) * c.opitch + b] = (a0 + a1) + (a2 + a3);
-        b += TASKS_PER_PASS;
-        while (b >= n_b) {
-          b -= n_b;
-          ++zl;
-        }
       }
     }
     __syncthreads();

@@ -53,6 +53,7 @@ struct K2Problem {
   int32_t* d_rmaxb = nullptr;       // [n_b] max over z of cnt (written by k2_ranges)
   const int32_t* woff = nullptr;    // [n_b + 1] first slot of each band inside a z-slice of W
   const int32_t* band_of = nullptr; // [wstride] band that owns a slot (-1: padding)
+  const int32_t* band_order = nullptr; // [n_b] bands by descending slot count (work balancing in the tiled kernel)
   double* W = nullptr;              // [n_z, wstride]
   int32_t tile_ok = 0;              // Fs is zero-padded to a multiple of 32 rows: the tiled contraction may be used
   const int64_t* row_map = nullptr; // [T] or nullptr

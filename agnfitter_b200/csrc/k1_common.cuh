@@ -4,7 +4,25 @@
 #include <cmath>
 #include <cstdint>
 
+#include "k1_lnprob.cuh"   // AGNF_POW2_DENOM
+
 namespace agnf {
+
+// shared memory through 32-bit shared-window addresses (no generic -> shared conversions)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
+  return v;
+}
+// Read of shared data that is written once before the kernel's first barrier and never again (tables,
+// grids): not volatile, so the compiler may schedule it freely; its address always depends on values
+// obtained after that barrier, which keeps it behind it.
+__device__ __forceinline__ double lds_f64_ro(uint32_t a) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
+  return v;
+}
 
 // 2^(j/64), j = 0..63 (the cooperative kernel stages every (64/D)-th entry, see AGNF_POW2_DENOM)
 __constant__ double c_exp2_tab[64] = {
@@ -21,6 +39,45 @@ __constant__ double c_exp2_tab[64] = {
     1.7373338352737062, 1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
     1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656, 1.9152065613971474,
     1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+
+// ---- 2^(t/D): the factors 10^(c E) with c pre-scaled by D log2(10) on the host (D = AGNF_POW2_DENOM) ----
+// t = k + r, k integer, |r| <= 1/2: 2^(t/D) = 2^(k/D) * exp(r ln2/D); 2^(k/D) = 2^(k div D) * tab[k mod D].
+// Polynomial coefficients (ln 2 / D)^n / n! sit in constant memory so the DFMAs take them as operands;
+// the first neglected term is < 4e-17 (D = 64, degree 5) / 2e-18 (D = 16, degree 7).
+#if AGNF_POW2_DENOM == 64
+constexpr int P2_DEG = 5, P2_SHIFT = 6;
+__constant__ double c_p2[5] = {0.010830424696249145, 5.86490495505617e-05, 2.1173137155464776e-07,
+                               5.732851688640402e-10, 1.2417843701716925e-12};
+#elif AGNF_POW2_DENOM == 16
+constexpr int P2_DEG = 7, P2_SHIFT = 4;
+__constant__ double c_p2[7] = {0.04332169878499658, 0.0009383847928089872, 1.3550807779497457e-05,
+                               1.467610032291943e-07, 1.2715871950558131e-09, 9.181219573844438e-12,
+                               5.682086126528621e-14};
+#else
+#error "AGNF_POW2_DENOM must be 16 or 64"
+#endif
+constexpr double P2_LOG2_10_D = (double)AGNF_POW2_DENOM * 3.321928094887362;   // D log2(10)
+
+// |t| >= 1000 D (or NaN) goes to the library
+static __device__ __noinline__ double pow2_64_slow(double t) { return exp2(t * (1.0 / AGNF_POW2_DENOM)); }
+
+__device__ __forceinline__ double pow2_64(double t, uint32_t tab_s) {
+  if (!(fabs(t) < 1000.0 * AGNF_POW2_DENOM)) return pow2_64_slow(t);
+  const double magic = 6755399441055744.0;                 // 1.5 * 2^52
+  const double km = t + magic;
+  const int k = __double2loint(km);
+  const double r = t - (km - magic);
+  double p = c_p2[P2_DEG - 1];
+#pragma unroll
+  for (int n = P2_DEG - 2; n >= 0; --n) p = fma(p, r, c_p2[n]);
+  p = fma(p, r, 1.0);
+  const double v = lds_f64_ro(tab_s + ((k << 3) & (8 * AGNF_POW2_DENOM - 8))) * p;
+  return __hiloint2double(__double2hiint(v) + ((k >> P2_SHIFT) << 20), __double2loint(v));
+}
+
+// 10^x for the normalisations through the same routine (|x| <= 10 in the prior box: relative error
+// <= |x| D log2(10) 2^-53 ln2 / D ~ 2.6e-15)
+__device__ __forceinline__ double pow10_via2(double x, uint32_t tab_s) { return pow2_64(x * P2_LOG2_10_D, tab_s); }
 
 // Given l = last index with sv[l] <= p (or -1), return the first-appearance index of the minimum
 // of |g - p| over the distinct grid values of one dimension == np.abs(keys_float - p).argmin()

@@ -76,12 +76,6 @@ CoopPlan make_plan(const K1Params& P, bool ens) {
 }
 
 // ---- shared memory through 32-bit shared-window addresses (no generic -> shared conversions) ------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ double lds_f64(uint32_t a) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
-  return v;
-}
 __device__ __forceinline__ double2 lds_v2f64(uint32_t a) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(a));
@@ -100,6 +94,16 @@ __device__ __forceinline__ int lds_s32(uint32_t a) {
 __device__ __forceinline__ unsigned lds_u16(uint32_t a) {
   unsigned short v;
   asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32_ro(uint32_t a) {          // see lds_f64_ro
+  int v;
+  asm("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u16_ro(uint32_t a) {
+  unsigned short v;
+  asm("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(a));
   return v;
 }
 __device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
@@ -138,60 +142,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// ---- 2^(t/D): the factors 10^(c E) with c pre-scaled by D log2(10) on the host (D = AGNF_POW2_DENOM) ----
-// t = k + r, k integer, |r| <= 1/2: 2^(t/D) = 2^(k/D) * exp(r ln2/D); 2^(k/D) = 2^(k div D) * tab[k mod D].
-// Polynomial coefficients (ln 2 / D)^n / n! sit in constant memory so the DFMAs take them as operands;
-// the first neglected term is < 4e-17 (D = 64, degree 5) / 2e-18 (D = 16, degree 7).
-#if AGNF_POW2_DENOM == 64
-constexpr int P2_DEG = 5, P2_SHIFT = 6;
-__constant__ double c_p2[5] = {0.010830424696249145, 5.86490495505617e-05, 2.1173137155464776e-07,
-                               5.732851688640402e-10, 1.2417843701716925e-12};
-#elif AGNF_POW2_DENOM == 16
-constexpr int P2_DEG = 7, P2_SHIFT = 4;
-__constant__ double c_p2[7] = {0.04332169878499658, 0.0009383847928089872, 1.3550807779497457e-05,
-                               1.467610032291943e-07, 1.2715871950558131e-09, 9.181219573844438e-12,
-                               5.682086126528621e-14};
-#else
-#error "AGNF_POW2_DENOM must be 16 or 64"
-#endif
-constexpr double P2_LOG2_10_D = (double)AGNF_POW2_DENOM * 3.321928094887362;   // D log2(10)
-
-// |t| >= 1000 D (or NaN) goes to the library
-static __device__ __noinline__ double pow2_64_slow(double t) { return exp2(t * (1.0 / AGNF_POW2_DENOM)); }
-
-__device__ __forceinline__ double pow2_64(double t, uint32_t tab_s) {
-  if (!(fabs(t) < 1000.0 * AGNF_POW2_DENOM)) return pow2_64_slow(t);
-  const double magic = 6755399441055744.0;                 // 1.5 * 2^52
-  const double km = t + magic;
-  const int k = __double2loint(km);
-  const double r = t - (km - magic);
-  double p = c_p2[P2_DEG - 1];
-#pragma unroll
-  for (int n = P2_DEG - 2; n >= 0; --n) p = fma(p, r, c_p2[n]);
-  p = fma(p, r, 1.0);
-  const double v = lds_f64(tab_s + ((k << 3) & (8 * AGNF_POW2_DENOM - 8))) * p;
-  return __hiloint2double(__double2hiint(v) + ((k >> P2_SHIFT) << 20), __double2loint(v));
-}
-
-// 10^x for the normalisations through the same routine (|x| <= 10 in the prior box: relative error
-// <= |x| D log2(10) 2^-53 ln2 / D ~ 2.6e-15)
-__device__ __forceinline__ double pow10_via2(double x, uint32_t tab_s) { return pow2_64(x * P2_LOG2_10_D, tab_s); }
-
 // snap through the cell table; see k1_common.cuh::snap_dim_lut for the argument (same steps, shared
 // window addresses, task constants from the kernel parameter bank)
 __device__ __forceinline__ int snap_task(const SnapTask& T, double p, uint32_t ext_s, uint32_t eperm_s, uint32_t lut_s,
                                          const double* ext_g, const int32_t* eperm_g) {
   if (T.lut_mmax >= 0) {
     const int c = min(max(__double2int_rz((p - T.lo) * T.inv), 0), T.lut_mmax);
-    int l = (int)lds_u16(lut_s + 2u * (unsigned)(T.lut_off + c));
+    int l = (int)lds_u16_ro(lut_s + 2u * (unsigned)(T.lut_off + c));
     const uint32_t base = ext_s + 8u * (unsigned)T.ext_off;
-    if (lds_f64(base + 8u * l) > p) --l;
-    if (lds_f64(base + 8u * l + 8u) <= p) ++l;
-    if (lds_f64(base + 8u * l + 8u) <= p) ++l;
-    const double a = lds_f64(base + 8u * l), b = lds_f64(base + 8u * l + 8u);
+    if (lds_f64_ro(base + 8u * l) > p) --l;
+    if (lds_f64_ro(base + 8u * l + 8u) <= p) ++l;
+    if (lds_f64_ro(base + 8u * l + 8u) <= p) ++l;
+    const double a = lds_f64_ro(base + 8u * l), b = lds_f64_ro(base + 8u * l + 8u);
     if (a <= p && p < b && fabs(p) <= T.big) {
       const uint32_t pb = eperm_s + 4u * (unsigned)(T.ext_off + l);
-      const int ia = lds_s32(pb), ib = lds_s32(pb + 4u);
+      const int ia = lds_s32_ro(pb), ib = lds_s32_ro(pb + 4u);
       const double da = fabs(a - p), db = fabs(b - p);
       return da < db ? ia : (db < da ? ib : min(ia, ib));
     }

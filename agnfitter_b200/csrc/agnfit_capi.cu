@@ -49,6 +49,11 @@ struct agnf_ctx {
   void* d_perm = nullptr;
   bool have_z = false, have_src = false;
 
+  // small-batch path of the host variant: one pinned block [params | source_id | lnp] so that a call is one
+  // upload, one launch, one download — all truly asynchronous — instead of three pageable copies
+  void* pin = nullptr;                          // cudaHostAlloc
+  void* pin_dev = nullptr;                      // device mirror of the block
+  int64_t small_rows = 4096;                    // batches up to this many rows take the path (0: off)
   // host-variant staging
   void* st_params = nullptr; size_t st_params_cap = 0;
   void* st_sid = nullptr;    size_t st_sid_cap = 0;
@@ -318,6 +323,7 @@ AGNF_API void agnf_ctx_destroy(agnf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->owned) cudaFree(p);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
   for (int i = 0; i < 3; ++i) {
     if (ctx->pipe[i]) cudaStreamSynchronize(ctx->pipe[i]);
     if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
@@ -376,6 +382,16 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     ctx->ens_fused = (int)value;
     return 0;
   }
+  if (strcmp(name, "small_rows") == 0) {
+    if (value < 0 || value > (1 << 20)) return fail(ctx, "small_rows must be in [0, 2^20]");
+    if (ctx->pin && value > ctx->small_rows) {          // the pinned block was sized for the old limit
+      cudaFreeHost(ctx->pin);
+      dev_free(ctx, ctx->pin_dev);
+      ctx->pin = ctx->pin_dev = nullptr;
+    }
+    ctx->small_rows = value;
+    return 0;
+  }
   if (strcmp(name, "pipeline_rows") == 0) {
     if (value < 0) return fail(ctx, "pipeline_rows must be >= 0");
     ctx->pipeline_rows = value;
@@ -390,6 +406,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "k1_last_kernel") == 0) *value = ctx->last_k1_kernel;
   else if (strcmp(name, "band_pitch") == 0) *value = ctx->have_cfg ? ctx->k1.nbp : 0;
   else if (strcmp(name, "pipeline_rows") == 0) *value = ctx->pipeline_rows;
+  else if (strcmp(name, "small_rows") == 0) *value = ctx->small_rows;
   else if (strcmp(name, "ens_fused") == 0) *value = ctx->ens_fused;
   else if (strcmp(name, "ens_source_offset") == 0) *value = ctx->ens_src_offset;
   else return fail(ctx, "unknown option '%s'", name);
@@ -605,6 +622,30 @@ AGNF_API int agnf_lnprob_batch(agnf_ctx* ctx, const double* params, const int32_
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (check_ready(ctx)) return 1;
   const size_t nb = ctx->k1.cfg.n_b, np = ctx->k1.cfg.n_par, nf = ctx->k1.cfg.n_fam, N = (size_t)n;
+  if (!rows && !ymodel && !lnprior && !lnlike && ctx->small_rows > 0 && n <= ctx->small_rows) {
+    // what a sampler sends per call (emcee: one half-ensemble; ultranest: a few hundred points)
+    const size_t cap = (size_t)ctx->small_rows;
+    const size_t off_sid = cap * AGNF_MAX_PARS * 8, off_out = off_sid + cap * 4, bytes = off_out + cap * 8;
+    if (!ctx->pin) {
+      CUDA_TRY(ctx, cudaHostAlloc(&ctx->pin, bytes, cudaHostAllocDefault));
+      if (dev_alloc(ctx, &ctx->pin_dev, bytes)) return 1;
+    }
+    char* h = static_cast<char*>(ctx->pin);
+    char* d = static_cast<char*>(ctx->pin_dev);
+    // pack [params | source_id] contiguously so that ONE copy carries both (lnp comes back from the tail)
+    const size_t pbytes = N * np * 8, pb16 = (pbytes + 15) & ~(size_t)15;
+    memcpy(h, params, pbytes);
+    memcpy(h + pb16, source_id, N * 4);
+    cudaStream_t s1 = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d, h, pb16 + N * 4, cudaMemcpyHostToDevice, s1));
+    if (agnf_lnprob_batch_device(ctx, reinterpret_cast<const double*>(d), reinterpret_cast<const int32_t*>(d + pb16), n,
+                                 reinterpret_cast<double*>(d + off_out), nullptr, nullptr, nullptr, nullptr, s1))
+      return 1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h + off_out, d + off_out, N * 8, cudaMemcpyDeviceToHost, s1));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s1));
+    memcpy(lnp, h + off_out, N * 8);
+    return 0;
+  }
   if (ensure(ctx, &ctx->st_params, &ctx->st_params_cap, N * np * sizeof(double))) return 1;
   if (ensure(ctx, &ctx->st_sid, &ctx->st_sid_cap, N * sizeof(int32_t))) return 1;
   // output staging: lnp | lnprior | lnlike | ymodel | rows

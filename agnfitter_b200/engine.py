@@ -214,11 +214,19 @@ class DictBuilder:
         else:
             out = np.zeros((n_z, T_total, self.n_b), dtype=np.float64)
             out_ptr = ptr(out)
-        # group templates by identical frequency grid (ragged families, e.g. DH02_CE01: 193 / 1366 points)
+        # group templates by identical frequency grid (ragged families, e.g. DH02_CE01: 193 / 1366 points).
+        # Loaders normally hand every template of a family the SAME array object: group by identity first
+        # and compare contents only between the distinct objects.
+        vals = list(templates.values())          # positional access: hashing tuple-of-string keys 10^4 times is slow
+        by_id = {}
+        for t, v in enumerate(vals):
+            by_id.setdefault(id(v[0]), (v[0], []))[1].append(t)
         groups = {}
-        for t, k in enumerate(keys):
-            nu = as_f64(templates[k][0]).reshape(-1)
-            groups.setdefault(nu.tobytes(), (nu, []))[1].append(t)
+        for arr, members in by_id.values():
+            nu = as_f64(arr).reshape(-1)
+            groups.setdefault(nu.tobytes(), (nu, []))[1].extend(members)
+        for _, members in groups.values():
+            members.sort()
         self.contract_ms = 0.0
         for nu, members in groups.values():
             lam = (_C / (10 ** nu) * _ANG)[::-1]                       # DICTIONARIES:450-451 without (1+z)
@@ -226,9 +234,10 @@ class DictBuilder:
             lam_sorted = as_f64(lam[order])
             n_lam = len(nu)
             perm = as_i32((n_lam - 1) - order)                          # column in the stored (unreversed) Fnu
-            F = np.empty((len(members), n_lam), dtype=np.float64)
-            for i, t in enumerate(members):
-                F[i] = np.asarray(templates[keys[t]][1], dtype=np.float64).reshape(-1)
+            F = np.concatenate([vals[t][1] for t in members], axis=None)
+            if F.size != len(members) * n_lam:
+                raise ValueError("a template's flux array does not match its frequency grid")
+            F = np.ascontiguousarray(F.reshape(len(members), n_lam), dtype=np.float64)
             identity = (len(members) == T_total)
             row_map = None if identity else as_i64(members)
             self.ctx.check(self.lib.agnf_dict_build(

@@ -321,6 +321,19 @@ def run_ours(args):
                         acceptance=float(acc.mean() / (args.ensemble_steps + 2)))
         del ens
 
+    # ---- the drop-in's own call shape: emcee hands ONE source's half-ensemble (W/2 rows) per call ----------
+    small_calls = {}
+    for rows_per_call in (W // 2, 16 * W):
+        sp_, ss_ = np.ascontiguousarray(pars[:rows_per_call]), np.ascontiguousarray(sid[:rows_per_call])
+        out_ = np.empty(rows_per_call)
+        for _ in range(20):
+            eng.lnprob(sp_, ss_, out=out_)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            eng.lnprob(sp_, ss_, out=out_)
+        small_calls["%d_rows" % rows_per_call] = {"us_per_call": (time.perf_counter() - t0) / 200 * 1e6}
+        small_calls["%d_rows" % rows_per_call]["evals_per_s"] = rows_per_call / small_calls["%d_rows" % rows_per_call]["us_per_call"] * 1e6
+
     # ---- end to end through the host-buffer entry point ----------------------------------------
     np_pars, np_sid, np_lnp = h_pars.numpy(), h_sid.numpy(), h_lnp.numpy()
     for _ in range(2):
@@ -395,6 +408,8 @@ def run_ours(args):
                              "sample": "oracle/agn_oracle.ln_probab on %d of the %d sources x %d walkers, vectorised "
                                        "over a source's walkers, fork Pool over sources" % (ns, S, W),
                              "one_core": cpu_one},
+            "small_batch": dict(small_calls, what="agnf_lnprob_batch (host buffers, pinned staging block), one call per batch: the "
+                                            "shape emcee (vectorize=True, one source) and ultranest produce"),
             "ensemble": None if not ens_info else {
                 "what": "agnf_ens_run: lock-step stretch moves for every source of the shard, walkers resident in "
                         "HBM; one fused launch per half-step (propose -> ln_probab -> accept inside k1_coop_kernel)",

@@ -130,6 +130,8 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
  * and "band_pitch" (n_b rounded up to even: the pitch to ask agnf_dict_build for).
  * "pipeline_rows" (default 2^20): agnf_lnprob_batch with only lnp requested cuts batches larger than
  * this into chunks whose upload / kernel / download overlap on three streams; 0 = one shot.
+ * "small_rows" (default 4096): batches of at most this many rows (what emcee / ultranest send per call) go
+ * through one pinned staging block — one upload, one launch, one download; 0 = off.
  * "ens_fused" (default 1): agnf_ens_run issues one fused launch per half-step (the cooperative K1 kernel
  * draws the proposal, evaluates it and applies the acceptance rule in place); 0 = separate propose / K1 /
  * accept kernels (same chain, bit for bit).

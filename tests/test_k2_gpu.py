@@ -90,3 +90,29 @@ def test_k2_dense_zgrid_linearity_and_row_map():
     c = builder.build_family(rag, z[:7])
     full_sub = builder.build_family({k: v for i, (k, v) in enumerate(to.items()) if i % 2 == 0}, z[:7])
     assert np.array_equal(c[:, 0::2], full_sub)
+
+
+def test_k2_full_dense_zgrid_is_slice_independent():
+    """BASELINE config C5: z = arange(0, 6, 0.001) (6 000 slices).  Size-independent properties at full size:
+    every slice of the dense build equals, bit for bit, the same slice built on its own (the batching of
+    z-slices inside the tiled kernel must not leak between slices), and sampled entries match the oracle."""
+    fd = synth.synthetic_filterdict()
+    builder = DictBuilder(fd, device=0)
+    tpl = synth.synthetic_templates()
+    keys = list(tpl["GA"]["F"].keys())[::10]                     # 1 100 galaxy templates
+    sub = {k: tpl["GA"]["F"][k] for k in keys}
+    z = np.round(np.arange(0.0, 6.0, 0.001), 3)
+    dense = builder.build_family(sub, z, on_device=True)          # [6000, 1100, 18] stays in HBM
+    assert tuple(dense.shape) == (6000, len(keys), 18)
+    rng = np.random.default_rng(2)
+    for zi in sorted(rng.choice(len(z), size=12, replace=False)) + [0, 1, 2, 3, 5997, 5998, 5999]:
+        alone = builder.build_family(sub, z[zi:zi + 1])[0]
+        assert np.array_equal(dense[zi].cpu().numpy(), alone), "slice %d depends on its neighbours" % zi
+    bands = fd[0]
+    lam = [np.asarray(fd[1][b][0]) for b in bands]
+    fac = [np.asarray(fd[2][b][0]) for b in bands]
+    for zi, ti in zip(rng.choice(len(z), size=25), rng.choice(len(keys), size=25)):
+        want = O.filtering_models(sub[keys[ti]][0], sub[keys[ti]][1], bands, lam, fac, float(z[zi]))
+        got = dense[zi, ti].cpu().numpy()
+        assert np.array_equal(got == 0.0, want == 0.0)
+        assert_close_with_specials(got, want, what="z=%g t=%d" % (z[zi], ti))

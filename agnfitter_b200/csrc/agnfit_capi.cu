@@ -72,6 +72,8 @@ struct agnf_ctx {
   double* ens_best_lnp = nullptr;
   int64_t ens_step = 0;              // stretch-move steps taken since agnf_ens_create (Philox counter)
   int ens_fused = 1;                 // 1: one fused K1 launch per half-step; 0: propose / K1 / accept kernels
+  int k2_shared_window = 1;          // 1: 4 z-slices share each template read when the family allows it
+  int k2_last_kernel = 0;            // contraction of the last agnf_dict_build: 1 per-slice kernels, 2 shared-window
   int64_t ens_src_offset = 0;        // catalogue row of the shard's first source (Philox counter)
   int64_t ens_hist_samples = 0;
 };
@@ -377,6 +379,11 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     if (ctx->have_ens) ctx->ens.src_offset = value;
     return 0;
   }
+  if (strcmp(name, "k2_shared_window") == 0) {
+    if (value != 0 && value != 1) return fail(ctx, "k2_shared_window must be 0 or 1");
+    ctx->k2_shared_window = (int)value;
+    return 0;
+  }
   if (strcmp(name, "ens_fused") == 0) {
     if (value != 0 && value != 1) return fail(ctx, "ens_fused must be 0 or 1");
     ctx->ens_fused = (int)value;
@@ -408,6 +415,8 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "pipeline_rows") == 0) *value = ctx->pipeline_rows;
   else if (strcmp(name, "small_rows") == 0) *value = ctx->small_rows;
   else if (strcmp(name, "ens_fused") == 0) *value = ctx->ens_fused;
+  else if (strcmp(name, "k2_shared_window") == 0) *value = ctx->k2_shared_window;
+  else if (strcmp(name, "k2_last_kernel") == 0) *value = ctx->k2_last_kernel;
   else if (strcmp(name, "ens_source_offset") == 0) *value = ctx->ens_src_offset;
   else return fail(ctx, "unknown option '%s'", name);
   return 0;
@@ -772,9 +781,11 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
 
   void *d_lam = nullptr, *d_perm = nullptr, *d_F = nullptr, *d_Fs = nullptr, *d_z = nullptr, *d_jlo = nullptr,
        *d_cnt = nullptr, *d_rmax = nullptr, *d_W = nullptr, *d_rowmap = nullptr, *d_out = nullptr, *d_woff = nullptr,
-       *d_bandof = nullptr, *d_border = nullptr;
+       *d_bandof = nullptr, *d_border = nullptr, *d_jb = nullptr, *d_cb = nullptr, *d_rmaxA = nullptr,
+       *d_woffA = nullptr, *d_bandofA = nullptr, *d_WA = nullptr;
   auto cleanup = [&]() {
-    for (void* q : {d_lam, d_perm, d_F, d_Fs, d_z, d_jlo, d_cnt, d_rmax, d_W, d_rowmap, d_woff, d_bandof, d_border})
+    for (void* q : {d_lam, d_perm, d_F, d_Fs, d_z, d_jlo, d_cnt, d_rmax, d_W, d_rowmap, d_woff, d_bandof, d_border,
+                    d_jb, d_cb, d_rmaxA, d_woffA, d_bandofA, d_WA})
       dev_free(ctx, q);
     if (!out_on_device) dev_free(ctx, d_out);
   };
@@ -854,9 +865,6 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   p.woff = static_cast<const int32_t*>(d_woff);
   p.band_of = static_cast<const int32_t*>(d_bandof);
   p.tile_ok = 1;
-  K2_ALLOC(d_W, (size_t)n_z * wstride * 8);
-  p.W = static_cast<double*>(d_W);
-  K2_TRY(launch_k2_weights(p, st));
   const size_t out_count = (size_t)n_z * (size_t)T_total * (size_t)n_b;
   if (out_on_device) {
     d_out = out;
@@ -865,6 +873,53 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
     if (row_map) K2_TRY(cudaMemcpyAsync(d_out, out, out_count * 8, cudaMemcpyHostToDevice, st));  // keep other rows
   }
   p.out = static_cast<double*>(d_out);
+  // shared-window plan: 4 consecutive slices share each read of the template window.  A non-finite template
+  // sample would leak into the neighbouring slices through 0 * inf, so such families take the per-slice kernels.
+  bool finite = ctx->k2_shared_window != 0;
+  for (int64_t i = 0, n = T * (int64_t)n_lam; finite && i < n; ++i) finite = std::isfinite(Fnu[i]);
+  if (finite) {
+    p.n_zb = (n_z + 3) / 4;
+    K2_ALLOC(d_jb, (size_t)p.n_zb * n_b * 4);
+    K2_ALLOC(d_cb, (size_t)p.n_zb * n_b * 4);
+    K2_ALLOC(d_rmaxA, (size_t)n_b * 4);
+    K2_TRY(cudaMemsetAsync(d_rmaxA, 0, (size_t)n_b * 4, st));
+    p.jb = static_cast<int32_t*>(d_jb);
+    p.cb = static_cast<int32_t*>(d_cb);
+    p.d_rmaxbA = static_cast<int32_t*>(d_rmaxA);
+    K2_TRY(launch_k2_batch_ranges(p, st));
+    std::vector<int32_t> rmaxA((size_t)n_b), woffA((size_t)n_b + 1, 0);
+    K2_TRY(cudaMemcpyAsync(rmaxA.data(), d_rmaxA, (size_t)n_b * 4, cudaMemcpyDeviceToHost, st));
+    K2_TRY(cudaStreamSynchronize(st));
+    for (int b = 0; b < n_b; ++b) woffA[(size_t)b + 1] = woffA[(size_t)b] + std::max(rmaxA[(size_t)b], 1);
+    p.wstrideA = woffA[(size_t)n_b];
+    p.sw_ok = 1;
+    if (k2_sw_fits(p)) {
+      std::vector<int32_t> band_ofA((size_t)p.wstrideA, -1);
+      for (int b = 0; b < n_b; ++b)
+        for (int32_t k = woffA[(size_t)b]; k < woffA[(size_t)b + 1]; ++k) band_ofA[(size_t)k] = b;
+      std::stable_sort(border.begin(), border.end(),
+                       [&](int32_t x, int32_t y) { return rmaxA[(size_t)x] > rmaxA[(size_t)y]; });
+      K2_TRY(cudaMemcpyAsync(d_border, border.data(), (size_t)n_b * 4, cudaMemcpyHostToDevice, st));
+      K2_ALLOC(d_woffA, ((size_t)n_b + 1) * 4);
+      K2_ALLOC(d_bandofA, (size_t)p.wstrideA * 4);
+      K2_TRY(cudaMemcpyAsync(d_woffA, woffA.data(), ((size_t)n_b + 1) * 4, cudaMemcpyHostToDevice, st));
+      K2_TRY(cudaMemcpyAsync(d_bandofA, band_ofA.data(), (size_t)p.wstrideA * 4, cudaMemcpyHostToDevice, st));
+      p.woffA = static_cast<const int32_t*>(d_woffA);
+      p.band_ofA = static_cast<const int32_t*>(d_bandofA);
+      K2_ALLOC(d_WA, (size_t)p.n_zb * p.wstrideA * 32);
+      p.WA = static_cast<double*>(d_WA);
+      K2_TRY(launch_k2_weights_aligned(p, st));
+      K2_TRY(cudaStreamSynchronize(st));      // the host vectors above feed asynchronous copies
+    } else {
+      p.sw_ok = 0;
+    }
+  }
+  if (!p.sw_ok) {
+    K2_ALLOC(d_W, (size_t)n_z * wstride * 8);
+    p.W = static_cast<double*>(d_W);
+    K2_TRY(launch_k2_weights(p, st));
+  }
+  ctx->k2_last_kernel = p.sw_ok ? 2 : 1;
   K2_TRY(cudaEventRecord(ctx->ev2, st));
   K2_TRY(launch_k2_contract(p, st));
   K2_TRY(cudaEventRecord(ctx->ev3, st));

@@ -1,6 +1,8 @@
 // K2 — dictionary build kernels (see k2_dictbuild.cuh for the mapping to the reference).
 #include "k2_dictbuild.cuh"
 
+#include <climits>
+
 namespace agnf {
 
 namespace {
@@ -56,6 +58,35 @@ __global__ void k2_ranges_kernel(K2Problem p) {
   atomicMax(p.d_rmaxb + b, c);
 }
 
+// weight of template sample j in band b at redshift index zi (j inside the band's window at that z)
+__device__ __forceinline__ double band_weight(const K2Problem& p, int zi, int b, int j) {
+  const int n = p.n_lam;
+  const double zp1 = __dadd_rn(1.0, __ldg(p.z + zi));
+  const double* __restrict__ fl = p.filt.lam;
+  const int64_t o0 = __ldg(p.filt.off + b), o1 = __ldg(p.filt.off + b + 1);
+  // samples that resample to j: searchsorted(mid, lam, 'left') == j  <=>  mid[j-1] < lam <= mid[j],
+  // and inside [x_0, x_last] (everything else is filled with 0).
+  int64_t lo = o0, hi = o1;
+  if (j == 0) {
+    const double x0 = x_at(p.lam0, 0, zp1);
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (__ldg(fl + m) < x0) lo = m + 1; else hi = m; }
+  } else {
+    const double thr = mid_at(p.lam0, j - 1, zp1);
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (__ldg(fl + m) <= thr) lo = m + 1; else hi = m; }
+  }
+  const int64_t i0 = lo;
+  const double up = (j == n - 1) ? x_at(p.lam0, n - 1, zp1) : mid_at(p.lam0, j, zp1);
+  lo = i0;
+  hi = o1;
+  while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (__ldg(fl + m) <= up) lo = m + 1; else hi = m; }
+  const int64_t i1 = lo;
+  double s = 0.0;
+  for (int64_t i = i0; i < i1; ++i) s += __ldg(p.filt.wn + i);
+  const double xj = x_at(p.lam0, j, zp1);
+  const double q = 1.0 / (xj * xj) * C_LIGHT * ANGSTROM;     // F_nu -> F_lambda at lam_j
+  return (q * s) * __ldg(p.filt.scale + b);
+}
+
 // One thread per (z, slot): the weight of template sample j = j_lo + r in band b at redshift z.
 __global__ void k2_weights_kernel(K2Problem p) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,35 +99,53 @@ __global__ void k2_weights_kernel(K2Problem p) {
   double w = 0.0;
   const int r = b >= 0 ? slot - __ldg(p.woff + b) : 0;
   const int zb = zi * n_b + (b >= 0 ? b : 0);
-  if (b >= 0 && r < __ldg(p.cnt + zb)) {
-    const int j = __ldg(p.jlo + zb) + r;
-    const int n = p.n_lam;
-    const double zp1 = __dadd_rn(1.0, __ldg(p.z + zi));
-    const double* __restrict__ fl = p.filt.lam;
-    const int64_t o0 = __ldg(p.filt.off + b), o1 = __ldg(p.filt.off + b + 1);
-    // samples that resample to j: searchsorted(mid, lam, 'left') == j  <=>  mid[j-1] < lam <= mid[j],
-    // and inside [x_0, x_last] (everything else is filled with 0).
-    int64_t lo = o0, hi = o1;
-    if (j == 0) {
-      const double x0 = x_at(p.lam0, 0, zp1);
-      while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (__ldg(fl + m) < x0) lo = m + 1; else hi = m; }
-    } else {
-      const double thr = mid_at(p.lam0, j - 1, zp1);
-      while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (__ldg(fl + m) <= thr) lo = m + 1; else hi = m; }
-    }
-    const int64_t i0 = lo;
-    const double up = (j == n - 1) ? x_at(p.lam0, n - 1, zp1) : mid_at(p.lam0, j, zp1);
-    lo = i0;
-    hi = o1;
-    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (__ldg(fl + m) <= up) lo = m + 1; else hi = m; }
-    const int64_t i1 = lo;
-    double s = 0.0;
-    for (int64_t i = i0; i < i1; ++i) s += __ldg(p.filt.wn + i);
-    const double xj = x_at(p.lam0, j, zp1);
-    const double q = 1.0 / (xj * xj) * C_LIGHT * ANGSTROM;     // F_nu -> F_lambda at lam_j
-    w = (q * s) * __ldg(p.filt.scale + b);
-  }
+  if (b >= 0 && r < __ldg(p.cnt + zb)) w = band_weight(p, zi, b, __ldg(p.jlo + zb) + r);
   p.W[idx] = w;
+}
+
+// Shared-window path.  One thread per (batch, band): the window all 4 slices of the batch see together.
+__global__ void k2_batch_ranges_kernel(K2Problem p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_b = p.filt.n_b;
+  if (idx >= p.n_zb * n_b) return;
+  const int zb = idx / n_b, b = idx - zb * n_b;
+  int lo = INT_MAX, hi = 0;
+  for (int zl = 0; zl < 4; ++zl) {
+    const int z = 4 * zb + zl;
+    if (z >= p.n_z) break;
+    const int c = __ldg(p.cnt + z * n_b + b);
+    if (c > 0) {
+      const int j = __ldg(p.jlo + z * n_b + b);
+      lo = min(lo, j);
+      hi = max(hi, j + c);
+    }
+  }
+  const int c = hi > lo ? hi - lo : 0;
+  p.jb[idx] = c ? lo : 0;
+  p.cb[idx] = c;
+  atomicMax(p.d_rmaxbA + b, c);
+}
+
+// One thread per (batch, slot, slice): weights re-aligned to the batch window, 4 slices interleaved.
+__global__ void k2_weights_aligned_kernel(K2Problem p) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_b = p.filt.n_b;
+  const int64_t total = (int64_t)p.n_zb * p.wstrideA * 4;
+  if (idx >= total) return;
+  const int zl = (int)(idx & 3);
+  const int64_t q = idx >> 2;
+  const int slot = (int)(q % p.wstrideA);
+  const int zb = (int)(q / p.wstrideA);
+  const int z = 4 * zb + zl;
+  const int b = __ldg(p.band_ofA + slot);
+  double w = 0.0;
+  if (b >= 0 && z < p.n_z) {
+    const int j = __ldg(p.jb + zb * n_b + b) + (slot - __ldg(p.woffA + b));
+    const int r = j - __ldg(p.jlo + z * n_b + b);
+    if (r >= 0 && r < __ldg(p.cnt + z * n_b + b) && slot - __ldg(p.woffA + b) < __ldg(p.cb + zb * n_b + b))
+      w = band_weight(p, z, b, j);
+  }
+  p.WA[idx] = w;
 }
 
 // Banded contraction.  grid = (n_z, ceil(T / K2_TILE_T)); the z-slice's weights are staged in
@@ -307,6 +356,166 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_tile_kernel(K2Prob
   }
 }
 
+// ---- shared-window contraction --------------------------------------------------------------------
+// The tiled kernel above spends 3 shared-memory wavefronts per warp-FMA (2 for the template sample, 1 for the
+// broadcast weight).  Consecutive z-slices see almost the same template samples (dz = 0.001 moves a band by a
+// fraction of a sample), so here a batch of 4 slices shares every read: per sample of the batch window one
+// LDS.64 of the template value and two broadcast LDS.128 of the 4 interleaved weights feed 4 FMAs
+// (1 wavefront per warp-FMA, 1.75 instructions).  Every slice keeps ONE accumulator that runs over the window
+// in ascending sample order; samples outside the slice's own window carry weight 0 and leave the sum
+// unchanged, so a slice's result does not depend on which slices share its batch (bit for bit).
+// A round is nb batches (4 nb slices): its (band, batch) units are dealt to the 16 warps longest band first
+// in snake order; weights of the next round arrive by a bulk copy while this one is computed.
+struct K2SwPlan {
+  int32_t nb;          // batches per round: 1, 2 or 4
+  int32_t nb_shift;
+  int32_t zbc;         // batches per CTA (a multiple of nb)
+  int32_t opitch;      // pitch of a result tile (out_pitch when slices leave by bulk stores, else + 1)
+  int32_t bulk_store;
+  int32_t off_w, off_o, off_bar, smem_bytes;
+};
+
+template <int TT>
+__global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Problem p, K2SwPlan c) {
+  extern __shared__ __align__(16) unsigned char k2_smem[];
+  double* Fs_s = reinterpret_cast<double*>(k2_smem);                        // [TT][ldF]
+  double* W_s = reinterpret_cast<double*>(k2_smem + c.off_w);               // [2][nb][wstrideA][4]
+  double* O_s = reinterpret_cast<double*>(k2_smem + c.off_o);               // [nb][4][TT][opitch]
+  const uint32_t bar = k2_smem_u32(k2_smem + c.off_bar);
+  const int n_b = p.filt.n_b, wsA = p.wstrideA, ldF = p.ldF, pitch = p.out_pitch;
+  constexpr int WARPS = K2T_THREADS / TT;
+  const int tt = threadIdx.x % TT, g = threadIdx.x / TT;
+  const int64_t t0 = (int64_t)blockIdx.y * TT;
+  const int nt = (int)min((int64_t)TT, p.T - t0);
+  const int zb0 = blockIdx.x * c.zbc;
+  const int zb1 = min(zb0 + c.zbc, p.n_zb);
+  const int NB = c.nb;
+  const int n_units = n_b * NB;
+  const size_t wround = (size_t)NB * wsA * 4;                               // doubles per weight buffer
+  if (threadIdx.x == 0) {
+    k2_mbar_init(bar, 1);
+    k2_mbar_init(bar + 8, 1);
+    k2_mbar_init(bar + 16, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < NB * 4 * TT * c.opitch; i += K2T_THREADS) O_s[i] = 0.0;   // pad columns stay zero
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t fbytes = (uint32_t)TT * (uint32_t)ldF * 8u;
+    k2_mbar_expect_tx(bar, fbytes);
+    k2_bulk_g2s(k2_smem_u32(Fs_s), p.Fs + t0 * ldF, fbytes, bar);
+    const uint32_t wbytes = (uint32_t)min(NB, zb1 - zb0) * (uint32_t)wsA * 32u;
+    k2_mbar_expect_tx(bar + 8, wbytes);
+    k2_bulk_g2s(k2_smem_u32(W_s), p.WA + (int64_t)zb0 * wsA * 4, wbytes, bar + 8);
+  }
+  k2_mbar_wait(bar, 0);
+  int ir = 0;
+  for (int zbr = zb0; zbr < zb1; zbr += NB, ++ir) {
+    const int buf = ir & 1;
+    const int nbr = min(NB, zb1 - zbr);
+    if (threadIdx.x == 0 && zbr + NB < zb1) {
+      const uint32_t wbytes = (uint32_t)min(NB, zb1 - zbr - NB) * (uint32_t)wsA * 32u;
+      k2_mbar_expect_tx(bar + 8 + 8 * (buf ^ 1), wbytes);
+      k2_bulk_g2s(k2_smem_u32(W_s + (size_t)(buf ^ 1) * wround), p.WA + (int64_t)(zbr + NB) * wsA * 4, wbytes,
+                  bar + 8 + 8 * (buf ^ 1));
+    }
+    k2_mbar_wait(bar + 8 + 8 * buf, (ir >> 1) & 1);
+    const double* __restrict__ Wb = W_s + (size_t)buf * wround;
+    for (int pass = 0, base = 0; base < n_units; ++pass, base += WARPS) {
+      const int u = base + ((pass & 1) ? (WARPS - 1 - g) : g);
+      if (u >= n_units) continue;
+      const int bi = u & (NB - 1);
+      if (bi >= nbr) continue;
+      const int b = __ldg(p.band_order + (u >> c.nb_shift));
+      const int zb = zbr + bi;
+      const int jbv = __ldg(p.jb + zb * n_b + b);
+      const int rend = __ldg(p.cb + zb * n_b + b);
+      const double* __restrict__ F = Fs_s + tt * ldF + jbv;
+      const double2* __restrict__ w2 =
+          reinterpret_cast<const double2*>(Wb + ((size_t)bi * wsA + (size_t)__ldg(p.woffA + b)) * 4);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+      for (int r = 0; r < rend; ++r) {
+        const double f = F[r];
+        const double2 wa = w2[2 * r], wb = w2[2 * r + 1];
+        a0 = fma(wa.x, f, a0);
+        a1 = fma(wa.y, f, a1);
+        a2 = fma(wb.x, f, a2);
+        a3 = fma(wb.y, f, a3);
+      }
+      double* o = O_s + ((size_t)(bi * 4) * TT + tt) * c.opitch + b;
+      o[0] = a0;
+      o[(size_t)TT * c.opitch] = a1;
+      o[(size_t)2 * TT * c.opitch] = a2;
+      o[(size_t)3 * TT * c.opitch] = a3;
+    }
+    __syncthreads();
+    const int nz = min(4 * nbr, p.n_z - 4 * zbr);          // slices of this round
+    if (c.bulk_store) {
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        for (int zl = 0; zl < nz; ++zl) {
+          double* dst = p.out + ((int64_t)(4 * zbr + zl) * p.T_total + t0) * pitch;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst),
+                       "r"(k2_smem_u32(O_s + (size_t)zl * TT * c.opitch)), "r"((uint32_t)(nt * pitch * 8))
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      }
+    } else {
+      const int per_z = nt * pitch;
+      const int d_tt = K2T_THREADS / pitch, d_col = K2T_THREADS - d_tt * pitch;
+      for (int zl = 0; zl < nz; ++zl) {
+        int t2 = threadIdx.x / pitch, col = threadIdx.x - t2 * pitch;
+        double* __restrict__ dst = p.out + ((int64_t)(4 * zbr + zl) * p.T_total) * pitch;
+        for (int i = threadIdx.x; i < per_z; i += K2T_THREADS) {
+          const int64_t row = p.row_map ? __ldg(p.row_map + t0 + t2) : t0 + t2;
+          dst[row * pitch + col] = O_s[(zl * TT + t2) * c.opitch + col];
+          t2 += d_tt;
+          col += d_col;
+          if (col >= pitch) {
+            col -= pitch;
+            ++t2;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+bool k2_sw_plan(const K2Problem& p, K2SwPlan* c) {
+  constexpr int TT = 32;
+  if (!p.sw_ok || p.wstrideA < 1) return false;
+  const bool bulk = !p.row_map && (p.out_pitch % 2 == 0) && (reinterpret_cast<uintptr_t>(p.out) % 16 == 0);
+  const int opitch = bulk ? p.out_pitch : p.out_pitch + 1;
+  const size_t f = (size_t)TT * p.ldF * 8;
+  const size_t off_w = (f + 15) & ~(size_t)15;
+  for (int nb = 4, sh = 2; nb >= 1; nb >>= 1, --sh) {
+    const size_t off_o = off_w + 2 * (size_t)nb * p.wstrideA * 32;
+    const size_t off_bar = (off_o + (size_t)nb * 4 * TT * opitch * 8 + 15) & ~(size_t)15;
+    const size_t total = off_bar + 32;
+    if (total > 225 * 1024) continue;
+    c->nb = nb;
+    c->nb_shift = sh;
+    c->opitch = opitch;
+    c->bulk_store = bulk ? 1 : 0;
+    c->off_w = (int32_t)off_w;
+    c->off_o = (int32_t)off_o;
+    c->off_bar = (int32_t)off_bar;
+    c->smem_bytes = (int32_t)total;
+    const int64_t tiles = (p.T + TT - 1) / TT;
+    int64_t zbc = ((int64_t)p.n_zb * tiles) / (4 * 148);
+    if (zbc > 16) zbc = 16;
+    zbc = zbc / nb * nb;
+    if (zbc < nb) zbc = nb;
+    c->zbc = (int32_t)zbc;
+    return true;
+  }
+  return false;
+}
+
 bool k2_tile_plan(const K2Problem& p, K2TilePlan* c) {
   if ((p.wstride & 1) || p.wstride < 2) return false;              // bulk copies move 16-byte multiples
   // a dense tile for the bulk store (two-way bank conflicts on the 18 x 32 result writes are cheaper than a
@@ -366,8 +575,36 @@ cudaError_t launch_k2_weights(const K2Problem& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_k2_batch_ranges(const K2Problem& p, cudaStream_t stream) {
+  const int total = p.n_zb * p.filt.n_b;
+  if (total == 0) return cudaSuccess;
+  k2_batch_ranges_kernel<<<(total + 127) / 128, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k2_weights_aligned(const K2Problem& p, cudaStream_t stream) {
+  const int64_t total = (int64_t)p.n_zb * p.wstrideA * 4;
+  if (total == 0) return cudaSuccess;
+  k2_weights_aligned_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+bool k2_sw_fits(const K2Problem& p) {
+  K2SwPlan c;
+  return k2_sw_plan(p, &c);
+}
+
 cudaError_t launch_k2_contract(const K2Problem& p, cudaStream_t stream) {
   if (p.n_z == 0 || p.T == 0) return cudaSuccess;
+  K2SwPlan sc;
+  if (p.tile_ok && k2_sw_plan(p, &sc)) {
+    cudaError_t e = cudaFuncSetAttribute(k2_contract_sw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         sc.smem_bytes);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((p.n_zb + sc.zbc - 1) / sc.zbc), (unsigned)((p.T + 31) / 32));
+    k2_contract_sw_kernel<32><<<grid, K2T_THREADS, (size_t)sc.smem_bytes, stream>>>(p, sc);
+    return cudaGetLastError();
+  }
   K2TilePlan c;
   if (p.tile_ok && k2_tile_plan(p, &c)) {
     dim3 grid((unsigned)((p.n_z + c.zc - 1) / c.zc), (unsigned)((p.T + c.tt - 1) / c.tt));

@@ -20,9 +20,12 @@
 //   k2_ranges    j_lo / cnt per (z, band) and the per-band max cnt       (integer work, bit-exact)
 //   k2_weights   W[z][woff[b] + r]: two binary searches + a short sequential sum per entry; band b owns
 //                rmax_b = max_z cnt[z][b] slots per z-slice (compact: no padding to the widest band)
-//   k2_contract  the banded contraction; writes the [n_z, T, pitch] table K1 gathers from.  The tiled
-//                kernel keeps 32 templates in shared memory across a chunk of z-slices; the per-slice
-//                kernel is the fallback when a slice of weights does not fit (X-ray power-law tails)
+//   k2_contract  the banded contraction; writes the [n_z, T, pitch] table K1 gathers from.  Three kernels:
+//                shared-window (32 templates resident in shared memory; 4 consecutive z-slices share every
+//                read of the template window, their weights re-aligned to the batch's common first sample),
+//                tiled (same tile, one slice at a time: used when a template holds a non-finite sample,
+//                which must not leak into a neighbouring slice), per-slice (fallback when a slice of
+//                weights does not fit shared memory: X-ray power-law tails)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -56,6 +59,16 @@ struct K2Problem {
   const int32_t* band_order = nullptr; // [n_b] bands by descending slot count (work balancing in the tiled kernel)
   double* W = nullptr;              // [n_z, wstride]
   int32_t tile_ok = 0;              // Fs is zero-padded to a multiple of 32 rows: the tiled contraction may be used
+  // shared-window path: 4 consecutive z-slices (a batch) are evaluated from ONE read of the template window
+  int32_t sw_ok = 0;                // every template sample is finite and the plan below was built
+  int32_t n_zb = 0;                 // batches = ceil(n_z / 4)
+  int32_t wstrideA = 0;             // slots per batch (each slot holds the 4 slices' weights)
+  int32_t* jb = nullptr;            // [n_zb, n_b] first template sample any slice of the batch sees in the band
+  int32_t* cb = nullptr;            // [n_zb, n_b] samples from jb to the last one any slice sees
+  int32_t* d_rmaxbA = nullptr;      // [n_b] max over batches of cb
+  const int32_t* woffA = nullptr;   // [n_b + 1]
+  const int32_t* band_ofA = nullptr; // [wstrideA]
+  double* WA = nullptr;             // [n_zb, wstrideA, 4]
   const int64_t* row_map = nullptr; // [T] or nullptr
   int64_t T_total = 0;
   int32_t out_pitch = 0;            // row pitch of out in doubles (>= n_b); pad columns are written as 0
@@ -66,6 +79,9 @@ cudaError_t launch_k2_permute(const double* Fnu, const int32_t* perm, double* Fs
                               int32_t ldF, cudaStream_t stream);
 cudaError_t launch_k2_ranges(const K2Problem& p, cudaStream_t stream);
 cudaError_t launch_k2_weights(const K2Problem& p, cudaStream_t stream);
+cudaError_t launch_k2_batch_ranges(const K2Problem& p, cudaStream_t stream);
+cudaError_t launch_k2_weights_aligned(const K2Problem& p, cudaStream_t stream);
+bool k2_sw_fits(const K2Problem& p);     // the shared-window kernel's tiles fit shared memory
 cudaError_t launch_k2_contract(const K2Problem& p, cudaStream_t stream);
 
 }  // namespace agnf

@@ -195,6 +195,14 @@ class DictBuilder:
             self.ctx.h, self.n_b, ptr(band_lam_c), ptr(off_a), ptr(lam_a), ptr(fac_a)))
         self.contract_ms = 0.0
 
+    def set_option(self, name, value):
+        self.ctx.check(self.lib.agnf_set_option(self.ctx.h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_int64()
+        self.ctx.check(self.lib.agnf_get_option(self.ctx.h, name.encode(), C.byref(v)))
+        return int(v.value)
+
     def build_family(self, templates, z_array, on_device=False):
         """templates: the reference's `*Fdict_4plot` ({key: (log10 nu, Fnu)}, insertion-ordered).
         Returns the band-flux table in key order: a NumPy array [n_z, T, n_b], or with on_device=True

@@ -92,6 +92,39 @@ def test_k2_dense_zgrid_linearity_and_row_map():
     assert np.array_equal(c[:, 0::2], full_sub)
 
 
+def test_k2_shared_window_and_per_slice_kernels_agree():
+    """The shared-window contraction (4 slices per read of the template window) against the per-slice kernels:
+    same zero pattern, values within 1e-13 (different summation grouping), on an even and an odd number of slices,
+    host and device outputs, and a family with an infinite sample falls back to the per-slice kernels."""
+    fd = synth.synthetic_filterdict()
+    builder = DictBuilder(fd, device=0)
+    tpl = synth.synthetic_templates()
+    for fam, nz in (("TO", 37), ("SB", 8), ("BB", 3), ("GA", 6)):
+        F = tpl[fam]["F"]
+        F = {k: F[k] for k in list(F.keys())[:211]}
+        z = np.round(np.linspace(0.0, 5.9, nz), 3)
+        builder.set_option("k2_shared_window", 1)
+        a = builder.build_family(F, z)
+        # the synthetic starburst grid (1 366 samples) does not leave room for a 32-template tile
+        assert builder.get_option("k2_last_kernel") == (1 if fam == "SB" else 2), fam
+        a_dev = builder.build_family(F, z, on_device=True).cpu().numpy()[:, :, :builder.n_b]
+        builder.set_option("k2_shared_window", 0)
+        b = builder.build_family(F, z)
+        assert builder.get_option("k2_last_kernel") == 1
+        builder.set_option("k2_shared_window", 1)
+        assert np.array_equal(a, a_dev), fam
+        assert np.array_equal(a == 0.0, b == 0.0), fam
+        assert_close_with_specials(a, b, rtol=1e-13, what="shared-window vs per-slice " + fam)
+    to = dict(list(tpl["TO"]["F"].items())[:40])
+    k0 = next(iter(to))
+    bad = np.array(to[k0][1], dtype=np.float64).copy()
+    bad[len(bad) // 2] = np.inf
+    to[k0] = (to[k0][0], bad)
+    got = builder.build_family(to, np.array([0.5, 0.501, 0.502, 0.503]))
+    assert builder.get_option("k2_last_kernel") == 1
+    assert np.isfinite(got[:, 1:]).all()
+
+
 def test_k2_full_dense_zgrid_is_slice_independent():
     """BASELINE config C5: z = arange(0, 6, 0.001) (6 000 slices).  Size-independent properties at full size:
     every slice of the dense build equals, bit for bit, the same slice built on its own (the batching of

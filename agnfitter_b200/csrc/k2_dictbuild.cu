@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_tile_kernel(K2Prob
 // unchanged, so a slice's result does not depend on which slices share its batch (bit for bit).
 // A round is nb batches (4 nb slices): its (band, batch) units are dealt to the 16 warps longest band first
 // in snake order; weights of the next round arrive by a bulk copy while this one is computed.
+constexpr int K2_SW_MAX_ROUNDS = 32;
 struct K2SwPlan {
   int32_t nb;          // batches per round: 1, 2 or 4
   int32_t nb_shift;
@@ -381,10 +382,11 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
   double* Fs_s = reinterpret_cast<double*>(k2_smem);                        // [TT][ldF]
   double* W_s = reinterpret_cast<double*>(k2_smem + c.off_w);               // [2][nb][wstrideA][4]
   double* O_s = reinterpret_cast<double*>(k2_smem + c.off_o);               // [nb][4][TT][opitch]
+  // barriers: +0 template tile, +8/+16 weight buffers, +24 "result tile drained"; then one unit counter per round
   const uint32_t bar = k2_smem_u32(k2_smem + c.off_bar);
+  int* next_unit = reinterpret_cast<int*>(k2_smem + c.off_bar + 32);        // [K2_SW_MAX_ROUNDS]
   const int n_b = p.filt.n_b, wsA = p.wstrideA, ldF = p.ldF, pitch = p.out_pitch;
-  constexpr int WARPS = K2T_THREADS / TT;
-  const int tt = threadIdx.x % TT, g = threadIdx.x / TT;
+  const int tt = threadIdx.x % TT;
   const int64_t t0 = (int64_t)blockIdx.y * TT;
   const int nt = (int)min((int64_t)TT, p.T - t0);
   const int zb0 = blockIdx.x * c.zbc;
@@ -396,8 +398,10 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
     k2_mbar_init(bar, 1);
     k2_mbar_init(bar + 8, 1);
     k2_mbar_init(bar + 16, 1);
+    k2_mbar_init(bar + 24, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  if (threadIdx.x < K2_SW_MAX_ROUNDS) next_unit[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < NB * 4 * TT * c.opitch; i += K2T_THREADS) O_s[i] = 0.0;   // pad columns stay zero
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -413,17 +417,26 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
   for (int zbr = zb0; zbr < zb1; zbr += NB, ++ir) {
     const int buf = ir & 1;
     const int nbr = min(NB, zb1 - zbr);
-    if (threadIdx.x == 0 && zbr + NB < zb1) {
-      const uint32_t wbytes = (uint32_t)min(NB, zb1 - zbr - NB) * (uint32_t)wsA * 32u;
-      k2_mbar_expect_tx(bar + 8 + 8 * (buf ^ 1), wbytes);
-      k2_bulk_g2s(k2_smem_u32(W_s + (size_t)(buf ^ 1) * wround), p.WA + (int64_t)(zbr + NB) * wsA * 4, wbytes,
-                  bar + 8 + 8 * (buf ^ 1));
+    if (threadIdx.x == 0) {
+      if (zbr + NB < zb1) {
+        const uint32_t wbytes = (uint32_t)min(NB, zb1 - zbr - NB) * (uint32_t)wsA * 32u;
+        k2_mbar_expect_tx(bar + 8 + 8 * (buf ^ 1), wbytes);
+        k2_bulk_g2s(k2_smem_u32(W_s + (size_t)(buf ^ 1) * wround), p.WA + (int64_t)(zbr + NB) * wsA * 4, wbytes,
+                    bar + 8 + 8 * (buf ^ 1));
+      }
+      if (ir > 0 && c.bulk_store) {      // the previous round's result tile has left shared memory: release it
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar + 24) : "memory");
+      }
     }
     k2_mbar_wait(bar + 8 + 8 * buf, (ir >> 1) & 1);
     const double* __restrict__ Wb = W_s + (size_t)buf * wround;
-    for (int pass = 0, base = 0; base < n_units; ++pass, base += WARPS) {
-      const int u = base + ((pass & 1) ? (WARPS - 1 - g) : g);
-      if (u >= n_units) continue;
+    // units (band, batch of the round), longest band first, handed out through a shared counter
+    for (;;) {
+      int u = 0;
+      if (tt == 0) u = atomicAdd(next_unit + ir, 1);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= n_units) break;
       const int bi = u & (NB - 1);
       if (bi >= nbr) continue;
       const int b = __ldg(p.band_order + (u >> c.nb_shift));
@@ -443,6 +456,7 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
         a2 = fma(wb.x, f, a2);
         a3 = fma(wb.y, f, a3);
       }
+      if (ir > 0 && c.bulk_store) k2_mbar_wait(bar + 24, (ir - 1) & 1);
       double* o = O_s + ((size_t)(bi * 4) * TT + tt) * c.opitch + b;
       o[0] = a0;
       o[(size_t)TT * c.opitch] = a1;
@@ -461,7 +475,6 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
                        : "memory");
         }
         asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
       }
     } else {
       const int per_z = nt * pitch;
@@ -480,9 +493,10 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
           }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
+  if (c.bulk_store && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
 }
 
 bool k2_sw_plan(const K2Problem& p, K2SwPlan* c) {
@@ -495,7 +509,7 @@ bool k2_sw_plan(const K2Problem& p, K2SwPlan* c) {
   for (int nb = 4, sh = 2; nb >= 1; nb >>= 1, --sh) {
     const size_t off_o = off_w + 2 * (size_t)nb * p.wstrideA * 32;
     const size_t off_bar = (off_o + (size_t)nb * 4 * TT * opitch * 8 + 15) & ~(size_t)15;
-    const size_t total = off_bar + 32;
+    const size_t total = off_bar + 32 + K2_SW_MAX_ROUNDS * 4;
     if (total > 225 * 1024) continue;
     c->nb = nb;
     c->nb_shift = sh;
@@ -506,8 +520,8 @@ bool k2_sw_plan(const K2Problem& p, K2SwPlan* c) {
     c->off_bar = (int32_t)off_bar;
     c->smem_bytes = (int32_t)total;
     const int64_t tiles = (p.T + TT - 1) / TT;
-    int64_t zbc = ((int64_t)p.n_zb * tiles) / (4 * 148);
-    if (zbc > 16) zbc = 16;
+    int64_t zbc = ((int64_t)p.n_zb * tiles) / (8 * 148);
+    if (zbc > K2_SW_MAX_ROUNDS) zbc = K2_SW_MAX_ROUNDS;      // rounds per CTA <= zbc / nb <= K2_SW_MAX_ROUNDS
     zbc = zbc / nb * nb;
     if (zbc < nb) zbc = nb;
     c->zbc = (int32_t)zbc;

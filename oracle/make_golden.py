@@ -4,6 +4,7 @@ functions (through oracle/ref_shim.py + oracle/ref_harness.py) on the real templ
 filter files under /root/reference.  Run in the build container only:
 
     python -m oracle.make_golden            # writes tests/golden/k1_*.npz, k2_*.npz
+    python -m oracle.make_golden sed        # writes tests/golden/sed_*.npz (SED realisations)
 
 Each K1 file holds: the flattened ModelSet (agnfitter_b200.flatten arrays), the raw
 per-source rows (nus, fluxes, fluxerrs, z, dlum), the reference's P['min']/P['max'],
@@ -330,7 +331,87 @@ def k2_families_case(name, filterset, zs):
     k2_write(name, fd, fnames, zs, fams, DIC)
 
 
+SED_MODELS = ['sb', 'bbb', 'bbbdered', 'gal', 'AGNfrac_opt', 'tor', 'tor+bbb', 'AGNfrac_IR', 'gal', 'bbb',
+              'AGNfrac_opt', 'tor', 'sb', 'tor+bbb', 'AGNfracTO', 'AGNfrac75-20mu', 'AGNfrac0.5-0.3mu']
+# first 13 rows: example/SETTINGS_AGNfitter.py:316-321 (microns)
+SED_RANGES_UM = [[8., 1000.], [0.1, 1.], [0.1, 1.], [0.1, 1.], [0.1, 1.], [1., 30.], [0.1, 30], [8., 1000.],
+                 [0.4, 0.5], [0.4, 0.5], [0.4, 0.5], [6, 6], [1., 30.], [12., 12.], [1., 100.], [20., 75.], [0.3, 0.5]]
+
+
+def sed_case(name, settings, filterset, zs, nR=0, nX=0, galaxy_ebv="grid", extra=(), n_real=10, seed=41, stride=7):
+    """SED realisations + integrated luminosities: the reference's own FLUXES_ARRAYS.fluxes
+    (PLOTandWRITE_AGNfitter.py:566-799) on rows drawn from a synthetic flat chain, for every source of the case.
+    Stores the model set, the full-resolution templates, the rows, nuLnu on every `stride`-th frequency and the
+    integrated luminosities (log10, as the reference keeps them)."""
+    from agnfitter_b200 import plotset
+    mods = ref_shim.install()
+    rng = np.random.default_rng(seed)
+    fd, fnames = loaders.make_filterdict(filterset, loaders.load_all_filters())
+    data_nus = loaders.data_nus_for(filterset)
+    n_b = len(fd[0])
+    gk = dict(age_slice=[0, 12, 24], tau_slice=[0, 10])
+    sk = dict(tdust_slice=range(0, 150, 30), fracpah_slice=range(0, 64, 16))
+    im = SED_MODELS + [e[0] for e in extra]
+    ir = np.array(SED_RANGES_UM + [e[1] for e in extra], dtype=np.float64)
+    MDs, pars_all, sid_all, nl_all, il_all, pmin, pmax, dl = [], [], [], [], [], [], [], []
+    for s, z in enumerate(zs):
+        MD = H.build_reference_dictionary(z, fd, settings, nRADdata=nR, nXRaysdata=nX, galaxy_ebv=galaxy_ebv,
+                                          galaxy_kw=gk, starburst_kw=sk)
+        MDs.append(MD)
+        models = H.make_models_4plot(MD, settings)
+        d = H.make_data(z, data_nus, np.ones(n_b) * 1e-27, np.ones(n_b) * 1e-28)
+        P = mods["PAR"].Pdict(d, models)
+        chain = rng.uniform(P['min'], P['max'], size=(200, len(P['min'])))
+        rows, nus, nuLnus, il = H.reference_fluxes(d, models, P, chain, chain[17], im, ir, n_real, seed + s)
+        pars_all.append(rows)
+        sid_all.append(np.full(len(rows), s, dtype=np.int32))
+        nl_all.append(np.stack([a[:, ::stride] for a in nuLnus], axis=1))       # [R, n_comp, G/stride]
+        il_all.append(il.T)                                                      # [R, n_models]
+        pmin.append(P['min'])
+        pmax.append(P['max'])
+        dl.append(d.dlum)
+    ms = flatten.modelset_from_modelsdicts(MDs, settings)
+    ps = plotset.plotset_from_modelsdict(MDs[0], ms)
+    arrs = flatten.modelset_to_arrays(ms, prefix="ms_")
+    arrs.update(plotset.plotset_to_arrays(ps))
+    arrs.update(dict(
+        src_z=np.array(zs, dtype=np.float64), src_dlum=np.array(dl), src_nus=np.tile(data_nus, (len(zs), 1)),
+        src_fluxes=np.full((len(zs), n_b), 1e-27), src_fluxerrs=np.full((len(zs), n_b), 1e-28),
+        ref_pmin=np.array(pmin, dtype=np.float64), ref_pmax=np.array(pmax, dtype=np.float64),
+        pars=np.concatenate(pars_all), source_id=np.concatenate(sid_all),
+        intlum_models=np.array(im), intlum_ranges_um=ir, intlum_ranges_hz=H.intlum_ranges_hz(ir),
+        all_nus_rest=nus, stride=np.array(stride),
+        ref_nuLnu=np.concatenate(nl_all), ref_int_lums=np.concatenate(il_all)))
+    path = os.path.join(OUT, "sed_%s.npz" % name)
+    np.savez_compressed(path, **arrs)
+    print("%-22s S=%d rows=%d G=%d comps=%d models=%d T=%s -> %.2f MB" % (
+        name, len(zs), len(arrs["pars"]), len(nus), arrs["ref_nuLnu"].shape[1], len(im),
+        [f.T for f in ms.families], os.path.getsize(path) / 1e6))
+
+
+def sed_main():
+    os.makedirs(OUT, exist_ok=True)
+    base = dict(H.DEFAULT_SETTINGS)
+    # classic model set: R06 disc with free E(B-V) (dereddened curve = template '0.0'), ragged DH02_CE01 grids
+    sed_case("classic18", base, loaders.FILTERSET_DEFAULT, [0.283, 1.58])
+    # free E(B-V)_gal (Calzetti on the full template), X-ray extended disc interpolated in two parts, S17 starburst
+    sed_case("freeebv_xray49", dict(base, STARBURST='S17', XRAYS=True), loaders.FILTERSET_EXAMPLE49, [0.129],
+             nX=1, galaxy_ebv="free", seed=43)
+    # X-ray disc with the Gamma grid dimension
+    sed_case("xray_gamma49", dict(base, XRAYS=True), loaders.FILTERSET_EXAMPLE49, [0.031024], nX=3, seed=44)
+    # five components: fitted synchrotron family, two-parameter SKIRTOR torus, radio-side luminosity fractions
+    sed_case("radio_r06_49", dict(base, RADIO=True, TORUS='SKIRTOR_2P'), loaders.FILTERSET_EXAMPLE49, [1.234],
+             nR=3, seed=45, extra=[('agn_rad', [1e4, 3e5]), ('AGNfrac_rad', [1e4, 3e5]),
+                                   ('AGNfrac1-10GHz', [3e4, 3e5]), ('AGNfrac_rad', [2e5, 2e5])])
+    # fixed radio template (one radio datum), KD18 disc (no BB norm: 4 pi dlum^2 path, dereddened = reddened)
+    sed_case("radio1_kd18_49", dict(base, RADIO=True, BBB='KD18', TORUS='NK0'), loaders.FILTERSET_EXAMPLE49, [0.5],
+             nR=1, seed=46)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sed":
+        sed_main()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "families":
         os.makedirs(OUT, exist_ok=True)
         k2_families_case("families18", loaders.FILTERSET_DEFAULT, [0.05, 1.0, 3.3])

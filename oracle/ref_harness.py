@@ -144,3 +144,81 @@ def reference_eval(pars, data, models, P):
             lnlike[i] = PAR.ln_likelihood(data.nus, data.fluxes, data.fluxerrs, data.z, y, models)
             lnp[i] = PAR.ln_probab(p, data, models, P)
     return lnp, ym, keys, lnprior, lnlike
+
+
+# ------------------------------------------------------------------------------------------------
+# SED realisations + integrated luminosities (PLOTandWRITE_AGNfitter.FLUXES_ARRAYS)
+# ------------------------------------------------------------------------------------------------
+C_ASTROPY = 299792458.0          # astropy.constants.c [m/s]: what u.spectral() converts wavelengths with
+
+
+class _FreqScalar(object):
+    """Stands in for an astropy Quantity element: `.value` in Hz and equality on it (PLT:859,873,956)."""
+
+    def __init__(self, v):
+        self.value = float(v)
+
+    def __eq__(self, other):
+        return self.value == other.value
+
+
+class _FreqRanges(object):
+    """out['intlum_freqranges'] for the unmodified integrated_luminosities: `ranges * unit` and
+    `.to(u.Hz, equivalencies=u.spectral())` (PLT:839) are astropy operations; here the conversion
+    nu = c / lambda is done once, up front, and both operations return the converted table."""
+
+    def __init__(self, ranges, unit_m):
+        self.hz = C_ASTROPY / (np.asarray(ranges, dtype=np.float64) * unit_m)
+
+    def __mul__(self, other):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def __getitem__(self, m):
+        return [_FreqScalar(self.hz[m][0]), _FreqScalar(self.hz[m][1])]
+
+
+def intlum_ranges_hz(ranges, unit_m=1e-6):
+    """The Hz table the reference's astropy conversion yields for out['intlum_freqranges'] (microns by default)."""
+    return C_ASTROPY / (np.asarray(ranges, dtype=np.float64) * unit_m)
+
+
+class _Chain(object):
+    """CHAIN after props() (PLT:438-492): the thinned flat chain and the best-fit row."""
+
+    def __init__(self, flatchain, best):
+        self.flatchain = np.array(flatchain, dtype=np.float64)
+        self.best_fit_pars = np.array(best, dtype=np.float64)
+
+    def props(self):
+        pass
+
+
+def make_models_4plot(MD, settings):
+    mods = ref_shim.install()
+    models = make_models(MD, settings)
+    models.dictkey_arrays_4plot = mods["DIC"].dictkey_arrays_4plot(MD)
+    return models
+
+
+def reference_fluxes(data, models, P, flatchain, best, intlum_models, intlum_ranges_um, n_real, seed,
+                     output_type='int_lums'):
+    """Run the UNMODIFIED FLUXES_ARRAYS.fluxes (PLT:566-799).  The rows it draws with np.random.choice are
+    reproduced by seeding NumPy's legacy generator; returns (rows used, all_nus_rest, nuLnus tuple, int_lums)."""
+    PLT = ref_shim.install_plot()
+    mods = ref_shim.install()
+    mods["MOD"].z2Dlum = loaders.z2Dlum            # astropy cosmology is absent: restated FlatLambdaCDM distance
+    out = {'realizations2int': n_real, 'realizations2plot': n_real, 'intlum_models': list(intlum_models),
+           'intlum_freqranges': _FreqRanges(intlum_ranges_um, 1e-6), 'intlum_freqranges_unit': None}
+    mc = {'sampling_algorithm': 'emcee'}
+    fa = PLT.FLUXES_ARRAYS(_Chain(flatchain, best), P, out, output_type, models.settings, mc)
+    np.random.seed(seed)
+    pick = np.random.choice(len(flatchain), n_real)
+    rows = np.array(flatchain, dtype=np.float64)[pick, :]
+    rows[-1] = best
+    np.random.seed(seed)
+    with np.errstate(all="ignore"):
+        fa.fluxes(data, models)
+    return rows, fa.all_nus_rest, fa.nuLnus4plotting, (fa.int_lums if output_type == 'int_lums' else None)

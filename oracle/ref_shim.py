@@ -105,3 +105,17 @@ def install():
                         ("PAR", "functions.PARAMETERSPACE_AGNfitter")):
         mods[short] = importlib.import_module(name)
     return mods
+
+
+def install_plot():
+    """Also import PLOTandWRITE_AGNfitter (the SED-realisation / integrated-luminosity stage).
+    matplotlib is absent here; the module only needs it at import time and inside plotting methods."""
+    install()
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.ticker", "matplotlib.colors", "matplotlib.cm",
+                 "matplotlib.patches", "matplotlib.gridspec", "matplotlib.backends",
+                 "matplotlib.backends.backend_pdf"):
+        if name not in sys.modules:
+            sys.modules[name] = _stub_module(name)
+    sys.modules["matplotlib"].ticker = sys.modules["matplotlib.ticker"]
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    return importlib.import_module("functions.PLOTandWRITE_AGNfitter")

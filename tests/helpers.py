@@ -18,6 +18,19 @@ def load_k1(name):
     return ms, g
 
 
+def load_sed(name):
+    """(ModelSet, PlotSet, arrays) of a SED-realisation golden case (tests/golden/sed_*.npz)."""
+    from agnfitter_b200 import plotset
+    with np.load(os.path.join(GOLDEN, "sed_%s.npz" % name), allow_pickle=False) as z:
+        g = {k: z[k] for k in z.files}
+    return flatten.modelset_from_arrays(g, prefix="ms_"), plotset.plotset_from_arrays(g), g
+
+
+def sed_component_order(ms):
+    """Order of the arrays in FLUXES4plotting / nuLnus4plotting (PLOTandWRITE_AGNfitter.py:778-782)."""
+    return ['sb', 'bb', 'ga', 'to'] + (['rad'] if ms.radio else []) + ['total', 'bbdered']
+
+
 def load_k2(name):
     with np.load(os.path.join(GOLDEN, "k2_%s.npz" % name), allow_pickle=False) as z:
         return {k: z[k] for k in z.files}

@@ -64,6 +64,14 @@ SIGNATURES = {
     "agnf_ens_best": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnf_ens_reset_stats": (C.c_int, [C.c_void_p]),
     "agnf_ens_percentiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "agnf_sed_config": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agnf_sed_family_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "agnf_sed_sources": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "agnf_sed_bands": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agnf_sed_intlum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    "agnf_sed_spectra": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
 }
 
 _lib = None

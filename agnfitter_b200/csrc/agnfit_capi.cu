@@ -16,6 +16,7 @@
 #include "k1_lnprob.cuh"
 #include "k2_dictbuild.cuh"
 #include "k3_ensemble.cuh"
+#include "k4_sed.cuh"
 
 using namespace agnf;
 
@@ -76,6 +77,13 @@ struct agnf_ctx {
   int k2_last_kernel = 0;            // contraction of the last agnf_dict_build: 1 per-slice kernels, 2 shared-window
   int64_t ens_src_offset = 0;        // catalogue row of the shard's first source (Philox counter)
   int64_t ens_hist_samples = 0;
+
+  // K4 SED realisations
+  K4Params k4{};
+  void* d_k4 = nullptr;              // device copy of k4
+  bool k4_cfg = false, k4_src = false, k4_bands = false, k4_dirty = true;
+  bool k4_fam[AGNF_MAX_FAMILIES] = {false, false, false, false, false};
+  int64_t k4_S = 0;
 };
 
 static thread_local std::string g_create_err;
@@ -1131,3 +1139,264 @@ AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, d
 }
 
 }  // extern "C"
+
+
+// ------------------------------------------------------------------------------------------- K4
+
+AGNF_API int agnf_sed_config(agnf_ctx* ctx, int32_t G, const double* grid, const double* xg, int32_t to_lo, int32_t to_hi,
+                    int32_t rad_hi, int32_t dered_mode, const int32_t* dered_row, const double* bands,
+                    const int32_t* bands_jt) {
+  if (!ctx) return 1;
+  if (!ctx->have_cfg) return fail(ctx, "agnf_modelset_config has not been called");
+  if (G < 2 || !grid || !xg) return fail(ctx, "agnf_sed_config: empty frequency grid");
+  if (to_lo < 0 || to_hi > G || rad_hi < 0 || rad_hi > G) return fail(ctx, "agnf_sed_config: cut-off outside the grid");
+  if (dered_mode < 0 || dered_mode > 3) return fail(ctx, "dered_mode must be 0..3");
+  if (dered_mode != 0 && !dered_row) return fail(ctx, "dered_mode %d needs dered_row", dered_mode);
+  if (dered_mode == 3 && (!bands || !bands_jt)) return fail(ctx, "dered_mode 3 needs the band centres and their table");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  K4Params& Q = ctx->k4;
+  Q.G = G;
+  Q.to_lo = to_lo;
+  Q.to_hi = to_hi;
+  Q.rad_hi = rad_hi;
+  Q.dered_mode = dered_mode;
+  if (upload(ctx, &Q.grid, grid, (size_t)G)) return 1;
+  if (upload(ctx, &Q.xg, xg, (size_t)G)) return 1;
+  if (dered_mode != 0) {
+    if (!ctx->fam_set[3]) return fail(ctx, "upload the accretion-disc family before agnf_sed_config");
+    if (upload(ctx, &Q.dered_row, dered_row, (size_t)ctx->k1.fam[3].T)) return 1;
+  }
+  if (dered_mode == 3) {
+    if (upload(ctx, &Q.bands_x, bands, (size_t)ctx->k1.cfg.n_b)) return 1;
+    if (upload(ctx, &Q.bands_jt, bands_jt, (size_t)G)) return 1;
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {     // bracket tables depend on the grid: families must follow
+    ctx->k4_fam[f] = false;
+    Q.fam[f].present = 0;
+  }
+  ctx->k4_cfg = true;
+  ctx->k4_dirty = true;
+  return 0;
+}
+
+AGNF_API int agnf_sed_family_upload(agnf_ctx* ctx, const agnf_sed_family* d) {
+  if (!ctx) return 1;
+  if (!ctx->k4_cfg) return fail(ctx, "call agnf_sed_config first");
+  if (!d || d->fam < 0 || d->fam >= ctx->k1.cfg.n_fam) return fail(ctx, "agnf_sed_family_upload: bad family id");
+  if (!ctx->fam_set[d->fam]) return fail(ctx, "family %d has no dictionary yet (agnf_family_upload)", d->fam);
+  if (d->T != ctx->k1.fam[d->fam].T)
+    return fail(ctx, "family %d: %lld full-resolution templates for %lld dictionary rows", d->fam, (long long)d->T,
+                (long long)ctx->k1.fam[d->fam].T);
+  if (d->mode < 0 || d->mode > 3) return fail(ctx, "mode must be 0..3");
+  if (d->n_groups < 1 || !d->group || !d->local || !d->g_nlam || !d->x || !d->val || !d->jtab)
+    return fail(ctx, "agnf_sed_family_upload: NULL argument");
+  if (d->mode != 0 && !d->k) return fail(ctx, "mode %d needs the reddening curve", d->mode);
+  const int n_par = ctx->k1.cfg.n_par;
+  if (d->mode != 0 && (d->e_col < 0 || d->e_col >= n_par)) return fail(ctx, "e_col out of range");
+  if (d->mode == 3 && (d->a_col < 0 || d->a_col >= n_par)) return fail(ctx, "a_col out of range");
+  const bool need2 = d->fam == 3 && (ctx->k4.dered_mode == 1 || ctx->k4.dered_mode == 2);
+  if (need2 && !d->val2) return fail(ctx, "the accretion-disc family needs val2 for dered_mode %d", ctx->k4.dered_mode);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int ng = d->n_groups;
+  std::vector<int32_t> xoff((size_t)ng), count((size_t)ng, 0);
+  std::vector<int64_t> voff((size_t)ng);
+  int64_t nx = 0;
+  int32_t max_nlam = 0;
+  for (int g = 0; g < ng; ++g) {
+    if (d->g_nlam[g] < 1) return fail(ctx, "family %d group %d has no samples", d->fam, g);
+    xoff[(size_t)g] = (int32_t)nx;
+    nx += d->g_nlam[g];
+    max_nlam = std::max(max_nlam, d->g_nlam[g]);
+  }
+  for (int64_t t = 0; t < d->T; ++t) {
+    if (d->group[t] < 0 || d->group[t] >= ng) return fail(ctx, "family %d: group[%lld] out of range", d->fam, (long long)t);
+    count[(size_t)d->group[t]] = std::max(count[(size_t)d->group[t]], d->local[t] + 1);
+  }
+  int64_t nv = 0;
+  for (int g = 0; g < ng; ++g) {
+    voff[(size_t)g] = nv;
+    nv += (int64_t)count[(size_t)g] * d->g_nlam[g];
+  }
+  std::vector<int64_t> t_off((size_t)d->T);
+  for (int64_t t = 0; t < d->T; ++t) {
+    if (d->local[t] < 0) return fail(ctx, "family %d: local[%lld] < 0", d->fam, (long long)t);
+    t_off[(size_t)t] = voff[(size_t)d->group[t]] + (int64_t)d->local[t] * d->g_nlam[d->group[t]];
+  }
+  for (int64_t i = 0, n = (int64_t)ng * ctx->k4.G; i < n; ++i) {
+    const int g = (int)(i / ctx->k4.G);
+    if (d->jtab[i] < -1 || d->jtab[i] >= d->g_nlam[g]) return fail(ctx, "family %d: bracket table entry out of range", d->fam);
+  }
+  K4Family& F = ctx->k4.fam[d->fam];
+  F.T = d->T;
+  F.mode = d->mode;
+  F.e_col = d->e_col;
+  F.a_col = d->a_col;
+  F.max_nlam = max_nlam;
+  if (upload(ctx, &F.x, d->x, (size_t)nx)) return 1;
+  if (d->mode != 0) {
+    if (upload(ctx, &F.k, d->k, (size_t)nx)) return 1;
+  }
+  if (upload(ctx, &F.val, d->val, (size_t)nv)) return 1;
+  if (need2) {
+    if (upload(ctx, &F.val2, d->val2, (size_t)nv)) return 1;
+  }
+  if (upload(ctx, &F.t_off, t_off.data(), (size_t)d->T)) return 1;
+  if (upload(ctx, &F.t_grp, d->group, (size_t)d->T)) return 1;
+  if (upload(ctx, &F.g_xoff, xoff.data(), (size_t)ng)) return 1;
+  if (upload(ctx, &F.g_nlam, d->g_nlam, (size_t)ng)) return 1;
+  if (upload(ctx, &F.jtab, d->jtab, (size_t)ng * (size_t)ctx->k4.G)) return 1;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));     // the vectors above feed asynchronous copies
+  F.present = 1;
+  ctx->k4_fam[d->fam] = true;
+  ctx->k4_dirty = true;
+  return 0;
+}
+
+AGNF_API int agnf_sed_sources(agnf_ctx* ctx, int64_t S, const double* z, const double* dlum) {
+  if (!ctx) return 1;
+  if (S < 1 || !z || !dlum) return fail(ctx, "agnf_sed_sources: empty");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (upload(ctx, &ctx->k4.src_z, z, (size_t)S)) return 1;
+  if (upload(ctx, &ctx->k4.src_dlum, dlum, (size_t)S)) return 1;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->k4_S = S;
+  ctx->k4_src = true;
+  ctx->k4_dirty = true;
+  return 0;
+}
+
+AGNF_API int agnf_sed_bands(agnf_ctx* ctx, int32_t n_ranges, const int32_t* i0, const int32_t* i1, const int32_t* mask,
+                   int32_t n_specs, const int32_t* kind, const int32_t* range, const int32_t* num,
+                   const int32_t* den) {
+  if (!ctx) return 1;
+  if (!ctx->k4_cfg) return fail(ctx, "call agnf_sed_config first");
+  if (n_ranges < 1 || n_ranges > K4_MAX_RANGES) return fail(ctx, "1..%d integration bands", K4_MAX_RANGES);
+  if (n_specs < 1 || n_specs > K4_MAX_SPECS) return fail(ctx, "1..%d output columns", K4_MAX_SPECS);
+  if (!i0 || !i1 || !mask || !kind || !range || !num || !den) return fail(ctx, "agnf_sed_bands: NULL argument");
+  K4Params& Q = ctx->k4;
+  const int all = (1 << K4_COMPS) - 1;
+  for (int q = 0; q < n_ranges; ++q) {
+    if (i0[q] < 0 || i0[q] > Q.G || (i1[q] >= 0 && (i1[q] < i0[q] || i1[q] > Q.G)) || (i1[q] < 0 && i0[q] >= Q.G))
+      return fail(ctx, "band %d lies outside the grid", q);
+    if (mask[q] & ~all) return fail(ctx, "band %d: unknown component bits", q);
+    if ((mask[q] & 16) && !ctx->k1.cfg.radio) return fail(ctx, "band %d asks for the radio component of a model set without one", q);
+    Q.r_i0[q] = i0[q];
+    Q.r_i1[q] = i1[q];
+    Q.r_mask[q] = mask[q];
+  }
+  for (int s = 0; s < n_specs; ++s) {
+    if (range[s] < 0 || range[s] >= n_ranges) return fail(ctx, "column %d: band out of range", s);
+    if ((num[s] | den[s]) & ~mask[range[s]]) return fail(ctx, "column %d uses a component its band does not compute", s);
+    if (kind[s] != 0 && kind[s] != 1) return fail(ctx, "column %d: kind must be 0 or 1", s);
+    Q.s_kind[s] = kind[s];
+    Q.s_range[s] = range[s];
+    Q.s_num[s] = num[s];
+    Q.s_den[s] = den[s];
+  }
+  Q.n_ranges = n_ranges;
+  Q.n_specs = n_specs;
+  ctx->k4_bands = true;
+  ctx->k4_dirty = true;
+  return 0;
+}
+
+namespace {
+
+int k4_ready(agnf_ctx* ctx, bool need_bands) {
+  if (check_ready(ctx)) return 1;
+  if (!ctx->k4_cfg) return fail(ctx, "agnf_sed_config has not been called");
+  for (int f = 0; f < ctx->k1.cfg.n_fam; ++f)
+    if (!ctx->k4_fam[f]) return fail(ctx, "full-resolution family %d has not been uploaded", f);
+  if (!ctx->k4_src) return fail(ctx, "agnf_sed_sources has not been called");
+  if (ctx->k4_S != ctx->k1.S) return fail(ctx, "agnf_sed_sources: %lld sources, agnf_sources_upload had %lld",
+                                          (long long)ctx->k4_S, (long long)ctx->k1.S);
+  if (need_bands && !ctx->k4_bands) return fail(ctx, "agnf_sed_bands has not been called");
+  if (ctx->k4_dirty) {
+    K4Params& Q = ctx->k4;
+    int off = 0;
+    for (int f = 0; f < ctx->k1.cfg.n_fam; ++f) {
+      Q.fam[f].smem_off = off;
+      off += (Q.fam[f].max_nlam + 1) & ~1;
+    }
+    Q.dered_off = off;
+    if (Q.dered_mode == 1 || Q.dered_mode == 2) off += (Q.fam[3].max_nlam + 1) & ~1;
+    if (Q.dered_mode == 3) off += (ctx->k1.cfg.n_b + 1) & ~1;
+    Q.smem_doubles = off;
+    if ((size_t)off * 8 > 160 * 1024) return fail(ctx, "templates of one realisation need %d KB of shared memory", off / 128);
+    if (!ctx->d_k4 && dev_alloc(ctx, &ctx->d_k4, sizeof(K4Params))) return 1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_k4, &Q, sizeof(K4Params), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->k4_dirty = false;
+  }
+  return 0;
+}
+
+int k4_run(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* out, int32_t on_device,
+           bool spectra) {
+  if (!ctx) return 1;
+  if (n < 0) return fail(ctx, "n < 0");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (k4_ready(ctx, !spectra)) return 1;
+  if (n == 0) return 0;
+  if (!params || !source_id || !out) return fail(ctx, "NULL argument");
+  if (n > 2147483647LL) return fail(ctx, "at most 2^31 - 1 rows per call");
+  const int n_par = ctx->k1.cfg.n_par;
+  const int n_comp = ctx->k1.cfg.radio ? 7 : 6;
+  const size_t out_per = spectra ? (size_t)n_comp * (size_t)ctx->k4.G : (size_t)ctx->k4.n_specs;
+  cudaStream_t st = ctx->stream;
+  void *dp = nullptr, *ds = nullptr, *dout = nullptr;
+  auto cleanup = [&]() {
+    if (!on_device) {
+      dev_free(ctx, dp);
+      dev_free(ctx, ds);
+      dev_free(ctx, dout);
+    }
+  };
+  if (on_device) {
+    dp = const_cast<double*>(params);
+    ds = const_cast<int32_t*>(source_id);
+    dout = out;
+  } else {
+    for (int64_t i = 0; i < n; ++i)
+      if (source_id[i] < 0 || source_id[i] >= ctx->k1.S) return fail(ctx, "source_id[%lld] out of range", (long long)i);
+    if (dev_alloc(ctx, &dp, (size_t)n * n_par * 8) || dev_alloc(ctx, &ds, (size_t)n * 4) ||
+        dev_alloc(ctx, &dout, (size_t)n * out_per * 8)) {
+      cleanup();
+      return 1;
+    }
+    cudaError_t e = cudaMemcpyAsync(dp, params, (size_t)n * n_par * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ds, source_id, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+      cleanup();
+      return fail(ctx, "upload failed: %s", cudaGetErrorString(e));
+    }
+  }
+  K4Batch B{static_cast<const double*>(dp), static_cast<const int32_t*>(ds), n,
+            spectra ? nullptr : static_cast<double*>(dout), spectra ? static_cast<double*>(dout) : nullptr};
+  cudaError_t e = cudaEventRecord(ctx->ev0, st);
+  if (e == cudaSuccess)
+    e = spectra ? launch_k4_spectra(ctx->k1, static_cast<const K4Params*>(ctx->d_k4), ctx->k4, B, st)
+                : launch_k4_intlum(ctx->k1, static_cast<const K4Params*>(ctx->d_k4), ctx->k4, B, st);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->ev1, st);
+  if (e == cudaSuccess && !on_device)
+    e = cudaMemcpyAsync(out, dout, (size_t)n * out_per * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) return fail(ctx, "K4 failed: %s", cudaGetErrorString(e));
+  ctx->k1_timed = true;
+  ctx->launches += 1;
+  return 0;
+}
+
+}  // namespace
+
+AGNF_API int agnf_sed_intlum(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* out,
+                    int32_t on_device) {
+  return k4_run(ctx, params, source_id, n, out, on_device, false);
+}
+
+AGNF_API int agnf_sed_spectra(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* out,
+                     int32_t on_device) {
+  return k4_run(ctx, params, source_id, n, out, on_device, true);
+}

@@ -13,8 +13,8 @@ settings (PLT:709-730); `dered_mode` records the branch:
     0  the reddened curve is reused                                    (PLT:729-730)
     1  one fixed template, key '0.0'            R06 / THB21 without X-rays  (PLT:709-712)
     2  the matched grid key with EBVbbb := 0.0, no alpha_ox scaling    XRAYS == True  (PLT:719-727)
-    3  SN12 without X-rays: the reference interpolates the FILTERED dictionary entry over the band centres
-       (PLT:714-717) — not supported here; asking for 'bbbdered' with it raises.
+    3  SN12 without X-rays: the matched grid key with EBVbbb := 0.0, but read from the FILTERED dictionary and
+       interpolated over the band centres (PLT:714-717)
 """
 from dataclasses import dataclass, field
 from typing import List
@@ -112,7 +112,7 @@ def dered_rows(ms, mode):
         if len(hit) == 0:
             raise ValueError("no accretion-disc template with key '0.0'")
         rows[:] = hit[0]
-    elif mode == 2:
+    elif mode in (2, 3):
         d = bb.par_names.index('EBVbbb')
         lut = {tuple(bb.keys_float[:, t]): t for t in range(T)}
         for t in range(T):

@@ -207,6 +207,59 @@ AGNF_API int agnf_ens_reset_stats(agnf_ctx* ctx);
  * PLOTandWRITE_AGNfitter.py:152-173); out [S, n_par, n_q]; resolution = (P.max - P.min) / n_bins. */
 AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, double* out);
 
+/* ---- K4: SED realisations + integrated luminosities ---------------------------------------
+ * Replaces the per-realisation loop of FLUXES_ARRAYS.fluxes (functions/PLOTandWRITE_AGNfitter.py:566-799), the
+ * `_4plot` get_fluxes it calls (functions/DICTIONARIES_AGNfitter.py:293-422), FLUXES2nuLnu_4plotting (:800-821) and
+ * integrated_luminosities (:824-964) for a batch of (source, parameter row) pairs.  The model set, its families and
+ * the sources must have been uploaded for K1 (rows are snapped with K1's grids).  Host-side preparation of the
+ * arrays below: agnfitter_b200/realizations.py. */
+typedef struct {
+  int32_t fam;              /* 0 GA, 1 SB, 2 TO, 3 BB, 4 RAD                                                      */
+  int32_t mode;             /* what `_4plot` get_fluxes does to the template (DICTIONARIES_AGNfitter.py:350-401):
+                               0 nothing; 1 Calzetti with E = params[e_col]; 2 Prevot with E = params[e_col];
+                               3 Prevot below 10^16.685 Hz, F * 10^(params[a_col] / 0.3838) at and above            */
+  int32_t e_col, a_col;
+  int32_t n_groups;         /* templates sharing a frequency grid form a group                                   */
+  int32_t reserved;
+  int64_t T;
+  const int32_t* group;     /* [T] group of template t (row order = key order of the dictionary)                   */
+  const int32_t* local;     /* [T] row of template t inside its group's block                                      */
+  const int32_t* g_nlam;    /* [n_groups] samples per template                                                     */
+  const double* x;          /* grids of all groups, each ascending (interp1d's mergesort order), concatenated      */
+  const double* k;          /* reddening curve k(lambda) on the same layout (modes 1-3) or NULL                    */
+  const double* val;        /* per group a [T_g, n_lam] block in sorted-x order, concatenated: F_nu (modes 1-3)
+                               or log10 F_nu (mode 0)                                                              */
+  const double* val2;       /* BB with dered_mode 1 or 2: log10 F_nu of the raw templates, same layout; else NULL  */
+  const int32_t* jtab;      /* [n_groups, G] j with x[j] <= grid[i] < x[j+1] (numpy.interp's bracket), -1: the point
+                               lies outside the (part of the) template that interp1d sees -> fill value -100       */
+} agnf_sed_family;
+
+/* grid = all_nus_rest (PLOTandWRITE_AGNfitter.py:633), xg = 10**grid; the torus is kept on grid points
+ * [to_lo, to_hi) (:733-734), the radio component on [0, rad_hi) (:693).  dered_mode / dered_row [T_BB]: which
+ * template the dereddened disc curve comes from (:709-730; agnfitter_b200/plotset.py).  bands_jt [G]: bracket table
+ * of the dictionary band centres, needed for dered_mode 3 only (else NULL). */
+AGNF_API int agnf_sed_config(agnf_ctx* ctx, int32_t G, const double* grid, const double* xg, int32_t to_lo, int32_t to_hi,
+                    int32_t rad_hi, int32_t dered_mode, const int32_t* dered_row, const double* bands,
+                    const int32_t* bands_jt);
+AGNF_API int agnf_sed_family_upload(agnf_ctx* ctx, const agnf_sed_family* fam);
+/* data.z and data.dlum of every source (same order as agnf_sources_upload) */
+AGNF_API int agnf_sed_sources(agnf_ctx* ctx, int64_t S, const double* z, const double* dlum);
+/* Integration bands (out['intlum_freqranges'], :839,859,873,939,943): band q covers grid points [i0, i1); i1 = -1
+ * marks a monochromatic luminosity at point i0; mask = components needed (bit 0 sb, 1 bbb, 2 gal, 3 tor,
+ * 4 agn_rad, 5 bbbdered).  Output column s (out['intlum_models'][s]) = sum of the `num` components of band
+ * `range[s]` (kind 0) or 10**(sum num / sum den) (kind 1, the AGN fractions). */
+AGNF_API int agnf_sed_bands(agnf_ctx* ctx, int32_t n_ranges, const int32_t* i0, const int32_t* i1, const int32_t* mask,
+                   int32_t n_specs, const int32_t* kind, const int32_t* range, const int32_t* num,
+                   const int32_t* den);
+/* out [n, n_specs]: integrated_luminosities(...) transposed, linear (the reference then takes log10, :797).
+ * on_device: params / source_id / out are device pointers. */
+AGNF_API int agnf_sed_intlum(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* out,
+                    int32_t on_device);
+/* out [n, n_comp, G]: nuLnus4plotting (:786) per row, n_comp = 6 (SB, BB, GA, TO, TOTAL, BBdered) or 7 with the
+ * radio component (SB, BB, GA, TO, RAD, TOTAL, BBdered). */
+AGNF_API int agnf_sed_spectra(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* out,
+                     int32_t on_device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -406,6 +406,10 @@ def sed_main():
     # fixed radio template (one radio datum), KD18 disc (no BB norm: 4 pi dlum^2 path, dereddened = reddened)
     sed_case("radio1_kd18_49", dict(base, RADIO=True, BBB='KD18', TORUS='NK0'), loaders.FILTERSET_EXAMPLE49, [0.5],
              nR=1, seed=46)
+    # SN12 disc without X-rays: the dereddened curve is interpolated over the band centres of the FILTERED
+    # dictionary (PLOTandWRITE_AGNfitter.py:714-717)
+    sed_case("radio2_sn12_49", dict(base, RADIO=True, BBB='SN12'), loaders.FILTERSET_EXAMPLE49, [0.129, 0.9],
+             nR=2, seed=47)
 
 
 def main():

@@ -103,6 +103,19 @@ def plotset_from_modelsdict(MD, ms):
     return ps
 
 
+def plotset_from_templates(templates, ms):
+    """templates: {'GA': {'F': {key: (log nu, Fnu)}, ...}, ...} (synth.synthetic_templates / the loaders' `*_4plot`
+    dicts) in the key order the ModelSet was built from."""
+    ps = PlotSet(dered_mode=dered_branch(ms.settings))
+    for fam in ms.families:
+        F = templates[fam.name]["F"]
+        if len(F) != fam.T:
+            raise ValueError("%s: %d full-resolution templates for %d dictionary rows" % (fam.name, len(F), fam.T))
+        ps.families.append(plot_family(fam.name, list(F.values())))
+    ps.dered_row = dered_rows(ms, ps.dered_mode)
+    return ps
+
+
 def dered_rows(ms, mode):
     bb = ms.fam("BB")
     T = bb.T

@@ -184,6 +184,28 @@ def cpu_dictionary_throughput(n_templates=400, bands=18):
     return len(keys) * len(b) / dt, len(keys)
 
 
+# example/SETTINGS_AGNfitter.py:316-321 (the reference's default output settings)
+EXAMPLE_INTLUM_MODELS = ['sb', 'bbb', 'bbbdered', 'gal', 'AGNfrac_opt', 'tor', 'tor+bbb', 'AGNfrac_IR', 'gal', 'bbb',
+                         'AGNfrac_opt', 'tor', 'sb']
+EXAMPLE_INTLUM_RANGES_UM = [[8., 1000.], [0.1, 1.], [0.1, 1.], [0.1, 1.], [0.1, 1.], [1., 30.], [0.1, 30],
+                            [8., 1000.], [0.4, 0.5], [0.4, 0.5], [0.4, 0.5], [6, 6], [1., 30.]]
+
+
+def cpu_sed_rate(ms, ps, src_raw, pars, W, n_rows=24):
+    """Rows/s of the oracle port of FLUXES_ARRAYS.fluxes + integrated_luminosities (one core) on rows of the
+    same workload: the CPU figure beside K4's."""
+    from agnfitter_b200.realizations import ranges_to_hz
+    from oracle import sed_oracle as SO
+    hz = ranges_to_hz(EXAMPLE_INTLUM_RANGES_UM)
+    t0 = time.perf_counter()
+    z, dl = float(src_raw["z"][0]), float(src_raw["dlum"][0])
+    with np.errstate(all="ignore"):
+        grid, fl = SO.realization_fluxes(ms, ps, pars[:n_rows], z, dl)
+        nl = SO.fluxes_to_nuLnu(grid, fl, z, dl)
+        SO.integrated_luminosities(EXAMPLE_INTLUM_MODELS, hz, grid, nl, ms.radio)
+    return n_rows / (time.perf_counter() - t0)
+
+
 def build_host_sample(ms, dev_tables, src_raw, sample_ids, pars, W):
     """Small host-side ModelSet (only the sampled sources' z-slices) + oracle inputs."""
     from agnfitter_b200.flatten import ModelSet, family_from_keys_float
@@ -321,6 +343,40 @@ def run_ours(args):
                         acceptance=float(acc.mean() / (args.ensemble_steps + 2)))
         del ens
 
+    # ---- output stage: integrated luminosities of 100 chain rows + best fit per source --------
+    sed_info = None
+    if args.sed_sources > 0:
+        from agnfitter_b200 import synth as _synth
+        from agnfitter_b200.plotset import plotset_from_templates
+        from agnfitter_b200.realizations import SedEngine, ranges_to_hz
+        ps = plotset_from_templates(_synth.synthetic_templates(), ms)
+        sed = SedEngine(eng, ps, raw["z"], raw["dlum"])
+        sed.set_bands(EXAMPLE_INTLUM_MODELS, ranges_to_hz(EXAMPLE_INTLUM_RANGES_UM))
+        n_src = min(args.sed_sources, S)
+        rows_per = min(W, 101)
+        idx = (np.arange(n_src)[:, None] * W + np.arange(rows_per)[None, :]).reshape(-1)
+        d_sp = d_pars[torch.from_numpy(idx).to(dev)].contiguous()
+        d_ss = d_sid[torch.from_numpy(idx).to(dev)].contiguous()
+        d_so = torch.empty((len(idx), sed.n_models), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        for _ in range(2):
+            sed.int_lums_device(d_sp, d_ss, d_so)
+        barrier()
+        l_s = eng.launch_count
+        t_k = []
+        for _ in range(3):
+            sed.int_lums_device(d_sp, d_ss, d_so)
+            t_k.append(eng.last_kernel_ms(1))
+        sed_launches = eng.launch_count - l_s
+        k4_ms = float(np.mean(t_k))
+        sed_info = dict(rows=int(len(idx)), rows_per_source=int(rows_per), grid_points=int(len(sed.grid)),
+                        columns=int(sed.n_models), kernel_ms=round(k4_ms, 3),
+                        rows_per_s=len(idx) / (k4_ms * 1e-3), sources_per_s=n_src / (k4_ms * 1e-3),
+                        launches=int(sed_launches))
+        if rank == 0:
+            sed_info["cpu_rows_per_s_one_core"] = cpu_sed_rate(ms, ps, raw, pars, W)
+        del sed, d_sp, d_ss, d_so
+
     # ---- the drop-in's own call shape: emcee hands ONE source's half-ensemble (W/2 rows) per call ----------
     small_calls = {}
     for rows_per_call in (W // 2, 16 * W):
@@ -417,6 +473,10 @@ def run_ours(args):
                 "evals_per_s": total_rows / (ens_ms_max * 1e-3),
                 "sources_fitted_per_s": total_rows / (ens_ms_max * 1e-3) / EVALS_PER_FIT,
                 "mean_acceptance": ens_info["acceptance"], "launches": ens_info["launches"]},
+            "sed_realizations": None if not sed_info else dict(
+                sed_info, what="agnf_sed_intlum (K4): full-resolution SEDs of 5 components on all_nus_rest and the "
+                               "example settings' 13 integrated luminosities / AGN fractions per chain row, "
+                               "rows resident in HBM; cpu = oracle port of FLUXES_ARRAYS.fluxes, one core"),
             "dictionary_build": {"entries": int(info["k2_entries"]), "wall_s": info["k2_wall_s"],
                                  "entries_per_s": info["k2_entries"] / info["k2_wall_s"],
                                  "what": "K2 over every family and every distinct z of the shard, tables left in HBM; "
@@ -491,6 +551,8 @@ def main():
     ap.add_argument("--bands", type=int, default=18, choices=[18, 49],
                     help="18: the default band set (the workload BASELINE.json names); 49: the example settings' "
                          "radio-to-X-ray set (C1/C2 shape at catalogue scale)")
+    ap.add_argument("--sed-sources", type=int, default=2000,
+                    help="sources whose 100 chain rows go through the SED / integrated-luminosity stage (0: skip)")
     ap.add_argument("--ensemble-steps", type=int, default=10,
                     help="also time this many lock-step stretch-move steps of the GPU-resident sampler (0: skip)")
     args = ap.parse_args()

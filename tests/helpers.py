@@ -1,5 +1,6 @@
 """Shared helpers for the parity tests (tests/ only)."""
 import os
+import types
 
 import numpy as np
 
@@ -61,3 +62,45 @@ def oracle_src(ms, g, s):
     return dict(z=float(g["src_z"][s]), dlum=float(g["src_dlum"][s]), nus=g["src_nus"][s],
                 fluxes=g["src_fluxes"][s], fluxerrs=g["src_fluxerrs"][s],
                 pmin=g["ref_pmin"][s], pmax=g["ref_pmax"][s], zi=zpos[float(g["src_z"][s])])
+
+
+def reference_objects(ms, g, s, ps=None):
+    """Stand-ins with exactly the attributes the reference's objects expose on this path:
+    MODELSDICT (DICTIONARIES_AGNfitter.py:86-136), MODELS (.settings, .dict_modelfluxes), DATA."""
+    zi = int(np.nonzero(ms.z_grid == float(g["src_z"][s]))[0][0])
+    md = types.SimpleNamespace(z=float(ms.z_grid[zi]))
+
+    def fdict(f):
+        if not f.fitted:
+            return {'-99.9': (ms.bands, f.table[zi, 0])}
+        out = {}
+        for t in range(f.T):
+            key = tuple(repr(float(v)) for v in f.keys_float[:, t])
+            out[key if f.keys_float.shape[0] > 1 else key[0]] = (ms.bands, f.table[zi, t])
+        return out
+
+    fams = {f.name: f for f in ms.families}
+    md.GALAXYFdict, md.STARBURSTFdict = fdict(fams["GA"]), fdict(fams["SB"])
+    md.TORUSFdict, md.BBBFdict = fdict(fams["TO"]), fdict(fams["BB"])
+    names = [fams[k].par_names for k in ("GA", "SB", "TO", "BB")]
+    types_ = [fams[k].par_types for k in ("GA", "SB", "TO", "BB")]
+    if "RAD" in fams:
+        md.AGN_RADFdict = fdict(fams["RAD"])
+        names.append(fams["RAD"].par_names)
+        types_.append(fams["RAD"].par_types)
+    md.all_parnames = names + [ms.norm_names]
+    md.all_partypes = types_ + [['free'] * len(ms.norm_names)]
+    if fams["GA"].aux is not None:
+        md.GALAXYatt_dict = dict(zip(md.GALAXYFdict.keys(), fams["GA"].aux))
+    md.STARBURST_LIRdict = dict(zip(md.STARBURSTFdict.keys(), fams["SB"].aux)) if fams["SB"].aux is not None else {}
+    if ps is not None:         # the full-resolution twins (DICTIONARIES_AGNfitter.py:92-131), same key order
+        for short, attr in (("GA", "GALAXY"), ("SB", "STARBURST"), ("TO", "TORUS"), ("BB", "BBB"), ("RAD", "AGN_RAD")):
+            if short in fams:
+                pf = ps.fam(short)
+                keys = list(getattr(md, attr + "Fdict").keys())
+                setattr(md, attr + "Fdict_4plot", {k: pf.template(t) for t, k in enumerate(keys)})
+    models = types.SimpleNamespace(settings=ms.settings, dict_modelfluxes=md)
+    data = types.SimpleNamespace(z=float(g["src_z"][s]), dlum=float(g["src_dlum"][s]), nus=g["src_nus"][s],
+                                 fluxes=g["src_fluxes"][s], fluxerrs=g["src_fluxerrs"][s])
+    P = {'names': list(ms.par_names), 'min': list(g["ref_pmin"][s]), 'max': list(g["ref_pmax"][s])}
+    return data, models, P

@@ -104,3 +104,47 @@ def test_k4_api_errors():
         sed.set_bands(['AGNfracTO'], [[1e13, 1e13]])            # the reference appends nothing for this
     with pytest.raises(RuntimeError):
         sed.spectra(g["pars"], np.full(len(g["pars"]), 99, dtype=np.int32))
+
+
+@pytest.mark.parametrize("case,output_type", [("classic18", "int_lums"), ("radio2_sn12_49", "plot")])
+def test_fluxes_arrays_mirror(case, output_type):
+    """FluxesArrays = FLUXES_ARRAYS with the reference's constructor / entry point / result attributes
+    (PLOTandWRITE_AGNfitter.py:541-799), fed the reference's kinds of objects (MODELSDICT with `_4plot` dicts)."""
+    import types
+    from helpers import reference_objects
+    from agnfitter_b200.realizations import FluxesArrays, ranges_to_hz
+    from oracle import agn_oracle as O
+    ms, ps, g = load_sed(case)
+    s = 0
+    data, models, P = reference_objects(ms, g, s, ps)
+    rng = np.random.default_rng(9)
+    flat = rng.uniform(g["ref_pmin"][s], g["ref_pmax"][s], size=(300, ms.n_par))
+    chain = types.SimpleNamespace(flatchain=flat, best_fit_pars=flat[5], props=lambda: None)
+    out = {'realizations2int': 12, 'realizations2plot': 7, 'intlum_models': [str(m) for m in g["intlum_models"]],
+           'intlum_freqranges': g["intlum_ranges_um"]}
+    fa = FluxesArrays(chain, P, out, output_type, ms.settings, {'sampling_algorithm': 'emcee'},
+                      rng=np.random.RandomState(4))
+    fa.fluxes(data, models)
+    n_real = 12 if output_type == 'int_lums' else 7
+    pick = np.random.RandomState(4).choice(len(flat), n_real)
+    par = flat[pick]
+    par[-1] = flat[5]
+    z, dlum = float(data.z), float(data.dlum)
+    grid, fl = SO.realization_fluxes(ms, ps, par, z, dlum)
+    nl = SO.fluxes_to_nuLnu(grid, fl, z, dlum)
+    assert np.array_equal(fa.all_nus_rest, grid)
+    assert len(fa.nuLnus4plotting) == len(sed_component_order(ms))
+    for got, c in zip(fa.nuLnus4plotting, sed_component_order(ms)):
+        assert_close_with_specials(got, nl[c], what=c)
+    if output_type == 'int_lums':
+        with np.errstate(all="ignore"):
+            want = np.log10(SO.integrated_luminosities(out['intlum_models'], ranges_to_hz(out['intlum_freqranges']),
+                                                       grid, nl, ms.radio))
+        assert_close_with_specials(fa.int_lums, want, what="int_lums")
+        assert np.array_equal(fa.int_lums_best, fa.int_lums[:, -1], equal_nan=True)
+    else:
+        src = dict(z=z, dlum=dlum, nus=data.nus, fluxes=data.fluxes, fluxerrs=data.fluxerrs, pmin=g["ref_pmin"][s],
+                   pmax=g["ref_pmax"][s], zi=0)
+        ym = O.ln_probab(ms, src, par, return_parts=True)[1]
+        want = ym * (4. * np.pi * dlum ** 2.) * 10 ** (np.asarray(data.nus))
+        assert_close_with_specials(fa.filtered_modelpoints_nuLnu, want, what="filtered model points")

@@ -72,6 +72,7 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnf_sed_intlum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
     "agnf_sed_spectra": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    "agnf_sed_intlum_ens": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -50,19 +50,27 @@ def build_modelset_on_device(templates, filterdict, z_grid, settings, builder):
     return ms, dev
 
 
-def summary_columns(n_par, n_q=len(REFERENCE_PERCENTILES)):
+INTLUM_PERCENTILES = (16.0, 50.0, 84.0)     # PLOTandWRITE_AGNfitter.py:152-173 writes median and +-1 sigma
+
+
+def summary_columns(n_par, n_q=len(REFERENCE_PERCENTILES), n_intlum=0):
     """Layout of one summary row."""
     return ["source_index", "z"] + ["p%d_q%d" % (p, q) for p in range(n_par) for q in range(n_q)] + \
-           ["best_%d" % p for p in range(n_par)] + ["best_lnp", "acceptance"]
+           ["best_%d" % p for p in range(n_par)] + ["best_lnp", "acceptance"] + \
+           ["L%d_q%d" % (m, int(q)) for m in range(n_intlum) for q in INTLUM_PERCENTILES]
 
 
 def fit_catalog(templates, filterdict, settings, z, dlum, nus, fluxes, fluxerrs, mc, seed=0, n_bins=1024,
-                rank=0, world=1, device=0):
+                rank=0, world=1, device=0, intlum_models=None, intlum_ranges_hz=None):
     """Fit every source of the catalogue this rank owns and gather the summaries.
 
     z, dlum [S]; nus [n_b] or [S, n_b]; fluxes, fluxerrs [S, n_b] in the reference's DATA conventions
     (DATA_AGNfitter.py:145-193 already applied).  mc: MCMC_settings() dict (Nwalkers, Nburnsets, Nburn, Nmcmc,
-    Nthin).  Returns on rank 0 an array [S_total, len(summary_columns)] ordered by z (None on other ranks)."""
+    Nthin).  intlum_models / intlum_ranges_hz (out['intlum_models'], out['intlum_freqranges'] in Hz): also run
+    the integrated-luminosity stage (K4) on the final walker positions of every source and append the 16/50/84
+    percentiles of log10 of each column (the reference draws realizations2int rows from the thinned chain,
+    PLOTandWRITE_AGNfitter.py:608; here the W walkers of the last step are those rows).
+    Returns on rank 0 an array [S_total, len(summary_columns)] ordered by z (None on other ranks)."""
     import torch
     z = np.asarray(z, dtype=np.float64)
     order, lo, hi = _shard.shard_catalog(z, rank, world)
@@ -86,9 +94,20 @@ def fit_catalog(templates, filterdict, settings, z, dlum, nus, fluxes, fluxerrs,
         ens = EnsembleSampler(eng, int(mc['Nwalkers']), seed=int(seed), n_bins=n_bins, source_offset=lo)
         rngs = [np.random.default_rng([int(seed), lo + i]) for i in range(len(mine))]
         out = ens.run_reference_schedule(mc, src.pmin, src.pmax, rngs)
-        rows = np.concatenate([mine[:, None].astype(np.float64), zs[:, None],
-                               out["percentiles"].reshape(len(mine), -1), out["best_pos"],
-                               out["best_lnp"][:, None], out["acceptance"][:, None]], axis=1)
+        blocks = [mine[:, None].astype(np.float64), zs[:, None], out["percentiles"].reshape(len(mine), -1),
+                  out["best_pos"], out["best_lnp"][:, None], out["acceptance"][:, None]]
+        if intlum_models is not None:
+            from .plotset import plotset_from_templates
+            from .realizations import SedEngine
+            ps = plotset_from_templates({short: templates[long_name] for short, long_name in FAMILY_OF
+                                         if long_name in templates}, ms)
+            sed = SedEngine(eng, ps, zs, np.asarray(dlum, dtype=np.float64)[mine])
+            sed.set_bands(intlum_models, intlum_ranges_hz)
+            with np.errstate(all="ignore"):
+                L = np.log10(sed.int_lums_ensemble(int(mc['Nwalkers'])))          # [S, W, n_models]
+            q = np.percentile(L, INTLUM_PERCENTILES, axis=1)                       # [3, S, n_models]
+            blocks.append(np.transpose(q, (1, 2, 0)).reshape(len(mine), -1))
+        rows = np.concatenate(blocks, axis=1)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dev_t = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")

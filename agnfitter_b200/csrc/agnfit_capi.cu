@@ -1400,3 +1400,30 @@ AGNF_API int agnf_sed_spectra(agnf_ctx* ctx, const double* params, const int32_t
                      int32_t on_device) {
   return k4_run(ctx, params, source_id, n, out, on_device, true);
 }
+
+AGNF_API int agnf_sed_intlum_ens(agnf_ctx* ctx, double* out) {
+  if (!ctx) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  if (!out) return fail(ctx, "NULL argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (k4_ready(ctx, true)) return 1;
+  const K3State& st = ctx->ens;
+  const int64_t n = st.S * st.W;
+  void *d_sid = nullptr, *d_out = nullptr;
+  if (dev_alloc(ctx, &d_sid, (size_t)n * 4)) return 1;
+  if (dev_alloc(ctx, &d_out, (size_t)n * ctx->k4.n_specs * 8)) {
+    dev_free(ctx, d_sid);
+    return 1;
+  }
+  cudaError_t e = launch_k3_fill_sid(static_cast<int32_t*>(d_sid), st.S, st.W, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  int rc = e == cudaSuccess ? 0 : fail(ctx, "k3_fill_sid failed: %s", cudaGetErrorString(e));
+  if (!rc) rc = k4_run(ctx, st.pos, static_cast<const int32_t*>(d_sid), n, static_cast<double*>(d_out), 1, false);
+  if (!rc) {
+    e = cudaMemcpy(out, d_out, (size_t)n * ctx->k4.n_specs * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(ctx, "download failed: %s", cudaGetErrorString(e));
+  }
+  dev_free(ctx, d_sid);
+  dev_free(ctx, d_out);
+  return rc;
+}

@@ -274,6 +274,15 @@ class SedEngine:
         self.ctx.check(self.lib.agnf_sed_spectra(self.ctx.h, ptr(params), ptr(sid), len(params), ptr(out), 0))
         return out
 
+    def int_lums_ensemble(self, walkers):
+        """[S, W, n_models] for the walker state of the EnsembleSampler bound to the same context: the W final
+        positions of each source are its posterior rows.  Positions never leave HBM."""
+        if not self.n_models:
+            raise RuntimeError("call set_bands first")
+        out = np.empty((self.S, int(walkers), self.n_models), dtype=np.float64)
+        self.ctx.check(self.lib.agnf_sed_intlum_ens(self.ctx.h, ptr(out)))
+        return out
+
     def int_lums_device(self, params_t, sid_t, out_t):
         """Device-resident variant: torch CUDA tensors [n, n_par] f64, [n] i32, [n, n_models] f64."""
         self.ctx.check(self.lib.agnf_sed_intlum(self.ctx.h, params_t.data_ptr(), sid_t.data_ptr(),

@@ -260,6 +260,11 @@ AGNF_API int agnf_sed_intlum(agnf_ctx* ctx, const double* params, const int32_t*
 AGNF_API int agnf_sed_spectra(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* out,
                      int32_t on_device);
 
+/* K4 over the ensemble's resident walker state (agnf_ens_*): every walker of every source is one row, the
+ * W final positions of a source standing in for the rows FLUXES_ARRAYS.fluxes draws from the thinned chain
+ * (:596-610).  out [S, W, n_specs] (host).  Nothing but the result leaves HBM. */
+AGNF_API int agnf_sed_intlum_ens(agnf_ctx* ctx, double* out);
+
 #ifdef __cplusplus
 }
 #endif

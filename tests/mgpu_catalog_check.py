@@ -10,6 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+INTLUM_MODELS = ['sb', 'bbb', 'bbbdered', 'gal', 'AGNfrac_opt', 'tor', 'tor+bbb', 'AGNfrac_IR', 'tor']
+INTLUM_RANGES_UM = [[8., 1000.], [0.1, 1.], [0.1, 1.], [0.1, 1.], [0.1, 1.], [1., 30.], [0.1, 30], [8., 1000.], [6, 6]]
+
+
 def make_inputs(S=24, seed=5):
     from agnfitter_b200 import synth, sources
     from agnfitter_b200.engine import Engine, DictBuilder
@@ -47,8 +51,10 @@ def main(out_path):
         dist.init_process_group("nccl" if n_dev >= world else "gloo")
     templates, fd, settings, z, dlum, nus, fl, fe = make_inputs()
     mc = dict(Nwalkers=16, Nburnsets=2, Nburn=15, Nmcmc=40, Nthin=2)
+    from agnfitter_b200.realizations import ranges_to_hz
     table = fit_catalog(templates, fd, settings, z, dlum, nus, fl, fe, mc, seed=123, n_bins=512,
-                        rank=rank, world=world, device=device)
+                        rank=rank, world=world, device=device, intlum_models=INTLUM_MODELS,
+                        intlum_ranges_hz=ranges_to_hz(INTLUM_RANGES_UM))
     if rank == 0:
         np.save(out_path, table)
     if world > 1:

@@ -30,7 +30,7 @@ def test_fit_catalog_is_independent_of_world_size(tmp_path):
     from agnfitter_b200.catalog import summary_columns
     one = _run(1, str(tmp_path / "w1.npy"))
     two = _run(2, str(tmp_path / "w2.npy"))
-    cols = summary_columns(10)
+    cols = summary_columns(10, n_intlum=9)
     assert one.shape == (24, len(cols)) and two.shape == one.shape
     assert np.array_equal(np.sort(one[:, 0]), np.arange(24))                 # every source exactly once
     assert np.all(np.diff(one[:, 1]) >= 0)                                    # ordered by z
@@ -39,3 +39,9 @@ def test_fit_catalog_is_independent_of_world_size(tmp_path):
     assert np.all((acc > 0.02) & (acc < 0.98))
     q = one[:, 2:2 + 50].reshape(24, 10, 5)
     assert np.all(np.diff(q, axis=2) >= 0), "percentiles must be ascending"
+    # integrated luminosities of the final walkers (K4): 16/50/84 percentiles of log10 L, plausible magnitudes,
+    # AGN fractions (columns 4 and 7) inside [0, 1]
+    L = one[:, cols.index("L0_q16"):].reshape(24, 9, 3)
+    assert np.all(np.isfinite(L)) and np.all(np.diff(L, axis=2) >= 0)
+    assert np.all((L[:, [0, 1, 3, 5], :] > 30) & (L[:, [0, 1, 3, 5], :] < 60))
+    assert np.all((L[:, [4, 7], :] >= 0) & (L[:, [4, 7], :] <= 1))

@@ -1144,15 +1144,15 @@ AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, d
 // ------------------------------------------------------------------------------------------- K4
 
 AGNF_API int agnf_sed_config(agnf_ctx* ctx, int32_t G, const double* grid, const double* xg, int32_t to_lo, int32_t to_hi,
-                    int32_t rad_hi, int32_t dered_mode, const int32_t* dered_row, const double* bands,
-                    const int32_t* bands_jt) {
+                    int32_t rad_hi, int32_t dered_mode, const int32_t* dered_row, const int32_t* bands_jt,
+                    const double* bands_wt) {
   if (!ctx) return 1;
   if (!ctx->have_cfg) return fail(ctx, "agnf_modelset_config has not been called");
   if (G < 2 || !grid || !xg) return fail(ctx, "agnf_sed_config: empty frequency grid");
   if (to_lo < 0 || to_hi > G || rad_hi < 0 || rad_hi > G) return fail(ctx, "agnf_sed_config: cut-off outside the grid");
   if (dered_mode < 0 || dered_mode > 3) return fail(ctx, "dered_mode must be 0..3");
   if (dered_mode != 0 && !dered_row) return fail(ctx, "dered_mode %d needs dered_row", dered_mode);
-  if (dered_mode == 3 && (!bands || !bands_jt)) return fail(ctx, "dered_mode 3 needs the band centres and their table");
+  if (dered_mode == 3 && (!bands_jt || !bands_wt)) return fail(ctx, "dered_mode 3 needs the bracket table of the band centres");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   K4Params& Q = ctx->k4;
   Q.G = G;
@@ -1167,8 +1167,13 @@ AGNF_API int agnf_sed_config(agnf_ctx* ctx, int32_t G, const double* grid, const
     if (upload(ctx, &Q.dered_row, dered_row, (size_t)ctx->k1.fam[3].T)) return 1;
   }
   if (dered_mode == 3) {
-    if (upload(ctx, &Q.bands_x, bands, (size_t)ctx->k1.cfg.n_b)) return 1;
-    if (upload(ctx, &Q.bands_jt, bands_jt, (size_t)G)) return 1;
+    std::vector<K4Bracket> bt((size_t)G);
+    for (int i = 0; i < G; ++i) {
+      if (bands_jt[i] < -1 || bands_jt[i] >= ctx->k1.cfg.n_b) return fail(ctx, "bands_jt[%d] out of range", i);
+      bt[(size_t)i] = K4Bracket{bands_jt[i] < 0 ? 0.0 : bands_wt[i], bands_jt[i], 0};
+    }
+    if (upload(ctx, &Q.bands_bt, bt.data(), (size_t)G)) return 1;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {     // bracket tables depend on the grid: families must follow
@@ -1189,7 +1194,7 @@ AGNF_API int agnf_sed_family_upload(agnf_ctx* ctx, const agnf_sed_family* d) {
     return fail(ctx, "family %d: %lld full-resolution templates for %lld dictionary rows", d->fam, (long long)d->T,
                 (long long)ctx->k1.fam[d->fam].T);
   if (d->mode < 0 || d->mode > 3) return fail(ctx, "mode must be 0..3");
-  if (d->n_groups < 1 || !d->group || !d->local || !d->g_nlam || !d->x || !d->val || !d->jtab)
+  if (d->n_groups < 1 || !d->group || !d->local || !d->g_nlam || !d->x || !d->val || !d->jtab || !d->wtab)
     return fail(ctx, "agnf_sed_family_upload: NULL argument");
   if (d->mode != 0 && !d->k) return fail(ctx, "mode %d needs the reddening curve", d->mode);
   const int n_par = ctx->k1.cfg.n_par;
@@ -1223,9 +1228,15 @@ AGNF_API int agnf_sed_family_upload(agnf_ctx* ctx, const agnf_sed_family* d) {
     if (d->local[t] < 0) return fail(ctx, "family %d: local[%lld] < 0", d->fam, (long long)t);
     t_off[(size_t)t] = voff[(size_t)d->group[t]] + (int64_t)d->local[t] * d->g_nlam[d->group[t]];
   }
+  std::vector<K4Bracket> bt((size_t)ng * (size_t)ctx->k4.G);
   for (int64_t i = 0, n = (int64_t)ng * ctx->k4.G; i < n; ++i) {
     const int g = (int)(i / ctx->k4.G);
-    if (d->jtab[i] < -1 || d->jtab[i] >= d->g_nlam[g]) return fail(ctx, "family %d: bracket table entry out of range", d->fam);
+    const int32_t j = d->jtab[i];
+    const double w = j < 0 ? 0.0 : d->wtab[i];
+    // a point strictly inside an interval needs the next sample; on a sample (w == 0) the last one is allowed
+    if (j < -1 || j >= d->g_nlam[g] || (w != 0.0 && j + 1 >= d->g_nlam[g]) || !(w >= 0.0 && w < 1.0))
+      return fail(ctx, "family %d: bracket table entry %lld out of range", d->fam, (long long)i);
+    bt[(size_t)i] = K4Bracket{w, j, 0};
   }
   K4Family& F = ctx->k4.fam[d->fam];
   F.T = d->T;
@@ -1245,7 +1256,7 @@ AGNF_API int agnf_sed_family_upload(agnf_ctx* ctx, const agnf_sed_family* d) {
   if (upload(ctx, &F.t_grp, d->group, (size_t)d->T)) return 1;
   if (upload(ctx, &F.g_xoff, xoff.data(), (size_t)ng)) return 1;
   if (upload(ctx, &F.g_nlam, d->g_nlam, (size_t)ng)) return 1;
-  if (upload(ctx, &F.jtab, d->jtab, (size_t)ng * (size_t)ctx->k4.G)) return 1;
+  if (upload(ctx, &F.btab, bt.data(), bt.size())) return 1;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));     // the vectors above feed asynchronous copies
   F.present = 1;
   ctx->k4_fam[d->fam] = true;

@@ -15,8 +15,7 @@ __constant__ int c_comp_fam[K4_COMPS] = {1, 3, 0, 2, 4, 3};
 __constant__ int c_sum_order[K4_COMPS] = {3, 0, 2, 1, 4, 5};
 
 struct RowCtx {
-  const double* x[K4_COMPS];        // template grid of the component's template
-  const int32_t* jt[K4_COMPS];      // bracket table of that grid
+  const K4Bracket* bt[K4_COMPS];    // bracket table of the component's template grid
   int32_t yoff[K4_COMPS];           // shared-memory offset of its log10 F_nu row
   int32_t active[K4_COMPS];
   double scale[K4_COMPS];           // 10**norm
@@ -25,16 +24,19 @@ struct RowCtx {
   double area, lumfactor, zp1;
 };
 
-// numpy.interp's arithmetic for one point inside the template range (compiled_base.c: arr_interp)
-__device__ __forceinline__ double interp_y(const double* y, const double* __restrict__ x, int j, double xq) {
-  if (j < 0) return K4_FILL;
-  const double xj = __ldg(x + j), yj = y[j];
-  if (xj == xq) return yj;
-  const double xn = __ldg(x + j + 1), yn = y[j + 1];
-  const double slope = __ddiv_rn(__dsub_rn(yn, yj), __dsub_rn(xn, xj));
-  double r = __dadd_rn(__dmul_rn(slope, __dsub_rn(xq, xj)), yj);
+// numpy.interp for one point (compiled_base.c: arr_interp): y_j on a template sample; else the linear
+// interpolant, written with the precomputed weight w = (x - x_j) / (x_j+1 - x_j) instead of slope * (x - x_j)
+// (same value to ~1e-16 |y|); the reference's NaN fall-backs — evaluate from the other end, then y_j if both ends
+// are equal — keep 10**-inf = 0 and NaN exactly where numpy puts them.
+__device__ __forceinline__ double interp_y(const double* y, const K4Bracket b) {
+  if (b.j < 0) return K4_FILL;
+  const double yj = y[b.j];
+  if (b.w == 0.0) return yj;
+  const double yn = y[b.j + 1];
+  const double d = yn - yj;
+  double r = fma(b.w, d, yj);
   if (r != r) {
-    r = __dadd_rn(__dmul_rn(slope, __dsub_rn(xq, xn)), yn);
+    r = fma(b.w - 1.0, d, yn);
     if (r != r && yj == yn) r = yj;
   }
   return r;
@@ -49,8 +51,11 @@ struct Eval {
   __device__ __forceinline__ double flux(int c, int i) const {
     if (c == 3 && (i < Q->to_lo || i >= Q->to_hi)) return 0.0;
     if (c == 4 && i >= Q->rad_hi) return 0.0;
-    const int j = __ldg(C->jt[c] + i);
-    const double yv = interp_y(rows + C->yoff[c], C->x[c], j, __ldg(Q->grid + i));
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(C->bt[c] + i));
+    K4Bracket b;
+    b.w = __hiloint2double(raw.y, raw.x);
+    b.j = raw.z;
+    const double yv = interp_y(rows + C->yoff[c], b);
     double f = pow10_via2(yv, tab_s);
     if (C->by_area[c]) f = f / C->area;
     return f * C->scale[c];
@@ -65,7 +70,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_sed_kernel(const __grid_constan
   double* tab = k4_smem;                         // 2^(j/D)
   double* rows = k4_smem + AGNF_POW2_DENOM;      // template rows
   double* wpart = rows + Q->smem_doubles;        // [n_ranges][K4_COMPS][K4_WARPS]
-  double* I_s = wpart + K4_MAX_RANGES * K4_COMPS * K4_WARPS;   // [n_ranges][K4_COMPS]
+  double* I_s = wpart + Q->n_ranges * K4_COMPS * K4_WARPS;     // [n_ranges][K4_COMPS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t r = blockIdx.x;
   const double* __restrict__ p = B.params + r * P.cfg.n_par;
@@ -99,11 +104,9 @@ __global__ void __launch_bounds__(K4_THREADS) k4_sed_kernel(const __grid_constan
         yoff = Q->dered_off;
       }
       const int g = __ldg(F.t_grp + t);
-      C.x[c] = F.x + __ldg(F.g_xoff + g);
-      C.jt[c] = F.jtab + (int64_t)g * Q->G;
+      C.bt[c] = F.btab + (int64_t)g * Q->G;
       if (c == 5 && Q->dered_mode == 3) {
-        C.x[c] = Q->bands_x;
-        C.jt[c] = Q->bands_jt;
+        C.bt[c] = Q->bands_bt;
         yoff = Q->dered_off;
       }
       C.yoff[c] = yoff;
@@ -275,8 +278,7 @@ template <bool SPECTRA>
 cudaError_t launch(const K1Params& P, const K4Params* Qdev, const K4Params& Qhost, const K4Batch& B,
                    cudaStream_t stream) {
   if (B.n == 0) return cudaSuccess;
-  const size_t smem = (size_t)(AGNF_POW2_DENOM + Qhost.smem_doubles + K4_MAX_RANGES * K4_COMPS * K4_WARPS +
-                               K4_MAX_RANGES * K4_COMPS) * 8;
+  const size_t smem = (size_t)(AGNF_POW2_DENOM + Qhost.smem_doubles + Qhost.n_ranges * K4_COMPS * (K4_WARPS + 1)) * 8;
   cudaError_t e = cudaFuncSetAttribute(k4_sed_kernel<SPECTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;

@@ -14,8 +14,9 @@
 //      (32 evaluations, neighbours exchanged by shuffle); all components the band needs are evaluated at the
 //      same point; fixed-order reductions, so results are reproducible run to run;
 //      spectra mode: every grid point once, all components + their total written as nu L_nu.
-// The bracketing interval of every grid point inside every template grid is a host-built table (the grids are
-// shared by all rows), so the inner loop is: 1 table read, 2-4 shared-memory reads, one 10^x.
+// The bracketing interval and interpolation weight of every grid point inside every template grid are a
+// host-built table (the grids are shared by all rows), so the inner loop is: one 16-byte table read, two
+// shared-memory reads, one 10^x.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -28,6 +29,14 @@ constexpr int K4_MAX_RANGES = 32;
 constexpr int K4_MAX_SPECS = 64;
 constexpr int K4_COMPS = 6;          // sb, bb, ga, to, rad, bbdered (FLUXES4plotting order without the total)
 
+// Where grid point i falls inside a template grid: x[j] <= grid_i < x[j+1] (numpy.interp's bracket; j = -1:
+// outside the template, interp1d's fill value) and w = (grid_i - x[j]) / (x[j+1] - x[j]), 0 on a template sample.
+struct __align__(16) K4Bracket {
+  double w;
+  int32_t j;
+  int32_t pad;
+};
+
 struct K4Family {
   const double* x = nullptr;         // sorted template grids of all groups, concatenated
   const double* k = nullptr;         // reddening curve on the same layout (modes 1-3) or nullptr
@@ -37,7 +46,7 @@ struct K4Family {
   const int32_t* t_grp = nullptr;    // [T] grid group of template t
   const int32_t* g_xoff = nullptr;   // [n_groups] offset of the group's grid inside x / k
   const int32_t* g_nlam = nullptr;   // [n_groups]
-  const int32_t* jtab = nullptr;     // [n_groups, G] index j with x[j] <= grid < x[j+1] (numpy.interp), -1: fill
+  const K4Bracket* btab = nullptr;   // [n_groups, G] bracket of every grid point inside the group's grid
   int64_t T = 0;
   int32_t mode = 0;                  // 0 plain; 1 Calzetti; 2 Prevot; 3 Prevot below 10^16.685 Hz, alpha_ox scaling above
   int32_t e_col = 0, a_col = 0;      // params columns of E(B-V) and alphaScat
@@ -57,8 +66,7 @@ struct K4Params {
   const int32_t* dered_row = nullptr;  // [T_BB]
   // dered_mode 3 (SN12 without X-rays, PLT:714-717): the dereddened curve is interpolated over the BAND CENTRES
   // from the filtered dictionary row (K1's table), not from a full-resolution template
-  const double* bands_x = nullptr;   // [n_b] dictionary band centres (ascending)
-  const int32_t* bands_jt = nullptr; // [G] bracket table of that grid
+  const K4Bracket* bands_bt = nullptr; // [G] brackets inside the grid of dictionary band centres
   const double* grid = nullptr;      // [G] all_nus_rest
   const double* xg = nullptr;        // [G] 10**all_nus_rest
   const double* src_z = nullptr;     // [S]
@@ -82,7 +90,7 @@ struct K4Batch {
   double* spectra;                   // [n, n_comp, G] nu L_nu (spectra mode), n_comp = 6 or 7 with radio
 };
 
-constexpr int K4_THREADS = 128;
+constexpr int K4_THREADS = 256;
 
 cudaError_t launch_k4_intlum(const K1Params& P, const K4Params* Qdev, const K4Params& Qhost, const K4Batch& B,
                              cudaStream_t stream);

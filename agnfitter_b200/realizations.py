@@ -34,7 +34,8 @@ class agnf_sed_family(C.Structure):
     _fields_ = [("fam", C.c_int32), ("mode", C.c_int32), ("e_col", C.c_int32), ("a_col", C.c_int32),
                 ("n_groups", C.c_int32), ("reserved", C.c_int32), ("T", C.c_int64),
                 ("group", C.c_void_p), ("local", C.c_void_p), ("g_nlam", C.c_void_p), ("x", C.c_void_p),
-                ("k", C.c_void_p), ("val", C.c_void_p), ("val2", C.c_void_p), ("jtab", C.c_void_p)]
+                ("k", C.c_void_p), ("val", C.c_void_p), ("val2", C.c_void_p), ("jtab", C.c_void_p),
+                ("wtab", C.c_void_p)]
 
 
 def all_nus_rest(settings):
@@ -69,6 +70,17 @@ def bracket_table(xs, grid, split):
     jb = one(xs[n_a:], grid[~lo])
     out[~lo] = np.where(jb >= 0, jb + n_a, -1)
     return out.astype(np.int32)
+
+
+def bracket_weights(xs, grid, jt):
+    """(grid - x_j) / (x_j+1 - x_j) for the brackets of bracket_table; 0 on a template sample and outside."""
+    w = np.zeros(len(grid))
+    inside = (jt >= 0) & (jt + 1 < len(xs))
+    j = jt[inside]
+    with np.errstate(all="ignore"):
+        w[inside] = (grid[inside] - xs[j]) / (xs[j + 1] - xs[j])
+    w[inside & (grid == xs[np.maximum(jt, 0)])] = 0.0
+    return w
 
 
 def family_mode(fam, par_offset):
@@ -183,15 +195,16 @@ class SedEngine:
         self.n_comp = 7 if ms.radio else 6
         self.component_names = ['sb', 'bb', 'ga', 'to'] + (['rad'] if ms.radio else []) + ['total', 'bbdered']
         dered_row = as_i32(ps.dered_row)
-        bands = bands_jt = None
+        bands_jt = bands_wt = None
         if ps.dered_mode == 3:
             bands = as_f64(ms.bands)
             if np.any(np.diff(bands) <= 0):
                 raise ValueError("dictionary band centres must be strictly ascending")
             bands_jt = bracket_table(bands, self.grid, False)
+            bands_wt = as_f64(bracket_weights(bands, self.grid, bands_jt))
         grid_a = as_f64(self.grid)
         self.ctx.check(self.lib.agnf_sed_config(self.ctx.h, G, ptr(grid_a), ptr(xg), to_lo, to_hi, rad_hi,
-                                                int(ps.dered_mode), ptr(dered_row), ptr(bands), ptr(bands_jt)))
+                                                int(ps.dered_mode), ptr(dered_row), ptr(bands_jt), ptr(bands_wt)))
         split = (S['BBB'] != 'KD18') and (S['XRAYS'] == True)                  # PLT:697
         idxs = ms.idxs
         k_fit = 0
@@ -213,7 +226,7 @@ class SedEngine:
 
     def _upload_family(self, name, pf, mode, e_col, a_col, split):
         need2 = name == "BB" and self.ps.dered_mode in (1, 2)
-        xs_all, k_all, val_all, val2_all, jt_all, nlam = [], [], [], [], [], []
+        xs_all, k_all, val_all, val2_all, jt_all, wt_all, nlam = [], [], [], [], [], [], []
         with np.errstate(all="ignore"):
             for g, x in enumerate(pf.lognu):
                 x_used = np.log10(10 ** x) if mode == 1 else x          # Calzetti hands back log10(10**nu), DIC:366
@@ -230,13 +243,15 @@ class SedEngine:
                 xs_all.append(xs)
                 nlam.append(len(xs))
                 jt_all.append(bracket_table(xs, self.grid, split))
+                wt_all.append(bracket_weights(xs, self.grid, jt_all[-1]))
         d = agnf_sed_family()
         d.fam, d.mode, d.e_col, d.a_col = _FAM_INDEX[name], mode, e_col, a_col
         d.n_groups, d.T = len(pf.lognu), pf.T
         keep = [as_i32(pf.group), as_i32(pf.local), as_i32(nlam), as_f64(np.concatenate(xs_all)),
                 as_f64(np.concatenate(k_all)) if mode else None, as_f64(np.concatenate(val_all)),
-                as_f64(np.concatenate(val2_all)) if need2 else None, as_i32(np.concatenate(jt_all))]
-        for field, arr in zip(("group", "local", "g_nlam", "x", "k", "val", "val2", "jtab"), keep):
+                as_f64(np.concatenate(val2_all)) if need2 else None, as_i32(np.concatenate(jt_all)),
+                as_f64(np.concatenate(wt_all))]
+        for field, arr in zip(("group", "local", "g_nlam", "x", "k", "val", "val2", "jtab", "wtab"), keep):
             setattr(d, field, None if arr is None else arr.ctypes.data)
         self.ctx.check(self.lib.agnf_sed_family_upload(self.ctx.h, C.byref(d)))
 

@@ -232,15 +232,16 @@ typedef struct {
   const double* val2;       /* BB with dered_mode 1 or 2: log10 F_nu of the raw templates, same layout; else NULL  */
   const int32_t* jtab;      /* [n_groups, G] j with x[j] <= grid[i] < x[j+1] (numpy.interp's bracket), -1: the point
                                lies outside the (part of the) template that interp1d sees -> fill value -100       */
+  const double* wtab;       /* [n_groups, G] (grid[i] - x[j]) / (x[j+1] - x[j]); 0 where grid[i] == x[j] or j < 0   */
 } agnf_sed_family;
 
 /* grid = all_nus_rest (PLOTandWRITE_AGNfitter.py:633), xg = 10**grid; the torus is kept on grid points
  * [to_lo, to_hi) (:733-734), the radio component on [0, rad_hi) (:693).  dered_mode / dered_row [T_BB]: which
- * template the dereddened disc curve comes from (:709-730; agnfitter_b200/plotset.py).  bands_jt [G]: bracket table
- * of the dictionary band centres, needed for dered_mode 3 only (else NULL). */
+ * template the dereddened disc curve comes from (:709-730; agnfitter_b200/plotset.py).  bands_jt / bands_wt [G]:
+ * bracket table (as agnf_sed_family.jtab / wtab) of the dictionary band centres, needed for dered_mode 3 only. */
 AGNF_API int agnf_sed_config(agnf_ctx* ctx, int32_t G, const double* grid, const double* xg, int32_t to_lo, int32_t to_hi,
-                    int32_t rad_hi, int32_t dered_mode, const int32_t* dered_row, const double* bands,
-                    const int32_t* bands_jt);
+                    int32_t rad_hi, int32_t dered_mode, const int32_t* dered_row, const int32_t* bands_jt,
+                    const double* bands_wt);
 AGNF_API int agnf_sed_family_upload(agnf_ctx* ctx, const agnf_sed_family* fam);
 /* data.z and data.dlum of every source (same order as agnf_sources_upload) */
 AGNF_API int agnf_sed_sources(agnf_ctx* ctx, int64_t S, const double* z, const double* dlum);

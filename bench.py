@@ -265,6 +265,44 @@ def make_workload(args, rank, device, need_gpu=True):
     return eng, ms, dev_tables, raw, pars, sid, info
 
 
+_ORIGINAL_AFFINITY = []
+
+
+def unbind_host_threads():
+    """The CPU-baseline legs use every host core again."""
+    if _ORIGINAL_AFFINITY:
+        os.sched_setaffinity(0, _ORIGINAL_AFFINITY[0])
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and, by first touch, its pinned staging buffers) to the NUMA node its GPU
+    hangs off, so that the host<->device copies of the e2e leg do not cross the socket interconnect.
+    Returns a short description for the JSON line; does nothing where sysfs does not say."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return "numa node %d has no allowed cpus" % node
+        _ORIGINAL_AFFINITY.append(allowed)
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:          # containers without sysfs topology: keep the default placement
+        return "unbound (%s)" % type(e).__name__
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -274,6 +312,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: default placement"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng, ms, dev_tables, raw, pars, sid, info = make_workload(args, rank, local)
@@ -425,6 +464,7 @@ def run_ours(args):
         achieved = bpe * n / (k1_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
         # CPU baseline: the oracle port on a bounded sample of the same workload
+        unbind_host_threads()
         ns = min(args.cpu_sources, S)
         sample_ids = np.linspace(0, S - 1, ns).astype(np.int64)
         small, srcs, pl = build_host_sample(ms, dev_tables, raw, sample_ids, pars, W)
@@ -445,7 +485,8 @@ def run_ours(args):
                        "rows_per_step_per_gpu": n, "n_bands": n_b, "n_par": n_par,
                        "l2_policy": "inputs larger than L2 (params %.0f MB + dictionary %.1f GB per GPU)" % (
                            n * n_par * 8 / 1e6, info["k2_entries"] * 8 / 1e9),
-                       "parallelism": "sources sharded over %d GPU(s), no data-path collective" % world},
+                       "parallelism": "sources sharded over %d GPU(s), no data-path collective" % world,
+                       "host_placement": numa},
             # measured through the sampler loop when it ran (key "ensemble"), else the K1-bound figure
             "sources_fitted_per_s": (total_rows / (ens_ms_max * 1e-3) / EVALS_PER_FIT) if ens_info
                                     else value / EVALS_PER_FIT,

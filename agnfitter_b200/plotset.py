@@ -160,3 +160,13 @@ def plotset_from_arrays(arrs, prefix="ps_"):
             Fnu=[np.asarray(arrs[p + "Fnu%d" % g], dtype=np.float64) for g in range(ng)],
             group=np.asarray(arrs[p + "group"], dtype=np.int32), local=np.asarray(arrs[p + "local"], dtype=np.int32)))
     return ps
+
+
+def save_plotset(path, ps):
+    """Dense `.npz` beside flatten.save_modelset: the full-resolution templates of a model set."""
+    np.savez_compressed(path, **plotset_to_arrays(ps))
+
+
+def load_plotset(path):
+    with np.load(path, allow_pickle=False) as z:
+        return plotset_from_arrays({k: z[k] for k in z.files})

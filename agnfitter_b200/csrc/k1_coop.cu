@@ -218,7 +218,7 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   // ================================ phase 1: thread per evaluation =================================
   int s;
   int64_t wrow = 0;                 // ensemble mode: this walker's row in pos / lnp / n_acc
-  double ens_factor = 0.0, ens_lnu = 0.0;
+  double ens_factor = 0.0, ens_lnu = 0.0, ens_lnp_old = 0.0;
   if (ENS) {
     // the proposal is drawn here instead of being read: q = c_j - (c_j - x_k) zz (k3_common.cuh)
     const int H = B.ens.W >> 1;
@@ -232,19 +232,37 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     // different lines per load).  x_k lands in the proposal area, c_j in the (still unused) partial-sum area.
     const int my_w = (int)wrow;
     const int my_c = (int)(src * B.ens.W + (B.ens.half ? 0 : H) + d.j);
+    ens_lnp_old = B.ens.lnp[wrow];          // needed only by the acceptance test: in flight during the evaluation
     {
+      // four block rows per round: their eight loads are issued back to back, then stored (a store to shared
+      // memory orders the loads before it, so load-store pairs would serialise 2 n_par memory round trips)
       const int d_row = 32 / n_par, d_col = 32 - d_row * n_par;
       int row = lane / n_par, col = lane - row * n_par;
-      for (int r = 0; r < n_par; ++r) {
-        const int wr = __shfl_sync(0xffffffffu, my_w, row), cr = __shfl_sync(0xffffffffu, my_c, row);
-        const unsigned e = (unsigned)(r * 32 + lane);
-        sts_f64(q_s + 8u * e, B.ens.pos[(int64_t)wr * n_par + col]);
-        sts_f64(part_s + 8u * e, B.ens.pos[(int64_t)cr * n_par + col]);
-        row += d_row;
-        col += d_col;
-        if (col >= n_par) {
-          col -= n_par;
-          ++row;
+      for (int r0 = 0; r0 < n_par; r0 += 4) {
+        double xv[4], cv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          xv[u] = 0.0;
+          cv[u] = 0.0;
+          if (r0 + u < n_par) {
+            const int wr = __shfl_sync(0xffffffffu, my_w, row), cr = __shfl_sync(0xffffffffu, my_c, row);
+            xv[u] = B.ens.pos[(int64_t)wr * n_par + col];
+            cv[u] = B.ens.pos[(int64_t)cr * n_par + col];
+            row += d_row;
+            col += d_col;
+            if (col >= n_par) {
+              col -= n_par;
+              ++row;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (r0 + u < n_par) {
+            const unsigned e = (unsigned)((r0 + u) * 32 + lane);
+            sts_f64(q_s + 8u * e, xv[u]);
+            sts_f64(part_s + 8u * e, cv[u]);
+          }
         }
       }
     }
@@ -512,11 +530,11 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   if (ENS) {
     // emcee's acceptance rule, in place: only this thread touches walker `wrow` during the launch, and the
     // partners it read belong to the other (frozen) half
-    const double lnpdiff = ens_factor + lnp_new - B.ens.lnp[wrow];
+    const double lnpdiff = ens_factor + lnp_new - ens_lnp_old;
     const bool accept = live && (lnpdiff > ens_lnu);          // false for NaN and for -inf proposals
     if (accept) {
       B.ens.lnp[wrow] = lnp_new;
-      B.ens.n_acc[wrow] += 1;
+      atomicAdd(B.ens.n_acc + wrow, 1);                       // result unused: a fire-and-forget reduction
     }
     // accepted rows go back to `pos` the way they came: consecutive lanes store consecutive coordinates
     const unsigned acc_mask = __ballot_sync(0xffffffffu, accept);

@@ -77,6 +77,11 @@ struct agnf_ctx {
   int k2_last_kernel = 0;            // contraction of the last agnf_dict_build: 1 per-slice kernels, 2 shared-window
   int64_t ens_src_offset = 0;        // catalogue row of the shard's first source (Philox counter)
   int64_t ens_hist_samples = 0;
+  // chain recording (agnf_ens_record): step-major copies of the walker state, for the reference's chain files
+  double* ens_chain = nullptr;       // [cap, S * W * n_par]
+  double* ens_chain_lnp = nullptr;   // [cap, S * W]
+  int64_t ens_chain_cap = 0, ens_chain_n = 0;
+  int32_t ens_chain_every = 1;
 
   // K4 SED realisations
   K4Params k4{};
@@ -956,6 +961,11 @@ AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, doub
                     (void*)ctx->ens_sc.sid, (void*)ctx->ens_hist.hist, (void*)ctx->ens_best_pos,
                     (void*)ctx->ens_best_lnp})
       dev_free(ctx, q);
+    dev_free(ctx, ctx->ens_chain);
+    dev_free(ctx, ctx->ens_chain_lnp);
+    ctx->ens_chain = nullptr;
+    ctx->ens_chain_lnp = nullptr;
+    ctx->ens_chain_cap = ctx->ens_chain_n = 0;
     ctx->have_ens = false;
   }
   const int64_t S = ctx->k1.S;
@@ -1068,8 +1078,60 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
       ctx->ens_hist_samples += st.W;
       ctx->launches += 1;
     }
+    if (ctx->ens_chain && (ctx->ens_step % ctx->ens_chain_every) == 0) {
+      if (ctx->ens_chain_n >= ctx->ens_chain_cap) {
+        cudaStreamSynchronize(s);
+        return fail(ctx, "chain buffer full after %lld recorded steps (agnf_ens_record)", (long long)ctx->ens_chain_n);
+      }
+      const size_t nw = (size_t)st.S * st.W;
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ens_chain + (size_t)ctx->ens_chain_n * nw * st.n_par, st.pos,
+                                    nw * st.n_par * 8, cudaMemcpyDeviceToDevice, s));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ens_chain_lnp + (size_t)ctx->ens_chain_n * nw, st.lnp, nw * 8,
+                                    cudaMemcpyDeviceToDevice, s));
+      ++ctx->ens_chain_n;
+    }
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return 0;
+}
+
+AGNF_API int agnf_ens_record(agnf_ctx* ctx, int64_t max_steps, int32_t every) {
+  if (!ctx) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  if (max_steps < 0 || every < 1) return fail(ctx, "agnf_ens_record: max_steps >= 0 and every >= 1");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  dev_free(ctx, ctx->ens_chain);
+  dev_free(ctx, ctx->ens_chain_lnp);
+  ctx->ens_chain = nullptr;
+  ctx->ens_chain_lnp = nullptr;
+  ctx->ens_chain_cap = ctx->ens_chain_n = 0;
+  ctx->ens_chain_every = every;
+  if (max_steps == 0) return 0;
+  const K3State& st = ctx->ens;
+  const size_t nw = (size_t)st.S * st.W;
+  void *a = nullptr, *b = nullptr;
+  if (dev_alloc(ctx, &a, (size_t)max_steps * nw * st.n_par * 8)) return 1;
+  if (dev_alloc(ctx, &b, (size_t)max_steps * nw * 8)) {
+    dev_free(ctx, a);
+    return 1;
+  }
+  ctx->ens_chain = static_cast<double*>(a);
+  ctx->ens_chain_lnp = static_cast<double*>(b);
+  ctx->ens_chain_cap = max_steps;
+  return 0;
+}
+
+AGNF_API int agnf_ens_chain(agnf_ctx* ctx, double* chain, double* lnp, int64_t* n_recorded) {
+  if (!ctx) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const K3State& st = ctx->ens;
+  const size_t nw = (size_t)st.S * st.W, n = (size_t)ctx->ens_chain_n;
+  if (n_recorded) *n_recorded = ctx->ens_chain_n;
+  if (chain && n)
+    CUDA_TRY(ctx, cudaMemcpyAsync(chain, ctx->ens_chain, n * nw * st.n_par * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (lnp && n) CUDA_TRY(ctx, cudaMemcpyAsync(lnp, ctx->ens_chain_lnp, n * nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

@@ -11,6 +11,7 @@ with the reference's names, argument order and return conventions, backed by the
     PARAMETERSPACE_AGNfitter.ymodel(nus, z, dlum, models, P, *par) :180-243  Posterior.ymodel
     DICTIONARIES_AGNfitter.filtering_models(nus, F, filterdict, z) :426-478  engine.DictBuilder.filtering_models
     MODELSDICT.construct_dictionaryarray_filtered / build  DIC:78-154      fill_modelsdict
+    MCMC_AGNfitter.main(data, models, P, mc), emcee leg     MCMC:33-149     main (sampler on the GPU, same chain files)
 
 `data`, `models`, `P` are the reference's own objects (DATA_AGNfitter.DATA, MODEL_AGNfitter.MODELS,
 PARAMETERSPACE_AGNfitter.Pdict): nothing in RUN_AGNfitter_multi.py or the settings files changes.
@@ -87,6 +88,29 @@ class Posterior:
         """-> (lum[n_b], bands) like PARAMETERSPACE_AGNfitter.ymodel."""
         _, _, ym, _, _ = self.engine.lnprob(np.asarray(par, dtype=np.float64)[None, :], detail=True)
         return ym[0], self.bands
+
+
+def main(data, models, P, mc, seed=None, device=0):
+    """Mirror of the emcee leg of MCMC_AGNfitter.main(data, models, P, mc) (MCMC_AGNfitter.py:33-149) with the
+    whole sampler on the GPU: initial ball, `Nburnsets` burn-in sets each restarted around the best sample,
+    production run, and the two chain files the rest of the pipeline reads —
+    `<data.output_folder><data.name>/samples_burn1-2-3.sav` and `samples_mcmc.sav` in the format of
+    MCMC_AGNfitter.save_chains (:192-206).  The move is emcee's stretch move (a = 2) with its acceptance rule; the
+    random numbers come from a counter-based generator keyed by `seed` (the reference's run is unseeded, so its
+    chains are not reproducible either way).  Returns the summary dict of EnsembleSampler.run_reference_schedule."""
+    import os
+    from .ensemble import EnsembleSampler
+    if mc.get('sampling_algorithm', 'emcee') != 'emcee':
+        raise ValueError("the GPU sampler implements the emcee leg; for ultranest pass Posterior.my_posterior / "
+                         "my_params_transform to ReactiveNestedSampler (MCMC_AGNfitter.py:79)")
+    post = Posterior(data, models, P, device=device)
+    seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
+    ens = EnsembleSampler(post.engine, int(mc['Nwalkers']), seed=seed, n_bins=1024)
+    rng = np.random.default_rng(seed)
+    out = ens.run_reference_schedule(mc, post.src.pmin, post.src.pmax, rng, save_dir=str(data.output_folder),
+                                     names=[str(data.name)])
+    out["seed"] = seed
+    return out
 
 
 class CatalogPosterior:

@@ -16,6 +16,33 @@ from ._lib import as_f64, ptr
 REFERENCE_PERCENTILES = (2.5, 16.0, 50.0, 84.0, 97.5)
 
 
+def integrated_time(chain, c=5):
+    """Integrated autocorrelation time per parameter of a chain [W, n, n_par], the way emcee estimates
+    `sampler.acor` (emcee.autocorr.integrated_time with c = 5, no convergence check — the reference patches emcee to
+    quiet=True for the same reason, MCMC_AGNfitter.py:100-112): autocorrelation function by FFT, averaged over
+    walkers, summed up to the first window M >= c * tau(M)."""
+    x = np.asarray(chain, dtype=np.float64)
+    W, n, n_par = x.shape
+    tau = np.full(n_par, np.nan)
+    if n < 2:
+        return tau
+    size = 1 << int(np.ceil(np.log2(2 * n)))
+    for p in range(n_par):
+        acf = np.zeros(n)
+        for w in range(W):
+            y = x[w, :, p] - x[w, :, p].mean()
+            f = np.fft.rfft(y, n=size)
+            a = np.fft.irfft(f * np.conjugate(f), n=size)[:n]
+            if a[0] > 0:
+                acf += a / a[0]
+        acf /= W
+        taus = 2.0 * np.cumsum(acf) - 1.0
+        m = np.arange(n) < c * taus
+        win = int(np.argmin(m)) if not m.all() else n - 1
+        tau[p] = taus[win]
+    return tau
+
+
 class EnsembleSampler:
     def __init__(self, engine, walkers, seed=0, a=2.0, n_bins=1024, source_offset=0):
         """engine: an Engine with sources uploaded.  walkers: even.  n_bins: histogram resolution of the
@@ -30,6 +57,7 @@ class EnsembleSampler:
         self.n_bins = int(n_bins)
         self.ctx.check(self.lib.agnf_set_option(self.ctx.h, b"ens_source_offset", int(source_offset)))
         self.ctx.check(self.lib.agnf_ens_create(self.ctx.h, self.W, int(seed) & (2 ** 64 - 1), float(a), self.n_bins))
+        self._steps = 0
 
     # -- positions --------------------------------------------------------------------------------
     @staticmethod
@@ -50,13 +78,16 @@ class EnsembleSampler:
         if pos.shape != (self.S, self.W, self.n_par):
             raise ValueError("positions must have shape (S, W, n_par) = %s" % ((self.S, self.W, self.n_par),))
         self.ctx.check(self.lib.agnf_ens_set_positions(self.ctx.h, ptr(pos)))
+        self._steps = 0                 # steps behind the acceptance counters
 
     # -- stepping ---------------------------------------------------------------------------------
     def run(self, n_steps, hist_every=0, track_best=False):
         self.ctx.check(self.lib.agnf_ens_run(self.ctx.h, int(n_steps), int(hist_every), int(bool(track_best))))
+        self._steps += int(n_steps)
 
     def reset_stats(self):
         self.ctx.check(self.lib.agnf_ens_reset_stats(self.ctx.h))
+        self._steps = 0
 
     def state(self):
         """-> pos [S, W, n_par], lnp [S, W], n_accepted [S, W]"""
@@ -78,12 +109,45 @@ class EnsembleSampler:
         self.ctx.check(self.lib.agnf_ens_percentiles(self.ctx.h, ptr(q), len(q), ptr(out)))
         return out
 
+    # -- chains (the reference's .sav files) ------------------------------------------------------
+    def record(self, max_steps, every=1):
+        """Keep the walker state of every `every`-th step from now on (device buffer of max_steps entries;
+        0 stops recording).  For runs whose chains are wanted on disk — a handful of sources, not a catalogue:
+        the buffer takes S * W * (n_par + 1) * 8 bytes per step."""
+        self.ctx.check(self.lib.agnf_ens_record(self.ctx.h, int(max_steps), int(every)))
+
+    def chain(self):
+        """-> chain [S, W, n, n_par], lnprob [S, W, n] in emcee's axis order (sampler.chain / .lnprobability)."""
+        n = C.c_int64()
+        self.ctx.check(self.lib.agnf_ens_chain(self.ctx.h, None, None, C.byref(n)))
+        n = int(n.value)
+        ch = np.empty((n, self.S, self.W, self.n_par))
+        lp = np.empty((n, self.S, self.W))
+        self.ctx.check(self.lib.agnf_ens_chain(self.ctx.h, ptr(ch), ptr(lp), None))
+        return np.ascontiguousarray(ch.transpose(1, 2, 0, 3)), np.ascontiguousarray(lp.transpose(1, 2, 0))
+
+    def save_chains(self, filename, s=0):
+        """Write source s the way MCMC_AGNfitter.save_chains does (MCMC_AGNfitter.py:192-206): a protocol-2
+        pickle of dict(chain [W, n, n_par], accept [W], lnprob [W, n], final_pos [W, n_par], state, acor [n_par])
+        that PARAMETERSPACE_AGNfitter.get_best_position (:268-294) and PLOTandWRITE's CHAIN.props (:471-492)
+        read back.  `state` (emcee's NumPy RNG state) has no counterpart — the walk is driven by a counter-based
+        generator — and is stored as None; `acor` is the integrated autocorrelation time of the walker-mean
+        series per parameter (emcee's estimator: windowed sum of the autocorrelation function, c = 5)."""
+        import pickle
+        ch, lp = self.chain()
+        pos, _, acc = self.state()
+        with open(filename, 'wb') as f:
+            pickle.dump(dict(chain=ch[s], accept=acc[s] / float(max(self._steps, 1)), lnprob=lp[s], final_pos=pos[s],
+                             state=None, acor=integrated_time(ch[s])), f, protocol=2)
+
     # -- the reference's schedule -----------------------------------------------------------------
-    def run_reference_schedule(self, mc, pmin, pmax, rng):
+    def run_reference_schedule(self, mc, pmin, pmax, rng, save_dir=None, names=None):
         """mc: the dict of MCMC_settings() (Nwalkers, Nburnsets, Nburn, Nmcmc, Nthin).  rng: a NumPy
         Generator, or a list of S Generators (one per source: the initial balls then do not depend on
-        which other sources share the shard).  Returns a summary dict: percentiles [S, n_par, 5] of the
-        thinned production chain, best position / lnP, mean acceptance fraction per source."""
+        which other sources share the shard).  save_dir: also write `<save_dir>/<name>/samples_burn1-2-3.sav`
+        and `samples_mcmc.sav` for every source, in the reference's format (MCMC_AGNfitter.py:156-206).
+        Returns a summary dict: percentiles [S, n_par, 5] of the thinned production chain, best position / lnP,
+        mean acceptance fraction per source."""
         if int(mc['Nwalkers']) != self.W:
             raise ValueError("mc['Nwalkers'] != walkers")
         per_source = isinstance(rng, (list, tuple))
@@ -98,14 +162,29 @@ class EnsembleSampler:
                 return self.ball_around(best_pos, self.W, rng)
             return np.concatenate([self.ball_around(best_pos[s], self.W, rng[s]) for s in range(self.S)])
 
+        nb, nburn, n = int(mc['Nburnsets']), int(mc['Nburn']), int(mc['Nmcmc'])
+        if save_dir is not None:
+            import os
+            names = list(names) if names is not None else ["%d" % s for s in range(self.S)]
+            for nm in names:
+                os.makedirs(os.path.join(save_dir, str(nm)), exist_ok=True)
+            self.record(max(nb * nburn, 1))         # emcee's sampler accumulates all burn-in sets (no reset between)
         self.set_positions(initial())
-        for _ in range(int(mc['Nburnsets'])):
-            self.run(int(mc['Nburn']), track_best=True)
+        for _ in range(nb):
+            self.run(nburn, track_best=True)
             best_pos, _ = self.best()
+            if save_dir is not None:                # run_burn_in rewrites the file after every set (MCMC:171)
+                for s_, nm in enumerate(names):
+                    self.save_chains(os.path.join(save_dir, str(nm), 'samples_burn1-2-3.sav'), s_)
             self.set_positions(ball(best_pos))
         self.reset_stats()
-        n = int(mc['Nmcmc'])
+        if save_dir is not None:
+            self.record(max(n, 1))                  # sampler.reset() (MCMC:182)
         self.run(n, hist_every=int(mc.get('Nthin', 1)) if self.n_bins else 0, track_best=True)
+        if save_dir is not None:
+            for s_, nm in enumerate(names):
+                self.save_chains(os.path.join(save_dir, str(nm), 'samples_mcmc.sav'), s_)
+            self.record(0)
         _, _, acc = self.state()
         bp, bl = self.best()
         return dict(percentiles=self.percentiles() if self.n_bins else None, best_pos=bp, best_lnp=bl,

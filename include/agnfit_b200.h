@@ -198,6 +198,12 @@ AGNF_API int agnf_ens_set_positions(agnf_ctx* ctx, const double* pos);
  * PLOTandWRITE_AGNfitter.py:471-492).  track_best: keep the best (position, lnP) seen per source
  * (what get_best_position reads back from the burn-in file). */
 AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, int32_t track_best);
+/* Chain recording for the reference's chain files (samples_burn1-2-3.sav / samples_mcmc.sav,
+ * MCMC_AGNfitter.py:192-206): from now on every `every`-th step of agnf_ens_run appends the walker state to a
+ * device buffer of max_steps entries (0: stop recording and free it).  agnf_ens_run fails when the buffer is full.
+ * agnf_ens_chain copies what was recorded: chain [n, S, W, n_par], lnp [n, S, W] (either may be NULL). */
+AGNF_API int agnf_ens_record(agnf_ctx* ctx, int64_t max_steps, int32_t every);
+AGNF_API int agnf_ens_chain(agnf_ctx* ctx, double* chain, double* lnp, int64_t* n_recorded);
 /* current state to host buffers (any may be NULL): pos [S, W, n_par], lnp [S, W], n_acc [S, W] */
 AGNF_API int agnf_ens_get(agnf_ctx* ctx, double* pos, double* lnp, int32_t* n_acc);
 AGNF_API int agnf_ens_best(agnf_ctx* ctx, double* best_pos, double* best_lnp);   /* [S, n_par], [S] */

@@ -56,3 +56,25 @@ def test_fill_modelsdict_matches_reference_dictionary():
         assert np.array_equal(b, bands)
         assert_close_with_specials(F, ref[1, i], what="TORUSFdict[%s]" % k)
     assert md.TORUSFdict_4plot is tpl
+
+
+def test_main_writes_the_reference_chain_files(tmp_path):
+    """dropin.main = MCMC_AGNfitter.main's emcee leg: same signature, same output files."""
+    import pickle
+    ms, g = load_k1("classic18")
+    data, models, P = _reference_objects(ms, g, 0)
+    data.output_folder, data.name = str(tmp_path) + "/", "obj7"
+    mc = dict(Nwalkers=20, Nburnsets=2, Nburn=12, Nmcmc=24, Nthin=2, iprint=1000, sampling_algorithm='emcee')
+    out = dropin.main(data, models, P, mc, seed=3)
+    again = dropin.main(data, models, P, mc, seed=3)
+    assert np.array_equal(out["best_pos"], again["best_pos"]) and out["best_lnp"][0] == again["best_lnp"][0]
+    with open(tmp_path / "obj7" / "samples_mcmc.sav", "rb") as f:
+        smp = pickle.load(f)
+    assert smp["chain"].shape == (20, 24, ms.n_par) and smp["lnprob"].shape == (20, 24)
+    # every recorded sample carries its own log-posterior (checked against the batch entry point)
+    post = dropin.Posterior(data, models, P)
+    flat = smp["chain"].reshape(-1, ms.n_par)
+    assert_close_with_specials(post.ln_probab_batch(flat), smp["lnprob"].ravel(), what="chain lnprob")
+    assert 0.0 < smp["accept"].mean() < 1.0
+    with pytest.raises(ValueError):
+        dropin.main(data, models, P, dict(mc, sampling_algorithm='ultranest'))

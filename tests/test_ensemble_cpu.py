@@ -42,3 +42,17 @@ def test_stretch_move_samples_a_gaussian():
     assert np.allclose(x.std(axis=0), sig, rtol=0.06)
     frac = acc.mean() / 1500
     assert 0.3 < frac < 0.8
+
+
+def test_integrated_time_estimator():
+    """AR(1) chains with known autocorrelation time tau = (1 + rho) / (1 - rho)."""
+    from agnfitter_b200.ensemble import integrated_time
+    rng = np.random.default_rng(0)
+    rho, n, W = 0.8, 20000, 8
+    x = np.zeros((W, n, 2))
+    e = rng.normal(size=(W, n, 2))
+    for t in range(1, n):
+        x[:, t, 0] = rho * x[:, t - 1, 0] + e[:, t, 0]
+    x[:, :, 1] = e[:, :, 1]
+    tau = integrated_time(x)
+    assert abs(tau[0] - 9.0) < 1.0 and abs(tau[1] - 1.0) < 0.15

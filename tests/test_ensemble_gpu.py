@@ -144,3 +144,61 @@ def test_reference_schedule_on_example_catalogue():
     assert np.allclose(out['best_lnp'], best_l, rtol=1e-10)
     assert np.array_equal(out['best_pos'], best_p)
     assert np.allclose(out['acceptance'], acc.mean(axis=1) / mc['Nmcmc'])
+
+
+def test_chain_recording_and_reference_chain_files(tmp_path):
+    """agnf_ens_record keeps the walker state of every step on the device; the recorded chain is exactly the
+    sequence of states (step for step); run_reference_schedule(save_dir=...) writes samples_burn1-2-3.sav /
+    samples_mcmc.sav that the reference's readers (get_best_position, PARAMETERSPACE:268-294; CHAIN.props,
+    PLOTandWRITE:471-492) can consume: same keys, axis order and dtypes as MCMC_AGNfitter.save_chains (:192-206)."""
+    import pickle
+    ms, eng, src, lnprob = _setup("cat49_catalog_example")
+    W = 16
+    ens = EnsembleSampler(eng, W, seed=77, n_bins=0)
+    rng = np.random.default_rng(1)
+    ens.set_positions(EnsembleSampler.initial_positions(src.pmin, src.pmax, W, rng))
+    ens.record(12)
+    states = []
+    for _ in range(12):
+        ens.run(1)
+        p, l, _ = ens.state()
+        states.append((p, l))
+    ch, lp = ens.chain()
+    assert ch.shape == (src.S, W, 12, ms.n_par) and lp.shape == (src.S, W, 12)
+    for k, (p, l) in enumerate(states):
+        assert np.array_equal(ch[:, :, k, :], p) and np.array_equal(lp[:, :, k], l, equal_nan=True)
+    with pytest.raises(RuntimeError):
+        ens.run(1)                                            # buffer full: fails instead of dropping samples
+    ens.record(6, every=2)
+    ens.run(12)
+    assert ens.chain()[0].shape[2] == 6
+    ens.record(0)
+    # the reference's files
+    mc = dict(Nwalkers=W, Nburnsets=2, Nburn=10, Nmcmc=30, Nthin=2)
+    ens = EnsembleSampler(eng, W, seed=78, n_bins=256)
+    names = ["srcA", "srcB"][:src.S]
+    out = ens.run_reference_schedule(mc, src.pmin, src.pmax, np.random.default_rng(2), save_dir=str(tmp_path),
+                                     names=names)
+    for s, nm in enumerate(names):
+        with open(tmp_path / nm / "samples_burn1-2-3.sav", "rb") as f:
+            burn = pickle.load(f)
+        with open(tmp_path / nm / "samples_mcmc.sav", "rb") as f:
+            mcmc = pickle.load(f)
+        assert set(mcmc.keys()) == {"chain", "accept", "lnprob", "final_pos", "state", "acor"}
+        assert burn["chain"].shape == (W, 20, ms.n_par) and burn["lnprob"].shape == (W, 20)
+        assert mcmc["chain"].shape == (W, 30, ms.n_par) and mcmc["lnprob"].shape == (W, 30)
+        assert mcmc["accept"].shape == (W,) and mcmc["acor"].shape == (ms.n_par,)
+        assert np.all((mcmc["accept"] >= 0) & (mcmc["accept"] <= 1))
+        # get_best_position's arithmetic on the burn-in file
+        i = burn["lnprob"].ravel().argmax()
+        ml = burn["chain"].reshape(-1, ms.n_par)[i]
+        assert np.all(ml >= src.pmin[s]) and np.all(ml <= src.pmax[s])
+        # CHAIN.props' arithmetic on the production file
+        nsamples = mcmc["chain"].shape[1]
+        flat = mcmc["chain"][:, int(nsamples / 2):nsamples:2, :].reshape(-1, ms.n_par)
+        lnflat = mcmc["lnprob"][:, int(nsamples / 2):nsamples:2].ravel()
+        best = flat[(-lnflat).argsort()[0]]
+        assert np.isfinite(lnflat).all() and flat.shape == (W * 8, ms.n_par)
+        assert lnflat.max() <= out["best_lnp"][s] + 1e-12
+        assert np.array_equal(mcmc["final_pos"], ens.state()[0][s])
+        assert np.all(best >= src.pmin[s]) and np.all(best <= src.pmax[s])

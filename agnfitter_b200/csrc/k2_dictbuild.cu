@@ -370,6 +370,8 @@ constexpr int K2_SW_MAX_ROUNDS = 32;
 struct K2SwPlan {
   int32_t nb;          // batches per round: 1, 2 or 4
   int32_t nb_shift;
+  int32_t nbuf;        // weight buffers: 2 = the next round's weights arrive during this one; 1 = wide filter sets
+                       // whose double-buffered weights would not fit (49 bands): loaded at the start of the round
   int32_t zbc;         // batches per CTA (a multiple of nb)
   int32_t opitch;      // pitch of a result tile (out_pitch when slices leave by bulk stores, else + 1)
   int32_t bulk_store;
@@ -415,21 +417,26 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
   k2_mbar_wait(bar, 0);
   int ir = 0;
   for (int zbr = zb0; zbr < zb1; zbr += NB, ++ir) {
-    const int buf = ir & 1;
+    const int buf = (c.nbuf == 2) ? (ir & 1) : 0;
     const int nbr = min(NB, zb1 - zbr);
     if (threadIdx.x == 0) {
-      if (zbr + NB < zb1) {
+      if (c.nbuf == 2 && zbr + NB < zb1) {
         const uint32_t wbytes = (uint32_t)min(NB, zb1 - zbr - NB) * (uint32_t)wsA * 32u;
         k2_mbar_expect_tx(bar + 8 + 8 * (buf ^ 1), wbytes);
         k2_bulk_g2s(k2_smem_u32(W_s + (size_t)(buf ^ 1) * wround), p.WA + (int64_t)(zbr + NB) * wsA * 4, wbytes,
                     bar + 8 + 8 * (buf ^ 1));
+      }
+      if (c.nbuf == 1 && ir > 0) {       // every warp left the previous round (barrier below): reuse the buffer
+        const uint32_t wbytes = (uint32_t)nbr * (uint32_t)wsA * 32u;
+        k2_mbar_expect_tx(bar + 8, wbytes);
+        k2_bulk_g2s(k2_smem_u32(W_s), p.WA + (int64_t)zbr * wsA * 4, wbytes, bar + 8);
       }
       if (ir > 0 && c.bulk_store) {      // the previous round's result tile has left shared memory: release it
         asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar + 24) : "memory");
       }
     }
-    k2_mbar_wait(bar + 8 + 8 * buf, (ir >> 1) & 1);
+    k2_mbar_wait(bar + 8 + 8 * buf, (c.nbuf == 2 ? (ir >> 1) : ir) & 1);
     const double* __restrict__ Wb = W_s + (size_t)buf * wround;
     // units (band, batch of the round), longest band first, handed out through a shared counter
     for (;;) {
@@ -506,11 +513,14 @@ bool k2_sw_plan(const K2Problem& p, K2SwPlan* c) {
   const int opitch = bulk ? p.out_pitch : p.out_pitch + 1;
   const size_t f = (size_t)TT * p.ldF * 8;
   const size_t off_w = (f + 15) & ~(size_t)15;
-  for (int nb = 4, sh = 2; nb >= 1; nb >>= 1, --sh) {
-    const size_t off_o = off_w + 2 * (size_t)nb * p.wstrideA * 32;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int nb = pass == 0 ? 4 : (pass == 1 ? 2 : 1), sh = pass == 0 ? 2 : (pass == 1 ? 1 : 0);
+    const int nbuf = pass == 3 ? 1 : 2;
+    const size_t off_o = off_w + (size_t)nbuf * nb * p.wstrideA * 32;
     const size_t off_bar = (off_o + (size_t)nb * 4 * TT * opitch * 8 + 15) & ~(size_t)15;
     const size_t total = off_bar + 32 + K2_SW_MAX_ROUNDS * 4;
     if (total > 225 * 1024) continue;
+    c->nbuf = nbuf;
     c->nb = nb;
     c->nb_shift = sh;
     c->opitch = opitch;

@@ -54,6 +54,8 @@ struct agnf_ctx {
   // upload, one launch, one download — all truly asynchronous — instead of three pageable copies
   void* pin = nullptr;                          // cudaHostAlloc
   void* pin_dev = nullptr;                      // device mirror of the block
+  void* pin_map = nullptr;                      // device-side address of the pinned block itself (zero copy)
+  int64_t zero_copy_rows = 256;                 // batches up to this many rows are read in place over PCIe
   int64_t small_rows = 4096;                    // batches up to this many rows take the path (0: off)
   // host-variant staging
   void* st_params = nullptr; size_t st_params_cap = 0;
@@ -402,6 +404,11 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     ctx->ens_fused = (int)value;
     return 0;
   }
+  if (strcmp(name, "zero_copy_rows") == 0) {
+    if (value < 0 || value > (1 << 20)) return fail(ctx, "zero_copy_rows must be in [0, 2^20]");
+    ctx->zero_copy_rows = value;
+    return 0;
+  }
   if (strcmp(name, "small_rows") == 0) {
     if (value < 0 || value > (1 << 20)) return fail(ctx, "small_rows must be in [0, 2^20]");
     if (ctx->pin && value > ctx->small_rows) {          // the pinned block was sized for the old limit
@@ -427,6 +434,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "band_pitch") == 0) *value = ctx->have_cfg ? ctx->k1.nbp : 0;
   else if (strcmp(name, "pipeline_rows") == 0) *value = ctx->pipeline_rows;
   else if (strcmp(name, "small_rows") == 0) *value = ctx->small_rows;
+  else if (strcmp(name, "zero_copy_rows") == 0) *value = ctx->zero_copy_rows;
   else if (strcmp(name, "ens_fused") == 0) *value = ctx->ens_fused;
   else if (strcmp(name, "k2_shared_window") == 0) *value = ctx->k2_shared_window;
   else if (strcmp(name, "k2_last_kernel") == 0) *value = ctx->k2_last_kernel;
@@ -649,7 +657,8 @@ AGNF_API int agnf_lnprob_batch(agnf_ctx* ctx, const double* params, const int32_
     const size_t cap = (size_t)ctx->small_rows;
     const size_t off_sid = cap * AGNF_MAX_PARS * 8, off_out = off_sid + cap * 4, bytes = off_out + cap * 8;
     if (!ctx->pin) {
-      CUDA_TRY(ctx, cudaHostAlloc(&ctx->pin, bytes, cudaHostAllocDefault));
+      CUDA_TRY(ctx, cudaHostAlloc(&ctx->pin, bytes, cudaHostAllocMapped));
+      CUDA_TRY(ctx, cudaHostGetDevicePointer(&ctx->pin_map, ctx->pin, 0));
       if (dev_alloc(ctx, &ctx->pin_dev, bytes)) return 1;
     }
     char* h = static_cast<char*>(ctx->pin);
@@ -659,6 +668,17 @@ AGNF_API int agnf_lnprob_batch(agnf_ctx* ctx, const double* params, const int32_
     memcpy(h, params, pbytes);
     memcpy(h + pb16, source_id, N * 4);
     cudaStream_t s1 = ctx->stream;
+    if (n <= ctx->zero_copy_rows) {
+      // a sampler's half-ensemble: the kernel reads the pinned block through its device mapping and writes the
+      // results back into it -- one launch and one synchronisation instead of copy, launch, copy, synchronise
+      char* m = static_cast<char*>(ctx->pin_map);
+      if (agnf_lnprob_batch_device(ctx, reinterpret_cast<const double*>(m), reinterpret_cast<const int32_t*>(m + pb16),
+                                   n, reinterpret_cast<double*>(m + off_out), nullptr, nullptr, nullptr, nullptr, s1))
+        return 1;
+      CUDA_TRY(ctx, cudaStreamSynchronize(s1));
+      memcpy(lnp, h + off_out, N * 8);
+      return 0;
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(d, h, pb16 + N * 4, cudaMemcpyHostToDevice, s1));
     if (agnf_lnprob_batch_device(ctx, reinterpret_cast<const double*>(d), reinterpret_cast<const int32_t*>(d + pb16), n,
                                  reinterpret_cast<double*>(d + off_out), nullptr, nullptr, nullptr, nullptr, s1))

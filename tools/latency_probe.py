@@ -26,6 +26,12 @@ lib, h = eng.lib, eng.ctx.h
 pp, ps, po = ptr(pars), ptr(sid), ptr(out)
 print("raw ctypes agnf_lnprob_batch       %.1f us" % timeit(lambda: lib.agnf_lnprob_batch(h, pp, ps, n, po, None, None, None, None)))
 print("raw ctypes agnf_synchronize        %.1f us" % timeit(lambda: lib.agnf_synchronize(h)))
+for zc in (0, 256):
+    eng.set_option("zero_copy_rows", zc)
+    for m in (50, 200):
+        pm = np.ascontiguousarray(np.tile(pars, (4, 1))[:m]); sm = np.zeros(m, dtype=np.int32); om = np.empty(m)
+        a, b, c = ptr(pm), ptr(sm), ptr(om)
+        print("raw, zero_copy_rows=%d, %d rows      %.1f us" % (zc, m, timeit(lambda: lib.agnf_lnprob_batch(h, a, b, m, c, None, None, None, None))))
 eng.set_option("small_rows", 0)
 print("raw, small_rows=0 (pageable copies) %.1f us" % timeit(lambda: lib.agnf_lnprob_batch(h, pp, ps, n, po, None, None, None, None)))
 eng.set_option("small_rows", 4096)

@@ -92,8 +92,7 @@ def fit_catalog(templates, filterdict, settings, z, dlum, nus, fluxes, fluxerrs,
         # random numbers are keyed by the source's position in the z-sorted catalogue, not by the shard:
         # the fit of a source does not depend on the number of GPUs
         ens = EnsembleSampler(eng, int(mc['Nwalkers']), seed=int(seed), n_bins=n_bins, source_offset=lo)
-        rngs = [np.random.default_rng([int(seed), lo + i]) for i in range(len(mine))]
-        out = ens.run_reference_schedule(mc, src.pmin, src.pmax, rngs)
+        out = ens.run_reference_schedule(mc, src.pmin, src.pmax, None)        # balls drawn on the device
         blocks = [mine[:, None].astype(np.float64), zs[:, None], out["percentiles"].reshape(len(mine), -1),
                   out["best_pos"], out["best_lnp"][:, None], out["acceptance"][:, None]]
         if intlum_models is not None:

@@ -1028,14 +1028,13 @@ AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, doub
   return 0;
 }
 
-AGNF_API int agnf_ens_set_positions(agnf_ctx* ctx, const double* pos) {
-  if (!ctx || !pos) return 1;
-  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+namespace {
+
+// the walkers have new positions: evaluate them, restart the acceptance counters and the running best
+int ens_positions_changed(agnf_ctx* ctx) {
   K3State& st = ctx->ens;
   cudaStream_t s = ctx->stream;
   const int64_t n = st.S * st.W;
-  CUDA_TRY(ctx, cudaMemcpyAsync(st.pos, pos, (size_t)n * st.n_par * 8, cudaMemcpyHostToDevice, s));
   CUDA_TRY(ctx, launch_k3_fill_sid(ctx->ens_sc.sid, st.S, st.W, s));
   if (agnf_lnprob_batch_device(ctx, st.pos, ctx->ens_sc.sid, n, st.lnp, nullptr, nullptr, nullptr, nullptr, s)) return 1;
   CUDA_TRY(ctx, launch_k3_fill_sid(ctx->ens_sc.sid, st.S, st.W / 2, s));
@@ -1046,6 +1045,34 @@ AGNF_API int agnf_ens_set_positions(agnf_ctx* ctx, const double* pos) {
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
   ctx->launches += 4;
   return 0;
+}
+
+}  // namespace
+
+AGNF_API int agnf_ens_set_positions(agnf_ctx* ctx, const double* pos) {
+  if (!ctx || !pos) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  K3State& st = ctx->ens;
+  CUDA_TRY(ctx, cudaMemcpyAsync(st.pos, pos, (size_t)st.S * st.W * st.n_par * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return ens_positions_changed(ctx);
+}
+
+AGNF_API int agnf_ens_set_ball(agnf_ctx* ctx, const double* centre, double scale, int32_t normal, uint32_t stream_id) {
+  if (!ctx || !centre) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  K3State& st = ctx->ens;
+  void* d_c = nullptr;
+  if (dev_alloc(ctx, &d_c, (size_t)st.S * st.n_par * 8)) return 1;
+  cudaError_t e = cudaMemcpyAsync(d_c, centre, (size_t)st.S * st.n_par * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+    e = launch_k3_ball(st, static_cast<const double*>(d_c), scale, normal ? 1 : 0, stream_id, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, d_c);
+  if (e != cudaSuccess) return fail(ctx, "agnf_ens_set_ball failed: %s", cudaGetErrorString(e));
+  ctx->launches += 1;
+  return ens_positions_changed(ctx);
 }
 
 AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, int32_t track_best) {

@@ -120,6 +120,37 @@ inline unsigned blocks_for(int64_t n) { return (unsigned)((n + K3_THREADS - 1) /
 
 }  // namespace
 
+// pos[s, w, p] = centre[s, p] + scale * d, d uniform in (-1, 1) or standard normal (Box-Muller), drawn from
+// Philox with counter (stream, 2 + p, source + offset, walker): disjoint from the stretch move's counters, whose
+// second word is the half-ensemble index 0 / 1
+__global__ void k3_ball_kernel(K3State st, const double* __restrict__ centre, double scale, int normal,
+                               uint32_t stream_id) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = st.S * st.W * st.n_par;
+  if (i >= n) return;
+  const int p = (int)(i % st.n_par);
+  const int64_t sw = i / st.n_par;
+  const int w = (int)(sw % st.W);
+  const int64_t s = sw / st.W;
+  uint32_t x[4];
+  philox4x32_10(stream_id, 2u + (uint32_t)p, (uint32_t)(s + st.src_offset), (uint32_t)w, (uint32_t)st.seed,
+                (uint32_t)(st.seed >> 32), x);
+  const double u1 = (double)((((uint64_t)x[0] << 32) | x[1]) >> 11) * 1.1102230246251565e-16;
+  const double u2 = (double)((((uint64_t)x[2] << 32) | x[3]) >> 11) * 1.1102230246251565e-16;
+  double d;
+  if (normal) d = sqrt(-2.0 * log1p(-u1)) * cospi(2.0 * u2);
+  else d = __dsub_rn(__dmul_rn(2.0, u1), 1.0);
+  st.pos[i] = __dadd_rn(centre[s * st.n_par + p], __dmul_rn(d, scale));
+}
+
+cudaError_t launch_k3_ball(const K3State& st, const double* centre, double scale, int normal, uint32_t stream_id,
+                           cudaStream_t stream) {
+  const int64_t n = st.S * st.W * st.n_par;
+  if (n == 0) return cudaSuccess;
+  k3_ball_kernel<<<blocks_for(n), K3_THREADS, 0, stream>>>(st, centre, scale, normal, stream_id);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_k3_fill_sid(int32_t* sid, int64_t S, int32_t half, cudaStream_t stream) {
   if (S * half <= 0) return cudaSuccess;
   k3_fill_sid_kernel<<<blocks_for(S * half), K3_THREADS, 0, stream>>>(sid, S, half);

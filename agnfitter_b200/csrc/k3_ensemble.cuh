@@ -45,6 +45,9 @@ struct K3Hist {
   int32_t n_bins;
 };
 
+// walker positions around per-source centres [S, n_par] (device): centre + scale * (uniform(-1, 1) | normal)
+cudaError_t launch_k3_ball(const K3State& st, const double* centre, double scale, int normal, uint32_t stream_id,
+                           cudaStream_t stream);
 cudaError_t launch_k3_fill_sid(int32_t* sid, int64_t S, int32_t half, cudaStream_t stream);
 cudaError_t launch_k3_propose(const K3State& st, const K3Scratch& sc, int64_t step, int half, cudaStream_t stream);
 cudaError_t launch_k3_accept(const K3State& st, const K3Scratch& sc, int half, cudaStream_t stream);

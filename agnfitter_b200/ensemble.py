@@ -43,6 +43,33 @@ def integrated_time(chain, c=5):
     return tau
 
 
+class ShardStream:
+    """Host-side random numbers for the initial balls of a catalogue shard, vectorised over its sources and
+    independent of the sharding: draw k of the source at catalogue row g is always the same number, whichever
+    rank holds g.  Every call opens a fresh Philox stream keyed by (seed, call number) and skips the blocks of
+    the rows before the shard (Philox.advance moves by whole 4-double blocks, so each source owns a whole number
+    of blocks)."""
+
+    def __init__(self, seed, first_source=0):
+        self.seed, self.first, self.stage = int(seed), int(first_source), 0
+
+    def _doubles(self, S, per_source):
+        blocks = (per_source + 3) // 4
+        bg = np.random.Philox(key=[self.seed & (2 ** 64 - 1), self.stage])
+        self.stage += 1
+        bg.advance(self.first * blocks)
+        return np.random.Generator(bg).random((S, 4 * blocks))[:, :per_source]
+
+    def uniform_block(self, S, W, n_par):
+        return self._doubles(S, W * n_par).reshape(S, W, n_par)
+
+    def normal_block(self, S, W, n_par):
+        """Box-Muller: a fixed number of uniforms per normal (the ziggurat's count varies, which would shift every
+        later source's numbers)."""
+        u = self._doubles(S, 2 * W * n_par).reshape(S, W, n_par, 2)
+        return np.sqrt(-2.0 * np.log1p(-u[..., 0])) * np.cos(2.0 * np.pi * u[..., 1])
+
+
 class EnsembleSampler:
     def __init__(self, engine, walkers, seed=0, a=2.0, n_bins=1024, source_offset=0):
         """engine: an Engine with sources uploaded.  walkers: even.  n_bins: histogram resolution of the
@@ -79,6 +106,16 @@ class EnsembleSampler:
             raise ValueError("positions must have shape (S, W, n_par) = %s" % ((self.S, self.W, self.n_par),))
         self.ctx.check(self.lib.agnf_ens_set_positions(self.ctx.h, ptr(pos)))
         self._steps = 0                 # steps behind the acceptance counters
+
+    def set_ball(self, centre, scale=0.00001, normal=False, stream_id=0):
+        """Positions drawn on the device around per-source centres [S, n_par]: centre + scale * uniform(-1, 1)
+        (the initial ball) or centre + scale * N(0, 1) (the restart ball).  Nothing but the centres is uploaded."""
+        centre = as_f64(centre)
+        if centre.shape != (self.S, self.n_par):
+            raise ValueError("centres must have shape (S, n_par) = %s" % ((self.S, self.n_par),))
+        self.ctx.check(self.lib.agnf_ens_set_ball(self.ctx.h, ptr(centre), float(scale), int(bool(normal)),
+                                                  int(stream_id) & 0xFFFFFFFF))
+        self._steps = 0
 
     # -- stepping ---------------------------------------------------------------------------------
     def run(self, n_steps, hist_every=0, track_best=False):
@@ -143,25 +180,38 @@ class EnsembleSampler:
     # -- the reference's schedule -----------------------------------------------------------------
     def run_reference_schedule(self, mc, pmin, pmax, rng, save_dir=None, names=None):
         """mc: the dict of MCMC_settings() (Nwalkers, Nburnsets, Nburn, Nmcmc, Nthin).  rng: a NumPy
-        Generator, or a list of S Generators (one per source: the initial balls then do not depend on
-        which other sources share the shard).  save_dir: also write `<save_dir>/<name>/samples_burn1-2-3.sav`
+        Generator, a list of S Generators (one per source), a ShardStream (vectorised), or None: the balls are
+        drawn on the device (set_ball).  With all but the first the balls of a source do not depend on which other
+        sources share the shard.  save_dir: also write `<save_dir>/<name>/samples_burn1-2-3.sav`
         and `samples_mcmc.sav` for every source, in the reference's format (MCMC_AGNfitter.py:156-206).
         Returns a summary dict: percentiles [S, n_par, 5] of the thinned production chain, best position / lnP,
         mean acceptance fraction per source."""
         if int(mc['Nwalkers']) != self.W:
             raise ValueError("mc['Nwalkers'] != walkers")
         per_source = isinstance(rng, (list, tuple))
+        pmin, pmax = np.atleast_2d(pmin), np.atleast_2d(pmax)
 
         def initial():
+            if isinstance(rng, ShardStream):         # same arithmetic as initial_positions, vectorised over sources
+                u = rng.uniform_block(self.S, self.W, self.n_par)
+                return 0.5 * (pmin + pmax)[:, None, :] + (2 * u - 1) * 0.00001
             if not per_source:
                 return self.initial_positions(pmin, pmax, self.W, rng)
             return np.concatenate([self.initial_positions(pmin[s], pmax[s], self.W, rng[s]) for s in range(self.S)])
 
         def ball(best_pos):
+            if isinstance(rng, ShardStream):
+                return best_pos[:, None, :] + rng.normal_block(self.S, self.W, self.n_par) * 0.00001
             if not per_source:
                 return self.ball_around(best_pos, self.W, rng)
             return np.concatenate([self.ball_around(best_pos[s], self.W, rng[s]) for s in range(self.S)])
 
+        if rng is None:                              # balls drawn on the device (catalogue scale)
+            calls = [0]
+
+            def device_ball(centre, normal):
+                calls[0] += 1
+                self.set_ball(centre, 0.00001, normal, stream_id=calls[0])
         nb, nburn, n = int(mc['Nburnsets']), int(mc['Nburn']), int(mc['Nmcmc'])
         if save_dir is not None:
             import os
@@ -169,14 +219,20 @@ class EnsembleSampler:
             for nm in names:
                 os.makedirs(os.path.join(save_dir, str(nm)), exist_ok=True)
             self.record(max(nb * nburn, 1))         # emcee's sampler accumulates all burn-in sets (no reset between)
-        self.set_positions(initial())
+        if rng is None:
+            device_ball(0.5 * (pmin + pmax), False)
+        else:
+            self.set_positions(initial())
         for _ in range(nb):
             self.run(nburn, track_best=True)
             best_pos, _ = self.best()
             if save_dir is not None:                # run_burn_in rewrites the file after every set (MCMC:171)
                 for s_, nm in enumerate(names):
                     self.save_chains(os.path.join(save_dir, str(nm), 'samples_burn1-2-3.sav'), s_)
-            self.set_positions(ball(best_pos))
+            if rng is None:
+                device_ball(best_pos, True)
+            else:
+                self.set_positions(ball(best_pos))
         self.reset_stats()
         if save_dir is not None:
             self.record(max(n, 1))                  # sampler.reset() (MCMC:182)

@@ -198,6 +198,12 @@ AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, doub
 /* pos [S, walkers, n_par] (host): initial positions (PARAMETERSPACE_AGNfitter.get_initial_positions /
  * get_best_position, :251-294); evaluates their ln_probab; clears the acceptance counters and the running best. */
 AGNF_API int agnf_ens_set_positions(agnf_ctx* ctx, const double* pos);
+/* The same with the positions drawn on the device: pos[s, w, :] = centre[s, :] + scale * d, d uniform in (-1, 1)
+ * (normal = 0: get_initial_positions' ball around mid-box, :260-263) or standard normal (normal = 1:
+ * get_best_position's ball around the best sample, :287-292).  centre [S, n_par] (host).  Draws come from the
+ * sampler's Philox generator with `stream_id` in the counter (use a different one per call); like the move's
+ * draws they depend on the source's catalogue row, not on the shard. */
+AGNF_API int agnf_ens_set_ball(agnf_ctx* ctx, const double* centre, double scale, int32_t normal, uint32_t stream_id);
 /* n_steps full stretch-move steps (2 half-steps each = 2 K1 launches).  hist_every > 0: every hist_every-th
  * step adds all walker positions to the histograms (the reference thins its chain the same way,
  * PLOTandWRITE_AGNfitter.py:471-492).  track_best: keep the best (position, lnP) seen per source

@@ -80,3 +80,21 @@ def step(pos, lnp, n_acc, lnprob_fn, step_idx, seed, a=2.0, src_offset=0):
         lnp[:, sl][accept] = new[accept]
         n_acc[:, sl] += accept
     return pos, lnp, n_acc
+
+
+def ball(centre, W, scale, normal, stream_id, seed, src_offset=0):
+    """Positions [S, W, n_par] of agnf_ens_set_ball: centre + scale * d with d uniform in (-1, 1) (the initial ball,
+    PARAMETERSPACE_AGNfitter.py:260-263) or standard normal by Box-Muller (the restart ball, :287-292); Philox
+    counter (stream_id, 2 + p, source, walker)."""
+    centre = np.atleast_2d(np.asarray(centre, dtype=np.float64))
+    S, n_par = centre.shape
+    s = (np.arange(S, dtype=np.int64) + int(src_offset)).astype(np.uint32)[:, None, None]
+    w = np.arange(W, dtype=np.uint32)[None, :, None]
+    p = (np.arange(n_par, dtype=np.uint32) + np.uint32(2))[None, None, :]
+    seed = int(seed) & (2 ** 64 - 1)
+    x0, x1, x2, x3 = philox4x32_10(np.uint32(stream_id), p, s, w, seed & 0xFFFFFFFF, seed >> 32)
+    to53 = lambda hi, lo: (((hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)) >> np.uint64(11)) \
+        .astype(np.float64) * 1.1102230246251565e-16
+    u1, u2 = to53(x0, x1), to53(x2, x3)
+    d = np.sqrt(-2.0 * np.log1p(-u1)) * np.cos(2.0 * np.pi * u2) if normal else 2.0 * u1 - 1.0
+    return centre[:, None, :] + d * scale

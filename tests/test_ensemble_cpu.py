@@ -56,3 +56,17 @@ def test_integrated_time_estimator():
     x[:, :, 1] = e[:, :, 1]
     tau = integrated_time(x)
     assert abs(tau[0] - 9.0) < 1.0 and abs(tau[1] - 1.0) < 0.15
+
+
+def test_shard_stream_is_independent_of_the_sharding():
+    """Source g draws the same numbers whether its shard starts at row 0 or at row g, and successive calls differ."""
+    from agnfitter_b200.ensemble import ShardStream
+    S, W, n_par = 11, 6, 5                       # W * n_par = 30: not a multiple of Philox's 4-double blocks
+    whole = ShardStream(9, 0)
+    u, n = whole.uniform_block(S, W, n_par), whole.normal_block(S, W, n_par)
+    for first in (0, 3, 10):
+        part = ShardStream(9, first)
+        assert np.array_equal(part.uniform_block(S - first, W, n_par), u[first:])
+        assert np.array_equal(part.normal_block(S - first, W, n_par), n[first:])
+    assert not np.array_equal(whole.uniform_block(S, W, n_par), u)
+    assert 0.0 <= u.min() and u.max() < 1.0 and np.isfinite(n).all() and abs(n.mean()) < 0.3 and 0.7 < n.std() < 1.3

@@ -202,3 +202,41 @@ def test_chain_recording_and_reference_chain_files(tmp_path):
         assert lnflat.max() <= out["best_lnp"][s] + 1e-12
         assert np.array_equal(mcmc["final_pos"], ens.state()[0][s])
         assert np.all(best >= src.pmin[s]) and np.all(best <= src.pmax[s])
+
+
+def test_device_balls_match_the_oracle_and_the_sharding():
+    """agnf_ens_set_ball: the uniform ball bit for bit, the normal one to a few ulp of the device's log / cos;
+    a shard that starts at catalogue row 1 draws what the full run draws for that row; the schedule with
+    rng=None (balls on the device) runs and restarts around the best sample."""
+    ms, eng, src, lnprob = _setup("cat49_catalog_example")
+    W, seed = 12, 99
+    ens = EnsembleSampler(eng, W, seed=seed, n_bins=0)
+    mid = 0.5 * (src.pmin + src.pmax)
+    ens.set_ball(mid, 1e-5, normal=False, stream_id=1)
+    pos, lnp, acc = ens.state()
+    assert np.array_equal(pos, E.ball(mid, W, 1e-5, False, 1, seed))
+    assert np.all(np.abs(pos - mid[:, None, :]) <= 1e-5) and not acc.any()
+    want_lnp = lnprob(pos)
+    fin = np.isfinite(want_lnp)
+    assert np.array_equal(np.isfinite(lnp), fin) and np.allclose(lnp[fin], want_lnp[fin], rtol=1e-10, atol=0)
+    ens.set_ball(mid, 0.5, normal=True, stream_id=2)
+    pos_n = ens.state()[0]
+    want = E.ball(mid, W, 0.5, True, 2, seed)
+    assert np.allclose(pos_n, want, rtol=0, atol=1e-13)
+    assert not np.array_equal(pos_n, pos)
+    d = (pos_n - mid[:, None, :]) / 0.5
+    assert abs(d.mean()) < 0.25 and 0.75 < d.std() < 1.25
+    if src.S > 1:                                   # the second source alone, as a shard starting at row 1
+        from agnfitter_b200 import sources as _s
+        ms1, g1 = load_k1("cat49_catalog_example")
+        one = _s.make_sources(ms, g1["src_z"][1:2], g1["src_dlum"][1:2], g1["src_nus"][1:2], g1["src_fluxes"][1:2],
+                              g1["src_fluxerrs"][1:2])
+        eng1 = Engine(ms, device=0)
+        eng1.set_sources(one)
+        ens1 = EnsembleSampler(eng1, W, seed=seed, n_bins=0, source_offset=1)
+        ens1.set_ball(mid[1:2], 0.5, normal=True, stream_id=2)
+        assert np.array_equal(ens1.state()[0][0], pos_n[1])
+    mc = dict(Nwalkers=W, Nburnsets=2, Nburn=8, Nmcmc=16, Nthin=2)
+    ens = EnsembleSampler(eng, W, seed=seed, n_bins=128)
+    out = ens.run_reference_schedule(mc, src.pmin, src.pmax, None)
+    assert np.isfinite(out["best_lnp"]).all() and np.all(out["acceptance"] >= 0)

@@ -13,6 +13,9 @@ t0 = time.perf_counter()
 templates, fd, settings, z, dlum, nus, fl, fe = M.make_inputs(S=S)
 print("inputs %.2f s" % (time.perf_counter() - t0))
 mc = dict(Nwalkers=100, Nburnsets=2, Nburn=20, Nmcmc=40, Nthin=2)
+if len(sys.argv) > 2 and sys.argv[2] == "example":       # example/SETTINGS_AGNfitter.py:265-268, out['Nthinning'] = 10
+    mc = dict(Nwalkers=100, Nburnsets=2, Nburn=12000, Nmcmc=25000, Nthin=10)
+import torch  # noqa: E402  (keep its import time out of the measurement)
 pr = cProfile.Profile()
 pr.enable()
 t0 = time.perf_counter()
@@ -20,5 +23,9 @@ table = fit_catalog(templates, fd, settings, z, dlum, nus, fl, fe, mc, seed=1, n
                     intlum_models=M.INTLUM_MODELS, intlum_ranges_hz=ranges_to_hz(M.INTLUM_RANGES_UM))
 dt = time.perf_counter() - t0
 pr.disable()
-print("fit_catalog: %d sources, %d steps, %.2f s  (%.1f us per source)" % (S, 80, dt, dt / S * 1e6))
+steps = mc['Nburnsets'] * mc['Nburn'] + mc['Nmcmc']
+print("fit_catalog: %d sources, %d steps, %.2f s  (%.1f us per source, %.1f sources/s, %.3g evals/s)" % (
+    S, steps, dt, dt / S * 1e6, S / dt, S * 100.0 * steps / dt))
+cols = table.shape[1]
+print("table", table.shape, "median acceptance %.3f" % np.median(table[:, 2 + 50 + 10 + 1]))
 pstats.Stats(pr).sort_stats("cumulative").print_stats(22)

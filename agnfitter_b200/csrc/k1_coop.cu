@@ -91,11 +91,6 @@ __device__ __forceinline__ int lds_s32(uint32_t a) {
   asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a));
   return v;
 }
-__device__ __forceinline__ unsigned lds_u16(uint32_t a) {
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(a));
-  return v;
-}
 __device__ __forceinline__ int lds_s32_ro(uint32_t a) {          // see lds_f64_ro
   int v;
   asm("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a));

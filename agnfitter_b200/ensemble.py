@@ -16,26 +16,32 @@ from ._lib import as_f64, ptr
 REFERENCE_PERCENTILES = (2.5, 16.0, 50.0, 84.0, 97.5)
 
 
-def integrated_time(chain, c=5):
+def integrated_time(chain, c=5, max_walkers=32):
     """Integrated autocorrelation time per parameter of a chain [W, n, n_par], the way emcee estimates
     `sampler.acor` (emcee.autocorr.integrated_time with c = 5, no convergence check — the reference patches emcee to
     quiet=True for the same reason, MCMC_AGNfitter.py:100-112): autocorrelation function by FFT, averaged over
-    walkers, summed up to the first window M >= c * tau(M)."""
+    walkers, summed up to the first window M >= c * tau(M).  A diagnostic (the reference prints its mean,
+    PLOTandWRITE_AGNfitter.py:491): at most `max_walkers` evenly spaced walkers enter the average."""
+    from scipy import fft as sfft
     x = np.asarray(chain, dtype=np.float64)
     W, n, n_par = x.shape
     tau = np.full(n_par, np.nan)
     if n < 2:
         return tau
-    size = 1 << int(np.ceil(np.log2(2 * n)))
+    if W > max_walkers:
+        x = x[np.linspace(0, W - 1, max_walkers).astype(int)]
+        W = max_walkers
+    y = np.ascontiguousarray(x.transpose(2, 0, 1))                        # [n_par, W, n]: FFTs along contiguous rows
+    y -= y.mean(axis=2, keepdims=True)
+    size = sfft.next_fast_len(2 * n, real=True)
+    f = sfft.rfft(y, n=size, axis=2, workers=-1)
+    f *= np.conjugate(f)
+    a = sfft.irfft(f, n=size, axis=2, workers=-1)[:, :, :n]
     for p in range(n_par):
-        acf = np.zeros(n)
-        for w in range(W):
-            y = x[w, :, p] - x[w, :, p].mean()
-            f = np.fft.rfft(y, n=size)
-            a = np.fft.irfft(f * np.conjugate(f), n=size)[:n]
-            if a[0] > 0:
-                acf += a / a[0]
-        acf /= W
+        ok = a[p, :, 0] > 0
+        if not ok.any():
+            continue
+        acf = (a[p, ok] / a[p, ok, :1]).sum(axis=0) / W
         taus = 2.0 * np.cumsum(acf) - 1.0
         m = np.arange(n) < c * taus
         win = int(np.argmin(m)) if not m.all() else n - 1
@@ -223,10 +229,12 @@ class EnsembleSampler:
             device_ball(0.5 * (pmin + pmax), False)
         else:
             self.set_positions(initial())
-        for _ in range(nb):
+        for k_set in range(nb):
             self.run(nburn, track_best=True)
             best_pos, _ = self.best()
-            if save_dir is not None:                # run_burn_in rewrites the file after every set (MCMC:171)
+            # run_burn_in rewrites the burn-in file after every set (MCMC:171); only the last version survives,
+            # and the restart point it is read back for (get_best_position) is tracked on the device
+            if save_dir is not None and k_set == nb - 1:
                 for s_, nm in enumerate(names):
                     self.save_chains(os.path.join(save_dir, str(nm), 'samples_burn1-2-3.sav'), s_)
             if rng is None:

@@ -169,19 +169,31 @@ class EnsembleSampler:
         self.ctx.check(self.lib.agnf_ens_chain(self.ctx.h, ptr(ch), ptr(lp), None))
         return np.ascontiguousarray(ch.transpose(1, 2, 0, 3)), np.ascontiguousarray(lp.transpose(1, 2, 0))
 
-    def save_chains(self, filename, s=0):
+    def save_chains(self, filename, s=0, background=False):
         """Write source s the way MCMC_AGNfitter.save_chains does (MCMC_AGNfitter.py:192-206): a protocol-2
         pickle of dict(chain [W, n, n_par], accept [W], lnprob [W, n], final_pos [W, n_par], state, acor [n_par])
         that PARAMETERSPACE_AGNfitter.get_best_position (:268-294) and PLOTandWRITE's CHAIN.props (:471-492)
         read back.  `state` (emcee's NumPy RNG state) has no counterpart — the walk is driven by a counter-based
-        generator — and is stored as None; `acor` is the integrated autocorrelation time of the walker-mean
-        series per parameter (emcee's estimator: windowed sum of the autocorrelation function, c = 5)."""
-        import pickle
+        generator — and is stored as None; `acor` is the integrated autocorrelation time (integrated_time).
+        background=True: the chain is fetched now, the autocorrelation estimate and the file write run on a
+        thread (returned; join it) while the sampler goes on — the library call releases the GIL."""
         ch, lp = self.chain()
         pos, _, acc = self.state()
-        with open(filename, 'wb') as f:
-            pickle.dump(dict(chain=ch[s], accept=acc[s] / float(max(self._steps, 1)), lnprob=lp[s], final_pos=pos[s],
-                             state=None, acor=integrated_time(ch[s])), f, protocol=2)
+        payload = dict(chain=ch[s], accept=acc[s] / float(max(self._steps, 1)), lnprob=lp[s], final_pos=pos[s],
+                       state=None)
+
+        def write():
+            import pickle
+            payload["acor"] = integrated_time(payload["chain"])
+            with open(filename, 'wb') as f:
+                pickle.dump(payload, f, protocol=2)
+        if not background:
+            write()
+            return None
+        import threading
+        t = threading.Thread(target=write)
+        t.start()
+        return t
 
     # -- the reference's schedule -----------------------------------------------------------------
     def run_reference_schedule(self, mc, pmin, pmax, rng, save_dir=None, names=None):
@@ -219,6 +231,7 @@ class EnsembleSampler:
                 calls[0] += 1
                 self.set_ball(centre, 0.00001, normal, stream_id=calls[0])
         nb, nburn, n = int(mc['Nburnsets']), int(mc['Nburn']), int(mc['Nmcmc'])
+        writers = []
         if save_dir is not None:
             import os
             names = list(names) if names is not None else ["%d" % s for s in range(self.S)]
@@ -234,9 +247,9 @@ class EnsembleSampler:
             best_pos, _ = self.best()
             # run_burn_in rewrites the burn-in file after every set (MCMC:171); only the last version survives,
             # and the restart point it is read back for (get_best_position) is tracked on the device
-            if save_dir is not None and k_set == nb - 1:
-                for s_, nm in enumerate(names):
-                    self.save_chains(os.path.join(save_dir, str(nm), 'samples_burn1-2-3.sav'), s_)
+            if save_dir is not None and k_set == nb - 1:     # written while the production run goes on
+                writers = [self.save_chains(os.path.join(save_dir, str(nm), 'samples_burn1-2-3.sav'), s_, True)
+                           for s_, nm in enumerate(names)]
             if rng is None:
                 device_ball(best_pos, True)
             else:
@@ -249,6 +262,8 @@ class EnsembleSampler:
             for s_, nm in enumerate(names):
                 self.save_chains(os.path.join(save_dir, str(nm), 'samples_mcmc.sav'), s_)
             self.record(0)
+            for t in writers:
+                t.join()
         _, _, acc = self.state()
         bp, bl = self.best()
         return dict(percentiles=self.percentiles() if self.n_bins else None, best_pos=bp, best_lnp=bl,

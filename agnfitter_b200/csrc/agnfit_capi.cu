@@ -49,6 +49,7 @@ struct agnf_ctx {
   void* d_grid = nullptr;
   void* d_perm = nullptr;
   bool have_z = false, have_src = false;
+  bool eb0_dirty = true;                        // K1Params::eb0 must be rebuilt (galaxy table or z-slices changed)
 
   // small-batch path of the host variant: one pinned block [params | source_id | lnp] so that a call is one
   // upload, one launch, one download — all truly asynchronous — instead of three pageable copies
@@ -290,7 +291,24 @@ int check_ready(agnf_ctx* ctx) {
     if (!ctx->fam_set[f]) return fail(ctx, "family %d has not been uploaded", f);
   if (!ctx->have_z) return fail(ctx, "agnf_zslices_upload has not been called");
   if (!ctx->have_src) return fail(ctx, "agnf_sources_upload has not been called");
-  return rebuild_grids(ctx);
+  if (rebuild_grids(ctx)) return 1;
+  // free E(B-V)_gal + energy balance: the unreddened integral of every galaxy row, once per dictionary / z-slice
+  // upload (needs an even, 16-byte aligned table: exactly the cooperative kernel's own preconditions)
+  K1Params& P = ctx->k1;
+  const bool want = P.cfg.ga_free_ebv && P.cfg.eb_mode != 0 && !(P.fam[0].pitch & 1) && !(P.nbp & 1) &&
+                    !(reinterpret_cast<uintptr_t>(P.fam[0].table) & 15);
+  if (want && ctx->eb0_dirty) {
+    if (P.eb0) dev_free(ctx, const_cast<double*>(P.eb0));
+    P.eb0 = nullptr;
+    void* d = nullptr;
+    if (dev_alloc(ctx, &d, (size_t)P.cfg.n_z * (size_t)P.fam[0].T * 8)) return 1;
+    CUDA_TRY(ctx, launch_k1_eb0(P, static_cast<double*>(d), ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    P.eb0 = static_cast<const double*>(d);
+    ctx->eb0_dirty = false;
+    ctx->launches += 1;
+  }
+  return 0;
 }
 
 }  // namespace
@@ -480,6 +498,7 @@ AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg) {
   ctx->k1.lognorm_s15 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 1.5));
   ctx->k1.lognorm_s01 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 0.1));
   ctx->have_cfg = true;
+  ctx->eb0_dirty = true;
   return 0;
 }
 
@@ -544,6 +563,7 @@ AGNF_API int agnf_family_upload(agnf_ctx* ctx, const agnf_family_desc* fd) {
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->fam_set[f] = true;
   ctx->grids_dirty = true;
+  if (f == 0) ctx->eb0_dirty = true;
   return 0;
 }
 
@@ -576,6 +596,7 @@ AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double
   if (upload_padded(ctx, &ctx->k1.omega, omega, nz, (int)nb, ctx->k1.nbp)) return 1;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->have_z = true;
+  ctx->eb0_dirty = true;
   return 0;
 }
 

@@ -66,7 +66,7 @@ CoopPlan make_plan(const K1Params& P, bool ens) {
   c.stage_pad = (P.stage_bytes + 15) & ~15;
   c.cpr = P.nbp / 2;
   c.cprp = c.cpr | 1;
-  const int a = 32 * c.cprp * (eb_free ? 3 : 1), b = 32 * P.cfg.n_par;
+  const int a = 32 * c.cprp * (eb_free ? 2 : 1), b = 32 * P.cfg.n_par;
   const int part = ((a > b ? a : b) + 1) & ~1;
   // ensemble mode keeps the proposal rows until the acceptance test: they cannot share the partial-sum area
   c.q_off = ens ? part : 0;
@@ -428,8 +428,6 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
         if (eb_free) {
           const double2 om = __ldg(om2 + (unsigned)(sv.y + k));
           sts_f64(part_s + 8u * (unsigned)(32 * CPRP + e * CPRP + k),
-                  om.x * (dga.x * 3.826e33) + om.y * (dga.y * 3.826e33));
-          sts_f64(part_s + 8u * (unsigned)(64 * CPRP + e * CPRP + k),
                   om.x * (((dga.x * 1e18) * rg0) * 3.826e33) + om.y * (((dga.y * 1e18) * rg1) * 3.826e33));
         }
         ga0 = dga.x * rg0;
@@ -469,8 +467,7 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
 #pragma unroll
     for (int k = 0; k < CPR; ++k) chi += lds_f64(mine + 8u * k);
     if (eb_free) {
-      for (int k = 0; k < CPR; ++k) ebA += lds_f64(mine + 8u * (32 * CPRP + k));
-      for (int k = 0; k < CPR; ++k) ebB += lds_f64(mine + 8u * (64 * CPRP + k));
+      for (int k = 0; k < CPR; ++k) ebB += lds_f64(mine + 8u * (32 * CPRP + k));
     }
   }
   const double lnlike = -0.5 * chi;
@@ -478,7 +475,10 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   double prior = 0.0;
   if (cfg.eb_mode != 0) {
     double L_att;
-    if (GA_FREE) L_att = fabs((ebA - ebB) * nGA);
+    if (GA_FREE) {
+      ebA = __ldg(P.eb0 + (int64_t)grow[0]);      // the unreddened integral of this galaxy row (walker-independent)
+      L_att = fabs((ebA - ebB) * nGA);
+    }
     else L_att = __ldg(P.fam[0].aux + row[0]) * nGA;
     const double L_sb = __ldg(P.fam[1].aux + row[1]) * nSB;
     double pr;
@@ -630,6 +630,7 @@ bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why) {
   else if (coop_smem_bytes(P, B.ens.pos != nullptr) > 200 * 1024) w = "grids + per-warp tiles exceed shared memory";
   else if (B.ens.pos && P.S * (int64_t)B.ens.W >= (int64_t)INT32_MAX) w = "too many walkers for 32-bit row indices";
   else if (P.S * (int64_t)(P.nbp / 2) >= (int64_t)INT32_MAX) w = "too many sources for 32-bit chunk offsets";
+  else if (P.cfg.ga_free_ebv && P.cfg.eb_mode != 0 && !P.eb0) w = "the unreddened galaxy integrals have not been built";
   else {
     for (int f = 0; f < P.cfg.n_fam && !w; ++f) {
       if (P.fam[f].pitch & 1) w = "a family table has an odd row pitch";
@@ -650,6 +651,30 @@ cudaError_t launch_k1_coop(const K1Params& P, const K1Batch& B, cudaStream_t str
   const bool gf = P.cfg.ga_free_ebv != 0, rad = P.cfg.radio != 0;
   if (gf) return rad ? launch_coop_bb<true, true>(P, B, stream) : launch_coop_bb<true, false>(P, B, stream);
   return rad ? launch_coop_bb<false, true>(P, B, stream) : launch_coop_bb<false, false>(P, B, stream);
+}
+
+// One thread per (z, galaxy row): the chunk sums the band phase used to write to its first energy-balance plane,
+// added in the order phase 3 added them -- bit-identical to evaluating them per walker.
+__global__ void k1_eb0_kernel(K1Params P, double* __restrict__ eb0) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const FamDesc& F = P.fam[0];
+  if (i >= (int64_t)P.cfg.n_z * F.T) return;
+  const int64_t zi = i / F.T;
+  const double2* __restrict__ row = reinterpret_cast<const double2*>(F.table + i * F.pitch);
+  const double2* __restrict__ om = reinterpret_cast<const double2*>(P.omega + zi * P.nbp);
+  double acc = 0.0;
+  for (int k = 0; k < P.nbp / 2; ++k) {
+    const double2 d = row[k], o = om[k];
+    acc += o.x * (d.x * 3.826e33) + o.y * (d.y * 3.826e33);
+  }
+  eb0[i] = acc;
+}
+
+cudaError_t launch_k1_eb0(const K1Params& P, double* eb0, cudaStream_t stream) {
+  const int64_t n = (int64_t)P.cfg.n_z * P.fam[0].T;
+  if (n == 0) return cudaSuccess;
+  k1_eb0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(P, eb0);
+  return cudaGetLastError();
 }
 
 // 10^x through the kernel's own routine (debug / unit test hook)

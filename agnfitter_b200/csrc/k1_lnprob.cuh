@@ -94,6 +94,9 @@ struct K1Params {
   const uint64_t* xray;       // [n_z]
   const int32_t* j1500;       // [n_z]
   const double* omega;        // [n_z, nbp]
+  // free E(B-V)_gal + energy balance: sum_b omega[z, b] * (F_GA[z, t, b] * 3.826e33) of every galaxy row, i.e. the
+  // unreddened integral of PRIORS_AGNfitter.py:89, which does not depend on the walker ([n_z, T_GA]; else nullptr)
+  const double* eb0;
   // sources (pad columns are zero)
   const int32_t* zi;          // [S]
   const double* y;            // [S, nbp]
@@ -143,6 +146,8 @@ cudaError_t launch_k1(const K1Params& P, const K1Batch& B, cudaStream_t stream);
 bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why);
 bool k1_coop_profitable(const K1Params& P, const K1Batch& B);   // false: the per-thread kernel is expected to win
 cudaError_t launch_k1_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream);
+// eb0[z, t] for the galaxy family (see K1Params::eb0), chunk sums in the order the kernel used to add them
+cudaError_t launch_k1_eb0(const K1Params& P, double* eb0, cudaStream_t stream);
 cudaError_t launch_exp10_fast(const double* x, double* y, int64_t n, cudaStream_t stream);
 
 }  // namespace agnf

@@ -67,9 +67,12 @@ def _bump(lognu, centre, width):
     return np.exp(-0.5 * ((lognu - centre) / width) ** 2)
 
 
-def synthetic_templates(seed=20260101):
+def synthetic_templates(seed=20260101, ga_free=False):
     """The four classic families as `*_4plot`-style dicts {key: (log10 nu, Fnu)} with the real key
-    strings' structure, plus GALAXYatt / STARBURST_LIR stand-ins."""
+    strings' structure, plus GALAXYatt / STARBURST_LIR stand-ins.  ga_free: the galaxy family in the shape of the
+    reference's default `BC03_metal` library instead — keys (metal, tau, age, EBVgal) with E(B-V)_gal a FREE
+    parameter applied on the fly (two key values per template, MODEL_AGNfitter.py:145-301), 4 x 11 x 25 x 2 = 2 200
+    unreddened templates, no GALAXYatt table (the energy-balance prior integrates on the fly, PRIORS:83-93)."""
     rng = np.random.default_rng(seed)
     out = {}
     # GALAXY: keys (tau, age, EBVgal) enumerated age-major like MODEL_AGNfitter.py:95-108
@@ -91,6 +94,16 @@ def synthetic_templates(seed=20260101):
                 ga[key] = (lognu, red * 1e-30)
                 att[key] = float(np.trapezoid(base - red, x=nu)) * 1e-12
     out["GA"] = dict(F=ga, names=['tau', 'age', 'EBVgal'], types=['grid', 'grid', 'grid'], aux=att)
+    if ga_free:
+        ga = {}
+        for m in (0.2, 0.4, 1.0, 2.5):
+            for a in age:
+                for t in tau:
+                    base = 1e-2 * (_bump(lognu, 14.2 + 0.08 * (10 - a) + 0.02 * m, 0.45)
+                                   + 0.3 * _bump(lognu, 14.9 - 0.03 * t, 0.25) + 1e-3)
+                    for e in (0.0, 0.8):
+                        ga[(str(m), str(t), str(a), str(e))] = (lognu, base * 1e-30)
+        out["GA"] = dict(F=ga, names=['metal', 'tau', 'age', 'EBVgal'], types=['grid', 'grid', 'grid', 'free'], aux=None)
     # STARBURST: 161 keys, descending-then-ascending irlum like DH02_CE01's key order
     irl = np.round(np.concatenate([np.linspace(14.3404, 8.3091, 100), np.linspace(8.3613, 13.5477, 61)]), 4)
     assert len(set(irl.tolist())) == 161

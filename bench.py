@@ -234,7 +234,7 @@ def make_workload(args, rank, device, need_gpu=True):
     from agnfitter_b200.engine import Engine, DictBuilder
     t_setup = time.perf_counter()
     fd = synth.synthetic_filterdict(which="example49" if args.bands == 49 else None)
-    tpl = synth.synthetic_templates()
+    tpl = synth.synthetic_templates(ga_free=args.ga_free)
     nus = np.asarray(fd[0])
     S, W = args.sources, args.walkers
     z, dlum, rng = synth.synthetic_catalog(None, S, seed=20260101 + rank)
@@ -390,7 +390,7 @@ def run_ours(args):
         from agnfitter_b200 import synth as _synth
         from agnfitter_b200.plotset import plotset_from_templates
         from agnfitter_b200.realizations import SedEngine, ranges_to_hz
-        ps = plotset_from_templates(_synth.synthetic_templates(), ms)
+        ps = plotset_from_templates(_synth.synthetic_templates(ga_free=args.ga_free), ms)
         sed = SedEngine(eng, ps, raw["z"], raw["dlum"])
         sed.set_bands(EXAMPLE_INTLUM_MODELS, ranges_to_hz(EXAMPLE_INTLUM_RANGES_UM))
         n_src = min(args.sed_sources, S)
@@ -477,10 +477,12 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3: synthetic %d sources x %d walkers per GPU, %s, classic "
-                                   "10-parameter model (11000+161+60+2 templates), dictionary of %d z-slices in HBM"
+            "config": {"workload": "C3: synthetic %d sources x %d walkers per GPU, %s, %s, dictionary of %d "
+                                   "z-slices in HBM"
                                    % (S, W, "18-band default set" if n_b == 18 else "%d-band example set" % n_b,
-                                      info["n_z"]),
+                                      "free-E(B-V) galaxy variant (%d parameters, %s templates)" % (
+                                          n_par, "+".join(str(f.T) for f in ms.families)) if args.ga_free else
+                                      "classic 10-parameter model (11000+161+60+2 templates)", info["n_z"]),
                        "positions": args.positions + " in prior box + 1% out-of-box rows",
                        "source_order": "random z" if args.no_sort_z else "sorted by z",
                        "k1_variant": "cooperative (k1_coop_kernel)" if eng.get_option("k1_last_kernel") == 1 else "per-thread (k1_lnprob_kernel)",
@@ -595,6 +597,9 @@ def main():
     ap.add_argument("--bands", type=int, default=18, choices=[18, 49],
                     help="18: the default band set (the workload BASELINE.json names); 49: the example settings' "
                          "radio-to-X-ray set (C1/C2 shape at catalogue scale)")
+    ap.add_argument("--ga-free", action="store_true",
+                    help="galaxy family in the shape of the reference's default BC03_metal library: E(B-V)_gal free, "
+                         "reddening and the energy-balance integral on the fly (not the BASELINE workload)")
     ap.add_argument("--sed-sources", type=int, default=2000,
                     help="sources whose 100 chain rows go through the SED / integrated-luminosity stage (0: skip)")
     ap.add_argument("--ensemble-steps", type=int, default=10,

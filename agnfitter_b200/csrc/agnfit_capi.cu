@@ -77,6 +77,7 @@ struct agnf_ctx {
   int64_t ens_step = 0;              // stretch-move steps taken since agnf_ens_create (Philox counter)
   int ens_fused = 1;                 // 1: one fused K1 launch per half-step; 0: propose / K1 / accept kernels
   int k2_shared_window = 1;          // 1: 4 z-slices share each template read when the family allows it
+  int k2_mma = 1;                    // 1: FP64 tensor-core contraction (8-slice batches) when the family allows it
   int k2_last_kernel = 0;            // contraction of the last agnf_dict_build: 1 per-slice kernels, 2 shared-window
   int64_t ens_src_offset = 0;        // catalogue row of the shard's first source (Philox counter)
   int64_t ens_hist_samples = 0;
@@ -412,6 +413,11 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     if (ctx->have_ens) ctx->ens.src_offset = value;
     return 0;
   }
+  if (strcmp(name, "k2_mma") == 0) {
+    if (value != 0 && value != 1) return fail(ctx, "k2_mma must be 0 or 1");
+    ctx->k2_mma = (int)value;
+    return 0;
+  }
   if (strcmp(name, "k2_shared_window") == 0) {
     if (value != 0 && value != 1) return fail(ctx, "k2_shared_window must be 0 or 1");
     ctx->k2_shared_window = (int)value;
@@ -455,6 +461,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "zero_copy_rows") == 0) *value = ctx->zero_copy_rows;
   else if (strcmp(name, "ens_fused") == 0) *value = ctx->ens_fused;
   else if (strcmp(name, "k2_shared_window") == 0) *value = ctx->k2_shared_window;
+  else if (strcmp(name, "k2_mma") == 0) *value = ctx->k2_mma;
   else if (strcmp(name, "k2_last_kernel") == 0) *value = ctx->k2_last_kernel;
   else if (strcmp(name, "ens_source_offset") == 0) *value = ctx->ens_src_offset;
   else return fail(ctx, "unknown option '%s'", name);
@@ -836,10 +843,12 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   void *d_lam = nullptr, *d_perm = nullptr, *d_F = nullptr, *d_Fs = nullptr, *d_z = nullptr, *d_jlo = nullptr,
        *d_cnt = nullptr, *d_rmax = nullptr, *d_W = nullptr, *d_rowmap = nullptr, *d_out = nullptr, *d_woff = nullptr,
        *d_bandof = nullptr, *d_border = nullptr, *d_jb = nullptr, *d_cb = nullptr, *d_rmaxA = nullptr,
-       *d_woffA = nullptr, *d_bandofA = nullptr, *d_WA = nullptr;
+       *d_woffA = nullptr, *d_bandofA = nullptr, *d_WA = nullptr, *d_jb8 = nullptr, *d_cb8 = nullptr,
+       *d_rmax8 = nullptr, *d_Fs8 = nullptr, *d_woff8 = nullptr, *d_bandof8 = nullptr, *d_WA8 = nullptr;
   auto cleanup = [&]() {
     for (void* q : {d_lam, d_perm, d_F, d_Fs, d_z, d_jlo, d_cnt, d_rmax, d_W, d_rowmap, d_woff, d_bandof, d_border,
-                    d_jb, d_cb, d_rmaxA, d_woffA, d_bandofA, d_WA})
+                    d_jb, d_cb, d_rmaxA, d_woffA, d_bandofA, d_WA, d_jb8, d_cb8, d_rmax8, d_Fs8, d_woff8, d_bandof8,
+                    d_WA8})
       dev_free(ctx, q);
     if (!out_on_device) dev_free(ctx, d_out);
   };
@@ -931,7 +940,54 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   // sample would leak into the neighbouring slices through 0 * inf, so such families take the per-slice kernels.
   bool finite = ctx->k2_shared_window != 0;
   for (int64_t i = 0, n = T * (int64_t)n_lam; finite && i < n; ++i) finite = std::isfinite(Fnu[i]);
-  if (finite) {
+  if (finite && ctx->k2_mma) {
+    // tensor-core plan: batches of 8 slices, windows aligned to multiples of 4 samples, templates re-laid out
+    // with a row pitch = 4 (mod 8) (conflict-free 8 x 4 fragments) and >= n_lam + 3 (windows are rounded up)
+    p.n_zb8 = (n_z + 7) / 8;
+    K2_ALLOC(d_jb8, (size_t)p.n_zb8 * n_b * 4);
+    K2_ALLOC(d_cb8, (size_t)p.n_zb8 * n_b * 4);
+    K2_ALLOC(d_rmax8, (size_t)n_b * 4);
+    K2_TRY(cudaMemsetAsync(d_rmax8, 0, (size_t)n_b * 4, st));
+    p.jb8 = static_cast<int32_t*>(d_jb8);
+    p.cb8 = static_cast<int32_t*>(d_cb8);
+    p.d_rmaxb8 = static_cast<int32_t*>(d_rmax8);
+    K2_TRY(launch_k2_batch_ranges8(p, st));
+    std::vector<int32_t> rmax8((size_t)n_b), woff8((size_t)n_b + 1, 0);
+    K2_TRY(cudaMemcpyAsync(rmax8.data(), d_rmax8, (size_t)n_b * 4, cudaMemcpyDeviceToHost, st));
+    K2_TRY(cudaStreamSynchronize(st));
+    for (int b = 0; b < n_b; ++b) woff8[(size_t)b + 1] = woff8[(size_t)b] + std::max(rmax8[(size_t)b], 4);
+    p.wstride8 = woff8[(size_t)n_b];
+    int32_t L = n_lam + 3;
+    L += ((4 - (L & 7)) + 8) & 7;
+    p.ldF8 = L;
+    p.mma_ok = 1;
+    if (k2_mma_fits(p)) {
+      K2_ALLOC(d_Fs8, (size_t)T_pad * p.ldF8 * 8);
+      K2_TRY(cudaMemsetAsync(d_Fs8, 0, (size_t)T_pad * p.ldF8 * 8, st));
+      K2_TRY(launch_k2_permute(static_cast<const double*>(d_F), static_cast<const int32_t*>(d_perm),
+                               static_cast<double*>(d_Fs8), T, n_lam, p.ldF8, st));
+      p.Fs8 = static_cast<const double*>(d_Fs8);
+      std::vector<int32_t> band_of8((size_t)p.wstride8, -1);
+      for (int b = 0; b < n_b; ++b)
+        for (int32_t k = woff8[(size_t)b]; k < woff8[(size_t)b + 1]; ++k) band_of8[(size_t)k] = b;
+      std::stable_sort(border.begin(), border.end(),
+                       [&](int32_t x, int32_t y) { return rmax8[(size_t)x] > rmax8[(size_t)y]; });
+      K2_TRY(cudaMemcpyAsync(d_border, border.data(), (size_t)n_b * 4, cudaMemcpyHostToDevice, st));
+      K2_ALLOC(d_woff8, ((size_t)n_b + 1) * 4);
+      K2_ALLOC(d_bandof8, (size_t)p.wstride8 * 4);
+      K2_TRY(cudaMemcpyAsync(d_woff8, woff8.data(), ((size_t)n_b + 1) * 4, cudaMemcpyHostToDevice, st));
+      K2_TRY(cudaMemcpyAsync(d_bandof8, band_of8.data(), (size_t)p.wstride8 * 4, cudaMemcpyHostToDevice, st));
+      p.woff8 = static_cast<const int32_t*>(d_woff8);
+      p.band_of8 = static_cast<const int32_t*>(d_bandof8);
+      K2_ALLOC(d_WA8, (size_t)p.n_zb8 * p.wstride8 * 64);
+      p.WA8 = static_cast<double*>(d_WA8);
+      K2_TRY(launch_k2_weights_aligned8(p, st));
+      K2_TRY(cudaStreamSynchronize(st));      // the host vectors above feed asynchronous copies
+    } else {
+      p.mma_ok = 0;
+    }
+  }
+  if (finite && !p.mma_ok) {
     p.n_zb = (n_z + 3) / 4;
     K2_ALLOC(d_jb, (size_t)p.n_zb * n_b * 4);
     K2_ALLOC(d_cb, (size_t)p.n_zb * n_b * 4);
@@ -968,12 +1024,12 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
       p.sw_ok = 0;
     }
   }
-  if (!p.sw_ok) {
+  if (!p.sw_ok && !p.mma_ok) {
     K2_ALLOC(d_W, (size_t)n_z * wstride * 8);
     p.W = static_cast<double*>(d_W);
     K2_TRY(launch_k2_weights(p, st));
   }
-  ctx->k2_last_kernel = p.sw_ok ? 2 : 1;
+  ctx->k2_last_kernel = p.mma_ok ? 3 : (p.sw_ok ? 2 : 1);
   K2_TRY(cudaEventRecord(ctx->ev2, st));
   K2_TRY(launch_k2_contract(p, st));
   K2_TRY(cudaEventRecord(ctx->ev3, st));

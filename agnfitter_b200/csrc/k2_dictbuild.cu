@@ -148,6 +148,55 @@ __global__ void k2_weights_aligned_kernel(K2Problem p) {
   p.WA[idx] = w;
 }
 
+// Tensor-core path.  One thread per (batch of 8 slices, band): the window all 8 slices see together, its start
+// rounded down and its length rounded up to multiples of 4 samples (the k extent of one mma).
+__global__ void k2_batch_ranges8_kernel(K2Problem p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_b = p.filt.n_b;
+  if (idx >= p.n_zb8 * n_b) return;
+  const int zb = idx / n_b, b = idx - zb * n_b;
+  int lo = INT_MAX, hi = 0;
+  for (int zl = 0; zl < 8; ++zl) {
+    const int z = 8 * zb + zl;
+    if (z >= p.n_z) break;
+    const int c = __ldg(p.cnt + z * n_b + b);
+    if (c > 0) {
+      const int j = __ldg(p.jlo + z * n_b + b);
+      lo = min(lo, j);
+      hi = max(hi, j + c);
+    }
+  }
+  int j0 = 0, c = 0;
+  if (hi > lo) {
+    j0 = lo & ~3;
+    c = (hi - j0 + 3) & ~3;
+  }
+  p.jb8[idx] = j0;
+  p.cb8[idx] = c;
+  atomicMax(p.d_rmaxb8 + b, c);
+}
+
+// One thread per (batch, slot, slice): weights re-aligned to the batch window, 8 slices interleaved.
+__global__ void k2_weights_aligned8_kernel(K2Problem p) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_b = p.filt.n_b;
+  const int64_t total = (int64_t)p.n_zb8 * p.wstride8 * 8;
+  if (idx >= total) return;
+  const int zl = (int)(idx & 7);
+  const int64_t q = idx >> 3;
+  const int slot = (int)(q % p.wstride8);
+  const int zb = (int)(q / p.wstride8);
+  const int z = 8 * zb + zl;
+  const int b = __ldg(p.band_of8 + slot);
+  double w = 0.0;
+  if (b >= 0 && z < p.n_z) {
+    const int j = __ldg(p.jb8 + zb * n_b + b) + (slot - __ldg(p.woff8 + b));
+    const int r = j - __ldg(p.jlo + z * n_b + b);
+    if (r >= 0 && r < __ldg(p.cnt + z * n_b + b)) w = band_weight(p, z, b, j);
+  }
+  p.WA8[idx] = w;
+}
+
 // Banded contraction.  grid = (n_z, ceil(T / K2_TILE_T)); the z-slice's weights are staged in
 // shared memory and reused by the tile's templates; outputs are written band-fastest so a warp
 // stores contiguous rows of the [n_z, T, n_b] table.
@@ -540,6 +589,175 @@ bool k2_sw_plan(const K2Problem& p, K2SwPlan* c) {
   return false;
 }
 
+// ---- tensor-core contraction -----------------------------------------------------------------------
+// D[32 templates x 8 slices] += A[32 x 4 samples] * B[4 samples x 8 slices] with FP64 mma.sync.m8n8k4: per k-block
+// one 256-byte fragment of weights and one per 8 templates feed 256 multiply-adds each — 0.31-0.375 shared-memory
+// wavefronts per 32 multiply-adds, against 1.0 in the shared-window kernel and 3.0 in the tiled one.  A slice's
+// weights are zero outside its own window and the k-blocks sit at absolute multiples of 4 samples, so which
+// products share an mma depends on the sample index only: a slice's value is the same bit for bit whichever
+// slices share its batch.  Row pitch = 4 (mod 8) makes the 8 x 4 template fragments conflict-free.
+// Work units = (band, half of the 32 templates), longest band first through a shared counter; weights of the next
+// batch arrive by a bulk copy during this one; the 8 result slices leave by bulk stores that drain during the next.
+struct K2MmaPlan {
+  int32_t nbuf;        // weight buffers (2, or 1 when two would not fit)
+  int32_t zbc;         // batches per CTA
+  int32_t opitch, bulk_store;
+  int32_t off_w, off_o, off_bar, smem_bytes;
+};
+
+__device__ __forceinline__ void k2_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_mma_kernel(K2Problem p, K2MmaPlan c) {
+  constexpr int TT = 32;
+  extern __shared__ __align__(16) unsigned char k2_smem[];
+  double* Fs_s = reinterpret_cast<double*>(k2_smem);                        // [TT][ldF8]
+  double* W_s = reinterpret_cast<double*>(k2_smem + c.off_w);               // [nbuf][wstride8][8]
+  double* O_s = reinterpret_cast<double*>(k2_smem + c.off_o);               // [8][TT][opitch]
+  const uint32_t bar = k2_smem_u32(k2_smem + c.off_bar);
+  int* next_unit = reinterpret_cast<int*>(k2_smem + c.off_bar + 32);        // [K2_SW_MAX_ROUNDS]
+  const int n_b = p.filt.n_b, ws8 = p.wstride8, ldF = p.ldF8, pitch = p.out_pitch;
+  const int lane = threadIdx.x & 31, grp = lane >> 2, tig = lane & 3;
+  const int64_t t0 = (int64_t)blockIdx.y * TT;
+  const int nt = (int)min((int64_t)TT, p.T - t0);
+  const int zb0 = blockIdx.x * c.zbc;
+  const int zb1 = min(zb0 + c.zbc, p.n_zb8);
+  const int n_units = 2 * n_b;
+  const uint32_t wbytes = (uint32_t)ws8 * 64u;
+  if (threadIdx.x == 0) {
+    k2_mbar_init(bar, 1);
+    k2_mbar_init(bar + 8, 1);
+    k2_mbar_init(bar + 16, 1);
+    k2_mbar_init(bar + 24, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (threadIdx.x < K2_SW_MAX_ROUNDS) next_unit[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < 8 * TT * c.opitch; i += K2T_THREADS) O_s[i] = 0.0;   // pad columns stay zero
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t fbytes = (uint32_t)TT * (uint32_t)ldF * 8u;
+    k2_mbar_expect_tx(bar, fbytes);
+    k2_bulk_g2s(k2_smem_u32(Fs_s), p.Fs8 + t0 * ldF, fbytes, bar);
+    k2_mbar_expect_tx(bar + 8, wbytes);
+    k2_bulk_g2s(k2_smem_u32(W_s), p.WA8 + (int64_t)zb0 * ws8 * 8, wbytes, bar + 8);
+  }
+  k2_mbar_wait(bar, 0);
+  int ir = 0;
+  for (int zb = zb0; zb < zb1; ++zb, ++ir) {
+    const int buf = (c.nbuf == 2) ? (ir & 1) : 0;
+    if (threadIdx.x == 0) {
+      if (c.nbuf == 2 && zb + 1 < zb1) {
+        k2_mbar_expect_tx(bar + 8 + 8 * (buf ^ 1), wbytes);
+        k2_bulk_g2s(k2_smem_u32(W_s + (size_t)(buf ^ 1) * ws8 * 8), p.WA8 + (int64_t)(zb + 1) * ws8 * 8, wbytes,
+                    bar + 8 + 8 * (buf ^ 1));
+      }
+      if (c.nbuf == 1 && ir > 0) {
+        k2_mbar_expect_tx(bar + 8, wbytes);
+        k2_bulk_g2s(k2_smem_u32(W_s), p.WA8 + (int64_t)zb * ws8 * 8, wbytes, bar + 8);
+      }
+      if (ir > 0 && c.bulk_store) {      // the previous batch's result tile has left shared memory: release it
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar + 24) : "memory");
+      }
+    }
+    k2_mbar_wait(bar + 8 + 8 * buf, (c.nbuf == 2 ? (ir >> 1) : ir) & 1);
+    const double* __restrict__ Wb = W_s + (size_t)buf * ws8 * 8;
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = atomicAdd(next_unit + ir, 1);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= n_units) break;
+      const int b = __ldg(p.band_order + (u >> 1));
+      const int half = u & 1;
+      const int jbv = __ldg(p.jb8 + zb * n_b + b);
+      const int nkb = __ldg(p.cb8 + zb * n_b + b) >> 2;
+      // A fragments: template row 16 half + grp (+ 8), samples jbv + 4 kb + tig; B fragment: sample tig, slice grp
+      const double* __restrict__ A0 = Fs_s + (16 * half + grp) * ldF + jbv + tig;
+      const double* __restrict__ A1 = A0 + 8 * ldF;
+      const double* __restrict__ Bp = Wb + (size_t)__ldg(p.woff8 + b) * 8 + tig * 8 + grp;
+      double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 2
+      for (int kb = 0; kb < nkb; ++kb) {
+        const double a0 = A0[4 * kb], a1 = A1[4 * kb], bw = Bp[32 * kb];
+        k2_dmma(c00, c01, a0, bw);
+        k2_dmma(c10, c11, a1, bw);
+      }
+      if (ir > 0 && c.bulk_store) k2_mbar_wait(bar + 24, (ir - 1) & 1);
+      // D fragment: template row grp (+ 8), slices 2 tig and 2 tig + 1
+      double* o = O_s + ((size_t)(2 * tig) * TT + 16 * half + grp) * c.opitch + b;
+      o[0] = c00;
+      o[(size_t)TT * c.opitch] = c01;
+      o[(size_t)8 * c.opitch] = c10;
+      o[(size_t)(TT + 8) * c.opitch] = c11;
+    }
+    __syncthreads();
+    const int nz = min(8, p.n_z - 8 * zb);
+    if (c.bulk_store) {
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        for (int zl = 0; zl < nz; ++zl) {
+          double* dst = p.out + ((int64_t)(8 * zb + zl) * p.T_total + t0) * pitch;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst),
+                       "r"(k2_smem_u32(O_s + (size_t)zl * TT * c.opitch)), "r"((uint32_t)(nt * pitch * 8))
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      }
+    } else {
+      const int per_z = nt * pitch;
+      const int d_tt = K2T_THREADS / pitch, d_col = K2T_THREADS - d_tt * pitch;
+      for (int zl = 0; zl < nz; ++zl) {
+        int t2 = threadIdx.x / pitch, col = threadIdx.x - t2 * pitch;
+        double* __restrict__ dst = p.out + ((int64_t)(8 * zb + zl) * p.T_total) * pitch;
+        for (int i = threadIdx.x; i < per_z; i += K2T_THREADS) {
+          const int64_t row = p.row_map ? __ldg(p.row_map + t0 + t2) : t0 + t2;
+          dst[row * pitch + col] = O_s[(zl * TT + t2) * c.opitch + col];
+          t2 += d_tt;
+          col += d_col;
+          if (col >= pitch) {
+            col -= pitch;
+            ++t2;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (c.bulk_store && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+
+bool k2_mma_plan(const K2Problem& p, K2MmaPlan* c) {
+  constexpr int TT = 32;
+  if (!p.mma_ok || p.wstride8 < 4 || (p.ldF8 & 7) != 4) return false;
+  const bool bulk = !p.row_map && (p.out_pitch % 2 == 0) && (reinterpret_cast<uintptr_t>(p.out) % 16 == 0);
+  const int opitch = bulk ? p.out_pitch : p.out_pitch + 1;
+  const size_t f = (size_t)TT * p.ldF8 * 8;
+  const size_t off_w = (f + 15) & ~(size_t)15;
+  for (int nbuf = 2; nbuf >= 1; --nbuf) {
+    const size_t off_o = off_w + (size_t)nbuf * p.wstride8 * 64;
+    const size_t off_bar = (off_o + (size_t)8 * TT * opitch * 8 + 15) & ~(size_t)15;
+    const size_t total = off_bar + 32 + K2_SW_MAX_ROUNDS * 4;
+    if (total > 225 * 1024) continue;
+    c->nbuf = nbuf;
+    c->opitch = opitch;
+    c->bulk_store = bulk ? 1 : 0;
+    c->off_w = (int32_t)off_w;
+    c->off_o = (int32_t)off_o;
+    c->off_bar = (int32_t)off_bar;
+    c->smem_bytes = (int32_t)total;
+    const int64_t tiles = (p.T + TT - 1) / TT;
+    int64_t zbc = ((int64_t)p.n_zb8 * tiles) / (8 * 148);
+    if (zbc > K2_SW_MAX_ROUNDS) zbc = K2_SW_MAX_ROUNDS;
+    if (zbc < 1) zbc = 1;
+    c->zbc = (int32_t)zbc;
+    return true;
+  }
+  return false;
+}
+
 bool k2_tile_plan(const K2Problem& p, K2TilePlan* c) {
   if ((p.wstride & 1) || p.wstride < 2) return false;              // bulk copies move 16-byte multiples
   // a dense tile for the bulk store (two-way bank conflicts on the 18 x 32 result writes are cheaper than a
@@ -613,6 +831,25 @@ cudaError_t launch_k2_weights_aligned(const K2Problem& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_k2_batch_ranges8(const K2Problem& p, cudaStream_t stream) {
+  const int total = p.n_zb8 * p.filt.n_b;
+  if (total == 0) return cudaSuccess;
+  k2_batch_ranges8_kernel<<<(total + 127) / 128, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k2_weights_aligned8(const K2Problem& p, cudaStream_t stream) {
+  const int64_t total = (int64_t)p.n_zb8 * p.wstride8 * 8;
+  if (total == 0) return cudaSuccess;
+  k2_weights_aligned8_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+bool k2_mma_fits(const K2Problem& p) {
+  K2MmaPlan c;
+  return k2_mma_plan(p, &c);
+}
+
 bool k2_sw_fits(const K2Problem& p) {
   K2SwPlan c;
   return k2_sw_plan(p, &c);
@@ -620,6 +857,15 @@ bool k2_sw_fits(const K2Problem& p) {
 
 cudaError_t launch_k2_contract(const K2Problem& p, cudaStream_t stream) {
   if (p.n_z == 0 || p.T == 0) return cudaSuccess;
+  K2MmaPlan mc;
+  if (p.tile_ok && k2_mma_plan(p, &mc)) {
+    cudaError_t e = cudaFuncSetAttribute(k2_contract_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         mc.smem_bytes);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((p.n_zb8 + mc.zbc - 1) / mc.zbc), (unsigned)((p.T + 31) / 32));
+    k2_contract_mma_kernel<<<grid, K2T_THREADS, (size_t)mc.smem_bytes, stream>>>(p, mc);
+    return cudaGetLastError();
+  }
   K2SwPlan sc;
   if (p.tile_ok && k2_sw_plan(p, &sc)) {
     cudaError_t e = cudaFuncSetAttribute(k2_contract_sw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -20,7 +20,9 @@
 //   k2_ranges    j_lo / cnt per (z, band) and the per-band max cnt       (integer work, bit-exact)
 //   k2_weights   W[z][woff[b] + r]: two binary searches + a short sequential sum per entry; band b owns
 //                rmax_b = max_z cnt[z][b] slots per z-slice (compact: no padding to the widest band)
-//   k2_contract  the banded contraction; writes the [n_z, T, pitch] table K1 gathers from.  Three kernels:
+//   k2_contract  the banded contraction; writes the [n_z, T, pitch] table K1 gathers from.  Four kernels:
+//                tensor-core (FP64 mma.m8n8k4: 32 templates x 8 consecutive z-slices per band, the k-blocks of 4
+//                samples aligned to absolute sample indices so that a slice's value does not depend on its batch),
 //                shared-window (32 templates resident in shared memory; 4 consecutive z-slices share every
 //                read of the template window, their weights re-aligned to the batch's common first sample),
 //                tiled (same tile, one slice at a time: used when a template holds a non-finite sample,
@@ -69,6 +71,18 @@ struct K2Problem {
   const int32_t* woffA = nullptr;   // [n_b + 1]
   const int32_t* band_ofA = nullptr; // [wstrideA]
   double* WA = nullptr;             // [n_zb, wstrideA, 4]
+  // tensor-core path (FP64 mma.m8n8k4): batches of 8 slices, windows aligned to absolute multiples of 4 samples
+  int32_t mma_ok = 0;
+  int32_t n_zb8 = 0;                // batches = ceil(n_z / 8)
+  int32_t wstride8 = 0;             // slots per batch (each slot holds the 8 slices' weights of one sample)
+  int32_t ldF8 = 0;                 // row pitch of Fs8: = 4 (mod 8), >= n_lam + 3
+  const double* Fs8 = nullptr;      // [T_pad, ldF8] templates in sorted-wavelength order, zero padded
+  int32_t* jb8 = nullptr;           // [n_zb8, n_b] first sample of the batch window, rounded down to a multiple of 4
+  int32_t* cb8 = nullptr;           // [n_zb8, n_b] window length, a multiple of 4
+  int32_t* d_rmaxb8 = nullptr;      // [n_b]
+  const int32_t* woff8 = nullptr;   // [n_b + 1]
+  const int32_t* band_of8 = nullptr; // [wstride8]
+  double* WA8 = nullptr;            // [n_zb8, wstride8, 8]
   const int64_t* row_map = nullptr; // [T] or nullptr
   int64_t T_total = 0;
   int32_t out_pitch = 0;            // row pitch of out in doubles (>= n_b); pad columns are written as 0
@@ -82,6 +96,9 @@ cudaError_t launch_k2_weights(const K2Problem& p, cudaStream_t stream);
 cudaError_t launch_k2_batch_ranges(const K2Problem& p, cudaStream_t stream);
 cudaError_t launch_k2_weights_aligned(const K2Problem& p, cudaStream_t stream);
 bool k2_sw_fits(const K2Problem& p);     // the shared-window kernel's tiles fit shared memory
+cudaError_t launch_k2_batch_ranges8(const K2Problem& p, cudaStream_t stream);
+cudaError_t launch_k2_weights_aligned8(const K2Problem& p, cudaStream_t stream);
+bool k2_mma_fits(const K2Problem& p);    // the tensor-core kernel's tiles fit shared memory
 cudaError_t launch_k2_contract(const K2Problem& p, cudaStream_t stream);
 
 }  // namespace agnf

@@ -92,29 +92,40 @@ def test_k2_dense_zgrid_linearity_and_row_map():
     assert np.array_equal(c[:, 0::2], full_sub)
 
 
-def test_k2_shared_window_and_per_slice_kernels_agree():
-    """The shared-window contraction (4 slices per read of the template window) against the per-slice kernels:
-    same zero pattern, values within 1e-13 (different summation grouping), on an even and an odd number of slices,
-    host and device outputs, and a family with an infinite sample falls back to the per-slice kernels."""
+def test_k2_contraction_kernels_agree():
+    """The tensor-core contraction (FP64 mma, 8 slices per batch), the shared-window contraction (4 slices per read
+    of the template window) and the per-slice kernels: same zero pattern, values within 1e-13 (different summation
+    grouping), on slice counts that are not multiples of the batch sizes, host and device outputs; a family with
+    an infinite sample falls back to the per-slice kernels."""
     fd = synth.synthetic_filterdict()
     builder = DictBuilder(fd, device=0)
     tpl = synth.synthetic_templates()
-    for fam, nz in (("TO", 37), ("SB", 8), ("BB", 3), ("GA", 6)):
+    # sparse grids (slices far apart: the union window of 8 slices may not fit -> 4-slice kernel) and dense ones
+    for fam, nz, dense in (("TO", 37, False), ("SB", 8, False), ("BB", 3, False), ("GA", 6, False), ("GA", 21, True),
+                           ("GA", 8, True)):
         F = tpl[fam]["F"]
         F = {k: F[k] for k in list(F.keys())[:211]}
-        z = np.round(np.linspace(0.0, 5.9, nz), 3)
+        z = np.round(0.731 + 0.001 * np.arange(nz), 3) if dense else np.round(np.linspace(0.0, 5.9, nz), 3)
+        got = {}
+        for name, mma, sw in (("mma", 1, 1), ("shared", 0, 1), ("slice", 0, 0)):
+            builder.set_option("k2_mma", mma)
+            builder.set_option("k2_shared_window", sw)
+            got[name] = builder.build_family(F, z)
+            kern = builder.get_option("k2_last_kernel")
+            # the 1 366-sample starburst grid does not leave room for a 32-template tile
+            want = 1 if (fam == "SB" or name == "slice") else (3 if name == "mma" else 2)
+            if name == "mma" and fam != "SB" and not (dense or fam == "TO"):
+                assert kern in (2, 3), (fam, name, kern)     # the 8-slice weight block may not fit next to the tile
+            else:
+                assert kern == want, (fam, name, kern)
+            if name != "slice":
+                dev = builder.build_family(F, z, on_device=True).cpu().numpy()[:, :, :builder.n_b]
+                assert np.array_equal(got[name], dev), (fam, name)
+        builder.set_option("k2_mma", 1)
         builder.set_option("k2_shared_window", 1)
-        a = builder.build_family(F, z)
-        # the synthetic starburst grid (1 366 samples) does not leave room for a 32-template tile
-        assert builder.get_option("k2_last_kernel") == (1 if fam == "SB" else 2), fam
-        a_dev = builder.build_family(F, z, on_device=True).cpu().numpy()[:, :, :builder.n_b]
-        builder.set_option("k2_shared_window", 0)
-        b = builder.build_family(F, z)
-        assert builder.get_option("k2_last_kernel") == 1
-        builder.set_option("k2_shared_window", 1)
-        assert np.array_equal(a, a_dev), fam
-        assert np.array_equal(a == 0.0, b == 0.0), fam
-        assert_close_with_specials(a, b, rtol=1e-13, what="shared-window vs per-slice " + fam)
+        for name in ("mma", "shared"):
+            assert np.array_equal(got[name] == 0.0, got["slice"] == 0.0), (fam, name)
+            assert_close_with_specials(got[name], got["slice"], rtol=1e-13, what="%s vs per-slice %s" % (name, fam))
     to = dict(list(tpl["TO"]["F"].items())[:40])
     k0 = next(iter(to))
     bad = np.array(to[k0][1], dtype=np.float64).copy()

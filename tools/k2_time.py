@@ -11,7 +11,8 @@ tpl = synth.synthetic_templates()
 z = np.round(np.arange(0.0, 6.0, 0.001), 3)
 for fam in ("GA", "SB", "TO", "BB"):
     F = tpl[fam]["F"]
-    for sw in (0, 1, 0, 1):
+    for mma, sw in ((0, 0), (0, 1), (1, 1), (0, 0), (0, 1), (1, 1)):
+        builder.set_option("k2_mma", mma)
         builder.set_option("k2_shared_window", sw)
         t = time.perf_counter()
         out = builder.build_family(F, z, on_device=True)

@@ -10,7 +10,8 @@ builder = DictBuilder(fd, device=0)
 tpl = synth.synthetic_templates()
 z = np.round(np.arange(0.0, 6.0, 0.002), 3)
 F = tpl["GA"]["F"]
-for sw in (0, 1, 0, 1):
+for mma, sw in ((0, 0), (0, 1), (1, 1), (0, 0), (0, 1), (1, 1)):
+    builder.set_option("k2_mma", mma)
     builder.set_option("k2_shared_window", sw)
     t = time.perf_counter()
     out = builder.build_family(F, z, on_device=True)

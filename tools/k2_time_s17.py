@@ -14,7 +14,8 @@ F = {}
 for i in range(9600):
     F[(str(20 + 0.1 * (i // 64)), str((i % 64) / 64.0))] = (lognu, 1e-28 * rng.lognormal(0, 1, size=721))
 z = np.round(np.arange(0.0, 6.0, 0.006), 3)
-for sw in (0, 1, 0, 1):
+for mma, sw in ((0, 0), (0, 1), (1, 1), (0, 0), (0, 1), (1, 1)):
+    builder.set_option("k2_mma", mma)
     builder.set_option("k2_shared_window", sw)
     t = time.perf_counter()
     out = builder.build_family(F, z, on_device=True)

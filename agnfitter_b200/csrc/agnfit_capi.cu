@@ -957,6 +957,8 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
     K2_TRY(cudaStreamSynchronize(st));
     for (int b = 0; b < n_b; ++b) woff8[(size_t)b + 1] = woff8[(size_t)b] + std::max(rmax8[(size_t)b], 4);
     p.wstride8 = woff8[(size_t)n_b];
+    p.hdr8 = ((2 * n_b * 4 + 15) / 16 * 16) / 8;
+    p.blk8 = (int64_t)p.hdr8 + (int64_t)p.wstride8 * 8;
     int32_t L = n_lam + 3;
     L += ((4 - (L & 7)) + 8) & 7;
     p.ldF8 = L;
@@ -979,7 +981,7 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
       K2_TRY(cudaMemcpyAsync(d_bandof8, band_of8.data(), (size_t)p.wstride8 * 4, cudaMemcpyHostToDevice, st));
       p.woff8 = static_cast<const int32_t*>(d_woff8);
       p.band_of8 = static_cast<const int32_t*>(d_bandof8);
-      K2_ALLOC(d_WA8, (size_t)p.n_zb8 * p.wstride8 * 64);
+      K2_ALLOC(d_WA8, (size_t)p.n_zb8 * (size_t)p.blk8 * 8);
       p.WA8 = static_cast<double*>(d_WA8);
       K2_TRY(launch_k2_weights_aligned8(p, st));
       K2_TRY(cudaStreamSynchronize(st));      // the host vectors above feed asynchronous copies

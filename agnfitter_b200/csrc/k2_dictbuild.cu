@@ -194,7 +194,19 @@ __global__ void k2_weights_aligned8_kernel(K2Problem p) {
     const int r = j - __ldg(p.jlo + z * n_b + b);
     if (r >= 0 && r < __ldg(p.cnt + z * n_b + b)) w = band_weight(p, z, b, j);
   }
-  p.WA8[idx] = w;
+  p.WA8[(int64_t)zb * p.blk8 + p.hdr8 + (int64_t)slot * 8 + zl] = w;
+}
+
+// Every batch's weight block starts with the window table of the batch (jb8[n_b] | cb8[n_b], int32): it reaches
+// shared memory with the same bulk copy as the weights, so a work unit starts without a global-memory round trip.
+__global__ void k2_headers8_kernel(K2Problem p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_b = p.filt.n_b;
+  if (idx >= p.n_zb8 * n_b) return;
+  const int zb = idx / n_b, b = idx - zb * n_b;
+  int32_t* h = reinterpret_cast<int32_t*>(p.WA8 + (int64_t)zb * p.blk8);
+  h[b] = p.jb8[idx];
+  h[n_b + b] = p.cb8[idx];
 }
 
 // Banded contraction.  grid = (n_z, ceil(T / K2_TILE_T)); the z-slice's weights are staged in
@@ -615,18 +627,21 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_mma_kernel(K2Probl
   constexpr int TT = 32;
   extern __shared__ __align__(16) unsigned char k2_smem[];
   double* Fs_s = reinterpret_cast<double*>(k2_smem);                        // [TT][ldF8]
-  double* W_s = reinterpret_cast<double*>(k2_smem + c.off_w);               // [nbuf][wstride8][8]
+  double* W_s = reinterpret_cast<double*>(k2_smem + c.off_w);               // [nbuf][header | wstride8 x 8]
   double* O_s = reinterpret_cast<double*>(k2_smem + c.off_o);               // [8][TT][opitch]
   const uint32_t bar = k2_smem_u32(k2_smem + c.off_bar);
   int* next_unit = reinterpret_cast<int*>(k2_smem + c.off_bar + 32);        // [K2_SW_MAX_ROUNDS]
-  const int n_b = p.filt.n_b, ws8 = p.wstride8, ldF = p.ldF8, pitch = p.out_pitch;
+  int* order_s = next_unit + K2_SW_MAX_ROUNDS;                              // [n_b] bands, longest first
+  int* woff_s = order_s + p.filt.n_b;                                       // [n_b] first slot of each band
+  const int n_b = p.filt.n_b, ldF = p.ldF8, pitch = p.out_pitch;
+  const int64_t blk = p.blk8;
   const int lane = threadIdx.x & 31, grp = lane >> 2, tig = lane & 3;
   const int64_t t0 = (int64_t)blockIdx.y * TT;
   const int nt = (int)min((int64_t)TT, p.T - t0);
   const int zb0 = blockIdx.x * c.zbc;
   const int zb1 = min(zb0 + c.zbc, p.n_zb8);
   const int n_units = 2 * n_b;
-  const uint32_t wbytes = (uint32_t)ws8 * 64u;
+  const uint32_t wbytes = (uint32_t)blk * 8u;
   if (threadIdx.x == 0) {
     k2_mbar_init(bar, 1);
     k2_mbar_init(bar + 8, 1);
@@ -635,6 +650,10 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_mma_kernel(K2Probl
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (threadIdx.x < K2_SW_MAX_ROUNDS) next_unit[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < n_b; i += K2T_THREADS) {
+    order_s[i] = __ldg(p.band_order + i);
+    woff_s[i] = __ldg(p.woff8 + i);
+  }
   for (int i = threadIdx.x; i < 8 * TT * c.opitch; i += K2T_THREADS) O_s[i] = 0.0;   // pad columns stay zero
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -642,7 +661,7 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_mma_kernel(K2Probl
     k2_mbar_expect_tx(bar, fbytes);
     k2_bulk_g2s(k2_smem_u32(Fs_s), p.Fs8 + t0 * ldF, fbytes, bar);
     k2_mbar_expect_tx(bar + 8, wbytes);
-    k2_bulk_g2s(k2_smem_u32(W_s), p.WA8 + (int64_t)zb0 * ws8 * 8, wbytes, bar + 8);
+    k2_bulk_g2s(k2_smem_u32(W_s), p.WA8 + (int64_t)zb0 * blk, wbytes, bar + 8);
   }
   k2_mbar_wait(bar, 0);
   int ir = 0;
@@ -651,12 +670,12 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_mma_kernel(K2Probl
     if (threadIdx.x == 0) {
       if (c.nbuf == 2 && zb + 1 < zb1) {
         k2_mbar_expect_tx(bar + 8 + 8 * (buf ^ 1), wbytes);
-        k2_bulk_g2s(k2_smem_u32(W_s + (size_t)(buf ^ 1) * ws8 * 8), p.WA8 + (int64_t)(zb + 1) * ws8 * 8, wbytes,
+        k2_bulk_g2s(k2_smem_u32(W_s + (size_t)(buf ^ 1) * blk), p.WA8 + (int64_t)(zb + 1) * blk, wbytes,
                     bar + 8 + 8 * (buf ^ 1));
       }
       if (c.nbuf == 1 && ir > 0) {
         k2_mbar_expect_tx(bar + 8, wbytes);
-        k2_bulk_g2s(k2_smem_u32(W_s), p.WA8 + (int64_t)zb * ws8 * 8, wbytes, bar + 8);
+        k2_bulk_g2s(k2_smem_u32(W_s), p.WA8 + (int64_t)zb * blk, wbytes, bar + 8);
       }
       if (ir > 0 && c.bulk_store) {      // the previous batch's result tile has left shared memory: release it
         asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
@@ -664,20 +683,21 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_mma_kernel(K2Probl
       }
     }
     k2_mbar_wait(bar + 8 + 8 * buf, (c.nbuf == 2 ? (ir >> 1) : ir) & 1);
-    const double* __restrict__ Wb = W_s + (size_t)buf * ws8 * 8;
+    const int* __restrict__ hdr = reinterpret_cast<const int*>(W_s + (size_t)buf * blk);
+    const double* __restrict__ Wb = W_s + (size_t)buf * blk + p.hdr8;
     for (;;) {
       int u = 0;
       if (lane == 0) u = atomicAdd(next_unit + ir, 1);
       u = __shfl_sync(0xffffffffu, u, 0);
       if (u >= n_units) break;
-      const int b = __ldg(p.band_order + (u >> 1));
+      const int b = order_s[u >> 1];
       const int half = u & 1;
-      const int jbv = __ldg(p.jb8 + zb * n_b + b);
-      const int nkb = __ldg(p.cb8 + zb * n_b + b) >> 2;
+      const int jbv = hdr[b];
+      const int nkb = hdr[n_b + b] >> 2;
       // A fragments: template row 16 half + grp (+ 8), samples jbv + 4 kb + tig; B fragment: sample tig, slice grp
       const double* __restrict__ A0 = Fs_s + (16 * half + grp) * ldF + jbv + tig;
       const double* __restrict__ A1 = A0 + 8 * ldF;
-      const double* __restrict__ Bp = Wb + (size_t)__ldg(p.woff8 + b) * 8 + tig * 8 + grp;
+      const double* __restrict__ Bp = Wb + (size_t)woff_s[b] * 8 + tig * 8 + grp;
       double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
 #pragma unroll 2
       for (int kb = 0; kb < nkb; ++kb) {
@@ -737,9 +757,9 @@ bool k2_mma_plan(const K2Problem& p, K2MmaPlan* c) {
   const size_t f = (size_t)TT * p.ldF8 * 8;
   const size_t off_w = (f + 15) & ~(size_t)15;
   for (int nbuf = 2; nbuf >= 1; --nbuf) {
-    const size_t off_o = off_w + (size_t)nbuf * p.wstride8 * 64;
+    const size_t off_o = off_w + (size_t)nbuf * p.blk8 * 8;
     const size_t off_bar = (off_o + (size_t)8 * TT * opitch * 8 + 15) & ~(size_t)15;
-    const size_t total = off_bar + 32 + K2_SW_MAX_ROUNDS * 4;
+    const size_t total = off_bar + 32 + K2_SW_MAX_ROUNDS * 4 + 2 * (size_t)p.filt.n_b * 4;
     if (total > 225 * 1024) continue;
     c->nbuf = nbuf;
     c->opitch = opitch;
@@ -842,6 +862,8 @@ cudaError_t launch_k2_weights_aligned8(const K2Problem& p, cudaStream_t stream) 
   const int64_t total = (int64_t)p.n_zb8 * p.wstride8 * 8;
   if (total == 0) return cudaSuccess;
   k2_weights_aligned8_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
+  const int nh = p.n_zb8 * p.filt.n_b;
+  k2_headers8_kernel<<<(nh + 127) / 128, 128, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

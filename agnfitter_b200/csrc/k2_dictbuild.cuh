@@ -82,7 +82,9 @@ struct K2Problem {
   int32_t* d_rmaxb8 = nullptr;      // [n_b]
   const int32_t* woff8 = nullptr;   // [n_b + 1]
   const int32_t* band_of8 = nullptr; // [wstride8]
-  double* WA8 = nullptr;            // [n_zb8, wstride8, 8]
+  int32_t hdr8 = 0;                 // doubles of header in front of every batch's weights: jb8[n_b] | cb8[n_b] (int32)
+  int64_t blk8 = 0;                 // doubles per batch block = hdr8 + wstride8 * 8
+  double* WA8 = nullptr;            // [n_zb8, blk8]
   const int64_t* row_map = nullptr; // [T] or nullptr
   int64_t T_total = 0;
   int32_t out_pitch = 0;            // row pitch of out in doubles (>= n_b); pad columns are written as 0

@@ -1004,6 +1004,8 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
     K2_TRY(cudaStreamSynchronize(st));
     for (int b = 0; b < n_b; ++b) woffA[(size_t)b + 1] = woffA[(size_t)b] + std::max(rmaxA[(size_t)b], 1);
     p.wstrideA = woffA[(size_t)n_b];
+    p.hdrA = ((2 * n_b * 4 + 15) / 16 * 16) / 8;
+    p.blkA = (int64_t)p.hdrA + (int64_t)p.wstrideA * 4;
     p.sw_ok = 1;
     if (k2_sw_fits(p)) {
       std::vector<int32_t> band_ofA((size_t)p.wstrideA, -1);
@@ -1018,7 +1020,7 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
       K2_TRY(cudaMemcpyAsync(d_bandofA, band_ofA.data(), (size_t)p.wstrideA * 4, cudaMemcpyHostToDevice, st));
       p.woffA = static_cast<const int32_t*>(d_woffA);
       p.band_ofA = static_cast<const int32_t*>(d_bandofA);
-      K2_ALLOC(d_WA, (size_t)p.n_zb * p.wstrideA * 32);
+      K2_ALLOC(d_WA, (size_t)p.n_zb * (size_t)p.blkA * 8);
       p.WA = static_cast<double*>(d_WA);
       K2_TRY(launch_k2_weights_aligned(p, st));
       K2_TRY(cudaStreamSynchronize(st));      // the host vectors above feed asynchronous copies

@@ -145,7 +145,18 @@ __global__ void k2_weights_aligned_kernel(K2Problem p) {
     if (r >= 0 && r < __ldg(p.cnt + z * n_b + b) && slot - __ldg(p.woffA + b) < __ldg(p.cb + zb * n_b + b))
       w = band_weight(p, z, b, j);
   }
-  p.WA[idx] = w;
+  p.WA[(int64_t)zb * p.blkA + p.hdrA + (int64_t)slot * 4 + zl] = w;
+}
+
+// window table of every batch (jb[n_b] | cb[n_b], int32) in front of its weights, see k2_headers8_kernel
+__global__ void k2_headersA_kernel(K2Problem p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_b = p.filt.n_b;
+  if (idx >= p.n_zb * n_b) return;
+  const int zb = idx / n_b, b = idx - zb * n_b;
+  int32_t* h = reinterpret_cast<int32_t*>(p.WA + (int64_t)zb * p.blkA);
+  h[b] = p.jb[idx];
+  h[n_b + b] = p.cb[idx];
 }
 
 // Tensor-core path.  One thread per (batch of 8 slices, band): the window all 8 slices see together, its start
@@ -448,7 +459,10 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
   // barriers: +0 template tile, +8/+16 weight buffers, +24 "result tile drained"; then one unit counter per round
   const uint32_t bar = k2_smem_u32(k2_smem + c.off_bar);
   int* next_unit = reinterpret_cast<int*>(k2_smem + c.off_bar + 32);        // [K2_SW_MAX_ROUNDS]
-  const int n_b = p.filt.n_b, wsA = p.wstrideA, ldF = p.ldF, pitch = p.out_pitch;
+  int* order_s = next_unit + K2_SW_MAX_ROUNDS;                              // [n_b] bands, longest first
+  int* woff_s = order_s + p.filt.n_b;                                       // [n_b] first slot of each band
+  const int n_b = p.filt.n_b, ldF = p.ldF, pitch = p.out_pitch;
+  const int64_t blkA = p.blkA;
   const int tt = threadIdx.x % TT;
   const int64_t t0 = (int64_t)blockIdx.y * TT;
   const int nt = (int)min((int64_t)TT, p.T - t0);
@@ -456,7 +470,7 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
   const int zb1 = min(zb0 + c.zbc, p.n_zb);
   const int NB = c.nb;
   const int n_units = n_b * NB;
-  const size_t wround = (size_t)NB * wsA * 4;                               // doubles per weight buffer
+  const size_t wround = (size_t)NB * blkA;                                  // doubles per weight buffer
   if (threadIdx.x == 0) {
     k2_mbar_init(bar, 1);
     k2_mbar_init(bar + 8, 1);
@@ -465,15 +479,19 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (threadIdx.x < K2_SW_MAX_ROUNDS) next_unit[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < n_b; i += K2T_THREADS) {
+    order_s[i] = __ldg(p.band_order + i);
+    woff_s[i] = __ldg(p.woffA + i);
+  }
   for (int i = threadIdx.x; i < NB * 4 * TT * c.opitch; i += K2T_THREADS) O_s[i] = 0.0;   // pad columns stay zero
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t fbytes = (uint32_t)TT * (uint32_t)ldF * 8u;
     k2_mbar_expect_tx(bar, fbytes);
     k2_bulk_g2s(k2_smem_u32(Fs_s), p.Fs + t0 * ldF, fbytes, bar);
-    const uint32_t wbytes = (uint32_t)min(NB, zb1 - zb0) * (uint32_t)wsA * 32u;
+    const uint32_t wbytes = (uint32_t)min(NB, zb1 - zb0) * (uint32_t)blkA * 8u;
     k2_mbar_expect_tx(bar + 8, wbytes);
-    k2_bulk_g2s(k2_smem_u32(W_s), p.WA + (int64_t)zb0 * wsA * 4, wbytes, bar + 8);
+    k2_bulk_g2s(k2_smem_u32(W_s), p.WA + (int64_t)zb0 * blkA, wbytes, bar + 8);
   }
   k2_mbar_wait(bar, 0);
   int ir = 0;
@@ -482,15 +500,15 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
     const int nbr = min(NB, zb1 - zbr);
     if (threadIdx.x == 0) {
       if (c.nbuf == 2 && zbr + NB < zb1) {
-        const uint32_t wbytes = (uint32_t)min(NB, zb1 - zbr - NB) * (uint32_t)wsA * 32u;
+        const uint32_t wbytes = (uint32_t)min(NB, zb1 - zbr - NB) * (uint32_t)blkA * 8u;
         k2_mbar_expect_tx(bar + 8 + 8 * (buf ^ 1), wbytes);
-        k2_bulk_g2s(k2_smem_u32(W_s + (size_t)(buf ^ 1) * wround), p.WA + (int64_t)(zbr + NB) * wsA * 4, wbytes,
+        k2_bulk_g2s(k2_smem_u32(W_s + (size_t)(buf ^ 1) * wround), p.WA + (int64_t)(zbr + NB) * blkA, wbytes,
                     bar + 8 + 8 * (buf ^ 1));
       }
       if (c.nbuf == 1 && ir > 0) {       // every warp left the previous round (barrier below): reuse the buffer
-        const uint32_t wbytes = (uint32_t)nbr * (uint32_t)wsA * 32u;
+        const uint32_t wbytes = (uint32_t)nbr * (uint32_t)blkA * 8u;
         k2_mbar_expect_tx(bar + 8, wbytes);
-        k2_bulk_g2s(k2_smem_u32(W_s), p.WA + (int64_t)zbr * wsA * 4, wbytes, bar + 8);
+        k2_bulk_g2s(k2_smem_u32(W_s), p.WA + (int64_t)zbr * blkA, wbytes, bar + 8);
       }
       if (ir > 0 && c.bulk_store) {      // the previous round's result tile has left shared memory: release it
         asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
@@ -507,13 +525,13 @@ __global__ void __launch_bounds__(K2T_THREADS, 1) k2_contract_sw_kernel(K2Proble
       if (u >= n_units) break;
       const int bi = u & (NB - 1);
       if (bi >= nbr) continue;
-      const int b = __ldg(p.band_order + (u >> c.nb_shift));
-      const int zb = zbr + bi;
-      const int jbv = __ldg(p.jb + zb * n_b + b);
-      const int rend = __ldg(p.cb + zb * n_b + b);
+      const int b = order_s[u >> c.nb_shift];
+      const int* __restrict__ hdr = reinterpret_cast<const int*>(Wb + (size_t)bi * blkA);
+      const int jbv = hdr[b];
+      const int rend = hdr[n_b + b];
       const double* __restrict__ F = Fs_s + tt * ldF + jbv;
       const double2* __restrict__ w2 =
-          reinterpret_cast<const double2*>(Wb + ((size_t)bi * wsA + (size_t)__ldg(p.woffA + b)) * 4);
+          reinterpret_cast<const double2*>(Wb + (size_t)bi * blkA + p.hdrA + (size_t)woff_s[b] * 4);
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll 4
       for (int r = 0; r < rend; ++r) {
@@ -577,9 +595,9 @@ bool k2_sw_plan(const K2Problem& p, K2SwPlan* c) {
   for (int pass = 0; pass < 4; ++pass) {
     const int nb = pass == 0 ? 4 : (pass == 1 ? 2 : 1), sh = pass == 0 ? 2 : (pass == 1 ? 1 : 0);
     const int nbuf = pass == 3 ? 1 : 2;
-    const size_t off_o = off_w + (size_t)nbuf * nb * p.wstrideA * 32;
+    const size_t off_o = off_w + (size_t)nbuf * nb * p.blkA * 8;
     const size_t off_bar = (off_o + (size_t)nb * 4 * TT * opitch * 8 + 15) & ~(size_t)15;
-    const size_t total = off_bar + 32 + K2_SW_MAX_ROUNDS * 4;
+    const size_t total = off_bar + 32 + K2_SW_MAX_ROUNDS * 4 + 2 * (size_t)p.filt.n_b * 4;
     if (total > 225 * 1024) continue;
     c->nbuf = nbuf;
     c->nb = nb;
@@ -848,6 +866,8 @@ cudaError_t launch_k2_weights_aligned(const K2Problem& p, cudaStream_t stream) {
   const int64_t total = (int64_t)p.n_zb * p.wstrideA * 4;
   if (total == 0) return cudaSuccess;
   k2_weights_aligned_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
+  const int nh = p.n_zb * p.filt.n_b;
+  k2_headersA_kernel<<<(nh + 127) / 128, 128, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

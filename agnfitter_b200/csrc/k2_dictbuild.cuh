@@ -70,7 +70,9 @@ struct K2Problem {
   int32_t* d_rmaxbA = nullptr;      // [n_b] max over batches of cb
   const int32_t* woffA = nullptr;   // [n_b + 1]
   const int32_t* band_ofA = nullptr; // [wstrideA]
-  double* WA = nullptr;             // [n_zb, wstrideA, 4]
+  int32_t hdrA = 0;                 // doubles of header in front of every batch's weights: jb[n_b] | cb[n_b] (int32)
+  int64_t blkA = 0;                 // doubles per batch block = hdrA + wstrideA * 4
+  double* WA = nullptr;             // [n_zb, blkA]
   // tensor-core path (FP64 mma.m8n8k4): batches of 8 slices, windows aligned to absolute multiples of 4 samples
   int32_t mma_ok = 0;
   int32_t n_zb8 = 0;                // batches = ceil(n_z / 8)

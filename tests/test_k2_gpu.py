@@ -136,6 +136,36 @@ def test_k2_contraction_kernels_agree():
     assert np.isfinite(got[:, 1:]).all()
 
 
+@pytest.mark.parametrize("n_b", [1, 5, 17])
+def test_k2_odd_band_counts(n_b):
+    """Band counts that are odd (host outputs have an odd row pitch: the result tile is stored by the store loop
+    instead of bulk stores) or tiny, through all three contraction paths and against the oracle."""
+    nus, nks, spans = synth.DEFAULT18_NU[:n_b], synth.DEFAULT18_NK[:n_b], synth.DEFAULT18_SPAN[:n_b]
+    fd = synth.synthetic_filterdict(nus=nus, nks=nks, spans=spans, decreasing=(0,))
+    builder = DictBuilder(fd, device=0)
+    tpl = synth.synthetic_templates()
+    F = dict(list(tpl["GA"]["F"].items())[:75])
+    z = np.round(1.204 + 0.001 * np.arange(19), 3)
+    got = {}
+    for name, mma, sw in (("mma", 1, 1), ("shared", 0, 1), ("slice", 0, 0)):
+        builder.set_option("k2_mma", mma)
+        builder.set_option("k2_shared_window", sw)
+        got[name] = builder.build_family(F, z)
+        assert builder.get_option("k2_last_kernel") == {"mma": 3, "shared": 2, "slice": 1}[name]
+        dev = builder.build_family(F, z, on_device=True).cpu().numpy()
+        assert np.array_equal(dev[:, :, :n_b], got[name]) and not dev[:, :, n_b:].any()      # pad column stays zero
+    for name in ("mma", "shared"):
+        assert np.array_equal(got[name] == 0.0, got["slice"] == 0.0)
+        assert_close_with_specials(got[name], got["slice"], rtol=1e-13, what=name)
+    bands = fd[0]
+    lam = [np.asarray(fd[1][b][0]) for b in bands]
+    fac = [np.asarray(fd[2][b][0]) for b in bands]
+    keys = list(F.keys())
+    for zi, ti in ((0, 0), (7, 33), (18, 74)):
+        want = O.filtering_models(F[keys[ti]][0], F[keys[ti]][1], bands, lam, fac, float(z[zi]))
+        assert_close_with_specials(got["mma"][zi, ti], want, what="oracle z=%g t=%d" % (z[zi], ti))
+
+
 def test_k2_full_dense_zgrid_is_slice_independent():
     """BASELINE config C5: z = arange(0, 6, 0.001) (6 000 slices).  Size-independent properties at full size:
     every slice of the dense build equals, bit for bit, the same slice built on its own (the batching of

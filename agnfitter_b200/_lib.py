@@ -64,6 +64,7 @@ SIGNATURES = {
     "agnf_ens_best": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnf_ens_reset_stats": (C.c_int, [C.c_void_p]),
     "agnf_ens_set_ball": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_uint32]),
+    "agnf_ens_reset_best": (C.c_int, [C.c_void_p]),
     "agnf_ens_record": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32]),
     "agnf_ens_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "agnf_ens_percentiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -1197,11 +1197,12 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
       ctx->launches += 2;
     }
     ++ctx->ens_step;
-    if (track_best) {
+    const bool thinned = hist_every > 0 && ((it + 1) % hist_every) == 0;     // counted from the start of this call
+    if (track_best == 1 || (track_best == 2 && thinned)) {
       CUDA_TRY(ctx, launch_k3_best(st, ctx->ens_best_pos, ctx->ens_best_lnp, s));
       ctx->launches += 1;
     }
-    if (hist_every > 0 && (ctx->ens_step % hist_every) == 0) {
+    if (thinned) {
       CUDA_TRY(ctx, launch_k3_hist(st, ctx->ens_hist, s));
       ctx->ens_hist_samples += st.W;
       ctx->launches += 1;
@@ -1286,6 +1287,17 @@ AGNF_API int agnf_ens_best(agnf_ctx* ctx, double* best_pos, double* best_lnp) {
                                   ctx->stream));
   if (best_lnp)
     CUDA_TRY(ctx, cudaMemcpyAsync(best_lnp, ctx->ens_best_lnp, (size_t)st.S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+AGNF_API int agnf_ens_reset_best(agnf_ctx* ctx) {
+  if (!ctx) return 1;
+  if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::vector<double> ninf((size_t)ctx->ens.S, -INFINITY);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ens_best_lnp, ninf.data(), (size_t)ctx->ens.S * 8, cudaMemcpyHostToDevice,
+                                ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }

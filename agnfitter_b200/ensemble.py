@@ -125,12 +125,18 @@ class EnsembleSampler:
 
     # -- stepping ---------------------------------------------------------------------------------
     def run(self, n_steps, hist_every=0, track_best=False):
-        self.ctx.check(self.lib.agnf_ens_run(self.ctx.h, int(n_steps), int(hist_every), int(bool(track_best))))
+        """hist_every: every hist_every-th step of this call feeds the percentile histograms.  track_best: True
+        (every step), 'thinned' (only at those steps) or False."""
+        tb = 2 if track_best == 'thinned' else int(bool(track_best))
+        self.ctx.check(self.lib.agnf_ens_run(self.ctx.h, int(n_steps), int(hist_every), tb))
         self._steps += int(n_steps)
 
     def reset_stats(self):
         self.ctx.check(self.lib.agnf_ens_reset_stats(self.ctx.h))
         self._steps = 0
+
+    def reset_best(self):
+        self.ctx.check(self.lib.agnf_ens_reset_best(self.ctx.h))
 
     def state(self):
         """-> pos [S, W, n_par], lnp [S, W], n_accepted [S, W]"""
@@ -202,8 +208,8 @@ class EnsembleSampler:
         drawn on the device (set_ball).  With all but the first the balls of a source do not depend on which other
         sources share the shard.  save_dir: also write `<save_dir>/<name>/samples_burn1-2-3.sav`
         and `samples_mcmc.sav` for every source, in the reference's format (MCMC_AGNfitter.py:156-206).
-        Returns a summary dict: percentiles [S, n_par, 5] of the thinned production chain, best position / lnP,
-        mean acceptance fraction per source."""
+        Returns a summary dict: percentiles [S, n_par, 5] and best position / lnP of the thinned second half of the
+        production chain (what CHAIN.props keeps), mean acceptance fraction per source over the production run."""
         if int(mc['Nwalkers']) != self.W:
             raise ValueError("mc['Nwalkers'] != walkers")
         per_source = isinstance(rng, (list, tuple))
@@ -257,7 +263,15 @@ class EnsembleSampler:
         self.reset_stats()
         if save_dir is not None:
             self.record(max(n, 1))                  # sampler.reset() (MCMC:182)
-        self.run(n, hist_every=int(mc.get('Nthin', 1)) if self.n_bins else 0, track_best=True)
+        # PLOTandWRITE's CHAIN.props keeps chain[:, int(n/2):n:Nthin] (PLOTandWRITE_AGNfitter.py:476-487): the second
+        # half of the production run, every Nthin-th state, for the percentiles AND for the best-fit row
+        half, nt = int(n / 2), max(int(mc.get('Nthin', 1)), 1)
+        self.run(half)
+        self.reset_best()
+        if n - half > 0:
+            he = 1 if self.n_bins else 0
+            self.run(1, hist_every=he, track_best='thinned' if he else True)
+            self.run(n - half - 1, hist_every=nt if self.n_bins else 0, track_best='thinned' if self.n_bins else True)
         if save_dir is not None:
             for s_, nm in enumerate(names):
                 self.save_chains(os.path.join(save_dir, str(nm), 'samples_mcmc.sav'), s_)

@@ -367,15 +367,16 @@ def run_ours(args):
     ens_info = None
     if args.ensemble_steps > 0:
         from agnfitter_b200.ensemble import EnsembleSampler
-        # as the production leg of the reference's schedule runs it (ensemble.run_reference_schedule): the running
-        # best sample is tracked every step and every 10th step (out['Nthinning']) feeds the percentile histograms
+        # as the second half of the production leg of the reference's schedule runs it
+        # (ensemble.run_reference_schedule): every 10th step (out['Nthinning']) feeds the percentile histograms and
+        # the best-fit tracker
         ens = EnsembleSampler(eng, W, seed=20260101 + rank, n_bins=256)
         ens.set_positions(pars.reshape(S, W, n_par))
-        ens.run(2, hist_every=10, track_best=True)            # warm-up
+        ens.run(2, hist_every=10, track_best='thinned')       # warm-up
         barrier()
         l_e = eng.launch_count
         t0 = time.perf_counter()
-        ens.run(args.ensemble_steps, hist_every=10, track_best=True)     # synchronises the ctx stream before returning
+        ens.run(args.ensemble_steps, hist_every=10, track_best='thinned')   # synchronises the ctx stream before returning
         ens_s = time.perf_counter() - t0
         ens_launches = eng.launch_count - l_e
         _, _, acc = ens.state()
@@ -514,7 +515,7 @@ def run_ours(args):
             "ensemble": None if not ens_info else {
                 "what": "agnf_ens_run: lock-step stretch moves for every source of the shard, walkers resident in "
                         "HBM; one fused launch per half-step (propose -> ln_probab -> accept inside k1_coop_kernel), "
-                        "best sample tracked every step, percentile histograms fed every 10th step",
+                        "percentile histograms and best-fit tracker fed every 10th step",
                 "steps": ens_info["steps"], "ms_per_step": ens_ms_max,
                 "evals_per_s": total_rows / (ens_ms_max * 1e-3),
                 "sources_fitted_per_s": total_rows / (ens_ms_max * 1e-3) / EVALS_PER_FIT,

@@ -207,9 +207,10 @@ AGNF_API int agnf_ens_set_positions(agnf_ctx* ctx, const double* pos);
  * draws they depend on the source's catalogue row, not on the shard. */
 AGNF_API int agnf_ens_set_ball(agnf_ctx* ctx, const double* centre, double scale, int32_t normal, uint32_t stream_id);
 /* n_steps full stretch-move steps (2 half-steps each = 2 K1 launches).  hist_every > 0: every hist_every-th
- * step adds all walker positions to the histograms (the reference thins its chain the same way,
- * PLOTandWRITE_AGNfitter.py:471-492).  track_best: keep the best (position, lnP) seen per source
- * (what get_best_position reads back from the burn-in file). */
+ * step of this call adds all walker positions to the histograms (the reference thins its chain the same way,
+ * PLOTandWRITE_AGNfitter.py:471-492).  track_best: 1 = keep the best (position, lnP) seen per source after every
+ * step (what get_best_position reads back from the burn-in file); 2 = only at the thinned steps (the best-fit row
+ * the reference picks from its thinned flat chain, :483-487); 0 = off. */
 AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, int32_t track_best);
 /* Chain recording for the reference's chain files (samples_burn1-2-3.sav / samples_mcmc.sav,
  * MCMC_AGNfitter.py:192-206): from now on every `every`-th step of agnf_ens_run appends the walker state to a
@@ -222,6 +223,8 @@ AGNF_API int agnf_ens_get(agnf_ctx* ctx, double* pos, double* lnp, int32_t* n_ac
 AGNF_API int agnf_ens_best(agnf_ctx* ctx, double* best_pos, double* best_lnp);   /* [S, n_par], [S] */
 /* zero the acceptance counters and histograms (after burn-in: sampler.reset(), MCMC_AGNfitter.py:178) */
 AGNF_API int agnf_ens_reset_stats(agnf_ctx* ctx);
+/* forget the best sample seen so far (the next tracked step starts a new search) */
+AGNF_API int agnf_ens_reset_best(agnf_ctx* ctx);
 /* q [n_q] ascending percentiles in [0, 100] (the reference reports 2.5/16/50/84/97.5,
  * PLOTandWRITE_AGNfitter.py:152-173); out [S, n_par, n_q]; resolution = (P.max - P.min) / n_bins. */
 AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, double* out);

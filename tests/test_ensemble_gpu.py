@@ -93,8 +93,9 @@ def test_ensemble_percentiles_and_best():
 
 
 def test_reference_schedule_on_example_catalogue():
-    """Burn-in sets restarted from the best sample, reset, production (MCMC_AGNfitter.py:122-135): the GPU
-    run and the oracle run with the same seeds give the same posterior percentiles."""
+    """Burn-in sets restarted from the best sample, reset, production (MCMC_AGNfitter.py:122-135), then the thinned
+    second half of the production chain that PLOTandWRITE keeps (:476-487): the GPU run and the oracle run with the
+    same seeds give the same percentiles and the same best-fit row."""
     ms, eng, src, lnprob = _setup("cat49_catalog_example")
     mc = dict(Nwalkers=20, Nburnsets=2, Nburn=25, Nmcmc=60, Nthin=2)
     seed, n_bins = 99, 4096
@@ -128,15 +129,15 @@ def test_reference_schedule_on_example_catalogue():
         pos = EnsembleSampler.ball_around(best_p, W, rng)
     lnp = lnprob(pos)
     best_l[:] = -np.inf
-    track(pos, lnp)
     acc = np.zeros((src.S, W), dtype=np.int64)
     kept = []
-    for _ in range(mc['Nmcmc']):
+    half = int(mc['Nmcmc'] / 2)
+    for k in range(mc['Nmcmc']):                    # state k = the ensemble after production step k + 1
         E.step(pos, lnp, acc, lnprob, step, seed)
         step += 1
-        track(pos, lnp)
-        if step % mc['Nthin'] == 0:
+        if k >= half and (k - half) % mc['Nthin'] == 0:          # CHAIN.props: chain[:, int(n/2):n:Nthin]
             kept.append(pos.copy())
+            track(pos, lnp)
     chain = np.stack(kept, axis=1)
     width = (src.pmax - src.pmin) / n_bins
     for s in range(src.S):

@@ -17,7 +17,7 @@ for fam in ("GA", "SB", "TO", "BB"):
         t = time.perf_counter()
         out = builder.build_family(F, z, on_device=True)
         dt = time.perf_counter() - t
-        print("%s T=%d shared_window=%d kernel=%d contract %.3f ms wall %.1f ms  %.3g entries/s" % (
-            fam, len(F), sw, builder.get_option("k2_last_kernel"), builder.contract_ms, dt * 1e3,
+        print("%s T=%d mma=%d shared_window=%d kernel=%d contract %.3f ms wall %.1f ms  %.3g entries/s" % (
+            fam, len(F), mma, sw, builder.get_option("k2_last_kernel"), builder.contract_ms, dt * 1e3,
             out.shape[0] * out.shape[1] * builder.n_b / (builder.contract_ms * 1e-3)), flush=True)
         del out

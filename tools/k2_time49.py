@@ -16,7 +16,7 @@ for mma, sw in ((0, 0), (0, 1), (1, 1), (0, 0), (0, 1), (1, 1)):
     t = time.perf_counter()
     out = builder.build_family(F, z, on_device=True)
     dt = time.perf_counter() - t
-    print("GA T=%d n_z=%d bands=%d shared_window=%d kernel=%d contract %.3f ms wall %.1f ms  %.3g entries/s" % (
-        len(F), len(z), builder.n_b, sw, builder.get_option("k2_last_kernel"), builder.contract_ms, dt * 1e3,
+    print("GA T=%d n_z=%d bands=%d mma=%d shared_window=%d kernel=%d contract %.3f ms wall %.1f ms  %.3g entries/s" % (
+        len(F), len(z), builder.n_b, mma, sw, builder.get_option("k2_last_kernel"), builder.contract_ms, dt * 1e3,
         out.shape[0] * out.shape[1] * builder.n_b / (builder.contract_ms * 1e-3)), flush=True)
     del out

@@ -98,8 +98,11 @@ def _random_case(seed):
 
 
 def _positions(rng, ms, pmin, pmax, n):
-    span = pmax - pmin
-    p = rng.uniform(pmin - 0.02 * span, pmax + 0.02 * span, size=(n, ms.n_par))
+    # (a random grid can fall outside Pdict's overrides, e.g. EBVgal >= 0.05: the box is then empty, pmax < pmin,
+    # and every row is out of box — a legitimate case, so the generator must not choke on it)
+    span = np.abs(pmax - pmin)
+    lo, hi = np.minimum(pmin, pmax), np.maximum(pmin, pmax)
+    p = rng.uniform(lo - 0.02 * span, hi + 0.02 * span, size=(n, ms.n_par))
     p[: n // 8] = 0.5 * (pmin + pmax) + (2 * rng.uniform(size=(n // 8, ms.n_par)) - 1) * 1e-5
     col = 0
     for f in ms.families:

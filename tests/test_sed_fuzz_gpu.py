@@ -78,8 +78,9 @@ def test_k4_random_modelsets_match_the_oracle(seed):
     sed.set_bands(models, hz)
     order = sed_component_order(ms)
     for s in range(src.S):
-        span = src.pmax[s] - src.pmin[s]
-        pars = rng.uniform(src.pmin[s] - 0.03 * span, src.pmax[s] + 0.03 * span, size=(10, ms.n_par))
+        span = np.abs(src.pmax[s] - src.pmin[s])
+        lo, hi = np.minimum(src.pmin[s], src.pmax[s]), np.maximum(src.pmin[s], src.pmax[s])
+        pars = rng.uniform(lo - 0.03 * span, hi + 0.03 * span, size=(10, ms.n_par))
         sid = np.full(len(pars), s, dtype=np.int32)
         with np.errstate(all="ignore"):
             g2, fluxes = SO.realization_fluxes(ms, ps, pars, float(z[s]), float(dlum[s]))

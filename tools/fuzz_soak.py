@@ -5,11 +5,13 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pytest  # noqa: F401
 import test_k1_fuzz_gpu as K1
 import test_sed_fuzz_gpu as K4
+import test_k2_fuzz_gpu as K2
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 bad = 0
 for seed in range(16, 16 + n):
-    for name, fn in (("k1", K1.test_random_modelsets_match_the_oracle), ("k4", K4.test_k4_random_modelsets_match_the_oracle)):
+    for name, fn in (("k1", K1.test_random_modelsets_match_the_oracle),
+                     ("k4", K4.test_k4_random_modelsets_match_the_oracle), ("k2", K2.test_k2_random_filter_sets)):
         try:
             fn(seed)
         except BaseException as e:          # pytest.skip raises a BaseException subclass

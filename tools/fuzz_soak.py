@@ -6,12 +6,14 @@ import pytest  # noqa: F401
 import test_k1_fuzz_gpu as K1
 import test_sed_fuzz_gpu as K4
 import test_k2_fuzz_gpu as K2
+import test_ensemble_fuzz_gpu as K3
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 bad = 0
 for seed in range(16, 16 + n):
     for name, fn in (("k1", K1.test_random_modelsets_match_the_oracle),
-                     ("k4", K4.test_k4_random_modelsets_match_the_oracle), ("k2", K2.test_k2_random_filter_sets)):
+                     ("k4", K4.test_k4_random_modelsets_match_the_oracle), ("k2", K2.test_k2_random_filter_sets),
+                     ("k3", K3.test_ensemble_on_random_modelsets)):
         try:
             fn(seed)
         except BaseException as e:          # pytest.skip raises a BaseException subclass

@@ -1181,9 +1181,10 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
       if (fused) {
         FB.ens.half = half;
         FB.ens.step = ctx->ens_step;
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, s));
+        const bool timed = it + 1 == n_steps;           // events around the last step's launches only
+        if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, s));
         CUDA_TRY(ctx, launch_k1_coop(ctx->k1, FB, s));
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, s));
+        if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, s));
         ctx->k1_timed = true;
         ctx->last_k1_kernel = 1;
         ctx->launches += 1;

@@ -29,6 +29,7 @@ struct agnf_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // bracket the last K1 kernel
   cudaEvent_t ev2 = nullptr, ev3 = nullptr;     // bracket the last K2 contraction
   bool k1_timed = false, k2_timed = false;
+  bool untimed_once = false;                   // the next agnf_lnprob_batch_device call records no timing events
   std::string err;
   std::vector<void*> owned;                    // device allocations freed in destroy
   int64_t launches = 0;
@@ -655,7 +656,9 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
   if (check_ready(ctx)) return 1;
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
   K1Batch B{d_params, d_source_id, n, d_lnp, d_rows, d_ymodel, d_lnprior, d_lnlike};
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+  const bool timed = !ctx->untimed_once;          // latency-bound callers skip the two event records (~3 us each)
+  ctx->untimed_once = false;
+  if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
   const char* why = nullptr;
   if (ctx->k1_variant != 0 && k1_coop_supported(ctx->k1, B, &why) &&
       (ctx->k1_variant == 2 || k1_coop_profitable(ctx->k1, B))) {
@@ -665,8 +668,8 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
     CUDA_TRY(ctx, launch_k1(ctx->k1, B, st));
     ctx->last_k1_kernel = 0;
   }
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
-  ctx->k1_timed = true;
+  if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+  if (timed) ctx->k1_timed = true;
   ctx->launches += 1;
   return 0;
 }
@@ -700,6 +703,7 @@ AGNF_API int agnf_lnprob_batch(agnf_ctx* ctx, const double* params, const int32_
       // a sampler's half-ensemble: the kernel reads the pinned block through its device mapping and writes the
       // results back into it -- one launch and one synchronisation instead of copy, launch, copy, synchronise
       char* m = static_cast<char*>(ctx->pin_map);
+      ctx->untimed_once = true;
       if (agnf_lnprob_batch_device(ctx, reinterpret_cast<const double*>(m), reinterpret_cast<const int32_t*>(m + pb16),
                                    n, reinterpret_cast<double*>(m + off_out), nullptr, nullptr, nullptr, nullptr, s1))
         return 1;

@@ -134,7 +134,7 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
  * through one pinned staging block — one upload, one launch, one download; 0 = off.
  * "zero_copy_rows" (default 256): of those, batches of at most this many rows (a half-ensemble) are read by the
  * kernel straight from the pinned block through its device mapping and written back the same way — one launch,
- * one synchronisation; 0 = off.
+ * one synchronisation, no timing events (agnf_last_kernel_ms keeps the previous timed launch); 0 = off.
  * "k2_mma" (default 1): agnf_dict_build contracts on the FP64 tensor cores (8 z-slices per batch) when the family
  * allows it.  "k2_shared_window" (default 1): else it evaluates 4 z-slices per read of the template window when
  * possible; 0 (with k2_mma 0) = the per-slice kernels.  agnf_get_option("k2_last_kernel"): 3 tensor-core,

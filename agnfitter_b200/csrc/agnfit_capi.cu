@@ -207,7 +207,7 @@ int rebuild_grids(agnf_ctx* ctx) {
         const double span = sv[n - 1] - sv[0];
         if (min_gap >= 1e-6 * M && std::isfinite(span) && span > 0.0) {
           int m = 16;
-          while (m < 4 * n && m < 4096) m *= 2;
+          while (m < 2 * n && m < 4096) m *= 2;
           for (; m <= 4096; m *= 2) {
             std::vector<uint16_t> cand((size_t)m);
             bool ok = true;

@@ -67,8 +67,9 @@ CoopPlan make_plan(const K1Params& P, bool ens) {
   c.cpr = P.nbp / 2;
   c.cprp = c.cpr | 1;
   const int a = 32 * c.cprp * (eb_free ? 2 : 1), b = 32 * P.cfg.n_par;
-  const int part = ((a > b ? a : b) + 1) & ~1;
-  // ensemble mode keeps the proposal rows until the acceptance test: they cannot share the partial-sum area
+  // plain batches land their params block in the area the partial sums take over later; ensemble mode keeps its
+  // proposal rows in an area of their own until the acceptance test
+  const int part = (((ens || a > b) ? a : b) + 1) & ~1;
   c.q_off = ens ? part : 0;
   c.per_warp = 32 * Rec<EXT>::STRIDE + part + (ens ? ((32 * P.cfg.n_par + 1) & ~1) : 0);
   c.smem_bytes = 64 * 8 /*exp2 table*/ + 16 * 8 /*mbarriers*/ + c.stage_pad + KC_WARPS * c.per_warp * 8;
@@ -222,25 +223,28 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     const StretchDraw d = stretch_draw(B.ens.seed, B.ens.a, B.ens.step, B.ens.half, src + B.ens.src_offset, kw, H);
     s = (int)src;
     wrow = src * B.ens.W + (B.ens.half ? H : 0) + kw;
-    // Both rows are fetched by the whole warp: element e of the flat [32][n_par] block goes to lane e % 32,
-    // so consecutive lanes read consecutive coordinates of one walker (a per-thread row read would touch 32
-    // different lines per load).  x_k lands in the proposal area, c_j in the (still unused) partial-sum area.
     const int my_w = (int)wrow;
     const int my_c = (int)(src * B.ens.W + (B.ens.half ? 0 : H) + d.j);
     ens_lnp_old = B.ens.lnp[wrow];          // needed only by the acceptance test: in flight during the evaluation
     {
-      // four block rows per round: their eight loads are issued back to back, then stored (a store to shared
-      // memory orders the loads before it, so load-store pairs would serialise 2 n_par memory round trips)
+      // Both walker rows are fetched by the whole warp: element e of the flat [32][n_par] block goes to lane
+      // e % 32, so consecutive lanes read consecutive coordinates of one walker (a per-thread row read would
+      // touch 32 different lines per load).  The proposal q = c - (c - x) zz is formed right here, element by
+      // element (the row's stretch factor comes by shuffle), and only q is stored.  Four block rows per round:
+      // their eight loads are issued back to back before the stores (a store to shared memory orders the loads
+      // before it, so load-store pairs would serialise 2 n_par memory round trips).
       const int d_row = 32 / n_par, d_col = 32 - d_row * n_par;
       int row = lane / n_par, col = lane - row * n_par;
       for (int r0 = 0; r0 < n_par; r0 += 4) {
-        double xv[4], cv[4];
+        double xv[4], cv[4], zv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           xv[u] = 0.0;
           cv[u] = 0.0;
+          zv[u] = 0.0;
           if (r0 + u < n_par) {
             const int wr = __shfl_sync(0xffffffffu, my_w, row), cr = __shfl_sync(0xffffffffu, my_c, row);
+            zv[u] = __shfl_sync(0xffffffffu, d.zz, row);
             xv[u] = B.ens.pos[(int64_t)wr * n_par + col];
             cv[u] = B.ens.pos[(int64_t)cr * n_par + col];
             row += d_row;
@@ -253,19 +257,11 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (r0 + u < n_par) {
-            const unsigned e = (unsigned)((r0 + u) * 32 + lane);
-            sts_f64(q_s + 8u * e, xv[u]);
-            sts_f64(part_s + 8u * e, cv[u]);
-          }
+          if (r0 + u < n_par) sts_f64(q_s + 8u * (unsigned)((r0 + u) * 32 + lane), stretch_coord(cv[u], xv[u], zv[u]));
         }
       }
     }
     __syncwarp();
-    for (int c = 0; c < n_par; ++c) {
-      const unsigned o = 8u * (unsigned)(lane * n_par + c);
-      sts_f64(q_s + o, stretch_coord(lds_f64(part_s + o), lds_f64(q_s + o), d.zz));
-    }
     ens_factor = (double)(n_par - 1) * log(d.zz);
     ens_lnu = d.lnu;
   } else {

@@ -36,6 +36,11 @@ class agnf_family_desc(C.Structure):
                 ("aux", C.c_void_p), ("table_pitch", C.c_int32), ("reserved", C.c_int32)]
 
 
+class agnf_extra_priors(C.Structure):
+    _fields_ = [("midir_uv", C.c_int32), ("ir_xray", C.c_int32), ("j_6um", C.c_int32), ("j_2500", C.c_int32),
+                ("bb_dered_row", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/agnfit_b200.h declares
 SIGNATURES = {
     "agnf_version": (C.c_int, []),
@@ -45,6 +50,7 @@ SIGNATURES = {
     "agnf_synchronize": (C.c_int, [C.c_void_p]),
     "agnf_modelset_config": (C.c_int, [C.c_void_p, C.POINTER(agnf_config)]),
     "agnf_family_upload": (C.c_int, [C.c_void_p, C.POINTER(agnf_family_desc)]),
+    "agnf_extra_priors_set": (C.c_int, [C.c_void_p, C.POINTER(agnf_extra_priors)]),
     "agnf_zslices_upload": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "agnf_sources_upload": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_int32] + [C.c_void_p] * 3),
     "agnf_lnprob_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5),

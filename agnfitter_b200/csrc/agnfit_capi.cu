@@ -505,6 +505,10 @@ AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg) {
   ctx->k1.lognorm_s2 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 2.0));
   ctx->k1.lognorm_s15 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 1.5));
   ctx->k1.lognorm_s01 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 0.1));
+  ctx->k1.lognorm_s06 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 0.6));
+  ctx->k1.lognorm_s05 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 0.5));
+  ctx->k1.xp_c6um = std::pow(10.0, 13.69897);       // (10**13.69897), PRIORS_AGNfitter.py:308
+  ctx->k1.xp_midir_uv = ctx->k1.xp_ir_xray = 0;
   ctx->have_cfg = true;
   ctx->eb0_dirty = true;
   return 0;
@@ -575,6 +579,34 @@ AGNF_API int agnf_family_upload(agnf_ctx* ctx, const agnf_family_desc* fd) {
   return 0;
 }
 
+AGNF_API int agnf_extra_priors_set(agnf_ctx* ctx, const agnf_extra_priors* xp) {
+  if (!ctx || !xp) return 1;
+  if (!ctx->have_cfg) return fail(ctx, "call agnf_modelset_config first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  K1Params& P = ctx->k1;
+  const bool any = xp->midir_uv || xp->ir_xray;
+  if (any && (xp->j_6um < 0 || xp->j_6um >= P.cfg.n_b))
+    return fail(ctx, "j_6um=%d outside the band set: the reference raises IndexError without a band at 6 um "
+                     "(PRIORS_AGNfitter.py:306,331)", xp->j_6um);
+  if (any && P.n_const < 4 && ctx->have_src) return fail(ctx, "sources were uploaded with n_const < 4");
+  if (xp->midir_uv) {
+    if (xp->j_2500 < 0 || xp->j_2500 >= P.cfg.n_b)
+      return fail(ctx, "j_2500=%d outside the band set (PRIORS_AGNfitter.py:347)", xp->j_2500);
+    if (!ctx->fam_set[3] || !ctx->fam_set[2]) return fail(ctx, "upload the torus and disc families first");
+    if (!xp->bb_dered_row) return fail(ctx, "prior_midIR_UV needs bb_dered_row");
+    for (int64_t t = 0; t < P.fam[3].T; ++t)
+      if (xp->bb_dered_row[t] < 0 || xp->bb_dered_row[t] >= P.fam[3].T)
+        return fail(ctx, "bb_dered_row[%lld] out of range", (long long)t);
+    if (upload(ctx, &P.xp_bb_dered, xp->bb_dered_row, (size_t)P.fam[3].T)) return 1;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  P.xp_midir_uv = xp->midir_uv ? 1 : 0;
+  P.xp_ir_xray = xp->ir_xray ? 1 : 0;
+  P.xp_j6 = xp->j_6um;
+  P.xp_j2500 = xp->j_2500;
+  return 0;
+}
+
 AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double* cbbb, const uint64_t* xray_bits,
                         const int32_t* j1500, const double* omega) {
   if (!ctx) return 1;
@@ -618,6 +650,8 @@ AGNF_API int agnf_sources_upload(agnf_ctx* ctx, int64_t S, const int32_t* zi, co
   if (!zi || !y || !inv_sigma || !valid_bits || !pmin || !pmax || !consts || !agn_branch || !irsyn_mode || !irsyn_j)
     return fail(ctx, "agnf_sources_upload: NULL argument");
   if (n_const < 1) return fail(ctx, "n_const must be >= 1");
+  if ((ctx->k1.xp_midir_uv || ctx->k1.xp_ir_xray) && n_const < 4)
+    return fail(ctx, "prior_midIR_UV / prior_IR_XRays need consts[1..3] (n_const >= 4)");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t nb = ctx->k1.cfg.n_b, np = ctx->k1.cfg.n_par, s = (size_t)S;
   for (size_t i = 0; i < s; ++i)

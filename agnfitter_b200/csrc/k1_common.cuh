@@ -148,4 +148,22 @@ __device__ __forceinline__ double gaussian_prior(double lognorm, double inv_var,
   return lognorm - 0.5 * (d * d) * inv_var;
 }
 
+// prior_midIR_UV (PRIORS_AGNfitter.py:327-357).  tor6 = torus band flux at 6 um times 10^TO; bb2500 = band flux of
+// the unreddened disc template at 2500 A times 10^BB; lumf = 4. pi dlum^2. (:331); lumf_bb = 4 pi (dlum)^2 (:346)
+__device__ __forceinline__ double prior_midir_uv(const K1Params& P, double tor6, double bb2500, double BB, double lumf,
+                                                 double lumf_bb) {
+  const double x = log10(tor6 * lumf) - 27.30103;
+  const double to_model = (16.2530786 + 1.024 * x - 0.047 * (x * x)) / 0.643;
+  if (BB != 0.0) bb2500 = bb2500 * lumf_bb;                   // decided by VALUE (:345)
+  return gaussian_prior(P.lognorm_s06, 1.0 / (0.6 * 0.6), 0.0, log10(bb2500) - to_model);
+}
+
+// prior_IR_XRays (PRIORS_AGNfitter.py:302-324).  logf_data = log10(F_2-10keV,data * lumfactor) (:317-318, host)
+__device__ __forceinline__ double prior_ir_xrays(const K1Params& P, double tor6, double lumf, double logf_data) {
+  const double nuLnu = (P.xp_c6um * tor6) * lumf;
+  const double x = log10(nuLnu / 1e41);
+  const double logf_model = 22.9494264 + 1.024 * x - 0.047 * (x * x);
+  return gaussian_prior(P.lognorm_s05, 1.0 / (0.5 * 0.5), 0.0, logf_data - logf_model);
+}
+
 }  // namespace agnf

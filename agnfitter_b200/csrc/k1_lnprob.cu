@@ -208,6 +208,16 @@ k1_lnprob_kernel(const __grid_constant__ K1Params P, const K1Batch B) {
     else pr = (frac < 0.0) ? -9999.0 : gaussian_prior(P.lognorm_s2, 0.25, 2.0, frac);
     prior += pr + gaussian_prior(P.lognorm_s15, 1.0 / 2.25, 4.5, GA);
   }
+  double tor6 = 0.0, lumf = 0.0;
+  if (P.xp_midir_uv | P.xp_ir_xray) {
+    tor6 = __ldg(tTO + P.xp_j6) * w.nTO;
+    lumf = __ldg(P.consts + (int64_t)s * P.n_const + 1);
+  }
+  if (P.xp_midir_uv) {
+    const int64_t dr = (int64_t)zi * P.fam[3].T + __ldg(P.xp_bb_dered + row[3]);
+    const double bb2500 = __ldg(P.fam[3].table + dr * P.fam[3].pitch + P.xp_j2500) * w.nBB;
+    prior += prior_midir_uv(P, tor6, bb2500, BB, lumf, __ldg(P.consts + (int64_t)s * P.n_const + 3));
+  }
   if (RADIO) {
     const int mode = __ldg(P.irsyn_mode + s);
     if (mode != 0) {
@@ -215,6 +225,7 @@ k1_lnprob_kernel(const __grid_constant__ K1Params P, const K1Batch B) {
       prior += gaussian_prior(P.lognorm_s2, 0.25, mode > 0 ? 2.0 : -2.0, f);
     }
   }
+  if (P.xp_ir_xray) prior += prior_ir_xrays(P, tor6, lumf, __ldg(P.consts + (int64_t)s * P.n_const + 2));
   const double lnprior = inbox ? prior : -INFINITY;
   const bool fin = (lnprior - lnprior) == 0.0;     // isfinite
   B.lnp[i] = fin ? lnprior + lnlike : -INFINITY;

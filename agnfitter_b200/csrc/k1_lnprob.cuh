@@ -112,6 +112,11 @@ struct K1Params {
   const int32_t* irsyn_mode;  // [S]
   const int32_t* irsyn_j;     // [S]
   int64_t S;
+  // prior_midIR_UV / prior_IR_XRays (agnf_extra_priors_set)
+  int32_t xp_midir_uv, xp_ir_xray, xp_j6, xp_j2500;
+  const int32_t* xp_bb_dered; // [T_BB]
+  double xp_c6um;             // 10**13.69897 (host libm)
+  double lognorm_s06, lognorm_s05;
 };
 
 // Ensemble mode of the cooperative kernel: row i = (source i / H, walker i % H of the active half);

@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import Context, as_f64, as_i32, as_i64, as_u64, ptr
 from .flatten import ModelSet, FAMILY_ORDER
-from .sources import SourceSet, ZSlices, make_zslices, C_NCONST
+from .sources import SourceSet, ZSlices, make_zslices, extra_prior_plan, C_NCONST
 
 _EB_MODE = {'Flexible': 1, 'Restrictive': 2}
 
@@ -35,11 +35,13 @@ class Engine:
             eb_mode=_EB_MODE.get(ms.settings.get('PRIOR_energy_balance'), 0),
             prior_agnfrac=int(ms.settings.get('PRIOR_AGNfraction') == True),
             ga_free_ebv=int(ms.ga_free_ebv), bb_mode=int(ms.bb_mode))
-        for key in ('PRIOR_midIR_UV', 'PRIOR_galaxy_only'):
-            if ms.settings.get(key) == True:
-                raise NotImplementedError("%s is not on the accelerated path (see DESIGN.md, out of scope)" % key)
-        if ms.settings.get('XRAYS') in ('Prior_UV', 'Prior_midIR'):
-            raise NotImplementedError("XRAYS=%r priors are not on the accelerated path" % ms.settings['XRAYS'])
+        # the two branches the reference itself cannot evaluate: prior_low_AGNfraction unpacks 4 of
+        # 5 values (PRIORS_AGNfitter.py:363), prior_UV_xrays reads an undefined name (:267)
+        if ms.settings.get('PRIOR_galaxy_only') == True:
+            raise NotImplementedError("PRIOR_galaxy_only raises in the reference (PRIORS_AGNfitter.py:363)")
+        if ms.settings.get('XRAYS') == 'Prior_UV':
+            raise NotImplementedError("XRAYS='Prior_UV' raises in the reference (PRIORS_AGNfitter.py:267)")
+        xp = extra_prior_plan(ms)
         self.ctx.check(self.lib.agnf_modelset_config(self.ctx.h, C.byref(cfg)))
         if [f.name for f in ms.families] != list(FAMILY_ORDER[:len(ms.families)]):
             raise ValueError("families must be ordered %s" % (FAMILY_ORDER,))
@@ -76,6 +78,11 @@ class Engine:
                                       grid_sorted=ptr(gs), grid_perm=ptr(gp), table=table_ptr, aux=ptr(aux),
                                       table_pitch=pitch, reserved=0)
             self.ctx.check(self.lib.agnf_family_upload(self.ctx.h, C.byref(d)))
+        if xp["midir_uv"] or xp["ir_xray"]:
+            dered = as_i32(xp["bb_dered_row"]) if xp["bb_dered_row"] is not None else None
+            d = _lib.agnf_extra_priors(midir_uv=int(xp["midir_uv"]), ir_xray=int(xp["ir_xray"]), j_6um=xp["j_6um"],
+                                       j_2500=xp["j_2500"], bb_dered_row=ptr(dered))
+            self.ctx.check(self.lib.agnf_extra_priors_set(self.ctx.h, C.byref(d)))
         zs = zslices if zslices is not None else make_zslices(ms)
         self.zslices = zs
         cgal, cbbb, xray, j1500, omega = (as_f64(zs.cgal), as_f64(zs.cbbb), as_u64(zs.xray), as_i32(zs.j1500),

@@ -16,6 +16,9 @@ from .flatten import ModelSet
 
 # consts block layout, per source (float64)
 C_INV4PIDL2 = 0     # 1 / (4 pi dlum^2)                       PARAMETERSPACE:232, PRIORS:178
+C_LUMFACTOR = 1     # 4. * pi * dlum**2.                       PRIORS:307,331
+C_LOGF_XRAY = 2     # log10(F_2-10keV,data * lumfactor)       PRIORS:317-318 (prior_IR_XRays only)
+C_LUMFACTOR_BB = 3  # 4*pi*(dlum)**2                           PRIORS:346
 C_NCONST = 4
 
 
@@ -48,6 +51,58 @@ def make_zslices(ms: ModelSet) -> ZSlices:
         j1500[i] = hostmath.band_1500(ms.bands, z)
         omega[i] = hostmath.trapz_weights((10 ** rest) / (1 + z))
     return ZSlices(cgal=cgal, cbbb=cbbb, xray=xray, j1500=j1500, omega=omega)
+
+
+def extra_prior_plan(ms: ModelSet):
+    """Which of prior_midIR_UV (PRIORS_AGNfitter.py:327-357, dispatch :50-54) and prior_IR_XRays (:302-324,
+    dispatch :68-71) the settings enable, and their walker-independent operands: the band read for the 6 um
+    torus flux (first band with 13.59897 < log nu < 13.79897 — dictionary band centres, observed frame), the
+    band read for the 2500 A disc flux (first with 14.8 < log nu < 15.15) and the row of the unreddened twin of
+    every disc template.  Raises what the reference raises when an operand does not exist."""
+    midir_uv = ms.settings.get('PRIOR_midIR_UV') == True
+    ir_xray = ms.settings.get('XRAYS') == 'Prior_midIR'
+    plan = dict(midir_uv=midir_uv, ir_xray=ir_xray, j_6um=-1, j_2500=-1, bb_dered_row=None)
+    if not (midir_uv or ir_xray):
+        return plan
+    to = ms.fam("TO")
+    if to.n_dim != 1:
+        raise TypeError("unhashable type: 'list' — TORUSFdict[tor_obj.matched_parkeys_grid] (PRIORS_AGNfitter.py:"
+                        "304,329) only works for one-parameter torus families; this one has %d" % to.n_dim)
+    b = ms.bands
+    hit = np.nonzero((13.59897 < b) & (b < 13.79897))[0]
+    if len(hit) == 0:
+        raise IndexError("no band with 13.59897 < log nu < 13.79897 (PRIORS_AGNfitter.py:306,331)")
+    plan["j_6um"] = int(hit[0])
+    if midir_uv:
+        hit = np.nonzero((14.8 < b) & (b < 15.15))[0]
+        if len(hit) == 0:
+            raise IndexError("no band with 14.8 < log nu < 15.15 (PRIORS_AGNfitter.py:347)")
+        plan["j_2500"] = int(hit[0])
+        bb = ms.fam("BB")
+        rows = np.arange(bb.T, dtype=np.int32)
+        if ms.settings['BBB'] in ('R06', 'THB21') and ms.settings['XRAYS'] != True:
+            if bb.n_dim != 1:
+                raise KeyError('0.0')
+            zero = np.nonzero(bb.keys_float[0] == 0.0)[0]         # BBBFdict['0.0'], PRIORS:336
+            if len(zero) == 0:
+                raise KeyError('0.0')
+            rows[:] = zero[0]
+        else:                                                       # params[EBVbbb_pos] = str(0.0), PRIORS:339-342
+            if bb.n_dim == 1:
+                raise TypeError("'str' object does not support item assignment (PRIORS_AGNfitter.py:341)")
+            d = bb.par_names.index('EBVbbb')
+            lut = {tuple(bb.keys_float[:, t]): t for t in range(bb.T)}
+            for t in range(bb.T):
+                k = list(bb.keys_float[:, t])
+                for dd in range(bb.n_dim):          # matched_parkeys_grid holds the FIRST key's value on free dims
+                    if bb.par_types[dd] == 'free':
+                        k[dd] = bb.keys_float[dd, 0]
+                k[d] = 0.0
+                if tuple(k) not in lut:
+                    raise KeyError(tuple(k))
+                rows[t] = lut[tuple(k)]
+        plan["bb_dered_row"] = rows
+    return plan
 
 
 def pdict_bounds(ms: ModelSet, z):
@@ -152,6 +207,19 @@ def make_sources(ms: ModelSet, z, dlum, nus, fluxes, fluxerrs, bounds_cache=None
 
     consts = np.zeros((S, C_NCONST))
     consts[:, C_INV4PIDL2] = 1.0 / (4 * np.pi * dlum ** 2)
+    consts[:, C_LUMFACTOR] = 4. * np.pi * dlum ** 2.
+    consts[:, C_LUMFACTOR_BB] = 4 * np.pi * (dlum) ** 2
+    if ms.settings.get('XRAYS') == 'Prior_midIR':
+        # PRIORS:316-318 — first datum with 17.685 < log nu_rest < 18.384
+        r = nus + np.log10(1 + zc)
+        ok = (17.685 < r) & (r < 18.384)
+        if not ok.any(axis=1).all():
+            bad = int(np.nonzero(~ok.any(axis=1))[0][0])
+            raise IndexError("source %d has no datum with 17.685 < log nu_rest < 18.384; prior_IR_XRays raises "
+                             "IndexError in the reference (PRIORS_AGNfitter.py:317)" % bad)
+        fx = fluxes[np.arange(S), np.argmax(ok, axis=1)]
+        with np.errstate(all="ignore"):
+            consts[:, C_LOGF_XRAY] = np.log10(fx * consts[:, C_LUMFACTOR])
     agn_branch = np.zeros(S, dtype=np.int32)
     irsyn_mode = np.zeros(S, dtype=np.int32)
     irsyn_j = np.zeros(S, dtype=np.int32)

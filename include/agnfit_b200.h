@@ -97,6 +97,25 @@ typedef struct {
 
 AGNF_API int agnf_family_upload(agnf_ctx* ctx, const agnf_family_desc* fam);
 
+/* The two torus-anchored priors of PRIORS_AGNfitter.PRIORS (dispatch PRIORS_AGNfitter.py:50-54, 68-71):
+ *   prior_midIR_UV  (PRIORS_AGNfitter.py:327-357, settings['PRIOR_midIR_UV'] == True)
+ *   prior_IR_XRays  (PRIORS_AGNfitter.py:302-324, settings['XRAYS'] == 'Prior_midIR')
+ * Both read the snapped torus row at the first band with 13.59897 < log nu < 13.79897 (j_6um); the first also
+ * reads the dereddened disc row (bb_dered_row[snapped BBB row]) at the first band with 14.8 < log nu < 15.15
+ * (j_2500).  Per source they need consts[1] = 4. * pi * dlum**2. (lumfactor), consts[3] = 4*pi*(dlum)**2 (the
+ * factor :346 applies when BB != 0) and consts[2] = log10(F_2-10keV,data * lumfactor) (:317-318); the host
+ * evaluates them with the reference's expressions (agnfitter_b200/sources.py).  Call after agnf_family_upload of
+ * the disc family; disabled by default and by a later agnf_modelset_config. */
+typedef struct {
+  int32_t midir_uv;             /* 1: add prior_midIR_UV                                      */
+  int32_t ir_xray;              /* 1: add prior_IR_XRays                                      */
+  int32_t j_6um;                /* band index, see above                                      */
+  int32_t j_2500;               /* band index (midir_uv only)                                 */
+  const int32_t* bb_dered_row;  /* [T_BB] row of the unreddened twin of every disc template (midir_uv only) */
+} agnf_extra_priors;
+
+AGNF_API int agnf_extra_priors_set(agnf_ctx* ctx, const agnf_extra_priors* xp);
+
 /* per-z-slice constants, all [n_z, n_b] / [n_z] host arrays (agnfitter_b200/sources.py:make_zslices) */
 AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double* cbbb, const uint64_t* xray_bits,
                         const int32_t* j1500, const double* omega);

@@ -144,11 +144,15 @@ _C_ASTROPY = 299792458.0  # m/s, astropy.constants.c used by u.spectral()
 
 
 def galaxy_BC03(root=REF_ROOT, ebv_type="grid", reddening_fn=None, ebv_free_pair=(0.0, 1.0),
-                age_slice=None, tau_slice=None):
+                age_slice=None, tau_slice=None, metal=None):
     """MODEL_AGNfitter.py:71-142 restated for BC03_275seds.pickle (same dict schema as the
     missing BC03_840seds).  `reddening_fn(nu, Fnu, ebv) -> (nu, Fnu_red)` must be the
     reference's GALAXYred_Calzetti (passed in by the caller, from the shimmed MOD module).
-    Returns the same six objects GALAXY() returns."""
+    Returns the same six objects GALAXY() returns.
+    metal: a metallicity value -> the key layout of the 'BC03_metal' branch the example settings name
+    (MODEL_AGNfitter.py:145-232: keys (metal, tau, age, EBVgal), names ['metal','tau','age','EBVgal'], the
+    free-E(B-V) pair (0., 0.8)); its library blob is absent from the mount, so the 275-SED library stands in
+    with a metallicity axis of size 1."""
     from scipy.integrate import trapezoid
     d = tolerant_load(os.path.join(root, "models/GALAXY/BC03_275seds.pickle"))
     tau_vals = np.asarray(d["tau-values"])
@@ -163,7 +167,7 @@ def galaxy_BC03(root=REF_ROOT, ebv_type="grid", reddening_fn=None, ebv_free_pair
     if ebv_type == "grid":
         ebv = np.array(np.arange(0., 100., 2.5) / 100)
     else:
-        ebv = np.array(ebv_free_pair)
+        ebv = np.array(ebv_free_pair if metal is None else (0., 0.8))
     F4plot, SFRd, attd = dict(), dict(), dict()
     # u.spectral(): nu = c / lambda  (lambda in Angstrom -> m)
     nus_all = (_C_ASTROPY / (wl * 1e-10))[::-1]
@@ -174,11 +178,15 @@ def galaxy_BC03(root=REF_ROOT, ebv_type="grid", reddening_fn=None, ebv_free_pair
         e_apply = ebv[ebvi] if ebv_type == "grid" else ebv[0]
         gal_nu, Fnu_red = reddening_fn(nus3, Fnu3, e_apply)
         key = (str(tau_vals[taui]), str(np.log10(age_vals[agei])), str(ebv[ebvi]))
+        if metal is not None:
+            key = (str(metal),) + key
         F4plot[key] = (np.log10(gal_nu), Fnu_red / 1e18)           # renorm_template('GA'), MOD:1458-1460
-        SFRd[key[:2]] = sfr[:, agei, taui, :, :].squeeze()
+        SFRd[key[:-1]] = sfr[:, agei, taui, :, :].squeeze()
         attd[key] = trapezoid(Fnu3, x=nus3) - trapezoid(Fnu_red, x=gal_nu)
     names = ['tau', 'age', 'EBVgal']
     types = ['grid', 'grid', ebv_type]
+    if metal is not None:
+        names, types = ['metal'] + names, ['grid'] + types
     return F4plot, SFRd, attd, names, types, [0]
 
 

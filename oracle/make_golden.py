@@ -104,7 +104,9 @@ def synth_fluxes(rng, mods, models, data_nus, z, dlum, P, frac_ul=0.1, frac_miss
 
 def run_case(name, settings, filterset, zs, catalog=None, galaxy_ebv="grid", galaxy_kw=None,
              starburst_kw=None, n_pos=(400, 60, 40, 100), seed=1, nRADdata=None, nXRaysdata=None,
-             force_uv_detection=True):
+             force_uv_detection=True, force_xray_detection=False, write=True, eval_rows=None):
+    """write=False, eval_rows=N: regenerate the case in memory and run the reference on the first N positions of
+    every source only (tests/test_golden_live.py compares them bit for bit with the stored file)."""
     mods = ref_shim.install()
     rng = np.random.default_rng(seed)
     allf = loaders.load_all_filters()
@@ -164,6 +166,13 @@ def run_case(name, settings, filterset, zs, catalog=None, galaxy_ebv="grid", gal
                 if len(win) and not np.any((y[win] > 0)):
                     y[win[-1]] = abs(rng.normal(1.0, 0.1)) * 1e-3
                     err[win[-1]] = 0.1 * y[win[-1]]
+            if force_xray_detection:
+                # prior_IR_XRays needs a datum with 17.685 < nu_rest < 18.384 (PRIORS:316-317); a disc without the
+                # X-ray extension predicts no flux there, so the synthetic catalogue would mark it missing
+                r = data_nus + np.log10(1 + z)
+                for j in np.nonzero((17.685 < r) & (r < 18.384))[0]:
+                    y[j] = abs(rng.normal(1.0, 0.3)) * 1e-6
+                    err[j] = 0.2 * y[j]
             rr = loaders.catalog_rows(y[None, :], err[None, :], data_nus, np.array([z]), flux_unit_cgs=1e-26)
             src_nus[s], src_fl[s], src_fe[s] = rr["nus"][0], rr["fluxes"][0], rr["fluxerrs"][0]
         data_l.append(H.make_data(z, src_nus[s], src_fl[s], src_fe[s], dlum=dl[s]))
@@ -178,6 +187,8 @@ def run_case(name, settings, filterset, zs, catalog=None, galaxy_ebv="grid", gal
     ref_mask = np.zeros((S, n_b), dtype=bool)
     for s in range(S):
         pars = walker_positions(rng, ms, pmin[s], pmax[s], *n_pos)
+        if eval_rows is not None:            # an even sample over the four kinds of positions
+            pars = pars[np.unique(np.linspace(0, len(pars) - 1, eval_rows).astype(int))]
         lnp, ym, keys, lpr, lll = H.reference_eval(pars, data_l[s], models_l[s], P_l[s])
         pars_all.append(pars)
         sid_all.append(np.full(len(pars), s, dtype=np.int32))
@@ -204,6 +215,8 @@ def run_case(name, settings, filterset, zs, catalog=None, galaxy_ebv="grid", gal
         ref_lnlike=np.concatenate(ref["lnlike"]), ref_mask=ref_mask,
         filter_names=np.array(fnames),
     ))
+    if not write:
+        return arrs
     path = os.path.join(OUT, "k1_%s.npz" % name)
     np.savez_compressed(path, **arrs)
     fin = np.isfinite(np.concatenate(ref["lnp"]))
@@ -213,7 +226,7 @@ def run_case(name, settings, filterset, zs, catalog=None, galaxy_ebv="grid", gal
     return ms
 
 
-def k2_case(name, filterset, zs, seed=3):
+def k2_case(name, filterset, zs, seed=3, write=True):
     """Reference filtering_models on a sample of every loadable family."""
     mods = ref_shim.install()
     MOD, DIC = mods["MOD"], mods["DIC"]
@@ -268,13 +281,15 @@ def k2_case(name, filterset, zs, seed=3):
         arrs["%s_len" % fname] = nlen
         arrs["%s_ref" % fname] = out
         n_entries += out.size
+    if not write:
+        return arrs
     path = os.path.join(OUT, "k2_%s.npz" % name)
     np.savez_compressed(path, **arrs)
     print("%-22s bands=%d z=%d entries=%d -> %.2f MB" % (name, len(bands), len(zs), n_entries,
                                                         os.path.getsize(path) / 1e6))
 
 
-def k2_write(name, fd, fnames, zs, fams, DIC):
+def k2_write(name, fd, fnames, zs, fams, DIC, write=True):
     """Run the reference's filtering_models over `fams` ({name: [(log nu, Fnu), ...]}) and store inputs + outputs."""
     bands = fd[0]
     arrs = dict(bands=bands, z=np.array(zs, dtype=np.float64), filter_names=np.array(fnames),
@@ -304,13 +319,15 @@ def k2_write(name, fd, fnames, zs, fams, DIC):
         arrs["%s_len" % fname] = nlen
         arrs["%s_ref" % fname] = out
         n_entries += out.size
+    if not write:
+        return arrs
     path = os.path.join(OUT, "k2_%s.npz" % name)
     np.savez_compressed(path, **arrs)
     print("%-22s bands=%d z=%d entries=%d -> %.2f MB" % (name, len(bands), len(zs), n_entries,
                                                         os.path.getsize(path) / 1e6))
 
 
-def k2_families_case(name, filterset, zs):
+def k2_families_case(name, filterset, zs, write=True):
     """The remaining template families of SURVEY §8a-T, loaded by the reference's OWN loaders
     (MODEL_AGNfitter.TORUS / BBB under the import shims): every torus option and the SN12 / KD18 discs."""
     mods = ref_shim.install()
@@ -328,7 +345,7 @@ def k2_families_case(name, filterset, zs):
         d4, *_ = MOD.BBB(root, dict(S, BBB=opt), 0)
         keys = list(d4.keys())
         fams["BB_" + opt] = [d4[k] for k in keys[::max(1, len(keys) // n_keep)][:n_keep]]
-    k2_write(name, fd, fnames, zs, fams, DIC)
+    return k2_write(name, fd, fnames, zs, fams, DIC, write=write)
 
 
 SED_MODELS = ['sb', 'bbb', 'bbbdered', 'gal', 'AGNfrac_opt', 'tor', 'tor+bbb', 'AGNfrac_IR', 'gal', 'bbb',
@@ -338,7 +355,8 @@ SED_RANGES_UM = [[8., 1000.], [0.1, 1.], [0.1, 1.], [0.1, 1.], [0.1, 1.], [1., 3
                  [0.4, 0.5], [0.4, 0.5], [0.4, 0.5], [6, 6], [1., 30.], [12., 12.], [1., 100.], [20., 75.], [0.3, 0.5]]
 
 
-def sed_case(name, settings, filterset, zs, nR=0, nX=0, galaxy_ebv="grid", extra=(), n_real=10, seed=41, stride=7):
+def sed_case(name, settings, filterset, zs, nR=0, nX=0, galaxy_ebv="grid", extra=(), n_real=10, seed=41, stride=7,
+             write=True, galaxy_kw=None):
     """SED realisations + integrated luminosities: the reference's own FLUXES_ARRAYS.fluxes
     (PLOTandWRITE_AGNfitter.py:566-799) on rows drawn from a synthetic flat chain, for every source of the case.
     Stores the model set, the full-resolution templates, the rows, nuLnu on every `stride`-th frequency and the
@@ -349,7 +367,7 @@ def sed_case(name, settings, filterset, zs, nR=0, nX=0, galaxy_ebv="grid", extra
     fd, fnames = loaders.make_filterdict(filterset, loaders.load_all_filters())
     data_nus = loaders.data_nus_for(filterset)
     n_b = len(fd[0])
-    gk = dict(age_slice=[0, 12, 24], tau_slice=[0, 10])
+    gk = dict(dict(age_slice=[0, 12, 24], tau_slice=[0, 10]), **(galaxy_kw or {}))
     sk = dict(tdust_slice=range(0, 150, 30), fracpah_slice=range(0, 64, 16))
     im = SED_MODELS + [e[0] for e in extra]
     ir = np.array(SED_RANGES_UM + [e[1] for e in extra], dtype=np.float64)
@@ -382,6 +400,8 @@ def sed_case(name, settings, filterset, zs, nR=0, nX=0, galaxy_ebv="grid", extra
         intlum_models=np.array(im), intlum_ranges_um=ir, intlum_ranges_hz=H.intlum_ranges_hz(ir),
         all_nus_rest=nus, stride=np.array(stride),
         ref_nuLnu=np.concatenate(nl_all), ref_int_lums=np.concatenate(il_all)))
+    if not write:
+        return arrs
     path = os.path.join(OUT, "sed_%s.npz" % name)
     np.savez_compressed(path, **arrs)
     print("%-22s S=%d rows=%d G=%d comps=%d models=%d T=%s -> %.2f MB" % (
@@ -412,9 +432,112 @@ def sed_main():
              nR=2, seed=47)
 
 
+K2_SPECS = {
+    "default18": (k2_case, (loaders.FILTERSET_DEFAULT, [0.0, 0.283, 1.58, 5.999])),
+    "example49": (k2_case, (loaders.FILTERSET_EXAMPLE49, [0.031024, 0.129, 2.2])),
+    "families18": (k2_families_case, (loaders.FILTERSET_DEFAULT, [0.05, 1.0, 3.3])),
+}
+
+
+def replay_k2(name):
+    fn, args = K2_SPECS[name]
+    return fn(name, *args, write=False)
+
+
+def sed_case_specs():
+    """{case name: (args, kwargs) of sed_case} read off sed_main()."""
+    global sed_case
+    rec, real = _Recorder(), sed_case
+    sed_case = rec
+    try:
+        sed_main()
+    finally:
+        sed_case = real
+    return rec.k1
+
+
+def replay_sed(name):
+    a, k = sed_case_specs()[name]
+    return sed_case(name, *a, **dict(k, write=False))
+
+
+class _Recorder:
+    """Collects the arguments main() / r2_main() pass to run_case, so that tests can replay any case."""
+
+    def __init__(self):
+        self.k1 = {}
+
+    def __call__(self, name, *a, **k):
+        self.k1[name] = (a, k)
+
+
+def k1_case_specs():
+    """{case name: (args, kwargs) of run_case} for every K1 golden file, read off main() and r2_main()."""
+    global run_case
+    rec, real = _Recorder(), run_case
+    k2a, k2b = globals()["k2_case"], globals()["k2_families_case"]
+    run_case = rec
+    globals()["k2_case"] = globals()["k2_families_case"] = lambda *a, **k: None
+    try:
+        argv, sys.argv = sys.argv, [sys.argv[0]]
+        main()
+        r2_main()
+    finally:
+        sys.argv = argv
+        run_case = real
+        globals()["k2_case"], globals()["k2_families_case"] = k2a, k2b
+    return rec.k1
+
+
+def replay_k1(name, eval_rows=100):
+    """Regenerate golden case `name` in memory with the reference evaluated on a sample of its positions."""
+    a, k = k1_case_specs()[name]
+    return run_case(name, *a, **dict(k, write=False, eval_rows=eval_rows))
+
+
+def r2_main(only=None):
+    """Cases added in round 2 (python -m oracle.make_golden r2 [name])."""
+    os.makedirs(OUT, exist_ok=True)
+    base = dict(H.DEFAULT_SETTINGS)
+    gk = dict(age_slice=[0, 6, 12, 18, 24], tau_slice=[0, 5, 10])
+    sk = dict(tdust_slice=range(0, 150, 15), fracpah_slice=range(0, 64, 8))
+    want = lambda nm: only is None or only == nm
+    # the example settings' own model set (example/SETTINGS_AGNfitter.py:193-236): BC03_metal-shaped galaxy keys with
+    # free E(B-V) (the 275-SED library stands in for the absent blob), S17, THB21 through the reference's own loader
+    # (raw-unpickled frame, ref_shim), SKIRTOR_1P, Flexible energy balance, AGN-fraction prior; both catalogue sources
+    if want("example_thb21_skirtor1p_49"):
+        cat = loaders.read_ascii_catalog(os.path.join(ref_shim.REF_ROOT, "data", "catalog_example.txt"))
+        run_case("example_thb21_skirtor1p_49",
+                 dict(base, GALAXY='BC03_metal', STARBURST='S17', BBB='THB21', TORUS='SKIRTOR_1P'),
+                 loaders.FILTERSET_EXAMPLE49, None, catalog=cat, galaxy_ebv="free", galaxy_kw=dict(gk, metal=0.02),
+                 starburst_kw=sk, n_pos=(300, 40, 30, 80), seed=51, nRADdata=0, nXRaysdata=0)
+    # Restrictive energy balance on grid-E(B-V) galaxies (PRIORS_AGNfitter.py:101-104 through GALAXYatt_dict, :80-81)
+    if want("restrictive18"):
+        run_case("restrictive18", dict(base, PRIOR_energy_balance='Restrictive'), loaders.FILTERSET_DEFAULT,
+                 [0.283, 2.4], galaxy_kw=gk, n_pos=(400, 50, 30, 80), seed=52)
+
+
+    # prior_midIR_UV (PRIORS_AGNfitter.py:327-357): R06 branch (BBBFdict['0.0']) on the default bands ...
+    if want("midir_uv18"):
+        run_case("midir_uv18", dict(base, PRIOR_midIR_UV=True), loaders.FILTERSET_DEFAULT, [0.283, 1.1],
+                 galaxy_kw=gk, n_pos=(400, 50, 30, 80), seed=53)
+    # ... and the branch that rewrites the E(B-V) key of a grid disc (SN12, no BB norm: BB == 0 by value), 49 bands
+    if want("midir_uv_sn12_49"):
+        run_case("midir_uv_sn12_49", dict(base, BBB='SN12', TORUS='SKIRTOR_1P', PRIOR_midIR_UV=True),
+                 loaders.FILTERSET_EXAMPLE49, [0.129], galaxy_kw=gk, n_pos=(300, 40, 30, 80), seed=54)
+    # prior_IR_XRays (PRIORS_AGNfitter.py:302-324, XRAYS='Prior_midIR'): THB21 disc, NK0 torus, X-ray bands in chi^2
+    if want("xray_midir49"):
+        run_case("xray_midir49", dict(base, BBB='THB21', TORUS='NK0', XRAYS='Prior_midIR', PRIOR_midIR_UV=True),
+                 loaders.FILTERSET_EXAMPLE49, [0.129, 0.8], galaxy_kw=gk, n_pos=(300, 40, 30, 80), seed=55,
+                 force_xray_detection=True)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "sed":
         sed_main()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "r2":
+        r2_main(sys.argv[2] if len(sys.argv) > 2 else None)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "families":
         os.makedirs(OUT, exist_ok=True)

@@ -18,7 +18,11 @@ that `functions.PARAMETERSPACE_AGNfitter`, `functions.PRIORS_AGNfitter`,
      reference (bypasses functions/__init__.py:9 `from acor import *`);
   2. removed-API aliases: collections.Iterable (PARAMETERSPACE:18),
      scipy.integrate.trapz (DICTIONARIES:21), np.float (DATA:103);
-  3. inert stub modules for astropy.* (MODEL:24-32, FILTERS:22-24).
+  3. inert stub modules for astropy.* (MODEL:24-32, FILTERS:22-24);
+  4. `pickle` as MODEL_AGNfitter sees it falls back to a raw unpickler for the one
+     pandas pickle pandas 3.0 refuses (models/BBB/THB21.pickle, MODEL:859: BlockPlacement
+     TypeError) and hands back its 2 x 1 object block behind the two accessors the
+     loader uses (`frame[col].values.item()`, MODEL:860).
 """
 import os
 import sys
@@ -67,6 +71,81 @@ def _stub_module(name):
     return m
 
 
+class _Column:
+    def __init__(self, arr):
+        self._arr = arr
+
+    @property
+    def values(self):
+        import numpy as np
+        out = np.empty(1, dtype=object)
+        out[0] = self._arr
+        return out
+
+
+class _RawFrame(dict):
+    """{'nu': _Column, 'SED': _Column}: what THB21dict['nu'].values.item() needs (MODEL:860)."""
+
+
+class _Cap:
+    def __new__(cls, *a, **k):
+        o = object.__new__(cls)
+        o.a, o.k = a, k
+        return o
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, s):
+        self.state = s
+
+    def __call__(self, *a, **k):
+        return _Cap(*a, **k)
+
+
+def raw_pandas_frame(fileobj):
+    """Columns of a pickled single-block object DataFrame without pandas: the BlockManager's arguments are
+    captured by stand-in classes; block values [n_col, n_row] and the column Index data are plain ndarrays."""
+    import pickle
+
+    class U(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.startswith("pandas"):
+                return type(name, (_Cap,), {})
+            if module.startswith("numpy.core"):
+                module = module.replace("numpy.core", "numpy._core")
+            if module == "__builtin__":
+                module = "builtins"
+            return super().find_class(module, name)
+
+    d = U(fileobj, encoding="latin1").load()
+    mgr = d.state["_mgr"]
+    blocks, axes = mgr.a
+    cols = [str(c) for c in axes[0].a[1]["data"]]
+    if len(blocks) != 1:
+        raise ValueError("expected a single-block frame")
+    vals = blocks[0].a[0]
+    if vals.shape[0] != len(cols) or vals.shape[1] != 1:
+        raise ValueError("unexpected block shape %r" % (vals.shape,))
+    return _RawFrame({c: _Column(vals[i, 0]) for i, c in enumerate(cols)})
+
+
+class _PickleProxy:
+    """`pickle` for the reference's MODEL_AGNfitter: identical except that a load pandas rejects is redone raw."""
+
+    def __getattr__(self, k):
+        import pickle
+        return getattr(pickle, k)
+
+    def load(self, f, *a, **k):
+        import pickle
+        try:
+            return pickle.load(f, *a, **k)
+        except TypeError:
+            f.seek(0)
+            return raw_pandas_frame(f)
+
+
 _installed = False
 
 
@@ -104,6 +183,8 @@ def install():
                         ("PRI", "functions.PRIORS_AGNfitter"),
                         ("PAR", "functions.PARAMETERSPACE_AGNfitter")):
         mods[short] = importlib.import_module(name)
+    if not isinstance(mods["MOD"].pickle, _PickleProxy):
+        mods["MOD"].pickle = _PickleProxy()
     return mods
 
 

@@ -30,7 +30,8 @@ def pytest_collection_modifyitems(config, items):
 
 
 K1_CASES = ["classic18", "cat49_catalog_example", "cat49_brown2018_test", "freeebv_xray49",
-            "xray_gamma49", "radio1_sn12_49", "radio2_sn12_49", "radio4_sn12_49", "agnoff18", "radio_xray49"]
+            "xray_gamma49", "radio1_sn12_49", "radio2_sn12_49", "radio4_sn12_49", "agnoff18", "radio_xray49",
+            "example_thb21_skirtor1p_49", "restrictive18", "midir_uv18", "midir_uv_sn12_49", "xray_midir49"]
 K2_CASES = ["default18", "example49", "families18"]
 SED_CASES = ["classic18", "freeebv_xray49", "xray_gamma49", "radio_r06_49", "radio1_kd18_49", "radio2_sn12_49"]
 

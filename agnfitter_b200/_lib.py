@@ -58,6 +58,7 @@ SIGNATURES = {
     "agnf_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "agnf_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "agnf_debug_exp10": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "agnf_debug_fp64_peak": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "agnf_launch_count": (C.c_int64, [C.c_void_p]),
     "agnf_last_kernel_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "agnf_filters_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

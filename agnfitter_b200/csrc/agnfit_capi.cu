@@ -20,6 +20,10 @@
 
 using namespace agnf;
 
+namespace agnf {
+cudaError_t launch_fp64_peak(int kind, double* scratch, int blocks, int iters, double* flops, cudaStream_t stream);
+}
+
 struct agnf_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -77,6 +81,7 @@ struct agnf_ctx {
   double* ens_best_lnp = nullptr;
   int64_t ens_step = 0;              // stretch-move steps taken since agnf_ens_create (Philox counter)
   int ens_fused = 1;                 // 1: one fused K1 launch per half-step; 0: propose / K1 / accept kernels
+  int ens_split = 1;                 // 1: emcee 3's random split of the walkers at every step; 0: fixed halves
   int k2_shared_window = 1;          // 1: 4 z-slices share each template read when the family allows it
   int k2_mma = 1;                    // 1: FP64 tensor-core contraction (8-slice batches) when the family allows it
   int k2_last_kernel = 0;            // contraction of the last agnf_dict_build: 1 per-slice kernels, 2 shared-window
@@ -163,6 +168,25 @@ int ensure(agnf_ctx* ctx, void** p, size_t* cap, size_t bytes) {
   if (dev_alloc(ctx, p, bytes)) return 1;
   *cap = bytes;
   return 0;
+}
+
+// The ensemble (walkers, scratch, histograms, chain buffer) is sized for one set of sources and one parameter
+// layout: a new model-set configuration or source upload invalidates it (agnf_ens_create must follow).
+void ens_teardown(agnf_ctx* ctx) {
+  if (!ctx->have_ens) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (void* q : {(void*)ctx->ens.pos, (void*)ctx->ens.lnp, (void*)ctx->ens.n_acc, (void*)ctx->ens.split,
+                  (void*)ctx->ens_sc.prop, (void*)ctx->ens_sc.prop_lnp, (void*)ctx->ens_sc.factor,
+                  (void*)ctx->ens_sc.lnu, (void*)ctx->ens_sc.sid, (void*)ctx->ens_hist.hist, (void*)ctx->ens_best_pos,
+                  (void*)ctx->ens_best_lnp, (void*)ctx->ens_chain, (void*)ctx->ens_chain_lnp})
+    dev_free(ctx, q);
+  ctx->ens = K3State{};
+  ctx->ens_sc = K3Scratch{};
+  ctx->ens_hist = K3Hist{};
+  ctx->ens_best_pos = ctx->ens_best_lnp = nullptr;
+  ctx->ens_chain = ctx->ens_chain_lnp = nullptr;
+  ctx->ens_chain_cap = ctx->ens_chain_n = 0;
+  ctx->have_ens = false;
 }
 
 int rebuild_grids(agnf_ctx* ctx) {
@@ -429,6 +453,13 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     ctx->ens_fused = (int)value;
     return 0;
   }
+  if (strcmp(name, "ens_split") == 0) {
+    if (value != 0 && value != 1) return fail(ctx, "ens_split must be 0 (fixed halves) or 1 (random split per step)");
+    if (ctx->have_ens && value != ctx->ens_split)
+      return fail(ctx, "ens_split must be chosen before agnf_ens_create");
+    ctx->ens_split = (int)value;
+    return 0;
+  }
   if (strcmp(name, "zero_copy_rows") == 0) {
     if (value < 0 || value > (1 << 20)) return fail(ctx, "zero_copy_rows must be in [0, 2^20]");
     ctx->zero_copy_rows = value;
@@ -461,6 +492,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "small_rows") == 0) *value = ctx->small_rows;
   else if (strcmp(name, "zero_copy_rows") == 0) *value = ctx->zero_copy_rows;
   else if (strcmp(name, "ens_fused") == 0) *value = ctx->ens_fused;
+  else if (strcmp(name, "ens_split") == 0) *value = ctx->ens_split;
   else if (strcmp(name, "k2_shared_window") == 0) *value = ctx->k2_shared_window;
   else if (strcmp(name, "k2_mma") == 0) *value = ctx->k2_mma;
   else if (strcmp(name, "k2_last_kernel") == 0) *value = ctx->k2_last_kernel;
@@ -486,6 +518,33 @@ AGNF_API int agnf_debug_exp10(agnf_ctx* ctx, const double* x, int64_t n, double*
   return 0;
 }
 
+AGNF_API int agnf_debug_fp64_peak(agnf_ctx* ctx, int32_t kind, double* tflops) {
+  if (!ctx || !tflops) return 1;
+  if (kind != 0 && kind != 1) return fail(ctx, "agnf_debug_fp64_peak: kind must be 0 (DFMA) or 1 (DMMA)");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+  const int blocks = prop.multiProcessorCount * 8;
+  void* scratch = nullptr;
+  if (dev_alloc(ctx, &scratch, (size_t)blocks * 256 * 8)) return 1;
+  double flops = 0.0, best = 0.0;
+  cudaError_t e = cudaSuccess;
+  for (int rep = 0; rep < 4 && e == cudaSuccess; ++rep) {            // first repetition warms up
+    e = cudaEventRecord(ctx->ev2, ctx->stream);
+    if (e == cudaSuccess) e = launch_fp64_peak(kind, static_cast<double*>(scratch), blocks, 20000, &flops, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev3, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev3);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+    if (e == cudaSuccess && rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  dev_free(ctx, scratch);
+  if (e != cudaSuccess) return fail(ctx, "agnf_debug_fp64_peak: %s", cudaGetErrorString(e));
+  ctx->launches += 4;
+  *tflops = best;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------- K1
 
 AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg) {
@@ -497,6 +556,12 @@ AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg) {
   if (cfg->n_z < 1) return fail(ctx, "n_z must be >= 1");
   if (cfg->eb_mode < 0 || cfg->eb_mode > 2) return fail(ctx, "eb_mode must be 0, 1 or 2");
   if (cfg->bb_mode < 0 || cfg->bb_mode > 3) return fail(ctx, "bb_mode must be 0..3");
+  // a new configuration invalidates everything uploaded for the previous one
+  ens_teardown(ctx);
+  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) ctx->fam_set[f] = false;
+  ctx->have_z = ctx->have_src = false;
+  ctx->grids_dirty = true;
+  ctx->k4_cfg = ctx->k4_src = ctx->k4_bands = false;
   ctx->k1.cfg = *cfg;
   const int n_norm = 3 + (cfg->bbb_has_norm ? 1 : 0) + (cfg->radio ? 1 : 0);
   ctx->k1.norm_offset = cfg->n_par - n_norm;
@@ -653,6 +718,7 @@ AGNF_API int agnf_sources_upload(agnf_ctx* ctx, int64_t S, const int32_t* zi, co
   if ((ctx->k1.xp_midir_uv || ctx->k1.xp_ir_xray) && n_const < 4)
     return fail(ctx, "prior_midIR_UV / prior_IR_XRays need consts[1..3] (n_const >= 4)");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ens_teardown(ctx);          // walkers belong to the previous set of sources
   const size_t nb = ctx->k1.cfg.n_b, np = ctx->k1.cfg.n_par, s = (size_t)S;
   for (size_t i = 0; i < s; ++i)
     if (zi[i] < 0 || zi[i] >= ctx->k1.cfg.n_z) return fail(ctx, "source %zu: z-slice %d out of range", i, zi[i]);
@@ -1094,19 +1160,7 @@ AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, doub
   if (walkers < 2 || (walkers & 1)) return fail(ctx, "walkers must be even and >= 2 (two half-ensembles)");
   if (!(a > 1.0)) return fail(ctx, "stretch scale a must be > 1");
   if (n_bins < 0) return fail(ctx, "n_bins < 0");
-  if (ctx->have_ens) {
-    for (void* q : {(void*)ctx->ens.pos, (void*)ctx->ens.lnp, (void*)ctx->ens.n_acc, (void*)ctx->ens_sc.prop,
-                    (void*)ctx->ens_sc.prop_lnp, (void*)ctx->ens_sc.factor, (void*)ctx->ens_sc.lnu,
-                    (void*)ctx->ens_sc.sid, (void*)ctx->ens_hist.hist, (void*)ctx->ens_best_pos,
-                    (void*)ctx->ens_best_lnp})
-      dev_free(ctx, q);
-    dev_free(ctx, ctx->ens_chain);
-    dev_free(ctx, ctx->ens_chain_lnp);
-    ctx->ens_chain = nullptr;
-    ctx->ens_chain_lnp = nullptr;
-    ctx->ens_chain_cap = ctx->ens_chain_n = 0;
-    ctx->have_ens = false;
-  }
+  ens_teardown(ctx);
   const int64_t S = ctx->k1.S;
   const int np = ctx->k1.cfg.n_par, H = walkers / 2;
   K3State& st = ctx->ens;
@@ -1132,15 +1186,25 @@ AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, doub
   ENS_ALLOC(ctx->ens_sc.sid, int32_t, S * walkers);       // [S*W] for the initial evaluation, [S*H] prefix per half-step
   ENS_ALLOC(ctx->ens_best_pos, double, S * np);
   ENS_ALLOC(ctx->ens_best_lnp, double, S);
+  st.split = nullptr;
+  if (ctx->ens_split) {
+    if (walkers > 65535) return fail(ctx, "the random split indexes walkers with 16 bits");
+    ENS_ALLOC(st.split, uint16_t, S * walkers);
+  }
   ctx->ens_hist.hist = nullptr;
   ctx->ens_hist.n_bins = n_bins;
-  ctx->ens_hist.pbox = ctx->k1.pbox;
+  ctx->ens_hist.pbox = nullptr;            // read from ctx->k1 at launch time
   if (n_bins > 0) {
     ENS_ALLOC(ctx->ens_hist.hist, uint32_t, S * np * n_bins);
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->ens_hist.hist, 0, (size_t)S * np * n_bins * 4, ctx->stream));
   }
 #undef ENS_ALLOC
   CUDA_TRY(ctx, cudaMemsetAsync(st.n_acc, 0, (size_t)S * walkers * 4, ctx->stream));
+  {
+    std::vector<double> ninf((size_t)S, -INFINITY);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ens_best_lnp, ninf.data(), (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   ctx->ens_step = 0;
   ctx->ens_hist_samples = 0;
   ctx->have_ens = true;
@@ -1149,7 +1213,10 @@ AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, doub
 
 namespace {
 
-// the walkers have new positions: evaluate them, restart the acceptance counters and the running best
+// The walkers have new positions: evaluate them.  The acceptance counters and the running best are NOT touched:
+// emcee's sampler keeps accumulating over the burn-in sets (the reference never resets it between them,
+// MCMC_AGNfitter.py:125-128), get_best_position takes the argmax over everything sampled so far
+// (PARAMETERSPACE_AGNfitter.py:281-283), and the starting positions themselves are not part of emcee's chain.
 int ens_positions_changed(agnf_ctx* ctx) {
   K3State& st = ctx->ens;
   cudaStream_t s = ctx->stream;
@@ -1157,12 +1224,8 @@ int ens_positions_changed(agnf_ctx* ctx) {
   CUDA_TRY(ctx, launch_k3_fill_sid(ctx->ens_sc.sid, st.S, st.W, s));
   if (agnf_lnprob_batch_device(ctx, st.pos, ctx->ens_sc.sid, n, st.lnp, nullptr, nullptr, nullptr, nullptr, s)) return 1;
   CUDA_TRY(ctx, launch_k3_fill_sid(ctx->ens_sc.sid, st.S, st.W / 2, s));
-  std::vector<double> ninf((size_t)st.S, -INFINITY);
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ens_best_lnp, ninf.data(), (size_t)st.S * 8, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(ctx, launch_k3_best(st, ctx->ens_best_pos, ctx->ens_best_lnp, s));
-  CUDA_TRY(ctx, cudaMemsetAsync(st.n_acc, 0, (size_t)n * 4, s));
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
-  ctx->launches += 4;
+  ctx->launches += 3;
   return 0;
 }
 
@@ -1212,9 +1275,15 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
   FB.ens.seed = st.seed;
   FB.ens.a = st.a;
   FB.ens.src_offset = st.src_offset;
+  FB.ens.split = st.split;
+  ctx->ens_hist.pbox = ctx->k1.pbox;
   const bool fused = ctx->k1_variant != 0 && ctx->ens_fused && k1_coop_supported(ctx->k1, FB, nullptr) &&
                      (ctx->k1_variant == 2 || k1_coop_profitable(ctx->k1, FB));
   for (int64_t it = 0; it < n_steps; ++it) {
+    if (st.split) {
+      CUDA_TRY(ctx, launch_k3_split(st, ctx->ens_step, s));
+      ctx->launches += 1;
+    }
     for (int half = 0; half < 2; ++half) {
       if (fused) {
         FB.ens.half = half;
@@ -1367,6 +1436,7 @@ AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, d
   const size_t n_out = (size_t)st.S * st.n_par * n_q;
   if (dev_alloc(ctx, &dq, (size_t)n_q * 8) || dev_alloc(ctx, &dout, n_out * 8)) return 1;
   cudaError_t e = cudaMemcpyAsync(dq, q, (size_t)n_q * 8, cudaMemcpyHostToDevice, ctx->stream);
+  ctx->ens_hist.pbox = ctx->k1.pbox;
   if (e == cudaSuccess)
     e = launch_k3_percentiles(ctx->ens_hist, st.S, st.n_par, static_cast<const double*>(dq), n_q,
                               static_cast<double*>(dout), ctx->stream);

@@ -222,9 +222,9 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     const int kw = (int)(i - src * H);
     const StretchDraw d = stretch_draw(B.ens.seed, B.ens.a, B.ens.step, B.ens.half, src + B.ens.src_offset, kw, H);
     s = (int)src;
-    wrow = src * B.ens.W + (B.ens.half ? H : 0) + kw;
+    wrow = src * B.ens.W + split_walker(B.ens.split, src, B.ens.W, (B.ens.half ? H : 0) + kw);
     const int my_w = (int)wrow;
-    const int my_c = (int)(src * B.ens.W + (B.ens.half ? 0 : H) + d.j);
+    const int my_c = (int)(src * B.ens.W + split_walker(B.ens.split, src, B.ens.W, (B.ens.half ? 0 : H) + d.j));
     ens_lnp_old = B.ens.lnp[wrow];          // needed only by the acceptance test: in flight during the evaluation
     {
       // Both walker rows are fetched by the whole warp: element e of the flat [32][n_par] block goes to lane

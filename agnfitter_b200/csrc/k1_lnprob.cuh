@@ -131,6 +131,7 @@ struct K1Ensemble {
   uint64_t seed = 0;
   double a = 2.0;
   int64_t src_offset = 0;     // see K3State
+  const uint16_t* split = nullptr;   // [S, W] this step's split (k3_ensemble.cuh), or nullptr = fixed halves
 };
 
 struct K1Batch {

@@ -48,6 +48,14 @@ __device__ __forceinline__ StretchDraw stretch_draw(uint64_t seed, double a, int
   return d;
 }
 
+// emcee 3's RedBlueMove shuffles the walkers into two equal sets at every step (`randomize_split=True`, the default):
+// `split` [S, W] lists, per source, the walkers of set 0 in slots [0, W/2) and of set 1 in slots [W/2, W)
+// (k3_split_kernel); nullptr = the fixed first-half / second-half split.
+constexpr uint32_t K3_SPLIT_TAG = 0xFFFFFFFFu;     // second counter word of the split's Philox stream
+__device__ __forceinline__ int split_walker(const uint16_t* __restrict__ split, int64_t s_local, int W, int slot) {
+  return split ? (int)split[s_local * W + slot] : slot;
+}
+
 // q = c - (c - x) * zz, no contraction
 __device__ __forceinline__ double stretch_coord(double c, double x, double zz) {
   return __dsub_rn(c, __dmul_rn(__dsub_rn(c, x), zz));

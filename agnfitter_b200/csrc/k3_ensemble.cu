@@ -26,8 +26,8 @@ __global__ void __launch_bounds__(K3_THREADS) k3_propose_kernel(K3State st, K3Sc
   const double zz = d.zz;
   const int j = d.j;
   const int np = st.n_par;
-  const double* __restrict__ xk = st.pos + ((s * st.W) + (half ? H : 0) + k) * np;       // walker being moved
-  const double* __restrict__ cj = st.pos + ((s * st.W) + (half ? 0 : H) + j) * np;       // partner, other half
+  const double* __restrict__ xk = st.pos + ((s * st.W) + split_walker(st.split, s, st.W, (half ? H : 0) + k)) * np;  // moved
+  const double* __restrict__ cj = st.pos + ((s * st.W) + split_walker(st.split, s, st.W, (half ? 0 : H) + j)) * np;  // partner
   double* __restrict__ q = sc.prop + i * np;
   for (int c = 0; c < np; ++c) q[c] = stretch_coord(cj[c], xk[c], zz);
   sc.factor[i] = (double)(np - 1) * log(zz);
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_accept_kernel(K3State st, K3Scr
   if (i >= st.S * H) return;
   const int64_t s = i / H;
   const int k = (int)(i - s * H);
-  const int64_t w = s * st.W + (half ? H : 0) + k;
+  const int64_t w = s * st.W + split_walker(st.split, s, st.W, (half ? H : 0) + k);
   const double newl = sc.prop_lnp[i];
   const double lnpdiff = sc.factor[i] + newl - st.lnp[w];
   if (lnpdiff > sc.lnu[i]) {          // false for NaN and for -inf proposals
@@ -50,6 +50,43 @@ __global__ void __launch_bounds__(K3_THREADS) k3_accept_kernel(K3State st, K3Scr
     for (int c = 0; c < np; ++c) x[c] = q[c];
     st.lnp[w] = newl;
     st.n_acc[w] += 1;
+  }
+}
+
+// one warp per source: rank every walker's key among the source's W keys (ties by walker index)
+__global__ void __launch_bounds__(K3_THREADS) k3_split_kernel(K3State st, int64_t step) {
+  extern __shared__ uint32_t s_keys[];                    // [warps per CTA][W rounded up to 4]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t s = (int64_t)blockIdx.x * (K3_THREADS / 32) + warp;
+  if (s >= st.S) return;
+  const int W = st.W, W4 = (W + 3) & ~3;
+  uint32_t* keys = s_keys + warp * W4;
+  for (int q = lane; q < W4 / 4; q += 32) {
+    uint32_t x[4];
+    philox4x32_10((uint32_t)step, K3_SPLIT_TAG, (uint32_t)(s + st.src_offset), (uint32_t)q, (uint32_t)st.seed,
+                  (uint32_t)(st.seed >> 32), x);
+    keys[4 * q] = x[0];
+    keys[4 * q + 1] = x[1];
+    keys[4 * q + 2] = x[2];
+    keys[4 * q + 3] = x[3];
+  }
+  __syncwarp();
+  for (int w0 = lane; w0 < W; w0 += 128) {               // four walkers per lane and pass
+    const int w1 = w0 + 32, w2 = w0 + 64, w3 = w0 + 96;
+    const uint32_t k0 = keys[w0], k1 = w1 < W ? keys[w1] : 0u, k2 = w2 < W ? keys[w2] : 0u, k3 = w3 < W ? keys[w3] : 0u;
+    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    for (int j = 0; j < W; ++j) {
+      const uint32_t kj = keys[j];
+      r0 += (kj < k0) || (kj == k0 && j < w0);
+      r1 += (kj < k1) || (kj == k1 && j < w1);
+      r2 += (kj < k2) || (kj == k2 && j < w2);
+      r3 += (kj < k3) || (kj == k3 && j < w3);
+    }
+    uint16_t* out = st.split + s * W;
+    out[r0] = (uint16_t)w0;
+    if (w1 < W) out[r1] = (uint16_t)w1;
+    if (w2 < W) out[r2] = (uint16_t)w2;
+    if (w3 < W) out[r3] = (uint16_t)w3;
   }
 }
 
@@ -154,6 +191,14 @@ cudaError_t launch_k3_ball(const K3State& st, const double* centre, double scale
 cudaError_t launch_k3_fill_sid(int32_t* sid, int64_t S, int32_t half, cudaStream_t stream) {
   if (S * half <= 0) return cudaSuccess;
   k3_fill_sid_kernel<<<blocks_for(S * half), K3_THREADS, 0, stream>>>(sid, S, half);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k3_split(const K3State& st, int64_t step, cudaStream_t stream) {
+  if (!st.split || st.S == 0) return cudaSuccess;
+  const int wpc = K3_THREADS / 32;
+  const size_t smem = (size_t)wpc * ((st.W + 3) & ~3) * sizeof(uint32_t);
+  k3_split_kernel<<<(unsigned)((st.S + wpc - 1) / wpc), K3_THREADS, smem, stream>>>(st, step);
   return cudaGetLastError();
 }
 

@@ -9,8 +9,11 @@
 // Move (Goodman & Weare 2010 as implemented by emcee's StretchMove/RedBlueMove with a = 2):
 //     zz = ((a - 1) u1 + 1)^2 / a            j = floor(u2 * W/2)          (partner in the other half)
 //     q  = c_j - (c_j - x_k) * zz            accept iff (n_par - 1) ln zz + lnp(q) - lnp(x_k) > ln u3
-// The halves are the fixed first/second half of the ensemble (emcee's `randomize_split=False`).
-// u1, u2, u3 come from Philox4x32-10 keyed by (seed) with counter (step, half, source, walker), so the
+// The two sets are drawn afresh at every step, as emcee 3's RedBlueMove does by default (`randomize_split=True`:
+// the reference builds EnsembleSampler with the default move, MCMC_AGNfitter.py:114): k3_split_kernel orders the W
+// walkers of a source by a 32-bit Philox key (counter (step, 0xFFFFFFFF, source, walker / 4)), the first W/2 form
+// set 0.  `split == nullptr` keeps the fixed first/second half (`randomize_split=False`).
+// u1, u2, u3 come from Philox4x32-10 keyed by (seed) with counter (step, half, source, slot), so the
 // stream is reproducible on the CPU (oracle/ensemble_oracle.py) bit for bit.
 #pragma once
 #include <cstdint>
@@ -28,6 +31,7 @@ struct K3State {
   double a;           // stretch scale (emcee default 2.0)
   int64_t src_offset; // added to the local source index in the Philox counter: a shard that starts at catalogue
                       // row `src_offset` draws exactly what a single-GPU run draws for those sources
+  uint16_t* split;    // [S, W] this step's split (see above), or nullptr
 };
 
 struct K3Scratch {
@@ -49,6 +53,8 @@ struct K3Hist {
 cudaError_t launch_k3_ball(const K3State& st, const double* centre, double scale, int normal, uint32_t stream_id,
                            cudaStream_t stream);
 cudaError_t launch_k3_fill_sid(int32_t* sid, int64_t S, int32_t half, cudaStream_t stream);
+// split[s, :] = walkers of source s ordered by their Philox key of `step` (ties by walker index)
+cudaError_t launch_k3_split(const K3State& st, int64_t step, cudaStream_t stream);
 cudaError_t launch_k3_propose(const K3State& st, const K3Scratch& sc, int64_t step, int half, cudaStream_t stream);
 cudaError_t launch_k3_accept(const K3State& st, const K3Scratch& sc, int half, cudaStream_t stream);
 cudaError_t launch_k3_hist(const K3State& st, const K3Hist& h, cudaStream_t stream);

@@ -10,7 +10,7 @@ with the reference's names, argument order and return conventions, backed by the
     my_params_transform(cube[n, ndim])                     MCMC:64-72      Posterior.my_params_transform
     PARAMETERSPACE_AGNfitter.ymodel(nus, z, dlum, models, P, *par) :180-243  Posterior.ymodel
     DICTIONARIES_AGNfitter.filtering_models(nus, F, filterdict, z) :426-478  engine.DictBuilder.filtering_models
-    MODELSDICT.construct_dictionaryarray_filtered / build  DIC:78-154      fill_modelsdict
+    MODELSDICT.construct_dictionaryarray_filtered / build  DIC:78-154      construct_dictionaryarray_filtered / build
     MCMC_AGNfitter.main(data, models, P, mc), emcee leg     MCMC:33-149     main (sampler on the GPU, same chain files)
 
 `data`, `models`, `P` are the reference's own objects (DATA_AGNfitter.DATA, MODEL_AGNfitter.MODELS,
@@ -159,3 +159,58 @@ def fill_modelsdict(md, builder: DictBuilder, z, templates_4plot):
         setattr(md, attr + "_4plot", tpl)
     md.z = z
     return md
+
+
+def construct_dictionaryarray_filtered(md, z, filterdict, model=None, builder=None):
+    """MODELSDICT.construct_dictionaryarray_filtered(z, filterdict) (DICTIONARIES_AGNfitter.py:78-136) with the
+    filtering loops on the GPU: the reference's own loaders (MODEL_AGNfitter.GALAXY / STARBURST / BBB / TORUS /
+    AGN_RAD) produce the `_4plot` dictionaries, K2 filters every template of a family in one call, and `md` ends up
+    with exactly the attributes the reference method sets (same names, same key order, `(bands, Fnu[n_b])` values).
+    `model`: the reference's MODEL_AGNfitter module (default: the one DICTIONARIES_AGNfitter imported)."""
+    import sys
+    if model is None:
+        model = sys.modules[type(md).__module__].model
+    if builder is None:
+        builder = DictBuilder(filterdict)
+    md.GALAXYFdict, md.STARBURSTFdict, md.BBBFdict, md.TORUSFdict = dict(), dict(), dict(), dict()
+    md.z = z
+    md.filterdict = filterdict
+    (md.GALAXYFdict_4plot, md.GALAXY_SFRdict, md.GALAXYatt_dict, galaxy_parnames, galaxy_partypes,
+     md.GALAXYfunctions) = model.GALAXY(md.path, md.modelsettings)
+    (md.STARBURSTFdict_4plot, md.STARBURST_LIRdict, starburst_parnames, starburst_partypes,
+     md.STARBURSTfunctions) = model.STARBURST(md.path, md.modelsettings)
+    md.BBBFdict_4plot, bbb_parnames, bbb_partypes, md.BBBfunctions = model.BBB(md.path, md.modelsettings, md.nXRaysdata)
+    md.TORUSFdict_4plot, torus_parnames, torus_partypes, md.TORUSfunctions = model.TORUS(md.path, md.modelsettings)
+    tpl = {'GALAXY': md.GALAXYFdict_4plot, 'STARBURST': md.STARBURSTFdict_4plot, 'BBB': md.BBBFdict_4plot,
+           'TORUS': md.TORUSFdict_4plot}
+    norm_parnames = ['GA', 'SB', 'BB', 'TO']
+    norm_partypes = ['free', 'free', 'free', 'free']
+    md.all_parnames = [galaxy_parnames, starburst_parnames, torus_parnames, bbb_parnames]
+    md.all_partypes = [galaxy_partypes, starburst_partypes, torus_partypes, bbb_partypes]
+    if md.modelsettings['RADIO'] == True:
+        md.AGN_RADFdict = dict()
+        md.AGN_RADFdict_4plot, agnrad_parnames, agnrad_partypes, md.AGN_RADfunctions = \
+            model.AGN_RAD(md.path, md.modelsettings, md.nRADdata)
+        tpl['AGN_RAD'] = md.AGN_RADFdict_4plot
+        norm_parnames.append('RAD')
+        norm_partypes.append('free')
+        md.all_parnames.extend((agnrad_parnames, norm_parnames))
+        md.all_partypes.extend((agnrad_partypes, norm_partypes))
+    else:
+        md.all_parnames.append(norm_parnames)
+        md.all_partypes.append(norm_partypes)
+    fill_modelsdict(md, builder, z, tpl)
+
+
+def build(md, model=None):
+    """MODELSDICT.build() (DICTIONARIES_AGNfitter.py:139-154): one dictionary per redshift of `md.z_array` (always
+    `[data.z]` in the live path, RUN_AGNfitter_multi.py:176), attributes left on `md`, `md.MD[str(z)] = None` as in
+    the reference (its construct method returns nothing)."""
+    md.MD = dict()
+    builder = None
+    for z in md.z_array:
+        filterdict = [md.fo.central_nu_array, md.fo.lambdas_dict, md.fo.factors_dict]
+        if builder is None:
+            builder = DictBuilder(filterdict)
+        construct_dictionaryarray_filtered(md, z, filterdict, model=model, builder=builder)
+        md.MD[str(z)] = None

@@ -77,11 +77,15 @@ class ShardStream:
 
 
 class EnsembleSampler:
-    def __init__(self, engine, walkers, seed=0, a=2.0, n_bins=1024, source_offset=0):
+    def __init__(self, engine, walkers, seed=0, a=2.0, n_bins=1024, source_offset=0, split="random"):
         """engine: an Engine with sources uploaded.  walkers: even.  n_bins: histogram resolution of the
         on-device percentiles ((P.max - P.min) / n_bins per parameter); 0 = no histograms.  source_offset:
         catalogue row of the first uploaded source (enters the random-number counter: a shard draws what a
-        single-GPU run draws for the same sources)."""
+        single-GPU run draws for the same sources).  split: "random" — the walkers are re-divided into two equal
+        sets at every step, what emcee 3's default move does (`RedBlueMove(randomize_split=True)`: the sampler the
+        reference builds, MCMC_AGNfitter.py:114) — or "fixed": first half / second half."""
+        if split not in ("random", "fixed"):
+            raise ValueError("split must be 'random' or 'fixed'")
         self.engine = engine
         self.ctx, self.lib = engine.ctx, engine.lib
         self.S, self.W, self.n_par = engine.S, int(walkers), engine.n_par
@@ -89,8 +93,17 @@ class EnsembleSampler:
             raise ValueError("upload sources first (Engine.set_sources)")
         self.n_bins = int(n_bins)
         self.ctx.check(self.lib.agnf_set_option(self.ctx.h, b"ens_source_offset", int(source_offset)))
+        self.split = split
+        self._set_split(split)
         self.ctx.check(self.lib.agnf_ens_create(self.ctx.h, self.W, int(seed) & (2 ** 64 - 1), float(a), self.n_bins))
         self._steps = 0
+
+    def _set_split(self, split):
+        # the option may only change while no ensemble exists: re-uploading the sources tears the old one down
+        rc = self.lib.agnf_set_option(self.ctx.h, b"ens_split", 1 if split == "random" else 0)
+        if rc != 0:
+            raise ValueError("an ensemble with the other split already exists on this context; upload the sources "
+                             "again (Engine.set_sources) before creating a sampler with split=%r" % split)
 
     # -- positions --------------------------------------------------------------------------------
     @staticmethod
@@ -110,8 +123,9 @@ class EnsembleSampler:
         pos = as_f64(pos)
         if pos.shape != (self.S, self.W, self.n_par):
             raise ValueError("positions must have shape (S, W, n_par) = %s" % ((self.S, self.W, self.n_par),))
+        # acceptance counters and the running best are NOT reset: emcee's sampler accumulates over the burn-in sets
+        # (MCMC_AGNfitter.py:125-128); reset_stats() / reset_best() do what sampler.reset() does (:182)
         self.ctx.check(self.lib.agnf_ens_set_positions(self.ctx.h, ptr(pos)))
-        self._steps = 0                 # steps behind the acceptance counters
 
     def set_ball(self, centre, scale=0.00001, normal=False, stream_id=0):
         """Positions drawn on the device around per-source centres [S, n_par]: centre + scale * uniform(-1, 1)
@@ -121,7 +135,6 @@ class EnsembleSampler:
             raise ValueError("centres must have shape (S, n_par) = %s" % ((self.S, self.n_par),))
         self.ctx.check(self.lib.agnf_ens_set_ball(self.ctx.h, ptr(centre), float(scale), int(bool(normal)),
                                                   int(stream_id) & 0xFFFFFFFF))
-        self._steps = 0
 
     # -- stepping ---------------------------------------------------------------------------------
     def run(self, n_steps, hist_every=0, track_best=False):
@@ -244,13 +257,19 @@ class EnsembleSampler:
             for nm in names:
                 os.makedirs(os.path.join(save_dir, str(nm)), exist_ok=True)
             self.record(max(nb * nburn, 1))         # emcee's sampler accumulates all burn-in sets (no reset between)
+        self.reset_stats()
+        self.reset_best()
+        centres = []
         if rng is None:
             device_ball(0.5 * (pmin + pmax), False)
         else:
             self.set_positions(initial())
         for k_set in range(nb):
+            # the sampler keeps accumulating over the sets (no reset, MCMC_AGNfitter.py:125-128): the restart centre is
+            # the best sample of ALL burn-in steps so far — what get_best_position reads back from the burn-in file
             self.run(nburn, track_best=True)
             best_pos, _ = self.best()
+            centres.append(best_pos)
             # run_burn_in rewrites the burn-in file after every set (MCMC:171); only the last version survives,
             # and the restart point it is read back for (get_best_position) is tracked on the device
             if save_dir is not None and k_set == nb - 1:     # written while the production run goes on
@@ -281,4 +300,4 @@ class EnsembleSampler:
         _, _, acc = self.state()
         bp, bl = self.best()
         return dict(percentiles=self.percentiles() if self.n_bins else None, best_pos=bp, best_lnp=bl,
-                    acceptance=acc.mean(axis=1) / max(n, 1))
+                    acceptance=acc.mean(axis=1) / max(n, 1), restart_centres=centres)

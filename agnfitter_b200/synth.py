@@ -67,12 +67,19 @@ def _bump(lognu, centre, width):
     return np.exp(-0.5 * ((lognu - centre) / width) ** 2)
 
 
-def synthetic_templates(seed=20260101, ga_free=False):
+C4_SETTINGS = dict(CLASSIC_SETTINGS, RADIO=True, XRAYS=True)
+
+
+def synthetic_templates(seed=20260101, ga_free=False, c4=False):
     """The four classic families as `*_4plot`-style dicts {key: (log10 nu, Fnu)} with the real key
     strings' structure, plus GALAXYatt / STARBURST_LIR stand-ins.  ga_free: the galaxy family in the shape of the
     reference's default `BC03_metal` library instead — keys (metal, tau, age, EBVgal) with E(B-V)_gal a FREE
     parameter applied on the fly (two key values per template, MODEL_AGNfitter.py:145-301), 4 x 11 x 25 x 2 = 2 200
-    unreddened templates, no GALAXYatt table (the energy-balance prior integrates on the fly, PRIORS:83-93)."""
+    unreddened templates, no GALAXYatt table (the energy-balance prior integrates on the fly, PRIORS:83-93).
+    c4: the radio-to-X-ray model of BASELINE configs[3] — the disc family in the shape of R06 + X-ray extension
+    (EBVbbb, alphaScat free, Gamma grid: 2 x 2 x 21 keys, 1 438 points, MODEL_AGNfitter.py:600-645) and a fitted
+    synchrotron family in the shape AGN_RAD builds for > 3 radio data (alpha1 x alpha2 x nu_t = 10 x 10 x 30 =
+    3 000 keys on 400 points, MODEL_AGNfitter.py:498-527): five components, 18 parameters."""
     rng = np.random.default_rng(seed)
     out = {}
     # GALAXY: keys (tau, age, EBVgal) enumerated age-major like MODEL_AGNfitter.py:95-108
@@ -123,6 +130,26 @@ def synthetic_templates(seed=20260101, ga_free=False):
     lognu_bb = 10.0 + 0.016 * np.arange(438)
     f = 1e-31 * 10 ** (0.3 * (lognu_bb - 10)) * np.exp(-10 ** (lognu_bb - 16.2))
     out["BB"] = dict(F={'0.0': (lognu_bb, f), '1.0': (lognu_bb, f)}, names=['EBVbbb'], types=['free'], aux=None)
+    if c4:
+        lognu_x = np.concatenate([lognu_bb, np.linspace(17.0, 19.0, 1000)])
+        bb = {}
+        for e in (0.0, 1.0):
+            for a in (-0.4, 0.4):
+                for g in np.arange(0.0, 3.15, 0.15):
+                    fx = 1e-31 * 10 ** (0.3 * (lognu_x - 10)) * np.exp(-10 ** (lognu_x - 16.2))
+                    hard = lognu_x >= 17.0
+                    fx[hard] = 1e-33 * 10 ** ((1.0 - g) * (lognu_x[hard] - 17.0))
+                    bb[(str(e), str(a), str(g))] = (lognu_x, fx)
+        out["BB"] = dict(F=bb, names=['EBVbbb', 'alphaScat', 'Gamma'], types=['free', 'free', 'grid'], aux=None)
+        lognu_r = np.arange(7, 15, 0.02)
+        rad = {}
+        for a1 in np.arange(-1.0, 1.0, 0.2):
+            for a2 in np.arange(-1.0, 0, 0.1):
+                for nt in np.arange(7, 13, 0.2):
+                    x = lognu_r - nt
+                    rad[(str(a1), str(a2), str(nt))] = (lognu_r, 1e-27 * 10 ** np.where(x < 0, a1 * x, a2 * x)
+                                                        * np.exp(-10 ** (lognu_r - 13.0)))
+        out["RAD"] = dict(F=rad, names=['alpha1', 'alpha2', 'nut'], types=['grid', 'grid', 'grid'], aux=None)
     return out
 
 
@@ -155,7 +182,9 @@ def build_modelset(templates, filterdict, z_grid, builder, settings=CLASSIC_SETT
     ms = ModelSet(settings=dict(settings), bands=np.asarray(filterdict[0], dtype=np.float64),
                   z_grid=np.asarray(z_grid, dtype=np.float64))
     dev = {}
-    for name in ("GA", "SB", "TO", "BB"):
+    for name in ("GA", "SB", "TO", "BB", "RAD"):
+        if name not in templates:
+            continue
         fam = templates[name]
         keys = list(fam["F"].keys())
         arr = np.array(keys)

@@ -11,10 +11,21 @@ is built on the GPU by K2 and stays in HBM; one step = one pass of the batched l
 over all 10^7 (source, walker) rows.  Sources are independent, so ranks hold independent shards
 (weak scaling, no data-path collective); the only collectives are the timing reductions.
 
-One JSON line on stdout (rank 0).  `value` = evals/s with inputs resident in HBM; `e2e` = the same
-through the host-buffer entry point (pinned host params -> H2D -> K1 -> D2H lnp) every step.
+One JSON line on stdout (rank 0).  `value` = evals/s with inputs resident in HBM over EXACTLY --steps
+passes; `sustained` = the same loop kept up for >= 2 s with the clocks sampled over it; `e2e` = the same
+metric through the host-buffer entry point (pinned host params -> H2D -> K1 -> D2H lnp) every step.
+Further keys: `roofline` (K1), `roofline_k2` (dictionary build: HBM-write, FP64 and DMMA fractions against
+peaks measured in this run), `ensemble` (the GPU-resident sampler loop, >= 2 s), `e2e_fit` (catalogue in host
+memory -> fit_catalog -> summary table on the host, final gather inside the timed region), `configs` (K1 on
+the other BASELINE shapes: 49 bands, free-E(B-V) galaxies, the 18-parameter radio-to-X-ray model), `strong`
+(N > 1: the 100k-source catalogue divided over the ranks), `cpu_baseline` (N = 1).
+
+`--impl reference` times the CPU restatement of the reference (oracle/agn_oracle.py, pinned to the reference by
+tests/golden) on all host cores on a bounded sample of THE SAME sources and walker positions; that process
+never loads libagnfit_b200.so (its dictionary slices come from oracle.filtering_models).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -234,18 +245,29 @@ def make_workload(args, rank, device, need_gpu=True):
     from agnfitter_b200.engine import Engine, DictBuilder
     t_setup = time.perf_counter()
     fd = synth.synthetic_filterdict(which="example49" if args.bands == 49 else None)
-    tpl = synth.synthetic_templates(ga_free=args.ga_free)
+    tpl = synth.synthetic_templates(ga_free=args.ga_free, c4=args.c4)
+    settings = synth.C4_SETTINGS if args.c4 else synth.CLASSIC_SETTINGS
     nus = np.asarray(fd[0])
     S, W = args.sources, args.walkers
-    z, dlum, rng = synth.synthetic_catalog(None, S, seed=20260101 + rank)
-    if not args.no_sort_z:
-        order = np.argsort(z, kind="stable")       # host-side processing order of the shard
-        z, dlum = z[order], dlum[order]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "strong" and world > 1:
+        # ONE catalogue of S sources (rank 0's) divided over the ranks along z (shard.shard_catalog)
+        from agnfitter_b200 import shard as _shard
+        z, dlum, rng = synth.synthetic_catalog(None, S, seed=20260101)
+        order, lo, hi = _shard.shard_catalog(z, rank, world)
+        z, dlum = z[order[lo:hi]], dlum[order[lo:hi]]
+        rng = np.random.default_rng(20260101 + 7919 * (rank + 1))
+        S = len(z)
+    else:
+        z, dlum, rng = synth.synthetic_catalog(None, S, seed=20260101 + rank)
+        if not args.no_sort_z:
+            order = np.argsort(z, kind="stable")       # host-side processing order of the shard
+            z, dlum = z[order], dlum[order]
     z_grid = np.unique(z)
     builder = DictBuilder(fd, device=device)
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
-    ms, dev_tables = synth.build_modelset(tpl, fd, z_grid, builder, on_device=True)
+    ms, dev_tables = synth.build_modelset(tpl, fd, z_grid, builder, settings=settings, on_device=True)
     torch.cuda.synchronize(device)
     k2_wall = time.perf_counter() - t0
     n_entries = len(z_grid) * sum(f.T for f in ms.families) * ms.n_b
@@ -261,8 +283,136 @@ def make_workload(args, rank, device, need_gpu=True):
     eng.set_sources(src)
     pars, sid = synth.walker_positions(rng, src.pmin, src.pmax, W, mode=args.positions, frac_out=0.01)
     raw = dict(z=z, dlum=dlum, nus=nus, fluxes=fl, fluxerrs=fe, pmin=src.pmin, pmax=src.pmax, zi=src.zi)
-    info = dict(k2_wall_s=k2_wall, k2_entries=n_entries, n_z=len(z_grid), setup_s=time.perf_counter() - t_setup)
+    info = dict(k2_wall_s=k2_wall, k2_entries=n_entries, n_z=len(z_grid), setup_s=time.perf_counter() - t_setup,
+                builder=builder, templates=tpl, filterdict=fd, z_grid=z_grid, S=S)
     return eng, ms, dev_tables, raw, pars, sid, info
+
+
+def workload_config(args, world, n_z, n_b, n_par, fam_T):
+    """`config` of the JSON line: a function of the workload only, so both arms print the same object."""
+    S, W = args.sources, args.walkers
+    n = S * W
+    dict_gb = n_z * sum(fam_T) * n_b * 8 / 1e9
+    if args.c4:
+        model = "radio-to-X-ray model (5 components, %d parameters, %s templates)" % (n_par, "+".join(map(str, fam_T)))
+    elif args.ga_free:
+        model = "free-E(B-V) galaxy variant (%d parameters, %s templates)" % (n_par, "+".join(map(str, fam_T)))
+    else:
+        model = "classic 10-parameter model (11000+161+60+2 templates)"
+    return {"workload": "C3: synthetic %d sources x %d walkers per GPU, %s, %s, dictionary of %d z-slices in HBM"
+                        % (S, W, "18-band default set" if n_b == 18 else "%d-band example set" % n_b, model, n_z),
+            "positions": args.positions + " in prior box + 1% out-of-box rows",
+            "source_order": "random z" if args.no_sort_z else "sorted by z",
+            "rows_per_step_per_gpu": n, "n_bands": n_b, "n_par": n_par,
+            "l2_policy": "inputs larger than L2 (params %.0f MB + dictionary %.1f GB per GPU)" % (
+                n * n_par * 8 / 1e6, dict_gb),
+            "parallelism": "sources sharded over %d GPU(s), no data-path collective" % world,
+            "scaling_mode": args.scaling}
+
+
+def shape_only_modelset(tpl, fd, z_grid, settings):
+    """ModelSet with the families' key grids but no tables (bounds, parameter layout)."""
+    from agnfitter_b200.flatten import ModelSet, family_from_keys_float
+    ms = ModelSet(settings=dict(settings), bands=np.asarray(fd[0], dtype=np.float64),
+                  z_grid=np.asarray(z_grid, dtype=np.float64))
+    for name in ("GA", "SB", "TO", "BB", "RAD"):
+        if name not in tpl:
+            continue
+        fam = tpl[name]
+        keys = list(fam["F"].keys())
+        kf = np.array(keys).T.astype(float)
+        aux = None if fam["aux"] is None else np.array([fam["aux"][k] for k in keys])
+        if name == "GA" and 'free' in fam["types"]:
+            aux = None
+        ms.families.append(family_from_keys_float(name, fam["names"], fam["types"], kf, True, None, aux))
+    return ms
+
+
+def _oracle_family_slices(job):
+    """Worker: band fluxes [T, n_b] of one family at one z through oracle.filtering_models."""
+    from oracle import agn_oracle as O
+    name, z = job
+    tpl, bands, lam, fac = _CPU_WORK
+    F = tpl[name]["F"]
+    out = np.empty((len(F), len(bands)))
+    for t, (nu, f) in enumerate(F.values()):
+        out[t] = O.filtering_models(nu, f, bands, lam, fac, z)
+    return name, z, out
+
+
+def reference_workload(args, rank=0):
+    """The GPU arm's workload rebuilt WITHOUT the product library, for a bounded sample of its sources: the same
+    catalogue (seed), the same truth parameters, fluxes and walker positions (the random streams are consumed in
+    the GPU arm's order and shapes), dictionary slices of the sampled redshifts from oracle.filtering_models."""
+    import multiprocessing as mp
+    from agnfitter_b200 import synth, sources
+    from agnfitter_b200.flatten import ModelSet, family_from_keys_float
+    from oracle import agn_oracle as O
+    global _CPU_WORK
+    fd = synth.synthetic_filterdict(which="example49" if args.bands == 49 else None)
+    tpl = synth.synthetic_templates(ga_free=args.ga_free, c4=args.c4)
+    settings = synth.C4_SETTINGS if args.c4 else synth.CLASSIC_SETTINGS
+    nus = np.asarray(fd[0])
+    S, W = args.sources, args.walkers
+    z, dlum, rng = synth.synthetic_catalog(None, S, seed=20260101 + rank)
+    if not args.no_sort_z:
+        order = np.argsort(z, kind="stable")
+        z, dlum = z[order], dlum[order]
+    z_grid = np.unique(z)
+    shape = shape_only_modelset(tpl, fd, z_grid, settings)
+    n_b, n_par = shape.n_b, shape.n_par
+    # sample: whole z-slices, evenly spread over the grid, until args.cpu_sources sources
+    per_slice = max(1, int(round(S / len(z_grid))))
+    n_slices = max(1, min(len(z_grid), args.cpu_sources // per_slice))
+    zs_sample = z_grid[np.unique(np.linspace(0, len(z_grid) - 1, n_slices).astype(int))]
+    sample_ids = np.nonzero(np.isin(z, zs_sample))[0][:args.cpu_sources]
+    zs_sample = np.unique(z[sample_ids])
+    cores = os.cpu_count() or 1
+    bands = fd[0]
+    lam = [np.asarray(fd[1][b][0]) for b in bands]
+    fac = [np.asarray(fd[2][b][0]) for b in bands]
+    _CPU_WORK = (tpl, bands, lam, fac)
+    jobs = [(name, float(zz)) for zz in zs_sample for name in tpl]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(min(cores, len(jobs))) as pool:
+        done = pool.map(_oracle_family_slices, jobs, chunksize=1)
+    dict_s = time.perf_counter() - t0
+    small = ModelSet(settings=dict(settings), bands=shape.bands, z_grid=zs_sample)
+    for f in shape.families:
+        tab = np.stack([next(o for (nm, zz, o) in done if nm == f.name and zz == float(zq)) for zq in zs_sample])
+        small.families.append(family_from_keys_float(f.name, f.par_names, f.par_types, f.keys_float, f.fitted, tab,
+                                                     f.aux))
+    # the GPU arm's random stream (make_workload): truth, fluxes, positions — full shapes, sample rows used
+    bounds = {}
+    pmin = np.empty((S, n_par))
+    pmax = np.empty((S, n_par))
+    for k, zk in enumerate(z_grid):
+        bounds[float(zk)] = sources.pdict_bounds(shape, float(zk))
+    for i in range(S):
+        pmin[i], pmax[i] = bounds[float(z[i])]
+    truth = pmin + rng.uniform(size=pmin.shape) * (pmax - pmin)
+    ym = np.zeros((S, n_b))
+    zpos = {float(v): i for i, v in enumerate(zs_sample)}
+    for i in sample_ids:
+        ym[i] = O.ymodel(small, zpos[float(z[i])], float(z[i]), float(dlum[i]), truth[i][None, :])[0][0]
+    fl, fe = synth.catalog_fluxes(rng, ym, nus, z)
+    pars, sid = synth.walker_positions(rng, pmin, pmax, W, mode=args.positions, frac_out=0.01)
+    srcs, pl = [], []
+    for i in sample_ids:
+        srcs.append(dict(z=float(z[i]), dlum=float(dlum[i]), nus=nus, fluxes=fl[i], fluxerrs=fe[i], pmin=pmin[i],
+                         pmax=pmax[i], zi=zpos[float(z[i])]))
+        pl.append(np.ascontiguousarray(pars[i * W:(i + 1) * W]))
+    info = dict(n_z=len(z_grid), n_b=n_b, n_par=n_par, fam_T=[f.T for f in shape.families],
+                dict_entries=len(zs_sample) * sum(f.T for f in shape.families) * n_b, dict_s=dict_s,
+                sample_ids=sample_ids)
+    return small, srcs, pl, info
+
+
+def product_library_mapped():
+    try:
+        return any("libagnfit_b200" in line for line in open("/proc/self/maps"))
+    except OSError:
+        return None
 
 
 _ORIGINAL_AFFINITY = []
@@ -303,6 +453,92 @@ def bind_to_gpu_numa_node(local):
         return "unbound (%s)" % type(e).__name__
 
 
+def timed_passes(eng, step, stream, n_steps, torch):
+    """CUDA events on the launching stream around n_steps calls of `step`; returns milliseconds."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(n_steps):
+        step()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def k1_leg(args, rank, local, overrides, steps, torch, seconds=0.5):
+    """K1 on another BASELINE shape: builds its own shard (dictionary + sources), times `steps` passes and a
+    `seconds`-long run; everything is released afterwards."""
+    a2 = argparse.Namespace(**dict(vars(args), **overrides))
+    eng, ms, dev_tables, raw, pars, sid, info = make_workload(a2, rank, local)
+    dev = torch.device("cuda", local)
+    d_pars = torch.from_numpy(pars).to(dev)
+    d_sid = torch.from_numpy(sid).to(dev)
+    d_lnp = torch.empty(len(pars), dtype=torch.float64, device=dev)
+    stream = torch.cuda.Stream(dev)
+    sp = stream.cuda_stream
+    step = lambda: eng.lnprob_device(d_pars, d_sid, d_lnp, stream_ptr=sp)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    ms_short = timed_passes(eng, step, stream, steps, torch) / steps
+    n_long = max(steps, int(seconds * 1e3 / max(ms_short, 1e-3)))
+    ms_long = timed_passes(eng, step, stream, n_long, torch) / n_long
+    n, n_comp = len(pars), len(ms.families)
+    bpe = k1_bytes_per_eval(n_comp, ms.n_b, ms.n_par, a2.walkers)
+    peak, _ = measured_peak()
+    kname = "k1_coop_kernel" if eng.get_option("k1_last_kernel") == 1 else "k1_lnprob_kernel"
+    out = dict(sources=a2.sources, walkers=a2.walkers, n_bands=ms.n_b, n_par=ms.n_par, components=n_comp,
+               templates="+".join(str(f.T) for f in ms.families), n_z=info["n_z"], rows_per_step=n,
+               ms_per_step=ms_short, evals_per_s=n / (ms_short * 1e-3), sustained_ms_per_step=ms_long,
+               sustained_evals_per_s=n / (ms_long * 1e-3), sustained_steps=n_long, bytes_per_eval=bpe,
+               roofline_frac=bpe * n / (ms_short * 1e-3) / 1e9 / peak, kernel=kname,
+               dictionary_entries=int(info["k2_entries"]), dictionary_wall_s=info["k2_wall_s"],
+               dictionary_entries_per_s=info["k2_entries"] / info["k2_wall_s"])
+    del eng, dev_tables, d_pars, d_sid, d_lnp, info
+    torch.cuda.empty_cache()
+    return out
+
+
+def fit_leg(args, rank, world, local, torch, dist):
+    """Product-level end to end: catalogue arrays in host memory -> catalog.fit_catalog (K2 for the shard's
+    redshifts, the reference's full burn-in / production schedule on the GPU-resident ensemble, percentiles, best
+    fit) -> summary table on rank 0's host, the final gather inside the timed region."""
+    from agnfitter_b200 import synth, catalog
+    S_tot = args.fit_sources * world
+    fd = synth.synthetic_filterdict()
+    tpl = synth.synthetic_templates()
+    long_names = dict(GA="GALAXY", SB="STARBURST", TO="TORUS", BB="BBB")
+    templates = {long_names[k]: v for k, v in tpl.items()}
+    rng = np.random.default_rng(77)
+    z = np.round(rng.uniform(0.01, 6.0, size=S_tot), 3)
+    dlum = synth.z2Dlum(z)
+    nus = np.asarray(fd[0])
+    y = 1e-27 * 10 ** (-0.5 * (nus[None, :] - 14.0)) * (1 + 0.1 * rng.normal(size=(S_tot, len(nus))))
+    y = np.abs(y)
+    mc = dict(Nwalkers=args.walkers, Nburnsets=2, Nburn=args.fit_nburn, Nmcmc=args.fit_nmcmc, Nthin=10)
+    torch.cuda.synchronize(local)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    table = catalog.fit_catalog(templates, fd, synth.CLASSIC_SETTINGS, z, dlum, nus, y, 0.1 * y, mc, seed=5,
+                                n_bins=256, rank=rank, world=world, device=local)
+    torch.cuda.synchronize(local)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=torch.device("cuda", local))
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt[0])
+    evals = S_tot * args.walkers * (2 * args.fit_nburn + args.fit_nmcmc)
+    out = dict(what="catalog.fit_catalog: catalogue arrays on the host -> K2 dictionary for the shard's redshifts -> "
+                    "2 burn-in sets + production run of the GPU-resident ensemble -> percentiles / best fit -> one "
+                    "gather of the per-source summaries to rank 0 (inside the timed region)",
+               sources_total=S_tot, sources_per_gpu=args.fit_sources, walkers=args.walkers,
+               schedule=dict(Nburnsets=2, Nburn=args.fit_nburn, Nmcmc=args.fit_nmcmc, Nthin=10),
+               seconds=dt, sources_per_s=S_tot / dt, evals_per_s=evals / dt,
+               summary_bytes=None if table is None else int(table.nbytes))
+    if table is not None:
+        assert table.shape[0] == S_tot and np.isfinite(table[:, 2:12]).all()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -316,7 +552,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng, ms, dev_tables, raw, pars, sid, info = make_workload(args, rank, local)
-    S, W, n = args.sources, args.walkers, len(pars)
+    S, W, n = info["S"], args.walkers, len(pars)
     n_b, n_par, n_comp = ms.n_b, ms.n_par, len(ms.families)
     dev = torch.device("cuda", local)
 
@@ -348,13 +584,8 @@ def run_ours(args):
     sampler.start()
     l0 = eng.launch_count
     per_launch = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_resident()
-    e1.record(stream)
+    ms_total = timed_passes(eng, step_resident, stream, args.steps, torch)
     barrier()
-    ms_total = e0.elapsed_time(e1)
     launches = eng.launch_count - l0
     # per-launch durations of the dominant kernel (events recorded by the library on the launching stream)
     for _ in range(min(args.steps, 5)):
@@ -362,6 +593,33 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         per_launch.append(eng.last_kernel_ms(1))
     k1_ms = float(np.mean(per_launch))
+
+    # ---- the same loop kept up for >= args.sustain_s seconds (steady-state clocks) ----------------------------
+    sustained = None
+    if args.sustain_s > 0:
+        n_long = max(args.steps, int(args.sustain_s * 1e3 / max(ms_total / args.steps, 1e-3)) + 1)
+        cs = ClockSampler(local)
+        cs.start()
+        barrier()
+        ms_long = timed_passes(eng, step_resident, stream, n_long, torch)
+        barrier()
+        cs.stop_flag = True
+        cs.join(timeout=2)
+        launches += n_long
+        sustained = dict(steps=n_long, ms=ms_long, clocks=cs.summary())
+
+    # ---- N > 1: the catalogue of `sources` sources divided over the ranks (strong scaling of the same pass) -------
+    strong_ms = 0.0
+    if world > 1 and args.scaling == "weak":
+        n_strong = (S // world) * W
+        d_ps, d_ss, d_ls = d_pars[:n_strong], d_sid[:n_strong], d_lnp[:n_strong]
+        step_s = lambda: eng.lnprob_device(d_ps, d_ss, d_ls, stream_ptr=sp)
+        for _ in range(3):
+            step_s()
+        barrier()
+        strong_ms = timed_passes(eng, step_s, stream, 20 * args.steps, torch) / (20 * args.steps)
+        barrier()
+        launches += 20 * args.steps
 
     # ---- the sampler loop the evaluations are for: S sources x W walkers, stretch moves on the GPU -----
     ens_info = None
@@ -372,22 +630,67 @@ def run_ours(args):
         # the best-fit tracker
         ens = EnsembleSampler(eng, W, seed=20260101 + rank, n_bins=256)
         ens.set_positions(pars.reshape(S, W, n_par))
-        ens.run(2, hist_every=10, track_best='thinned')       # warm-up
+        ens.run(10, hist_every=10, track_best='thinned')       # warm-up
         barrier()
+        cs = ClockSampler(local)
+        cs.start()
         l_e = eng.launch_count
         t0 = time.perf_counter()
         ens.run(args.ensemble_steps, hist_every=10, track_best='thinned')   # synchronises the ctx stream before returning
         ens_s = time.perf_counter() - t0
+        cs.stop_flag = True
+        cs.join(timeout=2)
         ens_launches = eng.launch_count - l_e
         _, _, acc = ens.state()
-        ens_info = dict(steps=args.ensemble_steps, s_per_step=ens_s / args.ensemble_steps,
+        ens_info = dict(steps=args.ensemble_steps, s_per_step=ens_s / args.ensemble_steps, seconds=ens_s,
                         evals_per_s=S * W * args.ensemble_steps / ens_s, launches=int(ens_launches),
-                        acceptance=float(acc.mean() / (args.ensemble_steps + 2)))
+                        acceptance=float(acc.mean() / (args.ensemble_steps + 10)), clocks=cs.summary())
         del ens
+
+    # ---- K2 on its own: the galaxy family of this shard once more, kernel and wall time; FP64 peaks -------------
+    k2_info = None
+    if rank == 0 and not args.no_k2_leg:
+        builder, tpl = info["builder"], info["templates"]
+        z_grid = info["z_grid"]
+        torch.cuda.synchronize(dev)
+        walls, kerns = [], []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            tab = builder.build_family(tpl["GA"]["F"], z_grid, on_device=True)
+            torch.cuda.synchronize(dev)
+            walls.append(time.perf_counter() - t0)
+            kerns.append(builder.contract_ms)
+            del tab
+        peaks = {}
+        for kind, nm in ((0, "dfma"), (1, "dmma")):
+            v = ctypes.c_double()
+            eng.ctx.check(eng.lib.agnf_debug_fp64_peak(eng.ctx.h, kind, ctypes.byref(v)))
+            peaks[nm] = float(v.value)
+        T_ga = len(tpl["GA"]["F"])
+        entries = len(z_grid) * T_ga * n_b
+        fd = info["filterdict"]
+        sum_nk = int(sum(len(fd[1][b][0]) for b in fd[0]))
+        k_ms = float(min(kerns))
+        peak_hbm, _ = measured_peak()
+        alg_flops = 2.0 * len(z_grid) * T_ga * sum_nk
+        k2_info = {"bound": "hbm", "family": "GA (%d templates x %d samples)" % (T_ga, len(next(iter(tpl["GA"]["F"].values()))[0])),
+                   "kernel": {3: "k2_contract_mma", 2: "k2_contract_sw", 1: "k2_contract_tile"}.get(builder.get_option("k2_last_kernel"), "?"),
+                   "entries": int(entries), "kernel_ms": k_ms, "wall_ms": float(min(walls)) * 1e3,
+                   "wall_over_kernel": float(min(walls)) * 1e3 / k_ms,
+                   "entries_per_s_kernel": entries / (k_ms * 1e-3), "entries_per_s_wall": entries / float(min(walls)),
+                   "achieved": entries * 8 / (k_ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                   "frac": entries * 8 / (k_ms * 1e-3) / 1e9 / peak_hbm,
+                   "algorithmic_bytes_per_launch": entries * 8,
+                   "fp64_peak_tflops": peaks,
+                   "algorithmic_flops_per_launch": alg_flops,
+                   "algorithmic_tflops": alg_flops / (k_ms * 1e-3) / 1e12,
+                   "note": "algorithmic flops = 2 n_k per entry (SURVEY 8d: one multiply-add per filter sample); the "
+                           "kernel contracts the filter curves to <= ~40 template samples per band first, so it "
+                           "executes far fewer — the output write is what bounds it"}
 
     # ---- output stage: integrated luminosities of 100 chain rows + best fit per source --------
     sed_info = None
-    if args.sed_sources > 0:
+    if args.sed_sources > 0 and not args.c4:
         from agnfitter_b200 import synth as _synth
         from agnfitter_b200.plotset import plotset_from_templates
         from agnfitter_b200.realizations import SedEngine, ranges_to_hz
@@ -415,7 +718,7 @@ def run_ours(args):
                         columns=int(sed.n_models), kernel_ms=round(k4_ms, 3),
                         rows_per_s=len(idx) / (k4_ms * 1e-3), sources_per_s=n_src / (k4_ms * 1e-3),
                         launches=int(sed_launches))
-        if rank == 0:
+        if rank == 0 and world == 1:
             sed_info["cpu_rows_per_s_one_core"] = cpu_sed_rate(ms, ps, raw, pars, W)
         del sed, d_sp, d_ss, d_so
 
@@ -445,17 +748,48 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     launches += eng.launch_count - l1
     barrier()
+    # a plain pinned host -> device copy of the same params block on every rank at once: what this box's host
+    # memory / PCIe fabric gives the e2e leg to work with
+    t0 = time.perf_counter()
+    for _ in range(3):
+        d_pars.copy_(h_pars, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    h2d_s = (time.perf_counter() - t0) / 3
+    barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
     check = float(np.nansum(np.where(np.isfinite(np_lnp), 1.0, 0.0)))
 
+    kname = "k1_coop_kernel" if eng.get_option("k1_last_kernel") == 1 else "k1_lnprob_kernel"
+    pipeline_rows = eng.get_option("pipeline_rows")
+
+    # ---- product-level end to end: fit_catalog ---------------------------------------------------------------
+    del d_lnp, h_lnp
+    fit_info = None
+    if args.fit_sources > 0 and not (args.c4 or args.ga_free or args.bands != 18):
+        fit_info = fit_leg(args, rank, world, local, torch, dist)
+
+    # ---- the other BASELINE shapes (N = 1): K1 at catalogue scale on each --------------------------------------
+    legs = {}
+    if world == 1 and not args.no_config_legs and not (args.c4 or args.ga_free or args.bands != 18):
+        del d_pars, d_sid, eng, dev_tables
+        torch.cuda.empty_cache()
+        S2 = min(args.sources, args.leg_sources)
+        legs["C1_C2_shape_49_bands"] = k1_leg(args, rank, local, dict(bands=49, sources=S2), args.steps, torch)
+        legs["free_ebv_galaxy_18_bands"] = k1_leg(args, rank, local, dict(ga_free=True, sources=S2), args.steps, torch)
+        legs["free_ebv_galaxy_49_bands"] = k1_leg(args, rank, local, dict(ga_free=True, bands=49, sources=S2),
+                                                  args.steps, torch)
+        legs["C4_radio_to_xray_49_bands"] = k1_leg(args, rank, local, dict(c4=True, bands=49, sources=S2),
+                                                   args.steps, torch)
+
     ens_ms = (ens_info["s_per_step"] * 1e3) if ens_info else 0.0
-    t_ms = torch.tensor([ms_total, e2e_s * 1e3, ens_ms], dtype=torch.float64, device=dev)
+    sus_ms = (sustained["ms"] / sustained["steps"]) if sustained else 0.0
+    t_ms = torch.tensor([ms_total, e2e_s * 1e3, ens_ms, sus_ms, strong_ms, h2d_s * 1e3], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(n)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total_max, e2e_ms_max, ens_ms_max = float(t_ms[0]), float(t_ms[1]), float(t_ms[2])
+    ms_total_max, e2e_ms_max, ens_ms_max, sus_ms_max, strong_ms_max, h2d_ms_max = [float(x) for x in t_ms]
     total_rows = float(cnt[0])
     value = total_rows * args.steps / (ms_total_max * 1e-3)
     e2e_value = total_rows * args.steps / (e2e_ms_max * 1e-3)
@@ -463,35 +797,36 @@ def run_ours(args):
     if rank == 0:
         bpe = k1_bytes_per_eval(n_comp, n_b, n_par, W)
         peak, peak_src = measured_peak()
-        kname = "k1_coop_kernel" if eng.get_option("k1_last_kernel") == 1 else "k1_lnprob_kernel"
         achieved = bpe * n / (k1_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
-        # CPU baseline: the oracle port on a bounded sample of the same workload
-        unbind_host_threads()
-        ns = min(args.cpu_sources, S)
-        sample_ids = np.linspace(0, S - 1, ns).astype(np.int64)
-        small, srcs, pl = build_host_sample(ms, dev_tables, raw, sample_ids, pars, W)
-        k2_cpu, k2_cpu_n = cpu_dictionary_throughput(bands=n_b)
-        cpu_all = cpu_port_throughput(small, srcs, pl, cores)
-        cpu_one = cpu_port_throughput(small, srcs[:max(1, ns // cores)], pl[:max(1, ns // cores)], 1)
+        cpu_block = None
+        k2_cpu = k2_cpu_n = None
+        if world == 1:
+            # CPU baseline: the oracle port on a bounded sample of the same workload (rank 0, N = 1 only)
+            unbind_host_threads()
+            small, srcs, pl, rinfo = reference_workload(args, rank)
+            ns = len(srcs)
+            k2_cpu, k2_cpu_n = cpu_dictionary_throughput(bands=n_b)
+            cpu_all = cpu_port_throughput(small, srcs, pl, cores)
+            cpu_one = cpu_port_throughput(small, srcs[:max(1, ns // cores)], pl[:max(1, ns // cores)], 1)
+            cpu_block = {"value": cpu_all, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "oracle/agn_oracle.ln_probab on %d of the %d sources x %d walkers (same sources "
+                                   "and positions), vectorised over a source's walkers, fork Pool over sources"
+                                   % (ns, S, W),
+                         "one_core": cpu_one}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3: synthetic %d sources x %d walkers per GPU, %s, %s, dictionary of %d "
-                                   "z-slices in HBM"
-                                   % (S, W, "18-band default set" if n_b == 18 else "%d-band example set" % n_b,
-                                      "free-E(B-V) galaxy variant (%d parameters, %s templates)" % (
-                                          n_par, "+".join(str(f.T) for f in ms.families)) if args.ga_free else
-                                      "classic 10-parameter model (11000+161+60+2 templates)", info["n_z"]),
-                       "positions": args.positions + " in prior box + 1% out-of-box rows",
-                       "source_order": "random z" if args.no_sort_z else "sorted by z",
-                       "k1_variant": "cooperative (k1_coop_kernel)" if eng.get_option("k1_last_kernel") == 1 else "per-thread (k1_lnprob_kernel)",
-                       "rows_per_step_per_gpu": n, "n_bands": n_b, "n_par": n_par,
-                       "l2_policy": "inputs larger than L2 (params %.0f MB + dictionary %.1f GB per GPU)" % (
-                           n * n_par * 8 / 1e6, info["k2_entries"] * 8 / 1e9),
-                       "parallelism": "sources sharded over %d GPU(s), no data-path collective" % world,
-                       "host_placement": numa},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world, info["n_z"], n_b, n_par, [f.T for f in ms.families]),
+            "run": {"k1_variant": "cooperative (k1_coop_kernel)" if kname == "k1_coop_kernel" else "per-thread (k1_lnprob_kernel)",
+                    "host_placement": numa},
+            "sustained": None if not sustained else {
+                "what": "the same pass repeated for >= %.1f s, CUDA events on the launch stream, max over ranks"
+                        % args.sustain_s,
+                "steps": sustained["steps"], "ms_per_step": sus_ms_max, "seconds": sus_ms_max * sustained["steps"] * 1e-3,
+                "value": total_rows / (sus_ms_max * 1e-3), "unit": UNIT,
+                "roofline_frac": bpe * n / (sus_ms_max * 1e-3) / 1e9 / peak, "clocks": sustained["clocks"]},
             # measured through the sampler loop when it ran (key "ensemble"), else the K1-bound figure
             "sources_fitted_per_s": (total_rows / (ens_ms_max * 1e-3) / EVALS_PER_FIT) if ens_info
                                     else value / EVALS_PER_FIT,
@@ -500,26 +835,34 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * n_par * 8 + n * 4),
                     "d2h_bytes_per_step": int(n * 8), "ms_per_step": e2e_ms_max / args.steps,
                     "api": "agnf_lnprob_batch (host buffers; %d-row chunks pipelined over 3 streams)"
-                           % eng.get_option("pipeline_rows")},
+                           % pipeline_rows,
+                    "pinned_h2d_alone": {"what": "plain pinned H2D copy of the params block, all ranks at once",
+                                         "ms": h2d_ms_max, "gb_per_s_per_gpu": n * n_par * 8 / (h2d_ms_max * 1e-3) / 1e9,
+                                         "gb_per_s_total": world * n * n_par * 8 / (h2d_ms_max * 1e-3) / 1e9}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(kname, n), "peak_source": peak_src, "kernel": kname,
                          "algorithmic_bytes_per_launch": bpe * n,
                          "bytes_per_eval": bpe, "kernel_ms": k1_ms},
-            "cpu_baseline": {"value": cpu_all, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "oracle/agn_oracle.ln_probab on %d of the %d sources x %d walkers, vectorised "
-                                       "over a source's walkers, fork Pool over sources" % (ns, S, W),
-                             "one_core": cpu_one},
+            "roofline_k2": k2_info,
+            "cpu_baseline": cpu_block,
             "small_batch": dict(small_calls, what="agnf_lnprob_batch (host buffers, pinned staging block), one call per batch: the "
                                             "shape emcee (vectorize=True, one source) and ultranest produce"),
             "ensemble": None if not ens_info else {
                 "what": "agnf_ens_run: lock-step stretch moves for every source of the shard, walkers resident in "
                         "HBM; one fused launch per half-step (propose -> ln_probab -> accept inside k1_coop_kernel), "
                         "percentile histograms and best-fit tracker fed every 10th step",
-                "steps": ens_info["steps"], "ms_per_step": ens_ms_max,
+                "steps": ens_info["steps"], "ms_per_step": ens_ms_max, "seconds": ens_ms_max * ens_info["steps"] * 1e-3,
                 "evals_per_s": total_rows / (ens_ms_max * 1e-3),
                 "sources_fitted_per_s": total_rows / (ens_ms_max * 1e-3) / EVALS_PER_FIT,
-                "mean_acceptance": ens_info["acceptance"], "launches": ens_info["launches"]},
+                "mean_acceptance": ens_info["acceptance"], "launches": ens_info["launches"],
+                "clocks": ens_info["clocks"]},
+            "strong": None if not strong_ms_max else {
+                "what": "the same pass over %d sources in total (%d per GPU): the catalogue of BASELINE configs[2] "
+                        "divided over the ranks" % ((S // world) * world, S // world),
+                "ms_per_step": strong_ms_max, "evals_per_s": (S // world) * world * W / (strong_ms_max * 1e-3)},
+            "e2e_fit": fit_info,
+            "configs": legs or None,
             "sed_realizations": None if not sed_info else dict(
                 sed_info, what="agnf_sed_intlum (K4): full-resolution SEDs of 5 components on all_nus_rest and the "
                                "example settings' 13 integrated luminosities / AGN fractions per chain row, "
@@ -529,7 +872,8 @@ def run_ours(args):
                                  "what": "K2 over every family and every distinct z of the shard, tables left in HBM; "
                                          "wall time incl. host preparation and uploads",
                                  "cpu_entries_per_s_one_core": k2_cpu,
-                                 "cpu_sample": "oracle filtering_models on %d galaxy templates x %d bands" % (k2_cpu_n, n_b)},
+                                 "cpu_sample": None if k2_cpu is None else
+                                 "oracle filtering_models on %d galaxy templates x %d bands" % (k2_cpu_n, n_b)},
             "clocks": sampler.summary(),
             "finite_rows_last_step": check,
         }
@@ -539,44 +883,37 @@ def run_ours(args):
 
 
 def run_reference(args):
-    """The reference's CPU implementation of the path.  The reference is Python and is not present
-    on the GPU box, so this arm times the oracle port (oracle/agn_oracle.py, pinned to the
-    reference by tests/golden) on all host cores, on bounded samples of the same workload."""
+    """The reference's CPU implementation of the path.  The reference is Python and is not present on the GPU box,
+    so this arm times its restatement (oracle/agn_oracle.py, pinned to the reference by tests/golden) on all host
+    cores, each step a bounded sample of the GPU arm's own sources and walker positions.  Nothing here touches the
+    product library: the sample's dictionary slices come from oracle.filtering_models."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    import torch
-    if not torch.cuda.is_available():
-        raise SystemExit("the reference arm builds its synthetic dictionary sample with K2; needs the GPU box")
-    a2 = argparse.Namespace(**vars(args))
-    a2.sources = min(args.sources, 4000)         # the sample's dictionary; evaluated subset below
-    eng, ms, dev_tables, raw, pars, sid, info = make_workload(a2, 0, 0)
+    small, srcs, pl, rinfo = reference_workload(args, 0)
     cores = os.cpu_count() or 1
-    ns = min(args.cpu_sources, a2.sources)
-    sample_ids = np.linspace(0, a2.sources - 1, ns).astype(np.int64)
-    small, srcs, pl = build_host_sample(ms, dev_tables, raw, sample_ids, pars, args.walkers)
+    ns = len(srcs)
     for _ in range(max(args.warmup, 1)):
         cpu_port_throughput(small, srcs[:cores], pl[:cores], cores)
     vals = [cpu_port_throughput(small, srcs, pl, cores) for _ in range(args.steps)]
     v = float(np.mean(vals))
     n_step = ns * args.walkers
+    mapped = product_library_mapped()
+    assert not mapped, "the reference arm must not load the product library"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 1), "ms_per_step": n_step / v * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C3: synthetic %d sources x %d walkers per GPU, 18-band default set, classic "
-                               "10-parameter model (11000+161+60+2 templates)" % (args.sources, args.walkers),
-                   "positions": args.positions + " in prior box + 1% out-of-box rows",
-                   "sample": "each step evaluates %d of the sources x %d walkers (bounded sample of the workload; "
-                             "the sample's dictionary z-slices were built with K2, outside the timed region)"
-                             % (ns, args.walkers),
-                   "n_bands": ms.n_b, "n_par": ms.n_par,
-                   "parallelism": "host cores of rank 0 only (%d); other ranks idle" % cores},
+        "warmup": max(args.warmup, 1), "ms_per_step": n_step / v * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world, rinfo["n_z"], rinfo["n_b"], rinfo["n_par"], rinfo["fam_T"]),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "oracle port (NumPy, vectorised over a source's %d walkers), fork Pool over %d "
-                                   "sources on %d cores" % (args.walkers, ns, cores)},
+                         "sample": "each step: oracle port (NumPy, vectorised over a source's %d walkers) on %d of the "
+                                   "workload's sources with the GPU arm's walker positions, fork Pool over sources on "
+                                   "%d cores; their %d dictionary entries from oracle.filtering_models (%.1f s, "
+                                   "outside the timed region)"
+                                   % (args.walkers, ns, cores, rinfo["dict_entries"], rinfo["dict_s"])},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "product_library_mapped": mapped,
     }
     print(json.dumps(line))
 
@@ -587,8 +924,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sources", type=int, default=100000, help="sources per GPU")
+    ap.add_argument("--sources", type=int, default=100000, help="sources per GPU (weak) / in total (strong)")
     ap.add_argument("--walkers", type=int, default=100)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --sources per GPU (the driver's scaling run); strong: one catalogue of --sources "
+                         "sources divided over the ranks along z")
     ap.add_argument("--positions", default="uniform", choices=["uniform", "ball"])
     ap.add_argument("--variant", type=int, default=1, help="K1 kernel: 1 cooperative (default), 0 per-thread")
     ap.add_argument("--no-sort-z", action="store_true",
@@ -601,10 +941,20 @@ def main():
     ap.add_argument("--ga-free", action="store_true",
                     help="galaxy family in the shape of the reference's default BC03_metal library: E(B-V)_gal free, "
                          "reddening and the energy-balance integral on the fly (not the BASELINE workload)")
+    ap.add_argument("--c4", action="store_true",
+                    help="the radio-to-X-ray model of BASELINE configs[3]: 5 components, 18 parameters")
     ap.add_argument("--sed-sources", type=int, default=2000,
                     help="sources whose 100 chain rows go through the SED / integrated-luminosity stage (0: skip)")
-    ap.add_argument("--ensemble-steps", type=int, default=10,
-                    help="also time this many lock-step stretch-move steps of the GPU-resident sampler (0: skip)")
+    ap.add_argument("--ensemble-steps", type=int, default=1000,
+                    help="lock-step stretch-move steps of the GPU-resident sampler to time (>= 2 s at C3; 0: skip)")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained K1 run in seconds (0: skip)")
+    ap.add_argument("--fit-sources", type=int, default=10000,
+                    help="sources per GPU of the fit_catalog end-to-end leg (0: skip)")
+    ap.add_argument("--fit-nburn", type=int, default=12000)
+    ap.add_argument("--fit-nmcmc", type=int, default=25000)
+    ap.add_argument("--leg-sources", type=int, default=20000, help="sources of each per-config K1 leg")
+    ap.add_argument("--no-config-legs", action="store_true")
+    ap.add_argument("--no-k2-leg", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -166,6 +166,11 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
  * sources (results do not depend on how the catalogue is split over GPUs). */
 AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value);
 AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value);
+/* measurement hook for the K2 roofline (BASELINE.md §3 asks for a MEASURED FP64 peak): peak TFLOP/s of a DFMA loop
+ * (kind 0, the FP64 pipe) or of an mma.sync.m8n8k4.f64 loop (kind 1, the FP64 tensor-core path k2_contract_mma
+ * uses) on this device, best of 3 launches timed with CUDA events. */
+AGNF_API int agnf_debug_fp64_peak(agnf_ctx* ctx, int32_t kind, double* tflops);
+
 /* y[i] = 10^x[i] through the kernels' own exp10 routine (host pointers; unit-test hook) */
 AGNF_API int agnf_debug_exp10(agnf_ctx* ctx, const double* x, int64_t n, double* y);
 

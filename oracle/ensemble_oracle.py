@@ -3,13 +3,20 @@ TEST INFRASTRUCTURE — CPU oracle of the ensemble step (K3).  NOT part of the p
 
 emcee is not installed here and the reference's chains are unpinned by the reference itself (unseeded
 RNG, PARAMETERSPACE_AGNfitter.py:260,287), so the sampler parity is pinned on the ALGORITHM emcee
-documents for `StretchMove` / `RedBlueMove` (emcee 3: moves/stretch.py, moves/red_blue.py), with
-`randomize_split=False`:
+documents for `StretchMove` / `RedBlueMove` (emcee 3: moves/stretch.py, moves/red_blue.py; the reference names no version — its
+`integrated_time(x, c=5, tol=50, quiet=False)` patch, MCMC_AGNfitter.py:107, is the emcee >= 3 signature — and builds
+the sampler with the default move, :114, i.e. `randomize_split=True`):
 
-    for each half S (the other half is C):
+    inds = arange(W) % 2; random.shuffle(inds)              a fresh equal split of the walkers at every step
+    for each set S (the other set is C):
         zz   = ((a - 1) * u1 + 1) ** 2 / a
         q    = C[j] - (C[j] - S) * zz[:, None]              j uniform over the other half
         lnpdiff = (ndim - 1) * log(zz) + lnp(q) - lnp(S);   accept where lnpdiff > log(u3)
+
+The split is restated as: order the walkers of a source by a 32-bit Philox key of (step, source, walker), ties by
+walker index; the first W/2 are set 0 (`split_perm`; any uniformly random equal partition is equivalent in
+distribution, because partners are drawn uniformly inside the complement).  `split=None` keeps the fixed
+first-half / second-half sets (`randomize_split=False`).
 
 The uniforms come from Philox4x32-10 (Salmon, Moraes, Dror & Shaw 2011; Random123's known-answer
 vectors are checked in tests/test_ensemble_cpu.py) with counter (step, half, source, walker) and the
@@ -52,33 +59,53 @@ def draws(step, half, S, H, seed, src_offset=0):
     return u1, j, np.log(u3)
 
 
-def proposals(pos, step, half, seed, a=2.0, src_offset=0):
-    """pos [S, W, n_par] -> (q [S, H, n_par], factor [S, H], ln u3 [S, H]) for one half-step."""
+SPLIT_TAG = 0xFFFFFFFF
+
+
+def split_perm(step, S, W, seed, src_offset=0):
+    """[S, W] walker indices: slots [0, W/2) hold set 0 of this step, slots [W/2, W) set 1."""
+    s = (np.arange(S, dtype=np.int64) + int(src_offset)).astype(np.uint32)[:, None]
+    q = np.arange((W + 3) // 4, dtype=np.uint32)[None, :]
+    seed = int(seed) & (2 ** 64 - 1)
+    x = philox4x32_10(np.uint32(int(step) & 0xFFFFFFFF), np.uint32(SPLIT_TAG), s, q, seed & 0xFFFFFFFF, seed >> 32)
+    keys = np.stack(x, axis=-1).reshape(S, -1)[:, :W]
+    return np.argsort(keys, axis=1, kind="stable")
+
+
+def proposals(pos, step, half, seed, a=2.0, src_offset=0, perm=None):
+    """pos [S, W, n_par] -> (q [S, H, n_par], factor [S, H], ln u3 [S, H], moved walkers [S, H]) for one half-step."""
     S, W, n_par = pos.shape
     H = W // 2
+    if perm is None:
+        perm = np.broadcast_to(np.arange(W), (S, W))
     u1, j, lnu = draws(step, half, S, H, seed, src_offset)
     t = (a - 1.0) * u1 + 1.0
     zz = (t * t) / a
-    mine = pos[:, H:] if half else pos[:, :H]
-    other = pos[:, :H] if half else pos[:, H:]
-    c = np.take_along_axis(other, j[:, :, None], axis=1)
+    mine_w = perm[:, H:] if half else perm[:, :H]
+    other_w = perm[:, :H] if half else perm[:, H:]
+    mine = np.take_along_axis(pos, mine_w[:, :, None], axis=1)
+    partner = np.take_along_axis(other_w, j, axis=1)
+    c = np.take_along_axis(pos, partner[:, :, None], axis=1)
     q = c - (c - mine) * zz[:, :, None]
-    return q, (n_par - 1) * np.log(zz), lnu
+    return q, (n_par - 1) * np.log(zz), lnu, mine_w
 
 
-def step(pos, lnp, n_acc, lnprob_fn, step_idx, seed, a=2.0, src_offset=0):
-    """One full stretch-move step in place.  lnprob_fn(q [S, H, n_par]) -> [S, H]."""
+def step(pos, lnp, n_acc, lnprob_fn, step_idx, seed, a=2.0, src_offset=0, split="random"):
+    """One full stretch-move step in place.  lnprob_fn(q [S, H, n_par]) -> [S, H].  split: "random" (emcee 3's
+    default) or "fixed"."""
     S, W, n_par = pos.shape
-    H = W // 2
+    perm = split_perm(step_idx, S, W, seed, src_offset) if split == "random" else None
+    rows = np.arange(S)[:, None]
     for half in (0, 1):
-        q, factor, lnu = proposals(pos, step_idx, half, seed, a, src_offset)
+        q, factor, lnu, mine_w = proposals(pos, step_idx, half, seed, a, src_offset, perm)
         new = lnprob_fn(q)
-        sl = slice(H, W) if half else slice(0, H)
         with np.errstate(invalid="ignore"):
-            accept = (factor + new - lnp[:, sl]) > lnu
-        pos[:, sl][accept] = q[accept]
-        lnp[:, sl][accept] = new[accept]
-        n_acc[:, sl] += accept
+            accept = (factor + new - lnp[rows, mine_w]) > lnu
+        si, ki = np.nonzero(accept)
+        wi = mine_w[si, ki]
+        pos[si, wi] = q[si, ki]
+        lnp[si, wi] = new[si, ki]
+        n_acc[si, wi] += 1
     return pos, lnp, n_acc
 
 

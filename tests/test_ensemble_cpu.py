@@ -23,8 +23,28 @@ def test_draw_ranges_and_independence():
     assert abs(u1.mean() - 0.5) < 0.03 and abs(j.mean() - 19.5) < 1.5
 
 
-def test_stretch_move_samples_a_gaussian():
-    """Detailed balance in practice: the oracle step samples N(mu, sigma^2) in 3-D."""
+def test_split_perm_is_an_equal_random_partition():
+    """emcee 3's RedBlueMove: every step divides the walkers afresh into two sets of W/2 (moves/red_blue.py)."""
+    S, W = 200, 30
+    p = E.split_perm(7, S, W, seed=5)
+    assert p.shape == (S, W) and np.array_equal(np.sort(p, axis=1), np.broadcast_to(np.arange(W), (S, W)))
+    p2 = E.split_perm(8, S, W, seed=5)
+    assert not np.array_equal(p, p2)
+    in0 = np.zeros((S, W))
+    np.put_along_axis(in0, p[:, : W // 2], 1.0, axis=1)
+    assert np.all(in0.sum(axis=1) == W // 2)
+    assert np.all(np.abs(in0.mean(axis=0) - 0.5) < 0.15)          # every walker lands in set 0 about half the time
+    # a shard starting at catalogue row 3 draws the split of rows 3.. of the full run
+    assert np.array_equal(E.split_perm(7, S - 3, W, seed=5, src_offset=3), p[3:])
+
+
+import pytest
+
+
+@pytest.mark.parametrize("split", ["random", "fixed"])
+def test_stretch_move_samples_a_gaussian(split):
+    """Detailed balance in practice: the oracle step samples N(mu, sigma^2) in 3-D — with emcee 3's per-step random
+    split (the default) and with the fixed halves alike."""
     rng = np.random.default_rng(0)
     S, W, n = 4, 40, 3
     mu, sig = np.array([1.0, -2.0, 0.5]), np.array([0.5, 2.0, 1.0])
@@ -34,7 +54,7 @@ def test_stretch_move_samples_a_gaussian():
     acc = np.zeros((S, W), dtype=np.int64)
     keep = []
     for it in range(1500):
-        E.step(pos, lnp, acc, lnprob, it, seed=42)
+        E.step(pos, lnp, acc, lnprob, it, seed=42, split=split)
         if it >= 300 and it % 5 == 0:
             keep.append(pos.copy())
     x = np.concatenate(keep, axis=1).reshape(-1, n)

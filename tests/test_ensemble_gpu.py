@@ -39,17 +39,19 @@ def _setup(case):
     return ms, eng, src, lnprob
 
 
+@pytest.mark.parametrize("split", ["random", "fixed"])
 @pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("case", ["classic18", "cat49_catalog_example"])
-def test_ensemble_matches_oracle_step_for_step(case, fused):
-    """fused = 1: one K1 launch per half-step draws, evaluates and accepts; 0: propose / K1 / accept kernels."""
+def test_ensemble_matches_oracle_step_for_step(case, fused, split):
+    """fused = 1: one K1 launch per half-step draws, evaluates and accepts; 0: propose / K1 / accept kernels.
+    split: emcee 3's per-step random division of the walkers (default) or the fixed halves."""
     ms, eng, src, lnprob = _setup(case)
     eng.set_option("ens_fused", fused)
     W, seed, n_steps = 24, 20260101, 40
     rng = np.random.default_rng(5)
     pos0 = src.pmin[:, None, :] + rng.uniform(size=(src.S, W, ms.n_par)) * (src.pmax - src.pmin)[:, None, :]
     pos0[:, : W // 3] = EnsembleSampler.initial_positions(src.pmin, src.pmax, W, rng)[:, : W // 3]
-    ens = EnsembleSampler(eng, W, seed=seed, n_bins=0)
+    ens = EnsembleSampler(eng, W, seed=seed, n_bins=0, split=split)
     ens.set_positions(pos0)
     gpos, glnp, gacc = ens.state()
     opos, olnp, oacc = pos0.copy(), lnprob(pos0), np.zeros((src.S, W), dtype=np.int64)
@@ -58,7 +60,7 @@ def test_ensemble_matches_oracle_step_for_step(case, fused):
     assert np.array_equal(np.isfinite(glnp), fin) and np.allclose(glnp[fin], olnp[fin], rtol=1e-10, atol=0)
     for it in range(n_steps):
         ens.run(1)
-        E.step(opos, olnp, oacc, lnprob, it, seed)
+        E.step(opos, olnp, oacc, lnprob, it, seed, split=split)
         gpos, glnp, gacc = ens.state()
         assert np.array_equal(gacc, oacc), "accept decisions differ at step %d" % it
         assert np.array_equal(gpos, opos), "positions differ at step %d" % it       # proposals are bit-identical
@@ -117,10 +119,10 @@ def test_reference_schedule_on_example_catalogue():
         best_l[up] = v[up]
         best_p[up] = pos[np.arange(src.S), k][up]
 
+    # emcee's sampler is not reset between the burn-in sets (MCMC_AGNfitter.py:125-128): get_best_position takes the
+    # argmax over everything sampled so far, and the starting positions are not part of the chain
     for _ in range(mc['Nburnsets']):
         lnp = lnprob(pos)
-        best_l[:] = -np.inf
-        track(pos, lnp)
         acc = np.zeros((src.S, W), dtype=np.int64)
         for _ in range(mc['Nburn']):
             E.step(pos, lnp, acc, lnprob, step, seed)
@@ -190,10 +192,15 @@ def test_chain_recording_and_reference_chain_files(tmp_path):
         assert mcmc["chain"].shape == (W, 30, ms.n_par) and mcmc["lnprob"].shape == (W, 30)
         assert mcmc["accept"].shape == (W,) and mcmc["acor"].shape == (ms.n_par,)
         assert np.all((mcmc["accept"] >= 0) & (mcmc["accept"] <= 1))
-        # get_best_position's arithmetic on the burn-in file
+        # get_best_position's arithmetic on the burn-in file (PARAMETERSPACE_AGNfitter.py:281-283): the production run
+        # started from a ball around exactly this sample — the running best over BOTH burn-in sets
         i = burn["lnprob"].ravel().argmax()
         ml = burn["chain"].reshape(-1, ms.n_par)[i]
         assert np.all(ml >= src.pmin[s]) and np.all(ml <= src.pmax[s])
+        assert np.array_equal(ml, out["restart_centres"][-1][s])
+        # ... and 'accept' covers all burn-in steps, like emcee's acceptance_fraction without a reset
+        moved = (np.abs(np.diff(burn["chain"], axis=1)).sum(axis=2) > 0).sum(axis=1)
+        assert np.all(burn["accept"] * 20 >= moved - 1e-9) and np.all(burn["accept"] * 20 <= 20)
         # CHAIN.props' arithmetic on the production file
         nsamples = mcmc["chain"].shape[1]
         flat = mcmc["chain"][:, int(nsamples / 2):nsamples:2, :].reshape(-1, ms.n_par)
@@ -241,3 +248,62 @@ def test_device_balls_match_the_oracle_and_the_sharding():
     ens = EnsembleSampler(eng, W, seed=seed, n_bins=128)
     out = ens.run_reference_schedule(mc, src.pmin, src.pmax, None)
     assert np.isfinite(out["best_lnp"]).all() and np.all(out["acceptance"] >= 0)
+
+
+def test_sampler_state_is_invalidated_by_a_new_source_upload():
+    """walkers belong to one set of sources; uploading others tears the ensemble down instead of
+    leaving it pointing at freed operands."""
+    from agnfitter_b200._lib import AgnfError
+    ms, eng, src, _ = _setup("classic18")
+    ens = EnsembleSampler(eng, 16, seed=1, n_bins=64)
+    ens.set_positions(EnsembleSampler.initial_positions(src.pmin, src.pmax, 16, np.random.default_rng(0)))
+    ens.run(3, hist_every=1)
+    eng.set_sources(src)
+    with pytest.raises(AgnfError, match="agnf_ens_create"):
+        ens.run(1)
+    ens2 = EnsembleSampler(eng, 16, seed=1, n_bins=64, split="fixed")       # the other split is allowed again
+    ens2.set_positions(EnsembleSampler.initial_positions(src.pmin, src.pmax, 16, np.random.default_rng(0)))
+    ens2.run(3, hist_every=1)
+    assert np.isfinite(ens2.percentiles()).all()
+
+
+def test_chains_agree_in_distribution_with_independent_oracle_chains():
+    """Distribution-level check on both example-catalogue sources: medians of R independent GPU ensembles (random
+    split, one Philox stream per replica) against independent CPU-oracle ensembles with other seeds.  Same algorithm,
+    same starting ball, same number of steps -> the two sets of medians are draws from ONE distribution whether or
+    not the chains have converged; their means must agree within the Monte Carlo error estimated from the replicas."""
+    ms, g = load_k1("cat49_catalog_example")
+    S0 = len(g["src_z"])
+    R_gpu, R_cpu, W, n_burn, n_keep = 48, 6, 24, 150, 150
+    rep = np.repeat(np.arange(S0), R_gpu)
+    eng = Engine(ms, device=0)
+    src = sources.make_sources(ms, g["src_z"][rep], g["src_dlum"][rep], g["src_nus"][rep], g["src_fluxes"][rep],
+                               g["src_fluxerrs"][rep])
+    eng.set_sources(src)
+    ens = EnsembleSampler(eng, W, seed=2024, n_bins=0)
+    mid = 0.5 * (src.pmin + src.pmax)
+    ens.set_ball(mid, 1e-5, normal=False, stream_id=1)
+    ens.run(n_burn)
+    ens.record(n_keep)
+    ens.run(n_keep)
+    ch, _ = ens.chain()                                                # [S0 * R_gpu, W, n_keep, n_par]
+    med_gpu = np.median(ch.reshape(S0, R_gpu, -1, ms.n_par), axis=2)   # [S0, R_gpu, n_par]
+    osrc = [oracle_src(ms, g, s) for s in range(S0)]
+    med_cpu = np.empty((S0, R_cpu, ms.n_par))
+    for s in range(S0):
+        lnprob = lambda q: np.stack([O.ln_probab(ms, osrc[s], q[r]) for r in range(q.shape[0])])
+        pos = E.ball(np.repeat(mid[s * R_gpu][None, :], R_cpu, axis=0), W, 1e-5, False, 1, seed=777 + s)
+        lnp = lnprob(pos)
+        acc = np.zeros((R_cpu, W), dtype=np.int64)
+        keep = []
+        for it in range(n_burn + n_keep):
+            E.step(pos, lnp, acc, lnprob, it, seed=777 + s)
+            if it >= n_burn:
+                keep.append(pos.copy())
+        med_cpu[s] = np.median(np.stack(keep, axis=1).reshape(R_cpu, -1, ms.n_par), axis=1)
+    span = (src.pmax[0] - src.pmin[0])
+    for s in range(S0):
+        sd = med_gpu[s].std(axis=0, ddof=1)
+        err = np.sqrt(sd ** 2 / R_gpu + sd ** 2 / R_cpu)
+        diff = np.abs(med_gpu[s].mean(axis=0) - med_cpu[s].mean(axis=0))
+        assert np.all(diff <= 4.5 * err + 1e-3 * span), (s, diff / np.maximum(err, 1e-300))

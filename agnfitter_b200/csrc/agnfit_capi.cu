@@ -115,6 +115,17 @@ int fail(agnf_ctx* ctx, const char* fmt, ...) {
   return 1;
 }
 
+// for the catch handlers of the entry points: must not throw itself
+int fail_noexcept(agnf_ctx* ctx, const char* what) noexcept {
+  try {
+    std::string& dst = ctx ? ctx->err : g_create_err;
+    dst.assign("internal error: ");
+    dst.append(what ? what : "?");
+  } catch (...) {
+  }
+  return 1;
+}
+
 #define CUDA_TRY(ctx, expr)                                                                  \
   do {                                                                                       \
     cudaError_t e__ = (expr);                                                                \
@@ -339,6 +350,15 @@ int check_ready(agnf_ctx* ctx) {
 
 }  // namespace
 
+// No exception leaves the library (include/agnfit_b200.h: "never throws"): host containers inside the entry points can
+// throw std::bad_alloc / std::length_error; every int-returning entry point turns that into an error code.
+#define AGNF_GUARD_BEGIN try {
+#define AGNF_GUARD_END(ctx)                                                                   \
+  }                                                                                           \
+  catch (const std::bad_alloc&) { return fail_noexcept(ctx, "out of host memory"); }          \
+  catch (const std::exception& e) { return fail_noexcept(ctx, e.what()); }                    \
+  catch (...) { return fail_noexcept(ctx, "unknown internal error"); }
+
 extern "C" {
 
 AGNF_API int agnf_version(void) { return AGNF_VERSION; }
@@ -346,6 +366,7 @@ AGNF_API int agnf_version(void) { return AGNF_VERSION; }
 AGNF_API const char* agnf_last_error(const agnf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 AGNF_API int agnf_ctx_create(int device, agnf_ctx** out) {
+  AGNF_GUARD_BEGIN
   if (!out) return fail(nullptr, "agnf_ctx_create: out is NULL");
   *out = nullptr;
   int n = 0;
@@ -377,6 +398,7 @@ AGNF_API int agnf_ctx_create(int device, agnf_ctx** out) {
   cudaEventCreate(&ctx->ev3);
   *out = ctx;
   return 0;
+  AGNF_GUARD_END(nullptr)
 }
 
 AGNF_API void agnf_ctx_destroy(agnf_ctx* ctx) {
@@ -399,15 +421,18 @@ AGNF_API void agnf_ctx_destroy(agnf_ctx* ctx) {
 }
 
 AGNF_API int agnf_synchronize(agnf_ctx* ctx) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int64_t agnf_launch_count(const agnf_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 AGNF_API int agnf_last_kernel_ms(agnf_ctx* ctx, int which, float* ms) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !ms) return 1;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (which == 1) {
@@ -423,9 +448,11 @@ AGNF_API int agnf_last_kernel_ms(agnf_ctx* ctx, int which, float* ms) {
     return 0;
   }
   return fail(ctx, "agnf_last_kernel_ms: which must be 1 or 2");
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !name) return 1;
   if (strcmp(name, "k1_variant") == 0) {
     if (value < 0 || value > 2) return fail(ctx, "k1_variant must be 0 (per-thread), 1 (automatic) or 2 (cooperative)");
@@ -481,9 +508,11 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     return 0;
   }
   return fail(ctx, "unknown option '%s'", name);
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !name || !value) return 1;
   if (strcmp(name, "k1_variant") == 0) *value = ctx->k1_variant;
   else if (strcmp(name, "k1_last_kernel") == 0) *value = ctx->last_k1_kernel;
@@ -499,9 +528,11 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "ens_source_offset") == 0) *value = ctx->ens_src_offset;
   else return fail(ctx, "unknown option '%s'", name);
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_debug_exp10(agnf_ctx* ctx, const double* x, int64_t n, double* y) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !x || !y || n < 0) return 1;
   if (n == 0) return 0;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -516,9 +547,11 @@ AGNF_API int agnf_debug_exp10(agnf_ctx* ctx, const double* x, int64_t n, double*
   if (e != cudaSuccess) return fail(ctx, "agnf_debug_exp10: %s", cudaGetErrorString(e));
   ctx->launches += 1;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_debug_fp64_peak(agnf_ctx* ctx, int32_t kind, double* tflops) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !tflops) return 1;
   if (kind != 0 && kind != 1) return fail(ctx, "agnf_debug_fp64_peak: kind must be 0 (DFMA) or 1 (DMMA)");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -543,11 +576,13 @@ AGNF_API int agnf_debug_fp64_peak(agnf_ctx* ctx, int32_t kind, double* tflops) {
   ctx->launches += 4;
   *tflops = best;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 // ------------------------------------------------------------------------------------------- K1
 
 AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !cfg) return 1;
   if (cfg->n_b < 1 || cfg->n_b > AGNF_MAX_BANDS) return fail(ctx, "n_b=%d outside [1,%d]", cfg->n_b, AGNF_MAX_BANDS);
   if (cfg->n_par < 3 || cfg->n_par > AGNF_MAX_PARS) return fail(ctx, "n_par=%d outside [3,%d]", cfg->n_par, AGNF_MAX_PARS);
@@ -577,9 +612,11 @@ AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg) {
   ctx->have_cfg = true;
   ctx->eb0_dirty = true;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_family_upload(agnf_ctx* ctx, const agnf_family_desc* fd) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !fd) return 1;
   if (!ctx->have_cfg) return fail(ctx, "call agnf_modelset_config first");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -642,9 +679,11 @@ AGNF_API int agnf_family_upload(agnf_ctx* ctx, const agnf_family_desc* fd) {
   ctx->grids_dirty = true;
   if (f == 0) ctx->eb0_dirty = true;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_extra_priors_set(agnf_ctx* ctx, const agnf_extra_priors* xp) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !xp) return 1;
   if (!ctx->have_cfg) return fail(ctx, "call agnf_modelset_config first");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -670,10 +709,12 @@ AGNF_API int agnf_extra_priors_set(agnf_ctx* ctx, const agnf_extra_priors* xp) {
   P.xp_j6 = xp->j_6um;
   P.xp_j2500 = xp->j_2500;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double* cbbb, const uint64_t* xray_bits,
                         const int32_t* j1500, const double* omega) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_cfg) return fail(ctx, "call agnf_modelset_config first");
   if (!cgal || !cbbb || !xray_bits || !j1500 || !omega) return fail(ctx, "agnf_zslices_upload: NULL argument");
@@ -703,12 +744,14 @@ AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double
   ctx->have_z = true;
   ctx->eb0_dirty = true;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_sources_upload(agnf_ctx* ctx, int64_t S, const int32_t* zi, const double* y, const double* inv_sigma,
                         const uint64_t* valid_bits, const double* pmin, const double* pmax,
                         const double* consts, int32_t n_const, const int32_t* agn_branch,
                         const int32_t* irsyn_mode, const int32_t* irsyn_j) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_cfg) return fail(ctx, "call agnf_modelset_config first");
   if (S < 1) return fail(ctx, "S must be >= 1");
@@ -743,11 +786,13 @@ AGNF_API int agnf_sources_upload(agnf_ctx* ctx, int64_t S, const int32_t* zi, co
   ctx->k1.S = S;
   ctx->have_src = true;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, const int32_t* d_source_id, int64_t n,
                              double* d_lnp, int32_t* d_rows, double* d_ymodel, double* d_lnprior,
                              double* d_lnlike, void* stream) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (n < 0) return fail(ctx, "n < 0");
   if (n == 0) return 0;
@@ -772,10 +817,12 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
   if (timed) ctx->k1_timed = true;
   ctx->launches += 1;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_lnprob_batch(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* lnp,
                       int32_t* rows, double* ymodel, double* lnprior, double* lnlike) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (n < 0) return fail(ctx, "n < 0");
   if (n == 0) return 0;
@@ -869,12 +916,14 @@ AGNF_API int agnf_lnprob_batch(agnf_ctx* ctx, const double* params, const int32_
   if (rows) CUDA_TRY(ctx, cudaMemcpyAsync(rows, o + off_rows, N * nf * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 // ------------------------------------------------------------------------------------------- K2
 
 AGNF_API int agnf_filters_upload(agnf_ctx* ctx, int32_t n_b, const double* band_lambda_c, const int64_t* offset,
                         const double* lambda_angstrom, const double* factor) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (n_b < 1 || n_b > AGNF_MAX_BANDS) return fail(ctx, "n_b=%d outside [1,%d]", n_b, AGNF_MAX_BANDS);
   if (!band_lambda_c || !offset || !lambda_angstrom || !factor) return fail(ctx, "agnf_filters_upload: NULL argument");
@@ -916,11 +965,13 @@ AGNF_API int agnf_filters_upload(agnf_ctx* ctx, int32_t n_b, const double* band_
   F.n_samples = N;
   ctx->have_filt = true;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int32_t* perm, const double* Fnu, int64_t T,
                     int32_t n_lam, const double* z, int32_t n_z, const int64_t* row_map, int64_t T_total,
                     double* out, int32_t out_on_device, int32_t out_pitch) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_filt) return fail(ctx, "call agnf_filters_upload first");
   if (!lam_sorted || !perm || !Fnu || !z || !out) return fail(ctx, "agnf_dict_build: NULL argument");
@@ -1149,11 +1200,13 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   return 0;
 #undef K2_TRY
 #undef K2_ALLOC
+  AGNF_GUARD_END(ctx)
 }
 
 // ------------------------------------------------------------------------------------------- K3
 
 AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, double a, int32_t n_bins) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (check_ready(ctx)) return 1;
@@ -1209,6 +1262,7 @@ AGNF_API int agnf_ens_create(agnf_ctx* ctx, int32_t walkers, uint64_t seed, doub
   ctx->ens_hist_samples = 0;
   ctx->have_ens = true;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 namespace {
@@ -1232,15 +1286,18 @@ int ens_positions_changed(agnf_ctx* ctx) {
 }  // namespace
 
 AGNF_API int agnf_ens_set_positions(agnf_ctx* ctx, const double* pos) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !pos) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   K3State& st = ctx->ens;
   CUDA_TRY(ctx, cudaMemcpyAsync(st.pos, pos, (size_t)st.S * st.W * st.n_par * 8, cudaMemcpyHostToDevice, ctx->stream));
   return ens_positions_changed(ctx);
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_ens_set_ball(agnf_ctx* ctx, const double* centre, double scale, int32_t normal, uint32_t stream_id) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !centre) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1255,9 +1312,11 @@ AGNF_API int agnf_ens_set_ball(agnf_ctx* ctx, const double* centre, double scale
   if (e != cudaSuccess) return fail(ctx, "agnf_ens_set_ball failed: %s", cudaGetErrorString(e));
   ctx->launches += 1;
   return ens_positions_changed(ctx);
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, int32_t track_best) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   if (n_steps < 0) return fail(ctx, "n_steps < 0");
@@ -1330,9 +1389,11 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_ens_record(agnf_ctx* ctx, int64_t max_steps, int32_t every) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   if (max_steps < 0 || every < 1) return fail(ctx, "agnf_ens_record: max_steps >= 0 and every >= 1");
@@ -1356,9 +1417,11 @@ AGNF_API int agnf_ens_record(agnf_ctx* ctx, int64_t max_steps, int32_t every) {
   ctx->ens_chain_lnp = static_cast<double*>(b);
   ctx->ens_chain_cap = max_steps;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_ens_chain(agnf_ctx* ctx, double* chain, double* lnp, int64_t* n_recorded) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1370,9 +1433,11 @@ AGNF_API int agnf_ens_chain(agnf_ctx* ctx, double* chain, double* lnp, int64_t* 
   if (lnp && n) CUDA_TRY(ctx, cudaMemcpyAsync(lnp, ctx->ens_chain_lnp, n * nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_ens_get(agnf_ctx* ctx, double* pos, double* lnp, int32_t* n_acc) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1383,9 +1448,11 @@ AGNF_API int agnf_ens_get(agnf_ctx* ctx, double* pos, double* lnp, int32_t* n_ac
   if (n_acc) CUDA_TRY(ctx, cudaMemcpyAsync(n_acc, st.n_acc, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_ens_best(agnf_ctx* ctx, double* best_pos, double* best_lnp) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1397,9 +1464,11 @@ AGNF_API int agnf_ens_best(agnf_ctx* ctx, double* best_pos, double* best_lnp) {
     CUDA_TRY(ctx, cudaMemcpyAsync(best_lnp, ctx->ens_best_lnp, (size_t)st.S * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_ens_reset_best(agnf_ctx* ctx) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1408,9 +1477,11 @@ AGNF_API int agnf_ens_reset_best(agnf_ctx* ctx) {
                                 ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_ens_reset_stats(agnf_ctx* ctx) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1421,9 +1492,11 @@ AGNF_API int agnf_ens_reset_stats(agnf_ctx* ctx) {
   ctx->ens_hist_samples = 0;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, double* out) {
+  AGNF_GUARD_BEGIN
   if (!ctx || !q || !out) return 1;
   if (!ctx->have_ens || !ctx->ens_hist.hist) return fail(ctx, "the ensemble has no histograms");
   if (n_q < 1 || n_q > 64) return fail(ctx, "n_q outside [1, 64]");
@@ -1447,6 +1520,7 @@ AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, d
   if (e != cudaSuccess) return fail(ctx, "agnf_ens_percentiles: %s", cudaGetErrorString(e));
   ctx->launches += 1;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 }  // extern "C"
@@ -1457,6 +1531,7 @@ AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, d
 AGNF_API int agnf_sed_config(agnf_ctx* ctx, int32_t G, const double* grid, const double* xg, int32_t to_lo, int32_t to_hi,
                     int32_t rad_hi, int32_t dered_mode, const int32_t* dered_row, const int32_t* bands_jt,
                     const double* bands_wt) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_cfg) return fail(ctx, "agnf_modelset_config has not been called");
   if (G < 2 || !grid || !xg) return fail(ctx, "agnf_sed_config: empty frequency grid");
@@ -1494,9 +1569,11 @@ AGNF_API int agnf_sed_config(agnf_ctx* ctx, int32_t G, const double* grid, const
   ctx->k4_cfg = true;
   ctx->k4_dirty = true;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_sed_family_upload(agnf_ctx* ctx, const agnf_sed_family* d) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->k4_cfg) return fail(ctx, "call agnf_sed_config first");
   if (!d || d->fam < 0 || d->fam >= ctx->k1.cfg.n_fam) return fail(ctx, "agnf_sed_family_upload: bad family id");
@@ -1573,9 +1650,11 @@ AGNF_API int agnf_sed_family_upload(agnf_ctx* ctx, const agnf_sed_family* d) {
   ctx->k4_fam[d->fam] = true;
   ctx->k4_dirty = true;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_sed_sources(agnf_ctx* ctx, int64_t S, const double* z, const double* dlum) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (S < 1 || !z || !dlum) return fail(ctx, "agnf_sed_sources: empty");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1586,11 +1665,13 @@ AGNF_API int agnf_sed_sources(agnf_ctx* ctx, int64_t S, const double* z, const d
   ctx->k4_src = true;
   ctx->k4_dirty = true;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_sed_bands(agnf_ctx* ctx, int32_t n_ranges, const int32_t* i0, const int32_t* i1, const int32_t* mask,
                    int32_t n_specs, const int32_t* kind, const int32_t* range, const int32_t* num,
                    const int32_t* den) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->k4_cfg) return fail(ctx, "call agnf_sed_config first");
   if (n_ranges < 1 || n_ranges > K4_MAX_RANGES) return fail(ctx, "1..%d integration bands", K4_MAX_RANGES);
@@ -1621,6 +1702,7 @@ AGNF_API int agnf_sed_bands(agnf_ctx* ctx, int32_t n_ranges, const int32_t* i0, 
   ctx->k4_bands = true;
   ctx->k4_dirty = true;
   return 0;
+  AGNF_GUARD_END(ctx)
 }
 
 namespace {
@@ -1715,15 +1797,20 @@ int k4_run(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_
 
 AGNF_API int agnf_sed_intlum(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* out,
                     int32_t on_device) {
+  AGNF_GUARD_BEGIN
   return k4_run(ctx, params, source_id, n, out, on_device, false);
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_sed_spectra(agnf_ctx* ctx, const double* params, const int32_t* source_id, int64_t n, double* out,
                      int32_t on_device) {
+  AGNF_GUARD_BEGIN
   return k4_run(ctx, params, source_id, n, out, on_device, true);
+  AGNF_GUARD_END(ctx)
 }
 
 AGNF_API int agnf_sed_intlum_ens(agnf_ctx* ctx, double* out) {
+  AGNF_GUARD_BEGIN
   if (!ctx) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   if (!out) return fail(ctx, "NULL argument");
@@ -1748,4 +1835,5 @@ AGNF_API int agnf_sed_intlum_ens(agnf_ctx* ctx, double* out) {
   dev_free(ctx, d_sid);
   dev_free(ctx, d_out);
   return rc;
+  AGNF_GUARD_END(ctx)
 }

@@ -47,3 +47,17 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_no_exception_can_cross_the_abi():
+    """Every int-returning extern "C" entry point runs inside the try/catch guard that turns a C++ exception
+    (std::bad_alloc from a host container, ...) into the error code + agnf_last_error convention."""
+    src = open(os.path.join(ROOT, "agnfitter_b200", "csrc", "agnfit_capi.cu")).read()
+    bodies = re.findall(r"^AGNF_API int (agnf_\w+)\([^{]*\{\n(.*?)^\}", src, flags=re.M | re.S)
+    assert len(bodies) >= 30
+    for name, body in bodies:
+        assert body.lstrip().startswith("AGNF_GUARD_BEGIN") and "AGNF_GUARD_END(" in body.rstrip().splitlines()[-1], name
+    int_decls = [n for n in _declared_symbols() if re.search(r"AGNF_API\s+int\s+%s\s*\(" % n,
+                                                             open(os.path.join(ROOT, "include", "agnfit_b200.h")).read())]
+    guarded = {n for n, _ in bodies} | {"agnf_version"}
+    assert set(int_decls) <= guarded, sorted(set(int_decls) - guarded)

@@ -198,9 +198,13 @@ def test_chain_recording_and_reference_chain_files(tmp_path):
         ml = burn["chain"].reshape(-1, ms.n_par)[i]
         assert np.all(ml >= src.pmin[s]) and np.all(ml <= src.pmax[s])
         assert np.array_equal(ml, out["restart_centres"][-1][s])
-        # ... and 'accept' covers all burn-in steps, like emcee's acceptance_fraction without a reset
+        # ... and 'accept' covers all burn-in steps, like emcee's acceptance_fraction without a reset (the jump to the
+        # restart ball between the two sets shows up in the chain as one more change that is not an accepted move)
         moved = (np.abs(np.diff(burn["chain"], axis=1)).sum(axis=2) > 0).sum(axis=1)
-        assert np.all(burn["accept"] * 20 >= moved - 1e-9) and np.all(burn["accept"] * 20 <= 20)
+        assert np.all(burn["accept"] * 20 >= moved - 1 - 1e-9) and np.all(burn["accept"] * 20 <= 20)
+        within = np.r_[0:9, 10:19]
+        moved_in = (np.abs(np.diff(burn["chain"], axis=1)).sum(axis=2) > 0)[:, within].sum(axis=1)
+        assert np.all(burn["accept"] * 20 >= moved_in - 1e-9)
         # CHAIN.props' arithmetic on the production file
         nsamples = mcmc["chain"].shape[1]
         flat = mcmc["chain"][:, int(nsamples / 2):nsamples:2, :].reshape(-1, ms.n_par)

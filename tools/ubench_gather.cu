@@ -148,6 +148,51 @@ __global__ void __launch_bounds__(256, 3) gatherB(Tabs T, uint32_t n, uint32_t r
   if (row0 + lane < n) out[row0 + lane] = acc;
 }
 
+// ---- C: what a thread-per-row K1 would do: GA/SB/TO rows by per-thread bulk copies into padded slots
+//         (slot pitch 3*144+16 bytes: quarter-warps read 8 distinct 16-byte bank groups), BB row by LDG.128 (2 rows
+//         per z: warp-uniform addresses), thread-per-row readback, NT threads per CTA, one tile per warp per round
+template <int NT, int NTMA>
+__global__ void __launch_bounds__(NT) gatherC(Tabs T, uint32_t n, uint32_t rows_per_z, double* out, int tiles_per_warp) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NW = NT / 32;
+  constexpr uint32_t SLOT = NTMA * ROWB + 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t bar0 = smem_u32(smem);
+  const uint32_t buf0 = smem_u32(smem) + 256 + warp * 32 * SLOT;
+  if (threadIdx.x < NW) mbar_init(bar0 + 8 * threadIdx.x, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncthreads();
+  const uint32_t gw = blockIdx.x * NW + warp;
+  const uint32_t bar = bar0 + 8 * warp;
+  for (int t = 0; t < tiles_per_warp; ++t) {
+    const uint32_t i = (gw * tiles_per_warp + t) * 32 + lane;
+    if (lane == 0) mbar_expect_tx(bar, 32 * NTMA * ROWB);
+    __syncwarp();
+    const double *a, *b, *c, *d;
+    pick_rows(T, i < n ? i : 0, rows_per_z, a, b, c, d);
+    const uint32_t dst = buf0 + lane * SLOT;
+    bulk_g2s(dst, a, ROWB, bar);
+    if (NTMA > 1) bulk_g2s(dst + ROWB, b, ROWB, bar);
+    if (NTMA > 2) bulk_g2s(dst + 2 * ROWB, c, ROWB, bar);
+    const double2* d2 = reinterpret_cast<const double2*>(d);
+    const double2* c2 = reinterpret_cast<const double2*>(c);
+    const double2* b2 = reinterpret_cast<const double2*>(b);
+    mbar_wait(bar, t & 1);
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < CPR; ++k) {
+      double m0 = 0.0, m1 = 0.0;
+      { const double2 v = lds_v2(dst + k * 16); m0 = fma(v.x, 1.0, m0); m1 = fma(v.y, 1.0, m1); }
+      { const double2 v = NTMA > 1 ? lds_v2(dst + ROWB + k * 16) : __ldg(b2 + k); m0 = fma(v.x, 2.0, m0); m1 = fma(v.y, 2.0, m1); }
+      { const double2 v = NTMA > 2 ? lds_v2(dst + 2 * ROWB + k * 16) : __ldg(c2 + k); m0 = fma(v.x, 3.0, m0); m1 = fma(v.y, 3.0, m1); }
+      { const double2 v = __ldg(d2 + k); m0 = fma(v.x, 4.0, m0); m1 = fma(v.y, 4.0, m1); }
+      acc += m0 * m0 + m1 * m1;
+    }
+    if (i < n) out[i] = acc;
+    __syncwarp();
+  }
+}
+
 int main(int argc, char** argv) {
   const uint32_t n = 10000000u, n_z = argc > 1 ? atoi(argv[1]) : 600;
   Tabs T{};
@@ -206,5 +251,23 @@ int main(int argc, char** argv) {
   }
   timeit("B coop LDG.128 4fam", [&]() { gatherB<4><<<(n + 255) / 256, 256>>>(T, n, rows_per_z, out); });
   timeit("B coop LDG.128 1fam(GA)", [&]() { gatherB<1><<<(n + 255) / 256, 256>>>(T, n, rows_per_z, out); });
+  auto runC = [&](auto kern, int NT, int NTMA, int tiles, const char* name) {
+    const int NW = NT / 32;
+    const size_t smem = 256 + (size_t)NW * 32 * (NTMA * ROWB + 16);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t warps = (n + 32 * tiles - 1) / (32 * tiles);
+    const uint32_t blocks = (warps + NW - 1) / NW;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    printf("[%d warps/SM] ", occ * NW);
+    timeit(name, [&]() { kern<<<blocks, NT, smem>>>(T, n, rows_per_z, out, tiles); });
+  };
+  runC(gatherC<128, 3>, 128, 3, 1, "C tma GA,SB,TO + ldg BB NT128 t1");
+  runC(gatherC<128, 3>, 128, 3, 4, "C tma GA,SB,TO + ldg BB NT128 t4");
+  runC(gatherC<64, 3>, 64, 3, 4, "C tma GA,SB,TO + ldg BB NT64 t4");
+  runC(gatherC<256, 3>, 256, 3, 1, "C tma GA,SB,TO + ldg BB NT256 t1");
+  runC(gatherC<128, 1>, 128, 1, 4, "C tma GA + ldg SB,TO,BB NT128 t4");
+  runC(gatherC<256, 1>, 256, 1, 4, "C tma GA + ldg SB,TO,BB NT256 t4");
+  runC(gatherC<128, 2>, 128, 2, 4, "C tma GA,SB + ldg TO,BB NT128 t4");
   return 0;
 }

@@ -37,9 +37,11 @@ struct agnf_ctx {
   std::string err;
   std::vector<void*> owned;                    // device allocations freed in destroy
   int64_t launches = 0;
-  int k1_variant = 1;                          // 1: cooperative kernel when supported and profitable; 2: whenever
-                                               // supported; 0: per-thread kernel
-  int last_k1_kernel = -1;                     // which kernel the last K1 launch used
+  K1TensorMaps maps{};                         // gather4 kernel: one tensor map per family table
+  int k1_variant = 1;                          // 1: automatic (the cooperative kernel when profitable, else
+                                               // per-thread); 0: per-thread kernel; 2: cooperative whenever
+                                               // supported; 3: gather4 (TMA) kernel whenever supported
+  int last_k1_kernel = -1;                     // which kernel the last K1 launch used (0 / 1 cooperative / 2 gather4)
 
   bool have_cfg = false;
   K1Params k1{};
@@ -47,6 +49,8 @@ struct agnf_ctx {
   std::vector<double> h_grid;                  // staged grid values (host mirror, rebuilt per upload)
   std::vector<int32_t> h_perm;
   void* d_stage = nullptr;
+  bool srcrec_dirty = true;                    // per-source records of the gather4 kernel
+  void* d_stage2 = nullptr;                    // decision tables of the gather4 kernel
   std::vector<int32_t> fam_grid_len = std::vector<int32_t>(AGNF_MAX_FAMILIES, 0);
   std::vector<std::vector<double>> fam_grid = std::vector<std::vector<double>>(AGNF_MAX_FAMILIES);
   std::vector<std::vector<int32_t>> fam_perm = std::vector<std::vector<int32_t>>(AGNF_MAX_FAMILIES);
@@ -200,6 +204,109 @@ void ens_teardown(agnf_ctx* ctx) {
   ctx->have_ens = false;
 }
 
+// ---- decision tables for the gather4 kernel's snap (k1_dev.cuh::snap_fast) -------------------------------------
+// Doubles in lattice order <-> int64 keys (monotone), for bisection over every representable value.
+inline int64_t dkey(double x) {
+  int64_t k;
+  memcpy(&k, &x, 8);
+  return k < 0 ? (int64_t)0x8000000000000000ull - k : k;
+}
+inline double dval(int64_t k) {
+  if (k < 0) k = (int64_t)0x8000000000000000ull - k;
+  double x;
+  memcpy(&x, &k, 8);
+  return x;
+}
+// the device's cell function, operation for operation (no contraction possible: subtract, multiply, truncate, clamp)
+inline int dcell(double p, double lo, double inv, int mmax) {
+  volatile double d = p - lo;
+  volatile double t = d * inv;
+  int c;
+  if (!(t == t)) c = 0;
+  else if (t >= 2147483647.0) c = INT32_MAX;
+  else if (t <= -2147483648.0) c = INT32_MIN;
+  else c = (int)t;                                   // truncation, like cvt.rzi
+  return std::min(std::max(c, 0), mmax);
+}
+// which of the two bracketing grid values a <= p <= b the reference's argmin picks (first-appearance indices ia, ib)
+inline bool picks_upper(double a, double b, int ia, int ib, double p) {
+  volatile double da = std::fabs(a - p), db = std::fabs(b - p);
+  return ia < ib ? (db < da) : (db <= da);
+}
+
+// One dimension: sorted values sv[n], first-appearance indices pv[n].  Appends cell codes to `dlut`, n - 1 switch
+// points to `thr` and (unless pv is the identity) n indices to `perm16`.  Returns the number of cells (0: no table).
+int build_decision_table(const double* sv, const int32_t* pv, int n, double big, std::vector<uint16_t>& dlut,
+                         std::vector<double>& thr, std::vector<uint16_t>& perm16, double* inv_out, int* perm_off) {
+  if (n < 2 || n >= 16000) return 0;
+  const double lo = sv[0], span = sv[n - 1] - sv[0];
+  if (!(span > 0.0) || !std::isfinite(span) || !(big > 0.0)) return 0;
+  // switch points: the smallest p in (sv[j], sv[j+1]] for which the argmin moves to the upper value
+  std::vector<double> sw((size_t)n - 1);
+  for (int j = 0; j + 1 < n; ++j) {
+    int64_t a = dkey(sv[j]), b = dkey(sv[j + 1]);     // picks_upper(a) false, picks_upper(b) true
+    while (b - a > 1) {
+      const int64_t mid = a + (b - a) / 2;
+      if (picks_upper(sv[j], sv[j + 1], pv[j], pv[j + 1], dval(mid))) b = mid; else a = mid;
+    }
+    sw[(size_t)j] = dval(b);
+  }
+  bool identity = true;
+  for (int k = 0; k < n; ++k) identity = identity && pv[k] == k;
+  int best_m = 0;
+  std::vector<uint16_t> codes;
+  int m0 = 32;
+  while (m0 < 2 * n) m0 *= 2;
+  for (int m = m0; m <= 8 * m0; m *= 2) {
+    const double inv = (double)m / span;
+    const int mmax = m - 1;
+    std::vector<int> first_str((size_t)m, -1), n_str((size_t)m, 0), first_after((size_t)m + 1, 0);
+    bool usable = true;
+    for (int j = 0; j + 1 < n && usable; ++j) {
+      const double t = sw[(size_t)j];
+      const int cs = dcell(t, lo, inv, mmax), cp = dcell(dval(dkey(t) - 1), lo, inv, mmax);
+      if (cs - cp > 1 || cp > cs) usable = false;     // a cell narrower than one ulp: no table at this size
+      if (cs == cp) {
+        if (n_str[(size_t)cs] == 0) first_str[(size_t)cs] = j;
+        n_str[(size_t)cs] += 1;
+        first_after[(size_t)cs + 1] += 1;             // cells after cs start past switch j
+      } else {
+        first_after[(size_t)cs] += 1;                 // the switch sits on the edge cp | cs
+      }
+    }
+    if (!usable) continue;
+    int crowded = 0;
+    std::vector<uint16_t> cand((size_t)m);
+    int s0 = 0;                                        // switches entirely below the cell = sorted position at its start
+    for (int c = 0; c < m; ++c) {
+      s0 += first_after[(size_t)c];
+      const int ns = n_str[(size_t)c];
+      if (ns == 0) cand[(size_t)c] = (uint16_t)pv[std::min(s0, n - 1)];
+      else if (ns <= 2 && first_str[(size_t)c] == s0)
+        cand[(size_t)c] = (uint16_t)(0x8000u | (ns == 2 ? 0x4000u : 0u) | (unsigned)s0);
+      else {
+        cand[(size_t)c] = 0xffffu;
+        ++crowded;
+      }
+    }
+    if (best_m == 0 || crowded == 0) {
+      best_m = m;
+      codes = cand;
+      *inv_out = inv;
+    }
+    if (crowded == 0) break;
+  }
+  if (best_m == 0) return 0;
+  dlut.insert(dlut.end(), codes.begin(), codes.end());
+  thr.insert(thr.end(), sw.begin(), sw.end());
+  *perm_off = -1;
+  if (!identity) {
+    *perm_off = (int)perm16.size();
+    for (int k = 0; k < n; ++k) perm16.push_back((uint16_t)pv[k]);
+  }
+  return best_m;
+}
+
 int rebuild_grids(agnf_ctx* ctx) {
   if (!ctx->grids_dirty) return 0;
   ctx->h_grid.clear();
@@ -207,6 +314,9 @@ int rebuild_grids(agnf_ctx* ctx) {
   std::vector<double> ext;          // sentinel-extended sorted grids
   std::vector<int32_t> eperm;
   std::vector<uint16_t> lut;
+  std::vector<uint16_t> dlut;       // decision tables (gather4 kernel)
+  std::vector<double> brec;         // switch points
+  std::vector<uint16_t> perm16;
   for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
     if (!ctx->fam_set[f]) continue;
     int off = (int)ctx->h_grid.size();
@@ -283,6 +393,25 @@ int rebuild_grids(agnf_ctx* ctx) {
       T.lo = D.lut_lo;
       T.inv = D.lut_inv;
       T.big = D.lut_big;
+      // decision table: needs the same guarantee as the cell table (lut_big > 0: spacing resolvable for |p| <= big)
+      T.smem_off = D.smem_off;
+      T.dlut_off = (int32_t)dlut.size();
+      T.brec_off = (int32_t)brec.size();
+      T.dmmax = -1;
+      T.dinv = 0.0;
+      T.perm_off = -1;
+      if (D.lut_m > 0) {
+        const int local_off = D.smem_off - off;
+        double dinv = 0.0;
+        int perm_off = -1;
+        const int m = build_decision_table(ctx->fam_grid[f].data() + local_off, ctx->fam_perm[f].data() + local_off,
+                                           D.size, D.lut_big, dlut, brec, perm16, &dinv, &perm_off);
+        if (m > 0) {
+          T.dmmax = m - 1;
+          T.dinv = dinv;
+          T.perm_off = perm_off;
+        }
+      }
     }
     ctx->h_grid.insert(ctx->h_grid.end(), ctx->fam_grid[f].begin(), ctx->fam_grid[f].end());
     ctx->h_perm.insert(ctx->h_perm.end(), ctx->fam_perm[f].begin(), ctx->fam_perm[f].end());
@@ -295,6 +424,32 @@ int rebuild_grids(agnf_ctx* ctx) {
   if (!ext.empty()) memcpy(blob.data() + off_grid, ext.data(), ext.size() * 8);
   if (!eperm.empty()) memcpy(blob.data() + off_perm, eperm.data(), eperm.size() * 4);
   if (!lut.empty()) memcpy(blob.data() + off_lut, lut.data(), lut.size() * 2);
+
+  ctx->k1.n_tasks = 0;
+  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
+    if (!ctx->fam_set[f]) continue;
+    for (int t = 0; t < ctx->k1.fam[f].n_snap; ++t) {
+      SnapTask T = ctx->k1.fam[f].snap[t];
+      T.fam = f;
+      ctx->k1.tasks[ctx->k1.n_tasks++] = T;
+    }
+  }
+  // blob of the gather4 kernel
+  const size_t off_dlut = 0, off_brec = pad16(dlut.size() * 2), off_p16 = off_brec + pad16(brec.size() * 8 + 8),
+               total2 = off_p16 + pad16(perm16.size() * 2);
+  std::vector<unsigned char> blob2(total2 + 16, 0);
+  if (!dlut.empty()) memcpy(blob2.data() + off_dlut, dlut.data(), dlut.size() * 2);
+  if (!brec.empty()) memcpy(blob2.data() + off_brec, brec.data(), brec.size() * 8);
+  if (!perm16.empty()) memcpy(blob2.data() + off_p16, perm16.data(), perm16.size() * 2);
+  if (ctx->d_stage2) dev_free(ctx, ctx->d_stage2);
+  ctx->d_stage2 = nullptr;
+  if (dev_alloc(ctx, &ctx->d_stage2, total2 + 16)) return 1;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage2, blob2.data(), total2 + 16, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->k1.stage2 = static_cast<const unsigned char*>(ctx->d_stage2);
+  ctx->k1.stage2_bytes = (int32_t)total2;
+  ctx->k1.stage2_off_dlut = (int32_t)off_dlut;
+  ctx->k1.stage2_off_brec = (int32_t)off_brec;
+  ctx->k1.stage2_off_perm = (int32_t)off_p16;
 
   if (ctx->d_grid) dev_free(ctx, ctx->d_grid);
   if (ctx->d_perm) dev_free(ctx, ctx->d_perm);
@@ -334,6 +489,17 @@ int check_ready(agnf_ctx* ctx) {
   K1Params& P = ctx->k1;
   const bool want = P.cfg.ga_free_ebv && P.cfg.eb_mode != 0 && !(P.fam[0].pitch & 1) && !(P.nbp & 1) &&
                     !(reinterpret_cast<uintptr_t>(P.fam[0].table) & 15);
+  if (ctx->srcrec_dirty) {
+    if (P.srcrec) dev_free(ctx, const_cast<K1SrcRec*>(P.srcrec));
+    P.srcrec = nullptr;
+    void* d = nullptr;
+    if (dev_alloc(ctx, &d, (size_t)std::max<int64_t>(P.S, 1) * sizeof(K1SrcRec))) return 1;
+    CUDA_TRY(ctx, launch_k1_srcrec(P, static_cast<K1SrcRec*>(d), ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    P.srcrec = static_cast<const K1SrcRec*>(d);
+    ctx->srcrec_dirty = false;
+    ctx->launches += 1;
+  }
   if (want && ctx->eb0_dirty) {
     if (P.eb0) dev_free(ctx, const_cast<double*>(P.eb0));
     P.eb0 = nullptr;
@@ -346,6 +512,28 @@ int check_ready(agnf_ctx* ctx) {
     ctx->launches += 1;
   }
   return 0;
+}
+
+// K1 launch through the kernel the options and the preconditions select; returns the kernel id in *which
+cudaError_t k1_dispatch(agnf_ctx* ctx, const K1Batch& B, cudaStream_t st, int* which) {
+  const int v = ctx->k1_variant;
+  if (v == 3 && k1_g4_supported(ctx->k1, ctx->maps, B, nullptr)) {
+    *which = 2;
+    return launch_k1_g4(ctx->k1, ctx->maps, B, st);
+  }
+  if (v != 0 && k1_coop_supported(ctx->k1, B, nullptr) && (v >= 2 || k1_coop_profitable(ctx->k1, B))) {
+    *which = 1;
+    return launch_k1_coop(ctx->k1, B, st);
+  }
+  *which = 0;
+  return B.ens.pos ? cudaErrorNotSupported : launch_k1(ctx->k1, B, st);
+}
+
+// fused stretch-move launches need the gather4 or the cooperative kernel
+bool k1_fused_available(agnf_ctx* ctx, const K1Batch& B) {
+  const int v = ctx->k1_variant;
+  if (v == 3 && k1_g4_supported(ctx->k1, ctx->maps, B, nullptr)) return true;
+  return v != 0 && k1_coop_supported(ctx->k1, B, nullptr) && (v >= 2 || k1_coop_profitable(ctx->k1, B));
 }
 
 }  // namespace
@@ -455,7 +643,8 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
   AGNF_GUARD_BEGIN
   if (!ctx || !name) return 1;
   if (strcmp(name, "k1_variant") == 0) {
-    if (value < 0 || value > 2) return fail(ctx, "k1_variant must be 0 (per-thread), 1 (automatic) or 2 (cooperative)");
+    if (value < 0 || value > 3)
+      return fail(ctx, "k1_variant must be 0 (per-thread), 1 (automatic), 2 (cooperative) or 3 (gather4)");
     ctx->k1_variant = (int)value;
     return 0;
   }
@@ -516,6 +705,11 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   if (!ctx || !name || !value) return 1;
   if (strcmp(name, "k1_variant") == 0) *value = ctx->k1_variant;
   else if (strcmp(name, "k1_last_kernel") == 0) *value = ctx->last_k1_kernel;
+  else if (strcmp(name, "k1_table_bytes") == 0) *value = ctx->k1.stage2_bytes;
+  else if (strncmp(name, "g4_prof", 7) == 0) {
+    cudaStreamSynchronize(ctx->stream);
+    *value = (int64_t)k1_g4_prof_read(name[7] - '0', name[8] == 'r');
+  }
   else if (strcmp(name, "band_pitch") == 0) *value = ctx->have_cfg ? ctx->k1.nbp : 0;
   else if (strcmp(name, "pipeline_rows") == 0) *value = ctx->pipeline_rows;
   else if (strcmp(name, "small_rows") == 0) *value = ctx->small_rows;
@@ -674,6 +868,8 @@ AGNF_API int agnf_family_upload(agnf_ctx* ctx, const agnf_family_desc* fd) {
     if (upload(ctx, &a, fd->aux, (size_t)fd->T)) return 1;
     F.aux = a;
   }
+  // gather4 kernel: a tensor map over the table (failure only disables that kernel)
+  k1_g4_make_map(ctx->maps, f, F.table, (int64_t)cfg.n_z * F.T, F.pitch);
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->fam_set[f] = true;
   ctx->grids_dirty = true;
@@ -743,6 +939,7 @@ AGNF_API int agnf_zslices_upload(agnf_ctx* ctx, const double* cgal, const double
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->have_z = true;
   ctx->eb0_dirty = true;
+  ctx->srcrec_dirty = true;
   return 0;
   AGNF_GUARD_END(ctx)
 }
@@ -785,6 +982,7 @@ AGNF_API int agnf_sources_upload(agnf_ctx* ctx, int64_t S, const int32_t* zi, co
   ctx->k1.n_const = n_const;
   ctx->k1.S = S;
   ctx->have_src = true;
+  ctx->srcrec_dirty = true;
   return 0;
   AGNF_GUARD_END(ctx)
 }
@@ -804,15 +1002,7 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
   const bool timed = !ctx->untimed_once;          // latency-bound callers skip the two event records (~3 us each)
   ctx->untimed_once = false;
   if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-  const char* why = nullptr;
-  if (ctx->k1_variant != 0 && k1_coop_supported(ctx->k1, B, &why) &&
-      (ctx->k1_variant == 2 || k1_coop_profitable(ctx->k1, B))) {
-    CUDA_TRY(ctx, launch_k1_coop(ctx->k1, B, st));
-    ctx->last_k1_kernel = 1;
-  } else {
-    CUDA_TRY(ctx, launch_k1(ctx->k1, B, st));
-    ctx->last_k1_kernel = 0;
-  }
+  CUDA_TRY(ctx, k1_dispatch(ctx, B, st, &ctx->last_k1_kernel));
   if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
   if (timed) ctx->k1_timed = true;
   ctx->launches += 1;
@@ -1336,8 +1526,7 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
   FB.ens.src_offset = st.src_offset;
   FB.ens.split = st.split;
   ctx->ens_hist.pbox = ctx->k1.pbox;
-  const bool fused = ctx->k1_variant != 0 && ctx->ens_fused && k1_coop_supported(ctx->k1, FB, nullptr) &&
-                     (ctx->k1_variant == 2 || k1_coop_profitable(ctx->k1, FB));
+  const bool fused = ctx->ens_fused && k1_fused_available(ctx, FB);
   for (int64_t it = 0; it < n_steps; ++it) {
     if (st.split) {
       CUDA_TRY(ctx, launch_k3_split(st, ctx->ens_step, s));
@@ -1349,10 +1538,9 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
         FB.ens.step = ctx->ens_step;
         const bool timed = it + 1 == n_steps;           // events around the last step's launches only
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, s));
-        CUDA_TRY(ctx, launch_k1_coop(ctx->k1, FB, s));
+        CUDA_TRY(ctx, k1_dispatch(ctx, FB, s, &ctx->last_k1_kernel));
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, s));
         ctx->k1_timed = true;
-        ctx->last_k1_kernel = 1;
         ctx->launches += 1;
         continue;
       }

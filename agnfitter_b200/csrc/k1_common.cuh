@@ -75,6 +75,22 @@ __device__ __forceinline__ double pow2_64(double t, uint32_t tab_s) {
   return __hiloint2double(__double2hiint(v) + ((k >> P2_SHIFT) << 20), __double2loint(v));
 }
 
+// The same arithmetic without the range branch: out-of-range (or NaN) arguments raise `bad` and return garbage; the
+// caller repeats the evaluation through pow2_64 (straight-line band loops: k1_g4.cu)
+__device__ __forceinline__ double pow2_64_nb(double t, uint32_t tab_s, bool& bad) {
+  bad = bad || !(fabs(t) < 1000.0 * AGNF_POW2_DENOM);
+  const double magic = 6755399441055744.0;                 // 1.5 * 2^52
+  const double km = t + magic;
+  const int k = __double2loint(km);
+  const double r = t - (km - magic);
+  double p = c_p2[P2_DEG - 1];
+#pragma unroll
+  for (int n = P2_DEG - 2; n >= 0; --n) p = fma(p, r, c_p2[n]);
+  p = fma(p, r, 1.0);
+  const double v = lds_f64_ro(tab_s + ((k << 3) & (8 * AGNF_POW2_DENOM - 8))) * p;
+  return __hiloint2double(__double2hiint(v) + ((k >> P2_SHIFT) << 20), __double2loint(v));
+}
+
 // 10^x for the normalisations through the same routine (|x| <= 10 in the prior box: relative error
 // <= |x| D log2(10) 2^-53 ln2 / D ~ 2.6e-15)
 __device__ __forceinline__ double pow10_via2(double x, uint32_t tab_s) { return pow2_64(x * P2_LOG2_10_D, tab_s); }

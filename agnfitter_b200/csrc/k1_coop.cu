@@ -3,9 +3,9 @@
 // A warp owns 32 consecutive rows of `params` (= 32 evaluations).
 //
 //   phase 1  thread-per-evaluation.  One 1-D bulk copy (TMA unit, mbarrier completion) per CTA brings
-//            the snapping grids and cell tables into shared memory, one per warp brings that warp's
-//            contiguous params rows.  Each thread box-tests its row, snaps every family (cell table +
-//            bracket test, k1_common.cuh), evaluates the normalisations 10^x, leaves a 10- or
+//            the snap decision tables into shared memory, one per warp brings that warp's
+//            contiguous params rows.  Each thread box-tests its row, snaps every family (decision
+//            table, k1_dev.cuh::snap_fast), evaluates the normalisations 10^x, leaves a 10- or
 //            14-double record in shared memory and prefetches its galaxy-template row into L2.
 //   phase 2  lane-per-chunk.  The 32 x nbp tile of band values is cut into 16-byte chunks
 //            (2 bands); chunk c = e * nbp/2 + k goes to lane c % 32 of iteration c / 32, so the
@@ -23,6 +23,7 @@
 // Only __syncwarp() separates the phases; the CTA synchronises once, to publish the mbarriers.
 #include "k1_lnprob.cuh"
 #include "k1_common.cuh"
+#include "k1_dev.cuh"
 #include "k3_common.cuh"
 
 namespace agnf {
@@ -34,6 +35,9 @@ namespace {
 #endif
 #ifndef KC_MINBLOCKS
 #define KC_MINBLOCKS 3
+#endif
+#ifndef KC_SNAP_GROUP
+#define KC_SNAP_GROUP 2
 #endif
 constexpr int KC_THREADS = KC_THREADS_DEF;
 constexpr int KC_WARPS = KC_THREADS / 32;
@@ -63,7 +67,7 @@ template <bool EXT>
 CoopPlan make_plan(const K1Params& P, bool ens) {
   CoopPlan c;
   const bool eb_free = P.cfg.ga_free_ebv != 0 && P.cfg.eb_mode != 0;
-  c.stage_pad = (P.stage_bytes + 15) & ~15;
+  c.stage_pad = (P.stage2_bytes + 15) & ~15;
   c.cpr = P.nbp / 2;
   c.cprp = c.cpr | 1;
   const int a = 32 * c.cprp * (eb_free ? 2 : 1), b = 32 * P.cfg.n_par;
@@ -74,90 +78,6 @@ CoopPlan make_plan(const K1Params& P, bool ens) {
   c.per_warp = 32 * Rec<EXT>::STRIDE + part + (ens ? ((32 * P.cfg.n_par + 1) & ~1) : 0);
   c.smem_bytes = 64 * 8 /*exp2 table*/ + 16 * 8 /*mbarriers*/ + c.stage_pad + KC_WARPS * c.per_warp * 8;
   return c;
-}
-
-// ---- shared memory through 32-bit shared-window addresses (no generic -> shared conversions) ------
-__device__ __forceinline__ double2 lds_v2f64(uint32_t a) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ int4 lds_v4s32(uint32_t a) {
-  int4 v;
-  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ int lds_s32(uint32_t a) {
-  int v;
-  asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ int lds_s32_ro(uint32_t a) {          // see lds_f64_ro
-  int v;
-  asm("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ unsigned lds_u16_ro(uint32_t a) {
-  unsigned short v;
-  asm("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
-  unsigned long long v;
-  asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
-  asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(a), "d"(v) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
-}
-
-// ---- mbarrier + bulk copy (TMA unit, 1-D) -------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (int spin = 0; !ok; ++spin) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (spin > (1 << 24)) __trap();      // a lost copy must not hang the device
-  }
-}
-
-// snap through the cell table; see k1_common.cuh::snap_dim_lut for the argument (same steps, shared
-// window addresses, task constants from the kernel parameter bank)
-__device__ __forceinline__ int snap_task(const SnapTask& T, double p, uint32_t ext_s, uint32_t eperm_s, uint32_t lut_s,
-                                         const double* ext_g, const int32_t* eperm_g) {
-  if (T.lut_mmax >= 0) {
-    const int c = min(max(__double2int_rz((p - T.lo) * T.inv), 0), T.lut_mmax);
-    int l = (int)lds_u16_ro(lut_s + 2u * (unsigned)(T.lut_off + c));
-    const uint32_t base = ext_s + 8u * (unsigned)T.ext_off;
-    if (lds_f64_ro(base + 8u * l) > p) --l;
-    if (lds_f64_ro(base + 8u * l + 8u) <= p) ++l;
-    if (lds_f64_ro(base + 8u * l + 8u) <= p) ++l;
-    const double a = lds_f64_ro(base + 8u * l), b = lds_f64_ro(base + 8u * l + 8u);
-    if (a <= p && p < b && fabs(p) <= T.big) {
-      const uint32_t pb = eperm_s + 4u * (unsigned)(T.ext_off + l);
-      const int ia = lds_s32_ro(pb), ib = lds_s32_ro(pb + 4u);
-      const double da = fabs(a - p), db = fabs(b - p);
-      return da < db ? ia : (db < da ? ib : min(ia, ib));
-    }
-  }
-  return snap_dim(ext_g + T.ext_off + 1, eperm_g + T.ext_off + 1, T.n, p);
 }
 
 // CPR_T: chunks per row as a compile-time constant (fully unrolled band phase), or 0 = runtime
@@ -177,12 +97,11 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   const uint32_t tab_s = smem_u32(smem_raw);                 // 64 doubles
   const uint32_t bar_s = tab_s + 64 * 8;                     // [0] blob, [1 + w] warp w
   const uint32_t stage_s = bar_s + 16 * 8;
-  const uint32_t ext_s = stage_s + P.stage_off_grid, eperm_s = stage_s + P.stage_off_perm,
-                 lut_s = stage_s + P.stage_off_lut;
+  const uint32_t dlut_s = stage_s + P.stage2_off_dlut, brec_s = stage_s + P.stage2_off_brec,
+                 perm_s = stage_s + P.stage2_off_perm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t scal_s = stage_s + C.stage_pad + (unsigned)warp * (unsigned)C.per_warp * 8u;
   const uint32_t part_s = scal_s + 32 * STRIDE * 8;
-  const unsigned char* stage_generic = smem_raw + 64 * 8 + 16 * 8;
 
   const int64_t row0 = ((int64_t)blockIdx.x * KC_WARPS + warp) * 32;
   const int rows_here = (int)max((int64_t)0, min((int64_t)32, B.n - row0));
@@ -198,9 +117,9 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     sts_f64(tab_s + 8u * threadIdx.x, c_exp2_tab[threadIdx.x * (64 / AGNF_POW2_DENOM)]);
   __syncthreads();
   // one bulk copy brings the grids + cell tables; one per warp brings that warp's params rows
-  if (threadIdx.x == 0 && P.stage_bytes > 0) {
-    mbar_expect_tx(bar_s, (uint32_t)P.stage_bytes);
-    bulk_g2s(stage_s, P.stage, (uint32_t)P.stage_bytes, bar_s);
+  if (threadIdx.x == 0 && P.stage2_bytes > 0) {
+    mbar_expect_tx(bar_s, (uint32_t)P.stage2_bytes);
+    bulk_g2s(stage_s, P.stage2, (uint32_t)P.stage2_bytes, bar_s);
   }
   if (lane == 0 && par_bytes > 0) {
     mbar_expect_tx(bar_s + 8u + 8u * warp, par_bytes);
@@ -293,25 +212,40 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     }
   }
 
-  if (P.stage_bytes > 0) mbar_wait(bar_s, 0);
-  const double* ext_g = reinterpret_cast<const double*>(stage_generic + P.stage_off_grid);
-  const int32_t* eperm_g = reinterpret_cast<const int32_t*>(stage_generic + P.stage_off_perm);
+  if (P.stage2_bytes > 0) mbar_wait(bar_s, 0);
+  // the snaps of all families through the decision tables (k1_dev.cuh::snap_fast: one 16-bit read, plus one 16-byte
+  // read when the cell straddles a switch point), four at a time as one straight-line block
   int row[AGNF_MAX_FAMILIES], grow[AGNF_MAX_FAMILIES];
 #pragma unroll
-  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
-    row[f] = 0;
-    grow[f] = 0;
-    if (f < (RADIO ? 5 : 4)) {
-      const FamDesc& F = P.fam[f];
-      int r = 0;
-      for (int t = 0; t < F.n_snap; ++t) {
-        const SnapTask& T = F.snap[t];
-        r += snap_task(T, lds_f64(p_s + 8u * T.col), ext_s, eperm_s, lut_s, ext_g, eperm_g) * T.stride;
-      }
-      row[f] = r;
-      grow[f] = zi * (int)F.T + r;
+  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) row[f] = 0;
+  bool slow = false;
+  for (int t0 = 0; t0 < P.n_tasks; t0 += KC_SNAP_GROUP) {
+    int idx[KC_SNAP_GROUP];
+    bool sl[KC_SNAP_GROUP];
+#pragma unroll
+    for (int u = 0; u < KC_SNAP_GROUP; ++u) {
+      const SnapTask& T = P.tasks[min(t0 + u, P.n_tasks - 1)];
+      sl[u] = false;
+      idx[u] = snap_fast(T, lds_f64(p_s + 8u * T.col), dlut_s, brec_s, perm_s, sl[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < KC_SNAP_GROUP; ++u) {
+      const SnapTask& T = P.tasks[min(t0 + u, P.n_tasks - 1)];
+      const bool on = t0 + u < P.n_tasks;
+      const int add = on ? idx[u] * T.stride : 0;
+      slow = slow || (on && sl[u]);
+#pragma unroll
+      for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) row[f] += (T.fam == f) ? add : 0;
     }
   }
+  if (slow) {        // NaN, huge values, crowded cells: the binary search over the full grids (global memory)
+#pragma unroll
+    for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
+      if (f < (RADIO ? 5 : 4)) row[f] = snap_family_slow(P, f, p_s);
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) grow[f] = f < (RADIO ? 5 : 4) ? zi * (int)P.fam[f].T + row[f] : 0;
   // start the only DRAM-bound gather early: this evaluation's galaxy row -> L2
   {
     const char* ga = reinterpret_cast<const char*>(P.fam[0].table + (int64_t)grow[0] * P.fam[0].pitch);

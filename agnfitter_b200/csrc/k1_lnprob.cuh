@@ -7,6 +7,8 @@
 //                 lane-per-16-byte-chunk over the warp's 32 x n_b tile so that every template
 //                 row is fetched by consecutive lanes with 128-bit loads (2 L1 wavefronts per
 //                 row instead of 9); the two layouts meet in per-warp shared memory.
+//   k1_g4.cu      thread per row, template rows through the TMA unit's gather4 mode (the default when its
+//                 preconditions hold; see the file header).
 //   k1_lnprob.cu  one thread per row end to end; no alignment or size requirements.  Used when
 //                 the cooperative kernel's preconditions do not hold, and as a cross-check.
 // All arithmetic is fp64.
@@ -22,6 +24,7 @@
 //   ln_probab           PARAMETERSPACE_AGNfitter.py:167-173
 #pragma once
 #include <cstdint>
+#include <cuda.h>            // CUtensorMap (types only: the library does not link libcuda)
 #include <cuda_runtime.h>
 #include "../../include/agnfit_b200.h"
 
@@ -56,7 +59,24 @@ struct SnapTask {
   int32_t lut_mmax;   // cells - 1; -1: no table (binary search)
   int32_t stride;     // rows per grid step
   double lo, inv, big;
+  // decision table of the gather4 kernel (agnfit_capi.cu::build_decision_table): cell c = int((p - lo) * dinv)
+  // answers with the snapped index itself, or names the ONE switch point the cell straddles
+  int32_t dlut_off;   // offset (entries) of this dimension's uint16 cell codes
+  int32_t dmmax;      // cells - 1; -1: no decision table
+  int32_t brec_off;   // offset (doubles) of this dimension's switch points
+  int32_t smem_off;   // offset of this dimension in grid_sorted / grid_perm (binary-search fallback)
+  double dinv;
+  int32_t fam;        // family the task belongs to (flat task list)
+  int32_t perm_off;   // offset (uint16 entries) of the first-appearance indices in sorted order; -1: the sorted
+                      // order IS the first-appearance order (index = sorted position)
 };
+
+// Decision tables.  Between two neighbouring grid values sv[j] < sv[j+1] the reference's argmin switches from one to the
+// other at exactly one double, thr[j] (the smallest p that snaps to the upper value, ties included).  A cell code is
+//   0xffff                      : not answerable here (binary search)
+//   bit 15 clear                : the snapped first-appearance index itself
+//   bit 15 set, low 14 bits = j : the cell straddles thr[j] (and, with bit 14, thr[j+1] too): sorted position
+//                                 j + (p >= thr[j]) [+ (p >= thr[j+1])], mapped through perm unless it is the identity
 
 struct FamDesc {
   const double* table;  // [n_z, T, pitch]; columns n_b..pitch-1 are zero
@@ -68,6 +88,14 @@ struct FamDesc {
   int32_t n_snap;
   DimDesc dim[AGNF_MAX_DIMS];
   SnapTask snap[AGNF_MAX_DIMS];
+};
+
+// what one evaluation needs to know about its source (gather4 kernel): 48 bytes, three 16-byte loads
+struct K1SrcRec {
+  int32_t zi, agn_branch, irsyn_mode, irsyn_j;
+  uint64_t valid, xray;
+  int32_t j1500, pad;
+  double inv4pidl2;
 };
 
 struct K1Params {
@@ -84,6 +112,12 @@ struct K1Params {
   //   each padded to 16 bytes
   const unsigned char* stage;
   int32_t stage_bytes, stage_off_grid, stage_off_perm, stage_off_lut;
+  // gather4 kernel: every snap task of every family in one list (groups of four run as one straight-line block)
+  int32_t n_tasks, pad3;
+  SnapTask tasks[AGNF_MAX_FAMILIES * AGNF_MAX_DIMS];
+  // cell codes uint16 | switch points double | first-appearance indices uint16, each padded to 16 bytes
+  const unsigned char* stage2;
+  int32_t stage2_bytes, stage2_off_dlut, stage2_off_brec, stage2_off_perm;
   // Gaussian_prior constants, evaluated on the host: log(1/(sqrt(2 pi) sigma)) for sigma = 2, 1.5, 0.1
   double lognorm_s2, lognorm_s15, lognorm_s01;
   // z-slices (pad columns are zero)
@@ -112,6 +146,7 @@ struct K1Params {
   const int32_t* irsyn_mode;  // [S]
   const int32_t* irsyn_j;     // [S]
   int64_t S;
+  const K1SrcRec* srcrec;     // [S] (gather4 kernel; rebuilt after every source / z-slice upload)
   // prior_midIR_UV / prior_IR_XRays (agnf_extra_priors_set)
   int32_t xp_midir_uv, xp_ir_xray, xp_j6, xp_j2500;
   const int32_t* xp_bb_dered; // [T_BB]
@@ -147,6 +182,17 @@ struct K1Batch {
 };
 
 cudaError_t launch_k1(const K1Params& P, const K1Batch& B, cudaStream_t stream);
+
+// gather4 kernel (k1_g4.cu): one TMA tensor map per family table
+struct K1TensorMaps {
+  CUtensorMap m[AGNF_MAX_FAMILIES];
+  int32_t valid[AGNF_MAX_FAMILIES];
+};
+int k1_g4_make_map(K1TensorMaps& M, int f, const double* table, int64_t rows, int pitch);   // 0 = ok
+bool k1_g4_supported(const K1Params& P, const K1TensorMaps& M, const K1Batch& B, const char** why);
+cudaError_t launch_k1_srcrec(const K1Params& P, K1SrcRec* out, cudaStream_t stream);
+unsigned long long k1_g4_prof_read(int i, bool reset);   // -DG4_PROF builds only (else 0)
+cudaError_t launch_k1_g4(const K1Params& P, const K1TensorMaps& M, const K1Batch& B, cudaStream_t stream);
 
 // cooperative kernel (k1_coop.cu); `why` receives a static string when unsupported
 bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why);

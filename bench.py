@@ -44,6 +44,9 @@ UNIT = "evals/s"
 EVALS_PER_FIT = 100 * (2 * 12000 + 25000)     # example/SETTINGS_AGNfitter.py:265-268
 
 
+K1_KERNEL_NAMES = {0: "k1_lnprob_kernel", 1: "k1_coop_kernel", 2: "k1_g4_kernel"}
+
+
 def k1_bytes_per_eval(n_comp, n_b, n_par, W):
     """gathered rows + parameters + result, plus per-source vectors amortised over W."""
     return 8 * (n_comp * n_b + n_par + 1) + 8 * 5 * n_b / W
@@ -485,7 +488,7 @@ def k1_leg(args, rank, local, overrides, steps, torch, seconds=0.5):
     n, n_comp = len(pars), len(ms.families)
     bpe = k1_bytes_per_eval(n_comp, ms.n_b, ms.n_par, a2.walkers)
     peak, _ = measured_peak()
-    kname = "k1_coop_kernel" if eng.get_option("k1_last_kernel") == 1 else "k1_lnprob_kernel"
+    kname = K1_KERNEL_NAMES[eng.get_option("k1_last_kernel")]
     out = dict(sources=a2.sources, walkers=a2.walkers, n_bands=ms.n_b, n_par=ms.n_par, components=n_comp,
                templates="+".join(str(f.T) for f in ms.families), n_z=info["n_z"], rows_per_step=n,
                ms_per_step=ms_short, evals_per_s=n / (ms_short * 1e-3), sustained_ms_per_step=ms_long,
@@ -760,7 +763,7 @@ def run_ours(args):
     sampler.join(timeout=2)
     check = float(np.nansum(np.where(np.isfinite(np_lnp), 1.0, 0.0)))
 
-    kname = "k1_coop_kernel" if eng.get_option("k1_last_kernel") == 1 else "k1_lnprob_kernel"
+    kname = K1_KERNEL_NAMES[eng.get_option("k1_last_kernel")]
     pipeline_rows = eng.get_option("pipeline_rows")
 
     # ---- product-level end to end: fit_catalog ---------------------------------------------------------------
@@ -819,7 +822,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world, info["n_z"], n_b, n_par, [f.T for f in ms.families]),
-            "run": {"k1_variant": "cooperative (k1_coop_kernel)" if kname == "k1_coop_kernel" else "per-thread (k1_lnprob_kernel)",
+            "run": {"k1_variant": kname,
                     "host_placement": numa},
             "sustained": None if not sustained else {
                 "what": "the same pass repeated for >= %.1f s, CUDA events on the launch stream, max over ranks"
@@ -930,7 +933,7 @@ def main():
                     help="weak: --sources per GPU (the driver's scaling run); strong: one catalogue of --sources "
                          "sources divided over the ranks along z")
     ap.add_argument("--positions", default="uniform", choices=["uniform", "ball"])
-    ap.add_argument("--variant", type=int, default=1, help="K1 kernel: 1 cooperative (default), 0 per-thread")
+    ap.add_argument("--variant", type=int, default=1, help="K1 kernel: 1 automatic (default: gather4 when supported), 0 per-thread, 2 cooperative, 3 gather4")
     ap.add_argument("--no-sort-z", action="store_true",
                     help="keep the catalogue in random z order (default: the shard is processed in z order so "
                          "that sources sharing a dictionary z-slice are adjacent)")

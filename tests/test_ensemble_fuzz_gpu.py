@@ -28,10 +28,12 @@ def test_ensemble_on_random_modelsets(seed):
     lo, hi = np.minimum(src.pmin, src.pmax), np.maximum(src.pmin, src.pmax)
     pos0 = lo[:, None, :] + rng.uniform(size=(src.S, W, ms.n_par)) * (hi - lo)[:, None, :]
     want_lnp0 = lnprob(pos0)
-    for fused in (1, 0):
+    for fused in (1, 3, 0):          # cooperative fused launch, gather4 fused launch, three kernels
         eng = Engine(ms, device=0)
         eng.set_sources(src)
-        eng.set_option("ens_fused", fused)
+        eng.set_option("ens_fused", 1 if fused else 0)
+        if fused == 3:
+            eng.set_option("k1_variant", 3)
         ens = EnsembleSampler(eng, W, seed=77 + seed, n_bins=0)
         ens.set_positions(pos0)
         opos, olnp, oacc = pos0.copy(), want_lnp0.copy(), np.zeros((src.S, W), dtype=np.int64)

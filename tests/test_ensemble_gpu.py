@@ -40,13 +40,16 @@ def _setup(case):
 
 
 @pytest.mark.parametrize("split", ["random", "fixed"])
-@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("fused", [1, 3, 0])
 @pytest.mark.parametrize("case", ["classic18", "cat49_catalog_example"])
 def test_ensemble_matches_oracle_step_for_step(case, fused, split):
-    """fused = 1: one K1 launch per half-step draws, evaluates and accepts; 0: propose / K1 / accept kernels.
+    """fused = 1: one K1 launch per half-step draws, evaluates and accepts (cooperative kernel, the default); 3: the
+    same through the gather4 kernel; 0: propose / K1 / accept kernels.
     split: emcee 3's per-step random division of the walkers (default) or the fixed halves."""
     ms, eng, src, lnprob = _setup(case)
-    eng.set_option("ens_fused", fused)
+    eng.set_option("ens_fused", 1 if fused else 0)
+    if fused == 3:
+        eng.set_option("k1_variant", 3)
     W, seed, n_steps = 24, 20260101, 40
     rng = np.random.default_rng(5)
     pos0 = src.pmin[:, None, :] + rng.uniform(size=(src.S, W, ms.n_par)) * (src.pmax - src.pmin)[:, None, :]
@@ -67,6 +70,7 @@ def test_ensemble_matches_oracle_step_for_step(case, fused, split):
         fin = np.isfinite(olnp)
         assert np.allclose(glnp[fin], olnp[fin], rtol=1e-10, atol=0)
     assert oacc.sum() > 0, "the test must exercise accepted moves"
+    assert eng.get_option("k1_last_kernel") == (2 if fused == 3 else 1), "the requested kernel must be the one that ran"
 
 
 def test_ensemble_percentiles_and_best():

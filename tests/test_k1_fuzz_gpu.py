@@ -126,7 +126,7 @@ def test_random_modelsets_match_the_oracle(seed):
     src = sources.make_sources(ms, z, dlum, nus, fl, fe)
     rng = np.random.default_rng(seed)
     n_per = 1500
-    for variant in (2, 0):
+    for variant in (3, 2, 0):
         eng = Engine(ms, device=0)
         eng.set_option("k1_variant", variant)
         eng.set_sources(src)
@@ -151,3 +151,5 @@ def test_random_modelsets_match_the_oracle(seed):
         if variant == 2 and not too_big:
             why = "n_b=%d ga_free=%s bb_mode=%d radio=%s" % (ms.n_b, ms.ga_free_ebv, ms.bb_mode, ms.radio)
             assert eng.get_option("k1_last_kernel") == 1, "cooperative kernel refused: " + why
+        if variant == 3 and ms.n_par <= 20:
+            assert eng.get_option("k1_last_kernel") == 2, "gather4 kernel refused: n_b=%d n_par=%d" % (ms.n_b, ms.n_par)

@@ -23,15 +23,18 @@ def _engine(ms, g, variant=None):
     return eng, src
 
 
-@pytest.mark.parametrize("variant", [0, 2])
+KERNEL_OF_VARIANT = {0: 0, 2: 1, 3: 2}
+
+
+@pytest.mark.parametrize("variant", [0, 2, 3])
 @pytest.mark.parametrize("case", K1_CASES)
 def test_k1_matches_reference_golden(case, variant):
-    """variant 2 = cooperative kernel (forced), 0 = per-thread kernel (fallback / cross-check); the default,
-    1, picks between them."""
+    """variant 3 = gather4 (TMA) kernel, 2 = cooperative kernel (forced; what the default, 1, picks when profitable),
+    0 = per-thread kernel (fallback / cross-check)."""
     ms, g = load_k1(case)
     eng, _ = _engine(ms, g, variant)
     lnp, rows, ym, lpr, lll = eng.lnprob(g["pars"], g["source_id"], detail=True)
-    assert eng.get_option("k1_last_kernel") == (1 if variant == 2 else 0), "the requested kernel must be the one that ran"
+    assert eng.get_option("k1_last_kernel") == KERNEL_OF_VARIANT[variant], "the requested kernel must be the one that ran"
     assert np.array_equal(rows, g["ref_rows"]), "template indices must be bit-exact"
     assert_close_with_specials(ym, g["ref_ymodel"], what="ymodel")
     assert_close_with_specials(lll, g["ref_lnlike"], what="ln_likelihood")
@@ -129,11 +132,12 @@ def test_k1_empty_and_errors():
 
 
 def test_k1_variants_agree_and_tail_handling():
-    """Both kernels on batches whose size is not a multiple of the warp / CTA size."""
+    """All kernels on batches whose size is not a multiple of the warp / CTA size; the gather4 and the cooperative
+    kernel do the same arithmetic in the same order: bit-identical."""
     ms, g = load_k1("classic18")
     rng = np.random.default_rng(3)
     outs = {}
-    for variant in (0, 2):
+    for variant in (0, 2, 3):
         eng, src = _engine(ms, g, variant)
         res = []
         for n in (1, 31, 33, 127, 129, 255, 257, 1000, 4097):
@@ -142,10 +146,11 @@ def test_k1_variants_agree_and_tail_handling():
             pars = src.pmin[sid] + r2.uniform(size=(n, ms.n_par)) * (src.pmax[sid] - src.pmin[sid])
             res.append(eng.lnprob(pars, sid, detail=True))
         outs[variant] = res
-    for a, b in zip(outs[0], outs[2]):
-        assert np.array_equal(a[1], b[1])                      # rows
+    for a, b, c in zip(outs[0], outs[2], outs[3]):
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[1], c[1])      # rows
         for k in (0, 2, 3, 4):
             assert_close_with_specials(b[k], a[k], rtol=1e-12, what="variant output %d" % k)
+            assert np.array_equal(b[k], c[k], equal_nan=True), "gather4 vs cooperative, output %d" % k
 
 
 def test_exp10_fast_accuracy():

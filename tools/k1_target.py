@@ -28,6 +28,7 @@ for o in a.opt:
     k, v = o.split("=")
     eng.set_option(k, int(v))
 S, W, n = info["S"], a.walkers, len(pars)
+print("snap tables: %d bytes" % eng.get_option("k1_table_bytes"))
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev)
 if a.mode == "plain":
@@ -46,6 +47,11 @@ if a.mode == "plain":
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / a.steps
     print("plain: %.4f ms per %d rows = %.4g evals/s (kernel %d)" % (t, n, n / t * 1e3, eng.get_option("k1_last_kernel")))
+    prof = [eng.get_option("g4_prof%d" % k) for k in range(8)]
+    if sum(prof):
+        tiles = (n + 31) // 32 * (a.steps + 3)
+        names = ["params wait", "snap", "box+norm reads / scalars", "rows wait", "band loop", "priors+out", "issue A", "fence+issue B"]
+        print("per tile (cycles): " + ", ".join("%s %.0f" % (nm, p / tiles) for nm, p in zip(names, prof)))
 else:
     from agnfitter_b200.ensemble import EnsembleSampler
     ens = EnsembleSampler(eng, W, seed=20260101, n_bins=256)

@@ -75,6 +75,9 @@ SIGNATURES = {
     "agnf_ens_record": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32]),
     "agnf_ens_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "agnf_ens_percentiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "agnf_ens_chain_percentiles": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                             C.c_void_p]),
+    "agnf_ens_record_state": (C.c_int, [C.c_void_p]),
     "agnf_sed_config": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnf_sed_family_upload": (C.c_int, [C.c_void_p, C.c_void_p]),

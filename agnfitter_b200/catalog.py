@@ -60,8 +60,29 @@ def summary_columns(n_par, n_q=len(REFERENCE_PERCENTILES), n_intlum=0):
            ["L%d_q%d" % (m, int(q)) for m in range(n_intlum) for q in INTLUM_PERCENTILES]
 
 
+def _chunk_bounds(zs, per_source_bytes, per_slice_bytes, budget_bytes, max_sources=None):
+    """Cut the rank's z-sorted block into chunks whose dictionary slices + sampler state fit `budget_bytes`; a chunk
+    never splits a run of equal redshifts unless the run alone exceeds the budget."""
+    n = len(zs)
+    bounds, start = [0], 0
+    while start < n:
+        used, end, n_z, last = 0.0, start, 0, None
+        while end < n:
+            new_z = zs[end] != last
+            need = per_source_bytes + (per_slice_bytes if new_z else 0.0)
+            if end > start and (used + need > budget_bytes or (max_sources and end - start >= max_sources)):
+                break
+            used += need
+            last = zs[end]
+            end += 1
+        bounds.append(end)
+        start = end
+    return bounds
+
+
 def fit_catalog(templates, filterdict, settings, z, dlum, nus, fluxes, fluxerrs, mc, seed=0, n_bins=1024,
-                rank=0, world=1, device=0, intlum_models=None, intlum_ranges_hz=None):
+                rank=0, world=1, device=0, intlum_models=None, intlum_ranges_hz=None, exact_percentiles=False,
+                memory_budget_bytes=None, max_sources_per_chunk=None):
     """Fit every source of the catalogue this rank owns and gather the summaries.
 
     z, dlum [S]; nus [n_b] or [S, n_b]; fluxes, fluxerrs [S, n_b] in the reference's DATA conventions
@@ -70,43 +91,73 @@ def fit_catalog(templates, filterdict, settings, z, dlum, nus, fluxes, fluxerrs,
     the integrated-luminosity stage (K4) on the final walker positions of every source and append the 16/50/84
     percentiles of log10 of each column (the reference draws realizations2int rows from the thinned chain,
     PLOTandWRITE_AGNfitter.py:608; here the W walkers of the last step are those rows).
+    exact_percentiles: keep the thinned second half of the production chain on the device and report
+    numpy.percentile-exact values (what PLOTandWRITE_AGNfitter.py:162 computes) instead of histogram quantiles of
+    resolution (P.max - P.min) / n_bins.
+    The rank's block is processed in chunks along z so that the dictionary slices of a chunk's redshifts, the walker
+    state and (exact_percentiles) the kept chain fit `memory_budget_bytes` (default: 60 % of the free device
+    memory) — a catalogue of unique redshifts needs one slice per source.  Random streams are keyed by the source's
+    position in the z-sorted catalogue and a dictionary slice does not depend on its neighbours, so the result is
+    the same for any chunking (tests/test_catalog_gpu.py).
     Returns on rank 0 an array [S_total, len(summary_columns)] ordered by z (None on other ranks)."""
     import torch
     z = np.asarray(z, dtype=np.float64)
     order, lo, hi = _shard.shard_catalog(z, rank, world)
     mine = order[lo:hi]
     nus = np.asarray(nus, dtype=np.float64)
+    dlum = np.asarray(dlum, dtype=np.float64)
     rows = None
-    n_par = None
     if len(mine):
-        zs = z[mine]
-        builder = DictBuilder(filterdict, device=device)
-        ms, dev = build_modelset_on_device(templates, filterdict, np.unique(zs), settings, builder)
-        eng = Engine(ms, device=device, ctx=builder.ctx, device_tables=dev)
-        src = _sources.make_sources(ms, zs, np.asarray(dlum, dtype=np.float64)[mine],
-                                    nus if nus.ndim == 1 else nus[mine],
-                                    np.asarray(fluxes, dtype=np.float64)[mine],
-                                    np.asarray(fluxerrs, dtype=np.float64)[mine])
-        eng.set_sources(src)
-        n_par = ms.n_par
-        # random numbers are keyed by the source's position in the z-sorted catalogue, not by the shard:
-        # the fit of a source does not depend on the number of GPUs
-        ens = EnsembleSampler(eng, int(mc['Nwalkers']), seed=int(seed), n_bins=n_bins, source_offset=lo)
-        out = ens.run_reference_schedule(mc, src.pmin, src.pmax, None)        # balls drawn on the device
-        blocks = [mine[:, None].astype(np.float64), zs[:, None], out["percentiles"].reshape(len(mine), -1),
-                  out["best_pos"], out["best_lnp"][:, None], out["acceptance"][:, None]]
-        if intlum_models is not None:
-            from .plotset import plotset_from_templates
-            from .realizations import SedEngine
-            ps = plotset_from_templates({short: templates[long_name] for short, long_name in FAMILY_OF
-                                         if long_name in templates}, ms)
-            sed = SedEngine(eng, ps, zs, np.asarray(dlum, dtype=np.float64)[mine])
-            sed.set_bands(intlum_models, intlum_ranges_hz)
-            with np.errstate(all="ignore"):
-                L = np.log10(sed.int_lums_ensemble(int(mc['Nwalkers'])))          # [S, W, n_models]
-            q = np.percentile(L, INTLUM_PERCENTILES, axis=1)                       # [3, S, n_models]
-            blocks.append(np.transpose(q, (1, 2, 0)).reshape(len(mine), -1))
-        rows = np.concatenate(blocks, axis=1)
+        zs_all = z[mine]
+        W = int(mc['Nwalkers'])
+        n_b = len(filterdict[0])
+        pitch = (n_b + 1) & ~1
+        T_sum = sum(len(templates[long_name]["F"]) for _, long_name in FAMILY_OF if long_name in templates)
+        n_par_guess = 24
+        n_keep = len(range(int(int(mc['Nmcmc']) / 2), int(mc['Nmcmc']), max(int(mc.get('Nthin', 1)), 1)))
+        per_source = W * n_par_guess * 8 * 6 + n_bins * n_par_guess * 4 + 16 * pitch * 8
+        if exact_percentiles:
+            per_source += n_keep * W * (n_par_guess + 1) * 8
+        per_slice = T_sum * pitch * 8 * 1.05
+        if memory_budget_bytes is None:
+            free, _ = torch.cuda.mem_get_info(device)
+            memory_budget_bytes = 0.6 * free
+        bounds = _chunk_bounds(zs_all, per_source, per_slice, float(memory_budget_bytes), max_sources_per_chunk)
+        chunks = []
+        for c0, c1 in zip(bounds[:-1], bounds[1:]):
+            sel = mine[c0:c1]
+            zs = z[sel]
+            builder = DictBuilder(filterdict, device=device)
+            ms, dev = build_modelset_on_device(templates, filterdict, np.unique(zs), settings, builder)
+            eng = Engine(ms, device=device, ctx=builder.ctx, device_tables=dev)
+            src = _sources.make_sources(ms, zs, dlum[sel], nus if nus.ndim == 1 else nus[sel],
+                                        np.asarray(fluxes, dtype=np.float64)[sel],
+                                        np.asarray(fluxerrs, dtype=np.float64)[sel])
+            eng.set_sources(src)
+            # random numbers are keyed by the source's position in the z-sorted catalogue, not by the shard or the
+            # chunk: the fit of a source does not depend on the number of GPUs or on the memory budget
+            ens = EnsembleSampler(eng, W, seed=int(seed), n_bins=0 if exact_percentiles else n_bins,
+                                  source_offset=lo + c0)
+            out = ens.run_reference_schedule(mc, src.pmin, src.pmax, None,              # balls drawn on the device
+                                             exact_percentiles=exact_percentiles)
+            blocks = [sel[:, None].astype(np.float64), zs[:, None], out["percentiles"].reshape(len(sel), -1),
+                      out["best_pos"], out["best_lnp"][:, None], out["acceptance"][:, None]]
+            if intlum_models is not None:
+                from .plotset import plotset_from_templates
+                from .realizations import SedEngine
+                ps = plotset_from_templates({short: templates[long_name] for short, long_name in FAMILY_OF
+                                             if long_name in templates}, ms)
+                sed = SedEngine(eng, ps, zs, dlum[sel])
+                sed.set_bands(intlum_models, intlum_ranges_hz)
+                with np.errstate(all="ignore"):
+                    L = np.log10(sed.int_lums_ensemble(W))                           # [S, W, n_models]
+                q = np.percentile(L, INTLUM_PERCENTILES, axis=1)                       # [3, S, n_models]
+                blocks.append(np.transpose(q, (1, 2, 0)).reshape(len(sel), -1))
+                del sed
+            chunks.append(np.concatenate(blocks, axis=1))
+            del ens, eng, dev, builder
+            torch.cuda.empty_cache()
+        rows = np.concatenate(chunks, axis=0)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dev_t = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -23,6 +24,12 @@ using namespace agnf;
 namespace agnf {
 cudaError_t launch_fp64_peak(int kind, double* scratch, int blocks, int iters, double* flops, cudaStream_t stream);
 }
+
+struct ScratchBlock {
+  void* ptr;
+  size_t bytes;
+  bool in_use;
+};
 
 struct agnf_ctx {
   int device = 0;
@@ -49,6 +56,8 @@ struct agnf_ctx {
   std::vector<double> h_grid;                  // staged grid values (host mirror, rebuilt per upload)
   std::vector<int32_t> h_perm;
   void* d_stage = nullptr;
+  std::vector<ScratchBlock> pool;              // scratch blocks of agnf_dict_build (scratch_alloc)
+  double k2_prof[10] = {0};                    // host-side time stamps of the last agnf_dict_build (us since entry)
   bool srcrec_dirty = true;                    // per-source records of the gather4 kernel
   void* d_stage2 = nullptr;                    // decision tables of the gather4 kernel
   std::vector<int32_t> fam_grid_len = std::vector<int32_t>(AGNF_MAX_FAMILIES, 0);
@@ -96,6 +105,7 @@ struct agnf_ctx {
   double* ens_chain_lnp = nullptr;   // [cap, S * W]
   int64_t ens_chain_cap = 0, ens_chain_n = 0;
   int32_t ens_chain_every = 1;
+  int64_t ens_chain_origin = 0;      // ens_step when recording was switched on
 
   // K4 SED realisations
   K4Params k4{};
@@ -150,6 +160,49 @@ void dev_free(agnf_ctx* ctx, void* p) {
   auto it = std::find(ctx->owned.begin(), ctx->owned.end(), p);
   if (it != ctx->owned.end()) ctx->owned.erase(it);
   cudaFree(p);
+}
+
+// Scratch memory of agnf_dict_build: blocks go back to a per-context pool instead of cudaFree (which synchronises
+// the device) and are handed out again to later calls.  Everything that touches them runs on ctx->stream, so reuse
+// is ordered.  Blocks are released in agnf_ctx_destroy (they sit in `owned`) or by agnf_set_option("release_scratch").
+int scratch_alloc(agnf_ctx* ctx, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 8;
+  size_t best = SIZE_MAX;
+  int arg = -1;
+  for (size_t i = 0; i < ctx->pool.size(); ++i) {
+    const auto& b = ctx->pool[i];
+    if (!b.in_use && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && b.bytes < best) {
+      best = b.bytes;
+      arg = (int)i;
+    }
+  }
+  if (arg >= 0) {
+    ctx->pool[(size_t)arg].in_use = true;
+    *p = ctx->pool[(size_t)arg].ptr;
+    return 0;
+  }
+  const size_t cap = bytes < 65536 ? ((bytes + 511) & ~(size_t)511) : ((bytes + 65535) & ~(size_t)65535);
+  if (dev_alloc(ctx, p, cap)) return 1;
+  ctx->pool.push_back({*p, cap, true});
+  return 0;
+}
+
+void scratch_free(agnf_ctx* ctx, void* p) {
+  if (!p) return;
+  for (auto& b : ctx->pool)
+    if (b.ptr == p) {
+      b.in_use = false;
+      return;
+    }
+  dev_free(ctx, p);
+}
+
+void scratch_release(agnf_ctx* ctx) {
+  for (auto& b : ctx->pool)
+    if (!b.in_use) dev_free(ctx, b.ptr);
+  ctx->pool.erase(std::remove_if(ctx->pool.begin(), ctx->pool.end(), [](const ScratchBlock& b) { return !b.in_use; }),
+                  ctx->pool.end());
 }
 
 template <typename T>
@@ -514,6 +567,20 @@ int check_ready(agnf_ctx* ctx) {
   return 0;
 }
 
+// append the current walker state to the recording buffer (two device-to-device copies on the ctx stream)
+int ens_append_state(agnf_ctx* ctx) {
+  const K3State& st = ctx->ens;
+  if (ctx->ens_chain_n >= ctx->ens_chain_cap)
+    return fail(ctx, "chain buffer full after %lld recorded steps (agnf_ens_record)", (long long)ctx->ens_chain_n);
+  const size_t nw = (size_t)st.S * st.W;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ens_chain + (size_t)ctx->ens_chain_n * nw * st.n_par, st.pos, nw * st.n_par * 8,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ens_chain_lnp + (size_t)ctx->ens_chain_n * nw, st.lnp, nw * 8,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+  ++ctx->ens_chain_n;
+  return 0;
+}
+
 // K1 launch through the kernel the options and the preconditions select; returns the kernel id in *which
 cudaError_t k1_dispatch(agnf_ctx* ctx, const K1Batch& B, cudaStream_t st, int* which) {
   const int v = ctx->k1_variant;
@@ -654,6 +721,11 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     if (ctx->have_ens) ctx->ens.src_offset = value;
     return 0;
   }
+  if (strcmp(name, "release_scratch") == 0) {
+    cudaStreamSynchronize(ctx->stream);
+    scratch_release(ctx);
+    return 0;
+  }
   if (strcmp(name, "k2_mma") == 0) {
     if (value != 0 && value != 1) return fail(ctx, "k2_mma must be 0 or 1");
     ctx->k2_mma = (int)value;
@@ -706,6 +778,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   if (strcmp(name, "k1_variant") == 0) *value = ctx->k1_variant;
   else if (strcmp(name, "k1_last_kernel") == 0) *value = ctx->last_k1_kernel;
   else if (strcmp(name, "k1_table_bytes") == 0) *value = ctx->k1.stage2_bytes;
+  else if (strncmp(name, "k2_prof", 7) == 0 && name[7] >= '0' && name[7] <= '9') *value = (int64_t)ctx->k2_prof[name[7] - '0'];
   else if (strncmp(name, "g4_prof", 7) == 0) {
     cudaStreamSynchronize(ctx->stream);
     *value = (int64_t)k1_g4_prof_read(name[7] - '0', name[8] == 'r');
@@ -1175,6 +1248,11 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
     if (!(lam_sorted[j] >= lam_sorted[j - 1])) return fail(ctx, "lam_sorted must be ascending");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  const auto t_entry = std::chrono::steady_clock::now();
+  auto stamp = [&](int i) {
+    ctx->k2_prof[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_entry).count();
+  };
+  for (double& v : ctx->k2_prof) v = 0.0;
   const int n_b = ctx->filt.n_b;
   K2Problem p;
   p.filt = ctx->filt;
@@ -1189,13 +1267,13 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
        *d_cnt = nullptr, *d_rmax = nullptr, *d_W = nullptr, *d_rowmap = nullptr, *d_out = nullptr, *d_woff = nullptr,
        *d_bandof = nullptr, *d_border = nullptr, *d_jb = nullptr, *d_cb = nullptr, *d_rmaxA = nullptr,
        *d_woffA = nullptr, *d_bandofA = nullptr, *d_WA = nullptr, *d_jb8 = nullptr, *d_cb8 = nullptr,
-       *d_rmax8 = nullptr, *d_Fs8 = nullptr, *d_woff8 = nullptr, *d_bandof8 = nullptr, *d_WA8 = nullptr;
+       *d_rmax8 = nullptr, *d_Fs8 = nullptr, *d_woff8 = nullptr, *d_bandof8 = nullptr, *d_WA8 = nullptr, *d_flag = nullptr;
   auto cleanup = [&]() {
     for (void* q : {d_lam, d_perm, d_F, d_Fs, d_z, d_jlo, d_cnt, d_rmax, d_W, d_rowmap, d_woff, d_bandof, d_border,
                     d_jb, d_cb, d_rmaxA, d_woffA, d_bandofA, d_WA, d_jb8, d_cb8, d_rmax8, d_Fs8, d_woff8, d_bandof8,
-                    d_WA8})
-      dev_free(ctx, q);
-    if (!out_on_device) dev_free(ctx, d_out);
+                    d_WA8, d_flag})
+      scratch_free(ctx, q);
+    if (!out_on_device) scratch_free(ctx, d_out);
   };
 #define K2_TRY(expr)                                                                                    \
   do {                                                                                                  \
@@ -1207,7 +1285,7 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   } while (0)
 #define K2_ALLOC(ptr, bytes)                 \
   do {                                       \
-    if (dev_alloc(ctx, &(ptr), (bytes))) {   \
+    if (scratch_alloc(ctx, &(ptr), (bytes))) {\
       cleanup();                             \
       return 1;                              \
     }                                        \
@@ -1228,6 +1306,8 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   K2_TRY(cudaMemcpyAsync(d_F, Fnu, (size_t)T * n_lam * 8, cudaMemcpyHostToDevice, st));
   K2_TRY(cudaMemcpyAsync(d_z, z, (size_t)n_z * 8, cudaMemcpyHostToDevice, st));
   K2_TRY(cudaMemsetAsync(d_rmax, 0, (size_t)n_b * 4, st));
+  K2_ALLOC(d_flag, 8);
+  K2_TRY(cudaMemsetAsync(d_flag, 0, 8, st));
   if (row_map) {
     for (int64_t t = 0; t < T; ++t)
       if (row_map[t] < 0 || row_map[t] >= T_total) {
@@ -1245,13 +1325,17 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   p.d_rmaxb = static_cast<int32_t*>(d_rmax);
   p.row_map = static_cast<const int64_t*>(d_rowmap);
 
+  stamp(0);          // allocations + uploads enqueued
   K2_TRY(launch_k2_permute(static_cast<const double*>(d_F), static_cast<const int32_t*>(d_perm),
-                           static_cast<double*>(d_Fs), T, n_lam, p.ldF, st));
+                           static_cast<double*>(d_Fs), T, n_lam, p.ldF, static_cast<int32_t*>(d_flag), st));
   K2_TRY(launch_k2_ranges(p, st));
   // compact weight layout: band b owns max_z cnt[z][b] slots of every z-slice
   std::vector<int32_t> rmaxb((size_t)n_b), woff((size_t)n_b + 1, 0);
+  int32_t nonfinite = 0;
   K2_TRY(cudaMemcpyAsync(rmaxb.data(), d_rmax, (size_t)n_b * 4, cudaMemcpyDeviceToHost, st));
+  K2_TRY(cudaMemcpyAsync(&nonfinite, d_flag, 4, cudaMemcpyDeviceToHost, st));
   K2_TRY(cudaStreamSynchronize(st));
+  stamp(1);          // uploads, permutation and ranges done
   for (int b = 0; b < n_b; ++b)     // even slot counts: every band's weight row starts 16-byte aligned
     woff[(size_t)b + 1] = woff[(size_t)b] + ((std::max(rmaxb[(size_t)b], 1) + 1) & ~1);
   const int32_t wstride = (woff[(size_t)n_b] + 1) & ~1;       // even: a z-slice of weights is a 16-byte multiple
@@ -1283,8 +1367,9 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   p.out = static_cast<double*>(d_out);
   // shared-window plan: 4 consecutive slices share each read of the template window.  A non-finite template
   // sample would leak into the neighbouring slices through 0 * inf, so such families take the per-slice kernels.
-  bool finite = ctx->k2_shared_window != 0;
-  for (int64_t i = 0, n = T * (int64_t)n_lam; finite && i < n; ++i) finite = std::isfinite(Fnu[i]);
+  stamp(2);
+  const bool finite = ctx->k2_shared_window != 0 && !nonfinite;      // scanned on the device by the permutation kernel
+  stamp(3);
   if (finite && ctx->k2_mma) {
     // tensor-core plan: batches of 8 slices, windows aligned to multiples of 4 samples, templates re-laid out
     // with a row pitch = 4 (mod 8) (conflict-free 8 x 4 fragments) and >= n_lam + 3 (windows are rounded up)
@@ -1312,7 +1397,7 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
       K2_ALLOC(d_Fs8, (size_t)T_pad * p.ldF8 * 8);
       K2_TRY(cudaMemsetAsync(d_Fs8, 0, (size_t)T_pad * p.ldF8 * 8, st));
       K2_TRY(launch_k2_permute(static_cast<const double*>(d_F), static_cast<const int32_t*>(d_perm),
-                               static_cast<double*>(d_Fs8), T, n_lam, p.ldF8, st));
+                               static_cast<double*>(d_Fs8), T, n_lam, p.ldF8, nullptr, st));
       p.Fs8 = static_cast<const double*>(d_Fs8);
       std::vector<int32_t> band_of8((size_t)p.wstride8, -1);
       for (int b = 0; b < n_b; ++b)
@@ -1379,6 +1464,7 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
     K2_TRY(launch_k2_weights(p, st));
   }
   ctx->k2_last_kernel = p.mma_ok ? 3 : (p.sw_ok ? 2 : 1);
+  stamp(4);          // weights built
   K2_TRY(cudaEventRecord(ctx->ev2, st));
   K2_TRY(launch_k2_contract(p, st));
   K2_TRY(cudaEventRecord(ctx->ev3, st));
@@ -1386,7 +1472,9 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
   ctx->launches += 4;
   if (!out_on_device) K2_TRY(cudaMemcpyAsync(out, d_out, out_count * 8, cudaMemcpyDeviceToHost, st));
   K2_TRY(cudaStreamSynchronize(st));
+  stamp(5);          // contraction done
   cleanup();
+  stamp(6);          // scratch released
   return 0;
 #undef K2_TRY
 #undef K2_ALLOC
@@ -1510,7 +1598,6 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
   if (!ctx) return 1;
   if (!ctx->have_ens) return fail(ctx, "call agnf_ens_create first");
   if (n_steps < 0) return fail(ctx, "n_steps < 0");
-  if (hist_every > 0 && !ctx->ens_hist.hist) return fail(ctx, "the ensemble was created without histograms");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   K3State& st = ctx->ens;
   cudaStream_t s = ctx->stream;
@@ -1557,25 +1644,85 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
       CUDA_TRY(ctx, launch_k3_best(st, ctx->ens_best_pos, ctx->ens_best_lnp, s));
       ctx->launches += 1;
     }
-    if (thinned) {
+    if (thinned && ctx->ens_hist.hist) {      // without histograms `hist_every` only marks the thinned steps (track_best 2)
       CUDA_TRY(ctx, launch_k3_hist(st, ctx->ens_hist, s));
       ctx->ens_hist_samples += st.W;
       ctx->launches += 1;
     }
-    if (ctx->ens_chain && (ctx->ens_step % ctx->ens_chain_every) == 0) {
-      if (ctx->ens_chain_n >= ctx->ens_chain_cap) {
+    if (ctx->ens_chain && ((ctx->ens_step - ctx->ens_chain_origin - 1) % ctx->ens_chain_every) == 0) {
+      if (ens_append_state(ctx)) {
         cudaStreamSynchronize(s);
-        return fail(ctx, "chain buffer full after %lld recorded steps (agnf_ens_record)", (long long)ctx->ens_chain_n);
+        return 1;
       }
-      const size_t nw = (size_t)st.S * st.W;
-      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ens_chain + (size_t)ctx->ens_chain_n * nw * st.n_par, st.pos,
-                                    nw * st.n_par * 8, cudaMemcpyDeviceToDevice, s));
-      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ens_chain_lnp + (size_t)ctx->ens_chain_n * nw, st.lnp, nw * 8,
-                                    cudaMemcpyDeviceToDevice, s));
-      ++ctx->ens_chain_n;
     }
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return 0;
+  AGNF_GUARD_END(ctx)
+}
+
+AGNF_API int agnf_ens_record_state(agnf_ctx* ctx) {
+  AGNF_GUARD_BEGIN
+  if (!ctx) return 1;
+  if (!ctx->have_ens || !ctx->ens_chain) return fail(ctx, "no recording buffer (agnf_ens_record)");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ens_append_state(ctx)) return 1;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+  AGNF_GUARD_END(ctx)
+}
+
+AGNF_API int agnf_ens_chain_percentiles(agnf_ctx* ctx, int64_t first, int64_t stride, const double* q, int32_t n_q,
+                                        double* out_pos, double* out_lnp) {
+  AGNF_GUARD_BEGIN
+  if (!ctx || !q || !out_pos) return 1;
+  if (!ctx->have_ens || !ctx->ens_chain) return fail(ctx, "no recorded chain (agnf_ens_record)");
+  if (n_q < 1 || n_q > K3_SELECT_MAX_Q) return fail(ctx, "n_q outside [1, %d]", K3_SELECT_MAX_Q);
+  for (int k = 0; k < n_q; ++k)
+    if (!(q[k] >= 0.0 && q[k] <= 100.0) || (k > 0 && q[k] < q[k - 1]))
+      return fail(ctx, "percentiles must be ascending values in [0, 100]");
+  if (first < 0 || stride < 1 || first >= ctx->ens_chain_n)
+    return fail(ctx, "agnf_ens_chain_percentiles: first = %lld, stride = %lld with %lld recorded entries",
+                (long long)first, (long long)stride, (long long)ctx->ens_chain_n);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const K3State& st = ctx->ens;
+  void *dq = nullptr, *dout = nullptr, *dout2 = nullptr;
+  const size_t n_pos = (size_t)st.S * st.n_par * n_q, n_lnp = (size_t)st.S * n_q;
+  if (scratch_alloc(ctx, &dq, (size_t)n_q * 8) || scratch_alloc(ctx, &dout, n_pos * 8) ||
+      scratch_alloc(ctx, &dout2, n_lnp * 8)) {
+    scratch_free(ctx, dq);
+    scratch_free(ctx, dout);
+    scratch_free(ctx, dout2);
+    return 1;
+  }
+  cudaStream_t s = ctx->stream;
+  cudaError_t e = cudaMemcpyAsync(dq, q, (size_t)n_q * 8, cudaMemcpyHostToDevice, s);
+  K3Select a;
+  a.S = st.S;
+  a.W = st.W;
+  a.first = first;
+  a.stride = stride;
+  a.n_used = (ctx->ens_chain_n - first + stride - 1) / stride;
+  a.q = static_cast<const double*>(dq);
+  a.n_q = n_q;
+  a.data = ctx->ens_chain;
+  a.E = st.n_par;
+  a.out = static_cast<double*>(dout);
+  if (e == cudaSuccess) e = launch_k3_select(a, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_pos, dout, n_pos * 8, cudaMemcpyDeviceToHost, s);
+  if (out_lnp) {
+    a.data = ctx->ens_chain_lnp;
+    a.E = 1;
+    a.out = static_cast<double*>(dout2);
+    if (e == cudaSuccess) e = launch_k3_select(a, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_lnp, dout2, n_lnp * 8, cudaMemcpyDeviceToHost, s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  scratch_free(ctx, dq);
+  scratch_free(ctx, dout);
+  scratch_free(ctx, dout2);
+  if (e != cudaSuccess) return fail(ctx, "agnf_ens_chain_percentiles: %s", cudaGetErrorString(e));
+  ctx->launches += out_lnp ? 2 : 1;
   return 0;
   AGNF_GUARD_END(ctx)
 }
@@ -1592,6 +1739,7 @@ AGNF_API int agnf_ens_record(agnf_ctx* ctx, int64_t max_steps, int32_t every) {
   ctx->ens_chain_lnp = nullptr;
   ctx->ens_chain_cap = ctx->ens_chain_n = 0;
   ctx->ens_chain_every = every;
+  ctx->ens_chain_origin = ctx->ens_step;
   if (max_steps == 0) return 0;
   const K3State& st = ctx->ens;
   const size_t nw = (size_t)st.S * st.W;

@@ -82,8 +82,10 @@ CoopPlan make_plan(const K1Params& P, bool ens) {
 
 // CPR_T: chunks per row as a compile-time constant (fully unrolled band phase), or 0 = runtime
 // ENS: fused stretch-move launch (propose -> ln_probab -> accept), see K1Ensemble
-template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS>
-__global__ void __launch_bounds__(KC_THREADS, KC_MINBLOCKS)
+// MINB: CTAs per SM the register allocation is sized for (3: 80 registers; 2: 128, for shapes whose per-warp tiles
+// leave room for two CTAs anyway)
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS, int MINB>
+__global__ void __launch_bounds__(KC_THREADS, MINB)
 k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPlan C) {
   constexpr bool EXT = GA_FREE || RADIO || BB_MODE >= 2;
   constexpr int STRIDE = Rec<EXT>::STRIDE;
@@ -496,9 +498,9 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   if (B.lnlike) B.lnlike[i] = lnlike;
 }
 
-template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS>
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS, int MINB>
 cudaError_t launch_coop_ens(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
-  auto kern = k1_coop_kernel<GA_FREE, BB_MODE, RADIO, CPR_T, ENS>;
+  auto kern = k1_coop_kernel<GA_FREE, BB_MODE, RADIO, CPR_T, ENS, MINB>;
   const CoopPlan C = make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, B.ens.pos != nullptr);
   static int attr_bytes[64] = {0};   // per instantiation and device
   int dev = 0;
@@ -523,7 +525,12 @@ constexpr bool TU_ENS = false;
 
 template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
 cudaError_t launch_coop_cpr(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
-  return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS>(P, B, stream);
+  if (CPR_T == 0) {
+    // three CTAs of this shape on an SM?  (227 KB, 1 KB reserved per CTA)
+    const size_t smem = (size_t)make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, B.ens.pos != nullptr).smem_bytes;
+    if (3 * (smem + 1024) > 228 * 1024) return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, 2>(P, B, stream);
+  }
+  return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, KC_MINBLOCKS>(P, B, stream);
 }
 
 // the default 18-band set has a fully unrolled instantiation; every other band count runs the

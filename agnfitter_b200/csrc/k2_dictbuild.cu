@@ -31,13 +31,17 @@ __device__ __forceinline__ int nearest_index(const double* __restrict__ lam0, in
   return lo;
 }
 
+// also raises *nonfinite when a template holds a NaN / inf sample (such families take the per-slice kernels)
 __global__ void k2_permute_kernel(const double* __restrict__ Fnu, const int32_t* __restrict__ perm,
-                                  double* __restrict__ Fs, int64_t T, int32_t n_lam, int32_t ldF) {
+                                  double* __restrict__ Fs, int64_t T, int32_t n_lam, int32_t ldF,
+                                  int32_t* __restrict__ nonfinite) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= T * (int64_t)ldF) return;
   const int64_t t = idx / ldF;
   const int j = (int)(idx - t * ldF);
-  Fs[idx] = (j < n_lam) ? __ldg(Fnu + t * n_lam + __ldg(perm + j)) : 0.0;
+  const double v = (j < n_lam) ? __ldg(Fnu + t * n_lam + __ldg(perm + j)) : 0.0;
+  Fs[idx] = v;
+  if (nonfinite && (v - v) != 0.0) *nonfinite = 1;      // benign race: every writer stores 1
 }
 
 __global__ void k2_ranges_kernel(K2Problem p) {
@@ -834,10 +838,10 @@ bool k2_tile_plan(const K2Problem& p, K2TilePlan* c) {
 }  // namespace
 
 cudaError_t launch_k2_permute(const double* Fnu, const int32_t* perm, double* Fs, int64_t T, int32_t n_lam,
-                              int32_t ldF, cudaStream_t stream) {
+                              int32_t ldF, int32_t* nonfinite, cudaStream_t stream) {
   const int64_t total = T * (int64_t)ldF;
   if (total == 0) return cudaSuccess;
-  k2_permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(Fnu, perm, Fs, T, n_lam, ldF);
+  k2_permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(Fnu, perm, Fs, T, n_lam, ldF, nonfinite);
   return cudaGetLastError();
 }
 

@@ -94,7 +94,7 @@ struct K2Problem {
 };
 
 cudaError_t launch_k2_permute(const double* Fnu, const int32_t* perm, double* Fs, int64_t T, int32_t n_lam,
-                              int32_t ldF, cudaStream_t stream);
+                              int32_t ldF, int32_t* nonfinite, cudaStream_t stream);
 cudaError_t launch_k2_ranges(const K2Problem& p, cudaStream_t stream);
 cudaError_t launch_k2_weights(const K2Problem& p, cudaStream_t stream);
 cudaError_t launch_k2_batch_ranges(const K2Problem& p, cudaStream_t stream);

@@ -153,6 +153,98 @@ __global__ void __launch_bounds__(K3_THREADS) k3_best_kernel(K3State st, double*
   }
 }
 
+// ---- exact percentiles by radix select ------------------------------------------------------------------------
+constexpr int K3_SEL_R = 2 * K3_SELECT_MAX_Q;            // order statistics per (source, column)
+
+__device__ __forceinline__ uint64_t sel_key(double v) {   // order-preserving: -inf < ... < -0 < +0 < ... < +inf < NaN
+  const uint64_t b = (uint64_t)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double sel_val(uint64_t k) {
+  const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(K3_THREADS) k3_select_kernel(K3Select a) {
+  extern __shared__ uint32_t s_hist[];                     // [slots][256]
+  __shared__ uint64_t s_prefix[K3_SEL_R];                  // key bits fixed so far, per order statistic
+  __shared__ uint64_t s_rank[K3_SEL_R];                    // rank among the samples that share the prefix
+  __shared__ int32_t s_slot[K3_SEL_R];                     // histogram of the statistic's prefix
+  __shared__ uint64_t s_slot_prefix[K3_SEL_R];
+  __shared__ int32_t s_nslots;
+  const int64_t s = blockIdx.x / a.E;
+  const int c = (int)(blockIdx.x - s * a.E);
+  const int64_t N = a.n_used * a.W;
+  const int R = 2 * a.n_q;
+  if (N <= 0) {
+    if (threadIdx.x < a.n_q) a.out[((int64_t)s * a.E + c) * a.n_q + threadIdx.x] = NAN;
+    return;
+  }
+  if (threadIdx.x < R) {
+    // numpy: virtual index (N - 1) * (q / 100), lower neighbour floor(), upper min(lower + 1, N - 1)
+    const double h = (double)(N - 1) * (a.q[threadIdx.x >> 1] / 100.0);
+    const int64_t lo = (int64_t)floor(h);
+    s_rank[threadIdx.x] = (uint64_t)((threadIdx.x & 1) ? min(lo + 1, N - 1) : lo);
+    s_prefix[threadIdx.x] = 0;
+  }
+  const int64_t row_stride = (int64_t)a.S * a.W * a.E;
+  const double* __restrict__ base = a.data + (a.first * a.S + s) * (int64_t)a.W * a.E + c;
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    __syncthreads();
+    if (threadIdx.x == 0) {                                // distinct prefixes -> histogram slots
+      int n = 0;
+      for (int r = 0; r < R; ++r) {
+        int f = -1;
+        for (int k = 0; k < n; ++k)
+          if (s_slot_prefix[k] == s_prefix[r]) f = k;
+        if (f < 0) {
+          f = n++;
+          s_slot_prefix[f] = s_prefix[r];
+        }
+        s_slot[r] = f;
+      }
+      s_nslots = n;
+    }
+    __syncthreads();
+    const int ns = s_nslots;
+    for (int i = threadIdx.x; i < ns * 256; i += K3_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < N; i += K3_THREADS) {
+      const int64_t r = i / a.W;
+      const int w = (int)(i - r * a.W);
+      const uint64_t k = sel_key(__ldg(base + r * a.stride * row_stride + (int64_t)w * a.E));
+      const uint64_t hi = pass == 0 ? 0 : (k >> (shift + 8));
+      const unsigned d = (unsigned)(k >> shift) & 255u;
+      for (int sl = 0; sl < ns; ++sl)
+        if (hi == s_slot_prefix[sl]) atomicAdd(&s_hist[sl * 256 + d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < R) {
+      const uint32_t* hh = s_hist + s_slot[threadIdx.x] * 256;
+      uint64_t rank = s_rank[threadIdx.x], cum = 0;
+      int d = 0;
+      for (; d < 255; ++d) {
+        if (cum + hh[d] > rank) break;
+        cum += hh[d];
+      }
+      s_rank[threadIdx.x] = rank - cum;
+      s_prefix[threadIdx.x] = (s_prefix[threadIdx.x] << 8) | (uint64_t)d;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < a.n_q) {
+    const double lo = sel_val(s_prefix[2 * threadIdx.x]), hi = sel_val(s_prefix[2 * threadIdx.x + 1]);
+    const double h = (double)(N - 1) * (a.q[threadIdx.x] / 100.0);
+    const double t = h - floor(h);
+    // numpy's _lerp: a + (b - a) t, and b - (b - a) (1 - t) where t >= 0.5
+    const double diff = hi - lo;
+    double v = __dadd_rn(lo, __dmul_rn(diff, t));
+    if (t >= 0.5) v = __dsub_rn(hi, __dmul_rn(diff, 1.0 - t));
+    a.out[((int64_t)s * a.E + c) * a.n_q + threadIdx.x] = v;
+  }
+}
+
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + K3_THREADS - 1) / K3_THREADS); }
 
 }  // namespace
@@ -220,6 +312,21 @@ cudaError_t launch_k3_hist(const K3State& st, const K3Hist& h, cudaStream_t stre
 cudaError_t launch_k3_percentiles(const K3Hist& h, int64_t S, int32_t n_par, const double* q, int32_t n_q,
                                   double* out, cudaStream_t stream) {
   k3_percentiles_kernel<<<blocks_for(S * n_par), K3_THREADS, 0, stream>>>(h, S, n_par, q, n_q, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k3_select(const K3Select& a, cudaStream_t stream) {
+  if (a.S <= 0 || a.E <= 0 || a.n_q <= 0) return cudaSuccess;
+  if (a.n_q > K3_SELECT_MAX_Q) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(2 * a.n_q) * 256 * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k3_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         2 * K3_SELECT_MAX_Q * 256 * (int)sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k3_select_kernel<<<(unsigned)(a.S * a.E), K3_THREADS, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -61,6 +61,23 @@ cudaError_t launch_k3_hist(const K3State& st, const K3Hist& h, cudaStream_t stre
 // percentiles (linear interpolation inside the bin) of every (source, parameter): out [S, n_par, n_q]
 cudaError_t launch_k3_percentiles(const K3Hist& h, int64_t S, int32_t n_par, const double* q, int32_t n_q,
                                   double* out, cudaStream_t stream);
+// EXACT percentiles of the recorded chain (numpy.percentile, method 'linear' — what PLOTandWRITE_AGNfitter.py:162-191
+// applies to CHAIN.props' thinned flat chain): one CTA per (source, column) finds the two order statistics every
+// percentile needs by an 8-bit radix select over the order-preserving 64-bit keys of its N = n_used * W samples
+// (8 passes, one 256-bin shared-memory histogram per distinct key prefix), then interpolates like numpy's _lerp.
+// The samples of (source s, column c): data[((first + r * stride) * S + s) * W * E + w * E + c], r < n_used, w < W
+// (E = n_par for the positions, 1 for the log-posterior).  out [S, E, n_q].
+struct K3Select {
+  const double* data;
+  int64_t S;
+  int32_t W, E;
+  int64_t first, stride, n_used;
+  const double* q;      // [n_q] ascending, in [0, 100] (device)
+  int32_t n_q;
+  double* out;
+};
+constexpr int K3_SELECT_MAX_Q = 16;
+cudaError_t launch_k3_select(const K3Select& a, cudaStream_t stream);
 // best (max lnp) walker of every source: best_pos [S, n_par], best_lnp [S]
 cudaError_t launch_k3_best(const K3State& st, double* best_pos, double* best_lnp, cudaStream_t stream);
 

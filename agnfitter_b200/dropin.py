@@ -12,6 +12,9 @@ with the reference's names, argument order and return conventions, backed by the
     DICTIONARIES_AGNfitter.filtering_models(nus, F, filterdict, z) :426-478  engine.DictBuilder.filtering_models
     MODELSDICT.construct_dictionaryarray_filtered / build  DIC:78-154      construct_dictionaryarray_filtered / build
     MCMC_AGNfitter.main(data, models, P, mc), emcee leg     MCMC:33-149     main (sampler on the GPU, same chain files)
+    MCMC_AGNfitter.main(...), ultranest leg                 MCMC:74-96      main_ultranest (ultranest on the CPU calling
+                                                                            the GPU posterior; many sources at once
+                                                                            through multiplex.PosteriorMultiplexer)
 
 `data`, `models`, `P` are the reference's own objects (DATA_AGNfitter.DATA, MODEL_AGNfitter.MODELS,
 PARAMETERSPACE_AGNfitter.Pdict): nothing in RUN_AGNfitter_multi.py or the settings files changes.
@@ -100,9 +103,11 @@ def main(data, models, P, mc, seed=None, device=0):
     chains are not reproducible either way).  Returns the summary dict of EnsembleSampler.run_reference_schedule."""
     import os
     from .ensemble import EnsembleSampler
-    if mc.get('sampling_algorithm', 'emcee') != 'emcee':
-        raise ValueError("the GPU sampler implements the emcee leg; for ultranest pass Posterior.my_posterior / "
-                         "my_params_transform to ReactiveNestedSampler (MCMC_AGNfitter.py:79)")
+    algo = mc.get('sampling_algorithm', 'emcee')
+    if algo == 'ultranest':
+        return main_ultranest(data, models, P, mc, device=device)
+    if algo != 'emcee':
+        raise ValueError("sampling_algorithm must be 'emcee' or 'ultranest' (MCMC_AGNfitter.py:74,98), got %r" % (algo,))
     post = Posterior(data, models, P, device=device)
     seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
     ens = EnsembleSampler(post.engine, int(mc['Nwalkers']), seed=seed, n_bins=1024)
@@ -111,6 +116,39 @@ def main(data, models, P, mc, seed=None, device=0):
                                      names=[str(data.name)])
     out["seed"] = seed
     return out
+
+
+def main_ultranest(data, models, P, mc, device=0, posterior=None):
+    """The ultranest leg of MCMC_AGNfitter.main (MCMC_AGNfitter.py:74-96), statement for statement, with the two
+    closures replaced by the GPU-backed callables: ultranest itself stays on the CPU and keeps calling a Python
+    log-posterior (`vectorized=True`: [n, ndim] -> [n]).  `posterior`: an object with `my_posterior` /
+    `my_params_transform` — a Posterior (default) or a multiplex.MuxClient when many sources are fitted concurrently.
+    ultranest is imported here: a machine without it gets ImportError from this function only."""
+    import os
+    import ultranest
+    import ultranest.stepsampler
+    post = posterior if posterior is not None else Posterior(data, models, P, device=device)
+    if not os.path.lexists(data.output_folder + str(data.name)):
+        os.mkdir(data.output_folder + str(data.name))
+    sampler = ultranest.ReactiveNestedSampler(P['names'], post.my_posterior, post.my_params_transform, resume=True,
+                                              log_dir=data.output_folder + str(data.name) + '/ultranest',
+                                              vectorized=True)
+    if mc['direction_generation'] == 'de-mix':
+        direction_stepsampler = ultranest.stepsampler.generate_mixture_random_direction
+    elif mc['direction_generation'] == 'region-slice':
+        direction_stepsampler = ultranest.stepsampler.generate_region_oriented_direction
+    elif mc['direction_generation'] == 'cube-ortho-harm':
+        direction_stepsampler = ultranest.stepsampler.OrthogonalDirectionGenerator(
+            ultranest.stepsampler.generate_random_direction)
+    else:
+        raise ValueError("direction_generation must be 'de-mix', 'region-slice' or 'cube-ortho-harm'")
+    sampler.stepsampler = ultranest.stepsampler.SliceSampler(nsteps=20, generate_direction=direction_stepsampler)
+    sampler.run(min_num_live_points=mc['live_points'], min_ess=mc['min_ess'],
+                max_num_improvement_loops=mc['num_loops'])
+    sampler.plot_run()
+    sampler.plot_trace()
+    sampler.plot_corner()
+    return sampler
 
 
 class CatalogPosterior:

@@ -233,12 +233,12 @@ class DictBuilder:
         # Loaders normally hand every template of a family the SAME array object: group by identity first
         # and compare contents only between the distinct objects.
         vals = list(templates.values())          # positional access: hashing tuple-of-string keys 10^4 times is slow
-        by_id = {}
-        for t, v in enumerate(vals):
-            by_id.setdefault(id(v[0]), (v[0], []))[1].append(t)
+        ids = np.fromiter(map(id, (v[0] for v in vals)), dtype=np.int64, count=T_total)
+        uniq, first, inverse = np.unique(ids, return_index=True, return_inverse=True)
         groups = {}
-        for arr, members in by_id.values():
-            nu = as_f64(arr).reshape(-1)
+        for u in range(len(uniq)):
+            nu = as_f64(vals[int(first[u])][0]).reshape(-1)
+            members = np.nonzero(inverse == u)[0].tolist() if len(uniq) > 1 else list(range(T_total))
             groups.setdefault(nu.tobytes(), (nu, []))[1].extend(members)
         for _, members in groups.values():
             members.sort()
@@ -249,10 +249,14 @@ class DictBuilder:
             lam_sorted = as_f64(lam[order])
             n_lam = len(nu)
             perm = as_i32((n_lam - 1) - order)                          # column in the stored (unreversed) Fnu
-            F = np.concatenate([vals[t][1] for t in members], axis=None)
-            if F.size != len(members) * n_lam:
+            # the template block is assembled directly in a pinned staging buffer (kept across calls): the upload
+            # inside agnf_dict_build is then a true asynchronous DMA instead of a staged pageable copy
+            parts = [vals[t][1] for t in members]
+            F = self._staging(len(members) * n_lam)
+            try:
+                np.concatenate(parts, axis=None, out=F, casting="unsafe")
+            except ValueError:          # total size != len(members) * n_lam
                 raise ValueError("a template's flux array does not match its frequency grid")
-            F = np.ascontiguousarray(F.reshape(len(members), n_lam), dtype=np.float64)
             identity = (len(members) == T_total)
             row_map = None if identity else as_i64(members)
             self.ctx.check(self.lib.agnf_dict_build(
@@ -262,6 +266,15 @@ class DictBuilder:
             self.ctx.check(self.lib.agnf_last_kernel_ms(self.ctx.h, 2, C.byref(ms)))
             self.contract_ms += float(ms.value)
         return out_t if on_device else out
+
+    def _staging(self, n):
+        """Pinned host buffer of n doubles (grow-only; reused by every build_family call of this builder)."""
+        import torch
+        buf = getattr(self, "_pin", None)
+        if buf is None or buf.numel() < n:
+            cap = max(n, 1 << 16)
+            self._pin = buf = torch.empty(cap, dtype=torch.float64).pin_memory()
+        return buf.numpy()[:n]
 
     def filtering_models(self, model_nus, model_fluxes, z):
         """Drop-in for DICTIONARIES_AGNfitter.filtering_models (one template, one z):

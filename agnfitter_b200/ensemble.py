@@ -171,6 +171,22 @@ class EnsembleSampler:
         self.ctx.check(self.lib.agnf_ens_percentiles(self.ctx.h, ptr(q), len(q), ptr(out)))
         return out
 
+    def chain_percentiles(self, q=REFERENCE_PERCENTILES, first=0, stride=1, with_lnp=False):
+        """EXACT percentiles (numpy.percentile, linear method) of the recorded chain entries first, first + stride,
+        ... over all walkers: [S, n_par, n_q] (and [S, n_q] for the log-posterior with with_lnp=True).  On a
+        recorded production run, first = int(n / 2), stride = Nthin reproduces what PLOTandWRITE_AGNfitter.py:162
+        computes from CHAIN.props' thinned flat chain — on the device, by radix select, without a sort."""
+        q = as_f64(q)
+        out = np.empty((self.S, self.n_par, len(q)))
+        lnp = np.empty((self.S, len(q))) if with_lnp else None
+        self.ctx.check(self.lib.agnf_ens_chain_percentiles(self.ctx.h, int(first), int(stride), ptr(q), len(q),
+                                                           ptr(out), ptr(lnp) if with_lnp else None))
+        return (out, lnp) if with_lnp else out
+
+    def record_state(self):
+        """Append the current walker state to the recording buffer without stepping."""
+        self.ctx.check(self.lib.agnf_ens_record_state(self.ctx.h))
+
     # -- chains (the reference's .sav files) ------------------------------------------------------
     def record(self, max_steps, every=1):
         """Keep the walker state of every `every`-th step from now on (device buffer of max_steps entries;
@@ -215,12 +231,15 @@ class EnsembleSampler:
         return t
 
     # -- the reference's schedule -----------------------------------------------------------------
-    def run_reference_schedule(self, mc, pmin, pmax, rng, save_dir=None, names=None):
+    def run_reference_schedule(self, mc, pmin, pmax, rng, save_dir=None, names=None, exact_percentiles=False):
         """mc: the dict of MCMC_settings() (Nwalkers, Nburnsets, Nburn, Nmcmc, Nthin).  rng: a NumPy
         Generator, a list of S Generators (one per source), a ShardStream (vectorised), or None: the balls are
         drawn on the device (set_ball).  With all but the first the balls of a source do not depend on which other
         sources share the shard.  save_dir: also write `<save_dir>/<name>/samples_burn1-2-3.sav`
         and `samples_mcmc.sav` for every source, in the reference's format (MCMC_AGNfitter.py:156-206).
+        exact_percentiles: keep the thinned second half of the production chain on the device (S * W * (n_par + 1) *
+        8 bytes per kept step) and report numpy.percentile-exact values (chain_percentiles) instead of histogram
+        quantiles; the log-posterior's percentiles come with them (`lnp_percentiles`).
         Returns a summary dict: percentiles [S, n_par, 5] and best position / lnP of the thinned second half of the
         production chain (what CHAIN.props keeps), mean acceptance fraction per source over the production run."""
         if int(mc['Nwalkers']) != self.W:
@@ -287,10 +306,22 @@ class EnsembleSampler:
         half, nt = int(n / 2), max(int(mc.get('Nthin', 1)), 1)
         self.run(half)
         self.reset_best()
+        thinned_only = exact_percentiles and save_dir is None and n - half > 0
+        if thinned_only:
+            self.record(len(range(half, n, nt)), every=nt)      # exactly chain[:, half:n:Nthin]
         if n - half > 0:
-            he = 1 if self.n_bins else 0
-            self.run(1, hist_every=he, track_best='thinned' if he else True)
-            self.run(n - half - 1, hist_every=nt if self.n_bins else 0, track_best='thinned' if self.n_bins else True)
+            # hist_every marks the thinned steps: they feed the histograms (if any) and, with track_best='thinned',
+            # the best-fit row — the reference picks it from the thinned flat chain (PLOTandWRITE:483-487)
+            mark = bool(self.n_bins) or bool(exact_percentiles)
+            tb = 'thinned' if mark else True
+            self.run(1, hist_every=1 if mark else 0, track_best=tb)
+            self.run(n - half - 1, hist_every=nt if mark else 0, track_best=tb)
+        exact = lnp_pct = None
+        if exact_percentiles and n - half > 0:
+            exact, lnp_pct = self.chain_percentiles(first=0 if thinned_only else half, stride=1 if thinned_only else nt,
+                                                    with_lnp=True)
+            if thinned_only:
+                self.record(0)
         if save_dir is not None:
             for s_, nm in enumerate(names):
                 self.save_chains(os.path.join(save_dir, str(nm), 'samples_mcmc.sav'), s_)
@@ -299,5 +330,6 @@ class EnsembleSampler:
                 t.join()
         _, _, acc = self.state()
         bp, bl = self.best()
-        return dict(percentiles=self.percentiles() if self.n_bins else None, best_pos=bp, best_lnp=bl,
-                    acceptance=acc.mean(axis=1) / max(n, 1), restart_centres=centres)
+        pct = exact if exact is not None else (self.percentiles() if self.n_bins else None)
+        return dict(percentiles=pct, percentiles_exact=exact is not None, lnp_percentiles=lnp_pct, best_pos=bp,
+                    best_lnp=bl, acceptance=acc.mean(axis=1) / max(n, 1), restart_centres=centres)

@@ -6,6 +6,8 @@ wavelengths, DH02_CE01-like 161 x 1366, S04-like 60 x 30, R06-like with free EBV
 points), and a catalogue generator.  No file of the reference is read: the GPU box has none.
 Shapes and grids are the real ones; spectra are smooth analytic stand-ins ("data": "synthetic").
 """
+import time
+
 import numpy as np
 
 from . import hostmath
@@ -189,7 +191,10 @@ def build_modelset(templates, filterdict, z_grid, builder, settings=CLASSIC_SETT
         keys = list(fam["F"].keys())
         arr = np.array(keys)
         kf = arr.T.astype(float)
-        tab = builder.build_family(fam["F"], z_grid, on_device=on_device)
+        t0 = time.perf_counter()
+        tab = builder.build_family(fam["F"], z_grid, on_device=on_device)     # synchronous (the ctx stream is drained)
+        builder.k2_wall_s = getattr(builder, "k2_wall_s", 0.0) + time.perf_counter() - t0
+        builder.k2_contract_ms = getattr(builder, "k2_contract_ms", 0.0) + builder.contract_ms
         aux = None if fam["aux"] is None else np.array([fam["aux"][k] for k in keys])
         if name == "GA" and 'free' in fam["types"]:
             aux = None

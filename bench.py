@@ -270,9 +270,18 @@ def make_workload(args, rank, device, need_gpu=True):
     builder = DictBuilder(fd, device=device)
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
+    builder.k2_wall_s = builder.k2_contract_ms = 0.0
     ms, dev_tables = synth.build_modelset(tpl, fd, z_grid, builder, settings=settings, on_device=True)
     torch.cuda.synchronize(device)
-    k2_wall = time.perf_counter() - t0
+    k2_cold = builder.k2_wall_s           # first build of the process: pinned staging, scratch pool, output allocation
+    del ms, dev_tables
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    builder.k2_wall_s = builder.k2_contract_ms = 0.0
+    ms, dev_tables = synth.build_modelset(tpl, fd, z_grid, builder, settings=settings, on_device=True)
+    torch.cuda.synchronize(device)
+    modelset_wall = time.perf_counter() - t0
+    k2_wall = builder.k2_wall_s           # DictBuilder.build_family calls only (templates in NumPy -> tables in HBM)
     n_entries = len(z_grid) * sum(f.T for f in ms.families) * ms.n_b
     eng = Engine(ms, device=device, ctx=builder.ctx, device_tables=dev_tables)
     eng.set_option("k1_variant", args.variant)
@@ -286,7 +295,8 @@ def make_workload(args, rank, device, need_gpu=True):
     eng.set_sources(src)
     pars, sid = synth.walker_positions(rng, src.pmin, src.pmax, W, mode=args.positions, frac_out=0.01)
     raw = dict(z=z, dlum=dlum, nus=nus, fluxes=fl, fluxerrs=fe, pmin=src.pmin, pmax=src.pmax, zi=src.zi)
-    info = dict(k2_wall_s=k2_wall, k2_entries=n_entries, n_z=len(z_grid), setup_s=time.perf_counter() - t_setup,
+    info = dict(k2_wall_s=k2_wall, k2_cold_wall_s=k2_cold, k2_entries=n_entries, modelset_wall_s=modelset_wall,
+                k2_contract_ms=builder.k2_contract_ms, n_z=len(z_grid), setup_s=time.perf_counter() - t_setup,
                 builder=builder, templates=tpl, filterdict=fd, z_grid=z_grid, S=S)
     return eng, ms, dev_tables, raw, pars, sid, info
 
@@ -726,6 +736,45 @@ def run_ours(args):
         del sed, d_sp, d_ss, d_so
 
     # ---- the drop-in's own call shape: emcee hands ONE source's half-ensemble (W/2 rows) per call ----------
+    # ---- ultranest's call shape at catalogue scale: one sampler thread per source, each asking for a few hundred
+    #      points per call (MCMC_AGNfitter.py:56-62, vectorized=True); the multiplexer merges the pending requests of
+    #      all threads into one launch per tick (agnfitter_b200/multiplex.py) ---------------------------------------
+    mux_info = None
+    if args.mux_sources > 0 and rank == 0:
+        import threading
+        from agnfitter_b200.multiplex import PosteriorMultiplexer
+        n_cl, n_calls, n_pts = min(args.mux_sources, S), 12, 400
+        rng_m = np.random.default_rng(7)
+        cubes = rng_m.uniform(size=(n_cl, n_pts, n_par))
+        reqs = [raw["pmin"][s] + cubes[s] * (raw["pmax"][s] - raw["pmin"][s]) for s in range(n_cl)]
+        sids = [np.full(n_pts, s, dtype=np.int32) for s in range(n_cl)]
+        for s in range(4):
+            eng.lnprob(reqs[s], sids[s])
+        t0 = time.perf_counter()
+        for k in range(2):                                   # the same requests, one call per source (no merging)
+            for s in range(n_cl):
+                eng.lnprob(reqs[s], sids[s])
+        per_source_s = (time.perf_counter() - t0) / 2
+        with PosteriorMultiplexer(evaluate=eng.lnprob, pmin=raw["pmin"], pmax=raw["pmax"], max_wait_s=5e-4) as mux:
+            def client(s):
+                with mux.client(s) as c:
+                    for k in range(n_calls):
+                        c.my_posterior(reqs[s])
+            th = [threading.Thread(target=client, args=(s,)) for s in range(n_cl)]
+            t0 = time.perf_counter()
+            [t.start() for t in th]
+            [t.join() for t in th]
+            mux_s = time.perf_counter() - t0
+            mux_info = dict(concurrent_sources=n_cl, calls_per_source=n_calls, points_per_call=n_pts,
+                            evals_per_s=n_cl * n_calls * n_pts / mux_s, merged_launches=int(mux.launches),
+                            requests=int(mux.requests),
+                            per_source_calls_evals_per_s=n_cl * n_pts / per_source_s,
+                            what="one Python thread per source calling my_posterior(400 points) like ultranest's "
+                                 "vectorised sampler; PosteriorMultiplexer merges the pending requests into one "
+                                 "agnf_lnprob_batch per tick (values bit-identical to per-source calls: "
+                                 "tests/test_multiplex_gpu.py); beside it the same requests issued one call per source")
+        launches += mux_info["merged_launches"] + 2 * n_cl + 4
+
     small_calls = {}
     for rows_per_call in (W // 2, 16 * W):
         sp_, ss_ = np.ascontiguousarray(pars[:rows_per_call]), np.ascontiguousarray(sid[:rows_per_call])
@@ -849,6 +898,7 @@ def run_ours(args):
                          "bytes_per_eval": bpe, "kernel_ms": k1_ms},
             "roofline_k2": k2_info,
             "cpu_baseline": cpu_block,
+            "ultranest_multiplex": mux_info,
             "small_batch": dict(small_calls, what="agnf_lnprob_batch (host buffers, pinned staging block), one call per batch: the "
                                             "shape emcee (vectorize=True, one source) and ultranest produce"),
             "ensemble": None if not ens_info else {
@@ -872,8 +922,15 @@ def run_ours(args):
                                "rows resident in HBM; cpu = oracle port of FLUXES_ARRAYS.fluxes, one core"),
             "dictionary_build": {"entries": int(info["k2_entries"]), "wall_s": info["k2_wall_s"],
                                  "entries_per_s": info["k2_entries"] / info["k2_wall_s"],
-                                 "what": "K2 over every family and every distinct z of the shard, tables left in HBM; "
-                                         "wall time incl. host preparation and uploads",
+                                 "contract_kernels_ms": info["k2_contract_ms"],
+                                 "first_build_wall_s": info["k2_cold_wall_s"],
+                                 "modelset_wall_s": info["modelset_wall_s"],
+                                 "what": "DictBuilder.build_family over every family and every distinct z of the shard: "
+                                         "template dictionaries in NumPy -> band-flux tables in HBM; wall time incl. "
+                                         "host preparation, uploads, helper kernels, second build of the process "
+                                         "(first_build_wall_s: the first, which also allocates the pinned staging "
+                                         "block, the scratch pool and the output; modelset_wall_s adds the parsing "
+                                         "of the key strings into snapping grids)",
                                  "cpu_entries_per_s_one_core": k2_cpu,
                                  "cpu_sample": None if k2_cpu is None else
                                  "oracle filtering_models on %d galaxy templates x %d bands" % (k2_cpu_n, n_b)},
@@ -956,6 +1013,8 @@ def main():
     ap.add_argument("--fit-nburn", type=int, default=12000)
     ap.add_argument("--fit-nmcmc", type=int, default=25000)
     ap.add_argument("--leg-sources", type=int, default=20000, help="sources of each per-config K1 leg")
+    ap.add_argument("--mux-sources", type=int, default=256,
+                    help="concurrent sampler threads of the ultranest-multiplexer leg (0: skip)")
     ap.add_argument("--no-config-legs", action="store_true")
     ap.add_argument("--no-k2-leg", action="store_true")
     args = ap.parse_args()

@@ -237,8 +237,9 @@ AGNF_API int agnf_ens_set_ball(agnf_ctx* ctx, const double* centre, double scale
  * the reference picks from its thinned flat chain, :483-487); 0 = off. */
 AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, int32_t track_best);
 /* Chain recording for the reference's chain files (samples_burn1-2-3.sav / samples_mcmc.sav,
- * MCMC_AGNfitter.py:192-206): from now on every `every`-th step of agnf_ens_run appends the walker state to a
- * device buffer of max_steps entries (0: stop recording and free it).  agnf_ens_run fails when the buffer is full.
+ * MCMC_AGNfitter.py:192-206): from now on the next step of agnf_ens_run and every `every`-th one after it append the
+ * walker state to a device buffer of max_steps entries (0: stop recording and free it; every = Nthin started at
+ * step int(n/2) records exactly the thinned flat chain of CHAIN.props).  agnf_ens_run fails when the buffer is full.
  * agnf_ens_chain copies what was recorded: chain [n, S, W, n_par], lnp [n, S, W] (either may be NULL). */
 AGNF_API int agnf_ens_record(agnf_ctx* ctx, int64_t max_steps, int32_t every);
 AGNF_API int agnf_ens_chain(agnf_ctx* ctx, double* chain, double* lnp, int64_t* n_recorded);
@@ -252,6 +253,15 @@ AGNF_API int agnf_ens_reset_best(agnf_ctx* ctx);
 /* q [n_q] ascending percentiles in [0, 100] (the reference reports 2.5/16/50/84/97.5,
  * PLOTandWRITE_AGNfitter.py:152-173); out [S, n_par, n_q]; resolution = (P.max - P.min) / n_bins. */
 AGNF_API int agnf_ens_percentiles(agnf_ctx* ctx, const double* q, int32_t n_q, double* out);
+/* EXACT percentiles of the recorded chain: numpy.percentile (method 'linear') over the samples of the recorded
+ * entries first, first + stride, ... of every walker — with first = int(n / 2), stride = Nthin on a recorded
+ * production run this is what PLOTandWRITE_AGNfitter.py:162-191 computes from CHAIN.props' flat chain
+ * (chain[:, int(n/2):n:Nthin, :], :476-487).  q [n_q <= 16] ascending in [0, 100]; out_pos [S, n_par, n_q];
+ * out_lnp [S, n_q] (the log-posterior column, may be NULL).  Radix select on the device: no sort, no host copy. */
+AGNF_API int agnf_ens_chain_percentiles(agnf_ctx* ctx, int64_t first, int64_t stride, const double* q, int32_t n_q,
+                                        double* out_pos, double* out_lnp);
+/* append the CURRENT walker state to the recording buffer (agnf_ens_record) without stepping */
+AGNF_API int agnf_ens_record_state(agnf_ctx* ctx);
 
 /* ---- K4: SED realisations + integrated luminosities ---------------------------------------
  * Replaces the per-realisation loop of FLUXES_ARRAYS.fluxes (functions/PLOTandWRITE_AGNfitter.py:566-799), the

@@ -5,6 +5,7 @@ filter files under /root/reference.  Run in the build container only:
 
     python -m oracle.make_golden            # writes tests/golden/k1_*.npz, k2_*.npz
     python -m oracle.make_golden sed        # writes tests/golden/sed_*.npz (SED realisations)
+    python -m oracle.make_golden chain      # writes tests/golden/chain_props.npz (CHAIN.props + percentiles, N2)
 
 Each K1 file holds: the flattened ModelSet (agnfitter_b200.flatten arrays), the raw
 per-source rows (nus, fluxes, fluxerrs, z, dlum), the reference's P['min']/P['max'],
@@ -532,7 +533,45 @@ def r2_main(only=None):
                  force_xray_detection=True)
 
 
+def chain_props_case(write=True):
+    """The reference's own chain reduction as the checker of N2: a synthetic samples_mcmc.sav (emcee leg format,
+    MCMC_AGNfitter.py:192-206) goes through the UNMODIFIED CHAIN.props (PLOTandWRITE_AGNfitter.py:438-492: thinning
+    [:, int(n/2):n:Nthin], flat chain, best-fit row) and the percentile statement of write_parameters_outputvalues
+    (:162: np.percentile(..., [2.5, 16, 50, 84, 97.5], axis=0)).  The chain is a random walk with repeated samples
+    (rejected proposals repeat a walker's position), ties and a -inf log-posterior entry."""
+    import pickle, tempfile
+    PLT = ref_shim.install_plot()
+    rng = np.random.default_rng(77)
+    W, n, n_par, Nthin = 12, 61, 10, 3          # n_par of the classic model set (the GPU test's ensemble)
+    step = rng.normal(size=(W, n, n_par)) * (rng.uniform(size=(W, n, 1)) < 0.35)      # ~65 % repeated positions
+    scale = np.array([1.0, 1e-3, 50.0, 1e-9, 7.0, 1.0, 0.1, 3.0, 1e5, 1e-300])
+    shift = np.array([0.0, 5.0, -300.0, 1e-6, 2.0, -1.0, 0.5, 10.0, -1e7, 0.0])
+    chain = np.cumsum(step, axis=1) * scale + shift
+    chain[:, :, 4] = np.round(chain[:, :, 4])                                           # many exact ties
+    lnprob = -0.5 * ((chain - chain.mean(axis=(0, 1))) ** 2).sum(axis=2)
+    lnprob[3, 40] = -np.inf
+    with tempfile.TemporaryDirectory() as d:
+        fn = os.path.join(d, "samples_mcmc.sav")
+        with open(fn, "wb") as f:
+            pickle.dump(dict(chain=chain, accept=np.full(W, 0.3), lnprob=lnprob, final_pos=chain[:, -1], state=None,
+                             acor=np.ones(n_par)), f, protocol=2)
+        ch = PLT.CHAIN(fn, None, dict(Nsample=1000, Nthinning=Nthin), dict(sampling_algorithm='emcee'))
+        ch.props()
+    pct = np.percentile(ch.flatchain_sorted, [2.5, 16, 50, 84, 97.5], axis=0)          # PLT:162 (chain_pars columns)
+    lnp_pct = np.percentile(ch.lnprob_flat, [2.5, 16, 50, 84, 97.5], axis=0)
+    out = dict(chain=chain, lnprob=lnprob, Nthin=np.int64(Nthin), ref_flatchain=np.asarray(ch.flatchain),
+               ref_lnprob_flat=np.asarray(ch.lnprob_flat), ref_best_fit_pars=np.asarray(ch.best_fit_pars),
+               ref_lnprob_max=np.asarray(ch.lnprob_max), ref_percentiles=pct, ref_lnp_percentiles=lnp_pct)
+    if write:
+        np.savez_compressed(os.path.join(OUT, "chain_props.npz"), **out)
+        print("wrote chain_props.npz", pct.shape)
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "chain":
+        chain_props_case()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "sed":
         sed_main()
         return

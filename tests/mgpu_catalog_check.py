@@ -52,9 +52,12 @@ def main(out_path):
     templates, fd, settings, z, dlum, nus, fl, fe = make_inputs()
     mc = dict(Nwalkers=16, Nburnsets=2, Nburn=15, Nmcmc=40, Nthin=2)
     from agnfitter_b200.realizations import ranges_to_hz
+    chunk = int(os.environ.get("CATALOG_CHUNK", "0")) or None
+    exact = os.environ.get("CATALOG_EXACT", "0") == "1"
     table = fit_catalog(templates, fd, settings, z, dlum, nus, fl, fe, mc, seed=123, n_bins=512,
                         rank=rank, world=world, device=device, intlum_models=INTLUM_MODELS,
-                        intlum_ranges_hz=ranges_to_hz(INTLUM_RANGES_UM))
+                        intlum_ranges_hz=ranges_to_hz(INTLUM_RANGES_UM), exact_percentiles=exact,
+                        max_sources_per_chunk=chunk)
     if rank == 0:
         np.save(out_path, table)
     if world > 1:

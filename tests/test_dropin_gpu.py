@@ -77,4 +77,50 @@ def test_main_writes_the_reference_chain_files(tmp_path):
     assert_close_with_specials(post.ln_probab_batch(flat), smp["lnprob"].ravel(), what="chain lnprob")
     assert 0.0 < smp["accept"].mean() < 1.0
     with pytest.raises(ValueError):
-        dropin.main(data, models, P, dict(mc, sampling_algorithm='ultranest'))
+        dropin.main(data, models, P, dict(mc, sampling_algorithm='metropolis'))
+
+
+def test_main_ultranest_leg_wiring(tmp_path, monkeypatch):
+    """sampling_algorithm='ultranest' (the example settings' choice, SETTINGS_AGNfitter.py:262): dropin.main hands
+    ultranest the GPU-backed callables the way MCMC_AGNfitter.main hands it its closures (:79-96).  ultranest is not
+    installed here, so a stand-in module records the calls and drives the two callables like the vectorised sampler
+    does."""
+    import sys
+    ms, g = load_k1("classic18")
+    data, models, P = _reference_objects(ms, g, 0)
+    data.output_folder, data.name = str(tmp_path) + "/", "obj9"
+    seen = {}
+
+    class FakeSampler:
+        def __init__(self, names, loglike, transform, resume, log_dir, vectorized):
+            seen.update(names=names, log_dir=log_dir, vectorized=vectorized, resume=resume)
+            self.loglike, self.transform = loglike, transform
+
+        def run(self, **kw):
+            seen["run"] = kw
+            cube = np.random.default_rng(0).uniform(size=(300, len(seen["names"])))
+            p = self.transform(cube)
+            seen["params"], seen["lnp"] = p, self.loglike(p)
+
+        def plot_run(self): seen["plots"] = seen.get("plots", 0) + 1
+        def plot_trace(self): seen["plots"] = seen.get("plots", 0) + 1
+        def plot_corner(self): seen["plots"] = seen.get("plots", 0) + 1
+
+    step = types.ModuleType("ultranest.stepsampler")
+    step.generate_mixture_random_direction = "de-mix"
+    step.generate_region_oriented_direction = "region"
+    step.generate_random_direction = "random"
+    step.OrthogonalDirectionGenerator = lambda f: ("ortho", f)
+    step.SliceSampler = lambda nsteps, generate_direction: ("slice", nsteps, generate_direction)
+    un = types.ModuleType("ultranest")
+    un.ReactiveNestedSampler, un.stepsampler = FakeSampler, step
+    monkeypatch.setitem(sys.modules, "ultranest", un)
+    monkeypatch.setitem(sys.modules, "ultranest.stepsampler", step)
+    mc = dict(sampling_algorithm='ultranest', direction_generation='de-mix', live_points=400, min_ess=400, num_loops=10)
+    sampler = dropin.main(data, models, P, mc)
+    assert seen["names"] == P['names'] and seen["vectorized"] is True and seen["resume"] is True
+    assert seen["log_dir"] == data.output_folder + "obj9/ultranest" and (tmp_path / "obj9").is_dir()
+    assert sampler.stepsampler == ("slice", 20, "de-mix") and seen["plots"] == 3
+    assert seen["run"] == dict(min_num_live_points=400, min_ess=400, max_num_improvement_loops=10)
+    want = dropin.Posterior(data, models, P).ln_probab_batch(seen["params"])
+    assert np.array_equal(seen["lnp"], want, equal_nan=True)

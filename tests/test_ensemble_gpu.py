@@ -1,6 +1,8 @@
 """GPU: the ensemble sampler (K3 + K1) against the CPU oracle step for step — same Philox stream, same
 proposals bit for bit, same accept decisions — and its on-device percentile reduction; then the
 reference's burn-in / production schedule on the example catalogue's two sources."""
+import os
+
 import numpy as np
 import pytest
 
@@ -315,3 +317,71 @@ def test_chains_agree_in_distribution_with_independent_oracle_chains():
         err = np.sqrt(sd ** 2 / R_gpu + sd ** 2 / R_cpu)
         diff = np.abs(med_gpu[s].mean(axis=0) - med_cpu[s].mean(axis=0))
         assert np.all(diff <= 4.5 * err + 1e-3 * span), (s, diff / np.maximum(err, 1e-300))
+
+
+def test_exact_percentiles_match_the_references_chain_props():
+    """N2 exact: the radix-select percentiles of the recorded chain equal what the reference's own CHAIN.props +
+    np.percentile (PLOTandWRITE_AGNfitter.py:471-492, :162) give for the same chain (tests/golden/chain_props.npz,
+    generated from the unmodified reference): thinning [:, n/2::Nthin], values to the last bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chain_props.npz"))
+    chain, nthin = g["chain"], int(g["Nthin"])                    # [W, n, n_par]
+    W, n, n_par = chain.shape
+    ms, g1 = load_k1("classic18")
+    assert ms.n_par == n_par
+    eng = Engine(ms, device=0)
+    # three copies of the source: source 1 gets the chain, its neighbours something else (indexing across sources)
+    rep = lambda a: np.repeat(np.asarray(a)[:1], 3, axis=0)
+    src = sources.make_sources(ms, rep(g1["src_z"]), rep(g1["src_dlum"]), rep(g1["src_nus"]), rep(g1["src_fluxes"]),
+                               rep(g1["src_fluxerrs"]))
+    eng.set_sources(src)
+    ens = EnsembleSampler(eng, W, seed=1, n_bins=0)
+    ens.record(n)
+    rng = np.random.default_rng(0)
+    other = rng.normal(size=(2, W, n, n_par))
+    for k in range(n):
+        ens.set_positions(np.stack([other[0, :, k], chain[:, k], other[1, :, k]]))
+        ens.record_state()
+    got, got_lnp = ens.chain_percentiles(first=int(n / 2), stride=nthin, with_lnp=True)
+    assert np.array_equal(got[1].T, g["ref_percentiles"]), np.abs(got[1].T - g["ref_percentiles"]).max()
+    for s, o in ((0, other[0]), (2, other[1])):
+        flat = o[:, int(n / 2):n:nthin].reshape(-1, n_par)
+        assert np.array_equal(got[s].T, np.percentile(flat, REFERENCE_PERCENTILES, axis=0))
+    # the log-posterior column (-inf for the out-of-box states of this synthetic chain) and other quantile sets
+    ch, lp = ens.chain()
+    with np.errstate(invalid="ignore"):
+        want = np.percentile(lp[:, :, int(n / 2):n:nthin].reshape(3, -1), REFERENCE_PERCENTILES, axis=1).T
+    assert np.array_equal(got_lnp, want, equal_nan=True)
+    q = [0.0, 1.0, 33.3, 50.0, 99.9, 100.0]
+    full = ens.chain_percentiles(q)
+    assert np.array_equal(full[1].T, np.percentile(chain.reshape(-1, n_par), q, axis=0))
+    with pytest.raises(RuntimeError):
+        ens.chain_percentiles(first=n)
+
+
+def test_reference_schedule_exact_percentiles():
+    """run_reference_schedule(exact_percentiles=True) keeps only the thinned second half of the production chain on
+    the device and reports np.percentile-exact values; with chain files requested the same numbers come from the
+    full recorded chain."""
+    import pickle, tempfile
+    ms, eng, src, _ = _setup("cat49_catalog_example")
+    mc = dict(Nwalkers=20, Nburnsets=1, Nburn=15, Nmcmc=41, Nthin=3)
+    a = EnsembleSampler(eng, 20, seed=5, n_bins=0).run_reference_schedule(mc, src.pmin, src.pmax, None,
+                                                                            exact_percentiles=True)
+    assert a["percentiles_exact"] and a["percentiles"].shape == (src.S, ms.n_par, 5)
+    with tempfile.TemporaryDirectory() as d:
+        eng.set_sources(src)
+        b = EnsembleSampler(eng, 20, seed=5, n_bins=0).run_reference_schedule(mc, src.pmin, src.pmax, None, save_dir=d,
+                                                                                names=["a", "b"][:src.S],
+                                                                                exact_percentiles=True)
+        assert np.array_equal(a["percentiles"], b["percentiles"]) and np.array_equal(a["best_pos"], b["best_pos"])
+        for s, nm in enumerate(["a", "b"][:src.S]):
+            with open(os.path.join(d, nm, "samples_mcmc.sav"), "rb") as f:
+                smp = pickle.load(f)
+            n = smp["chain"].shape[1]
+            flat = smp["chain"][:, int(n / 2):n:3, :].reshape(-1, ms.n_par)
+            lnflat = smp["lnprob"][:, int(n / 2):n:3].ravel()
+            assert np.array_equal(b["percentiles"][s].T, np.percentile(flat, REFERENCE_PERCENTILES, axis=0))
+            assert np.array_equal(b["lnp_percentiles"][s], np.percentile(lnflat, REFERENCE_PERCENTILES))
+            assert lnflat.max() == b["best_lnp"][s]
+            assert np.array_equal(eng.lnprob(b["best_pos"][s][None, :], np.array([s], dtype=np.int32)), [lnflat.max()])

@@ -58,6 +58,7 @@ struct agnf_ctx {
   void* d_stage = nullptr;
   std::vector<ScratchBlock> pool;              // scratch blocks of agnf_dict_build (scratch_alloc)
   double k2_prof[10] = {0};                    // host-side time stamps of the last agnf_dict_build (us since entry)
+  int64_t snap_crowded = 0, snap_cells = 0, snap_no_table = 0;   // decision-table statistics (debug options)
   bool srcrec_dirty = true;                    // per-source records of the gather4 kernel
   void* d_stage2 = nullptr;                    // decision tables of the gather4 kernel
   std::vector<int32_t> fam_grid_len = std::vector<int32_t>(AGNF_MAX_FAMILIES, 0);
@@ -97,6 +98,7 @@ struct agnf_ctx {
   int ens_split = 1;                 // 1: emcee 3's random split of the walkers at every step; 0: fixed halves
   int k2_shared_window = 1;          // 1: 4 z-slices share each template read when the family allows it
   int k2_mma = 1;                    // 1: FP64 tensor-core contraction (8-slice batches) when the family allows it
+  double k2_last_flops = 0.0;        // multiply-adds x 2 the last contraction executed (windows as laid out)
   int k2_last_kernel = 0;            // contraction of the last agnf_dict_build: 1 per-slice kernels, 2 shared-window
   int64_t ens_src_offset = 0;        // catalogue row of the shard's first source (Philox counter)
   int64_t ens_hist_samples = 0;
@@ -479,14 +481,19 @@ int rebuild_grids(agnf_ctx* ctx) {
   if (!lut.empty()) memcpy(blob.data() + off_lut, lut.data(), lut.size() * 2);
 
   ctx->k1.n_tasks = 0;
+  ctx->snap_no_table = 0;
   for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
     if (!ctx->fam_set[f]) continue;
     for (int t = 0; t < ctx->k1.fam[f].n_snap; ++t) {
       SnapTask T = ctx->k1.fam[f].snap[t];
       T.fam = f;
       ctx->k1.tasks[ctx->k1.n_tasks++] = T;
+      if (T.dmmax < 0) ctx->snap_no_table += 1;
     }
   }
+  ctx->snap_cells = (int64_t)dlut.size();
+  ctx->snap_crowded = 0;
+  for (uint16_t c : dlut) ctx->snap_crowded += c == 0xffffu;
   // blob of the gather4 kernel
   const size_t off_dlut = 0, off_brec = pad16(dlut.size() * 2), off_p16 = off_brec + pad16(brec.size() * 8 + 8),
                total2 = off_p16 + pad16(perm16.size() * 2);
@@ -778,6 +785,9 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   if (strcmp(name, "k1_variant") == 0) *value = ctx->k1_variant;
   else if (strcmp(name, "k1_last_kernel") == 0) *value = ctx->last_k1_kernel;
   else if (strcmp(name, "k1_table_bytes") == 0) *value = ctx->k1.stage2_bytes;
+  else if (strcmp(name, "k1_table_cells") == 0) *value = ctx->snap_cells;
+  else if (strcmp(name, "k1_table_crowded_cells") == 0) *value = ctx->snap_crowded;
+  else if (strcmp(name, "k1_tasks_without_table") == 0) *value = ctx->snap_no_table;
   else if (strncmp(name, "k2_prof", 7) == 0 && name[7] >= '0' && name[7] <= '9') *value = (int64_t)ctx->k2_prof[name[7] - '0'];
   else if (strncmp(name, "g4_prof", 7) == 0) {
     cudaStreamSynchronize(ctx->stream);
@@ -792,6 +802,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "k2_shared_window") == 0) *value = ctx->k2_shared_window;
   else if (strcmp(name, "k2_mma") == 0) *value = ctx->k2_mma;
   else if (strcmp(name, "k2_last_kernel") == 0) *value = ctx->k2_last_kernel;
+  else if (strcmp(name, "k2_last_mflops") == 0) *value = (int64_t)(ctx->k2_last_flops * 1e-6);
   else if (strcmp(name, "ens_source_offset") == 0) *value = ctx->ens_src_offset;
   else return fail(ctx, "unknown option '%s'", name);
   return 0;
@@ -1464,6 +1475,10 @@ AGNF_API int agnf_dict_build(agnf_ctx* ctx, const double* lam_sorted, const int3
     K2_TRY(launch_k2_weights(p, st));
   }
   ctx->k2_last_kernel = p.mma_ok ? 3 : (p.sw_ok ? 2 : 1);
+  // flops the contraction executes: every band's (padded) window x templates x slices of a batch
+  if (p.mma_ok) ctx->k2_last_flops = 2.0 * (double)p.n_zb8 * 8.0 * (double)p.wstride8 * (double)T_pad;
+  else if (p.sw_ok) ctx->k2_last_flops = 2.0 * (double)p.n_zb * 4.0 * (double)p.wstrideA * (double)T_pad;
+  else ctx->k2_last_flops = 2.0 * (double)n_z * (double)wstride * (double)T;
   stamp(4);          // weights built
   K2_TRY(cudaEventRecord(ctx->ev2, st));
   K2_TRY(launch_k2_contract(p, st));

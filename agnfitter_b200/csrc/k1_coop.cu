@@ -67,7 +67,11 @@ template <bool EXT>
 CoopPlan make_plan(const K1Params& P, bool ens) {
   CoopPlan c;
   const bool eb_free = P.cfg.ga_free_ebv != 0 && P.cfg.eb_mode != 0;
+#ifdef KC_OLD_SNAP
+  c.stage_pad = (P.stage_bytes + 15) & ~15;
+#else
   c.stage_pad = (P.stage2_bytes + 15) & ~15;
+#endif
   c.cpr = P.nbp / 2;
   c.cprp = c.cpr | 1;
   const int a = 32 * c.cprp * (eb_free ? 2 : 1), b = 32 * P.cfg.n_par;
@@ -99,8 +103,14 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   const uint32_t tab_s = smem_u32(smem_raw);                 // 64 doubles
   const uint32_t bar_s = tab_s + 64 * 8;                     // [0] blob, [1 + w] warp w
   const uint32_t stage_s = bar_s + 16 * 8;
+#ifdef KC_OLD_SNAP
+  const uint32_t ext_s = stage_s + P.stage_off_grid, eperm_s = stage_s + P.stage_off_perm,
+                 lut_s = stage_s + P.stage_off_lut;
+  const unsigned char* stage_generic = smem_raw + 64 * 8 + 16 * 8;
+#else
   const uint32_t dlut_s = stage_s + P.stage2_off_dlut, brec_s = stage_s + P.stage2_off_brec,
                  perm_s = stage_s + P.stage2_off_perm;
+#endif
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t scal_s = stage_s + C.stage_pad + (unsigned)warp * (unsigned)C.per_warp * 8u;
   const uint32_t part_s = scal_s + 32 * STRIDE * 8;
@@ -119,10 +129,17 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     sts_f64(tab_s + 8u * threadIdx.x, c_exp2_tab[threadIdx.x * (64 / AGNF_POW2_DENOM)]);
   __syncthreads();
   // one bulk copy brings the grids + cell tables; one per warp brings that warp's params rows
+#ifdef KC_OLD_SNAP
+  if (threadIdx.x == 0 && P.stage_bytes > 0) {
+    mbar_expect_tx(bar_s, (uint32_t)P.stage_bytes);
+    bulk_g2s(stage_s, P.stage, (uint32_t)P.stage_bytes, bar_s);
+  }
+#else
   if (threadIdx.x == 0 && P.stage2_bytes > 0) {
     mbar_expect_tx(bar_s, (uint32_t)P.stage2_bytes);
     bulk_g2s(stage_s, P.stage2, (uint32_t)P.stage2_bytes, bar_s);
   }
+#endif
   if (lane == 0 && par_bytes > 0) {
     mbar_expect_tx(bar_s + 8u + 8u * warp, par_bytes);
     bulk_g2s(q_s, B.params + row0 * n_par, par_bytes, bar_s + 8u + 8u * warp);   // 256-byte aligned source
@@ -214,6 +231,27 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
     }
   }
 
+#ifdef KC_OLD_SNAP
+  if (P.stage_bytes > 0) mbar_wait(bar_s, 0);
+  const double* ext_g = reinterpret_cast<const double*>(stage_generic + P.stage_off_grid);
+  const int32_t* eperm_g = reinterpret_cast<const int32_t*>(stage_generic + P.stage_off_perm);
+  int row[AGNF_MAX_FAMILIES], grow[AGNF_MAX_FAMILIES];
+#pragma unroll
+  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
+    row[f] = 0;
+    grow[f] = 0;
+    if (f < (RADIO ? 5 : 4)) {
+      const FamDesc& F = P.fam[f];
+      int r = 0;
+      for (int t = 0; t < F.n_snap; ++t) {
+        const SnapTask& T = F.snap[t];
+        r += snap_task(T, lds_f64(p_s + 8u * T.col), ext_s, eperm_s, lut_s, ext_g, eperm_g) * T.stride;
+      }
+      row[f] = r;
+      grow[f] = zi * (int)F.T + r;
+    }
+  }
+#else
   if (P.stage2_bytes > 0) mbar_wait(bar_s, 0);
   // the snaps of all families through the decision tables (k1_dev.cuh::snap_fast: one 16-bit read, plus one 16-byte
   // read when the cell straddles a switch point), four at a time as one straight-line block
@@ -248,6 +286,7 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   }
 #pragma unroll
   for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) grow[f] = f < (RADIO ? 5 : 4) ? zi * (int)P.fam[f].T + row[f] : 0;
+#endif
   // start the only DRAM-bound gather early: this evaluation's galaxy row -> L2
   {
     const char* ga = reinterpret_cast<const char*>(P.fam[0].table + (int64_t)grow[0] * P.fam[0].pitch);
@@ -526,9 +565,13 @@ constexpr bool TU_ENS = false;
 template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
 cudaError_t launch_coop_cpr(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
   if (CPR_T == 0) {
-    // three CTAs of this shape on an SM?  (227 KB, 1 KB reserved per CTA)
+    // Three CTAs of this shape on an SM only if they fit the 196 KB shared-memory carve-out: at the next step (228 KB)
+    // the L1 keeps 28 KB and the gathers of the small families miss (measured on the 49-band set: 0.81 ms per 2e6
+    // rows with three CTAs of 80 registers, 0.70 ms with two of 114)
     const size_t smem = (size_t)make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, B.ens.pos != nullptr).smem_bytes;
-    if (3 * (smem + 1024) > 228 * 1024) return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, 2>(P, B, stream);
+#ifndef KC_FORCE_MINB3
+    if (3 * (smem + 1024) > 196 * 1024) return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, 2>(P, B, stream);
+#endif
   }
   return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, KC_MINBLOCKS>(P, B, stream);
 }

@@ -686,6 +686,8 @@ def run_ours(args):
         k_ms = float(min(kerns))
         peak_hbm, _ = measured_peak()
         alg_flops = 2.0 * len(z_grid) * T_ga * sum_nk
+        exe_flops = builder.get_option("k2_last_mflops") * 1e6
+        on_tc = builder.get_option("k2_last_kernel") == 3
         k2_info = {"bound": "hbm", "family": "GA (%d templates x %d samples)" % (T_ga, len(next(iter(tpl["GA"]["F"].values()))[0])),
                    "kernel": {3: "k2_contract_mma", 2: "k2_contract_sw", 1: "k2_contract_tile"}.get(builder.get_option("k2_last_kernel"), "?"),
                    "entries": int(entries), "kernel_ms": k_ms, "wall_ms": float(min(walls)) * 1e3,
@@ -695,6 +697,12 @@ def run_ours(args):
                    "frac": entries * 8 / (k_ms * 1e-3) / 1e9 / peak_hbm,
                    "algorithmic_bytes_per_launch": entries * 8,
                    "fp64_peak_tflops": peaks,
+                   "executed_flops_per_launch": exe_flops,
+                   "executed_tflops": exe_flops / (k_ms * 1e-3) / 1e12,
+                   "frac_of_fp64_peak": exe_flops / (k_ms * 1e-3) / 1e12 / max(peaks["dmma" if on_tc else "dfma"], 1e-9),
+                   "binding": "fp64 (the contraction's multiply-adds over the 8-slice union windows against the "
+                              "measured %s peak); the HBM write of the result (`frac`) overlaps it" % (
+                                  "DMMA" if on_tc else "DFMA"),
                    "algorithmic_flops_per_launch": alg_flops,
                    "algorithmic_tflops": alg_flops / (k_ms * 1e-3) / 1e12,
                    "note": "algorithmic flops = 2 n_k per entry (SURVEY 8d: one multiply-add per filter sample); the "

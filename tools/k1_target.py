@@ -28,7 +28,9 @@ for o in a.opt:
     k, v = o.split("=")
     eng.set_option(k, int(v))
 S, W, n = info["S"], a.walkers, len(pars)
-print("snap tables: %d bytes" % eng.get_option("k1_table_bytes"))
+print("snap tables: %d bytes, %d cells (%d crowded), %d tasks without a table" % (
+    eng.get_option("k1_table_bytes"), eng.get_option("k1_table_cells"), eng.get_option("k1_table_crowded_cells"),
+    eng.get_option("k1_tasks_without_table")))
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev)
 if a.mode == "plain":

@@ -94,6 +94,8 @@ struct agnf_ctx {
   double* ens_best_pos = nullptr;
   double* ens_best_lnp = nullptr;
   int64_t ens_step = 0;              // stretch-move steps taken since agnf_ens_create (Philox counter)
+  int ens_persist = -1;              // persistent per-source sampler: -1 automatic (small shards), 0 never, 1 whenever possible
+  int ens_last_persist = 0;          // whether the last agnf_ens_run took the persistent kernel
   int ens_fused = 1;                 // 1: one fused K1 launch per half-step; 0: propose / K1 / accept kernels
   int ens_split = 1;                 // 1: emcee 3's random split of the walkers at every step; 0: fixed halves
   int k2_shared_window = 1;          // 1: 4 z-slices share each template read when the family allows it
@@ -743,6 +745,11 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     ctx->k2_shared_window = (int)value;
     return 0;
   }
+  if (strcmp(name, "ens_persist") == 0) {
+    if (value < -1 || value > 1) return fail(ctx, "ens_persist must be -1 (automatic), 0 or 1");
+    ctx->ens_persist = (int)value;
+    return 0;
+  }
   if (strcmp(name, "ens_fused") == 0) {
     if (value != 0 && value != 1) return fail(ctx, "ens_fused must be 0 or 1");
     ctx->ens_fused = (int)value;
@@ -798,6 +805,8 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "small_rows") == 0) *value = ctx->small_rows;
   else if (strcmp(name, "zero_copy_rows") == 0) *value = ctx->zero_copy_rows;
   else if (strcmp(name, "ens_fused") == 0) *value = ctx->ens_fused;
+  else if (strcmp(name, "ens_persist") == 0) *value = ctx->ens_persist;
+  else if (strcmp(name, "ens_last_persist") == 0) *value = ctx->ens_last_persist;
   else if (strcmp(name, "ens_split") == 0) *value = ctx->ens_split;
   else if (strcmp(name, "k2_shared_window") == 0) *value = ctx->k2_shared_window;
   else if (strcmp(name, "k2_mma") == 0) *value = ctx->k2_mma;
@@ -1629,6 +1638,50 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
   FB.ens.split = st.split;
   ctx->ens_hist.pbox = ctx->k1.pbox;
   const bool fused = ctx->ens_fused && k1_fused_available(ctx, FB);
+  // Small shards: ONE launch for all n_steps, one CTA per source (k1_coop_kernel<..., PERSIST>): the lock-step path
+  // pays ~5 launches per step, which is all a shard of a few hundred sources costs.  Same Philox counters, same
+  // arithmetic: the chain is identical bit for bit (tests/test_ensemble_gpu.py).
+  const int v = ctx->k1_variant;
+  const bool persist = ctx->ens_fused && v != 0 && v != 3 && n_steps > 0 && ctx->ens_persist != 0 &&
+                       k1_coop_persist_supported(ctx->k1, FB) && (ctx->ens_persist == 1 || st.S <= 1184);
+  ctx->ens_last_persist = persist ? 1 : 0;
+  if (persist) {
+    K1Persist A;
+    A.step0 = ctx->ens_step;
+    A.n_steps = n_steps;
+    A.hist_every = hist_every;
+    A.track_best = track_best;
+    A.hist = ctx->ens_hist.hist;
+    A.pbox = ctx->k1.pbox;
+    A.n_bins = ctx->ens_hist.n_bins;
+    A.best_pos = ctx->ens_best_pos;
+    A.best_lnp = ctx->ens_best_lnp;
+    A.S = st.S;
+    int64_t n_rec = 0, n_thin = 0;
+    if (hist_every > 0) n_thin = n_steps / hist_every;
+    if (ctx->ens_chain) {
+      for (int64_t k = 0; k < n_steps; ++k)
+        n_rec += ((ctx->ens_step + k - ctx->ens_chain_origin) % ctx->ens_chain_every) == 0;
+      if (ctx->ens_chain_n + n_rec > ctx->ens_chain_cap)
+        return fail(ctx, "chain buffer full after %lld recorded steps (agnf_ens_record)", (long long)ctx->ens_chain_cap);
+      A.chain = ctx->ens_chain;
+      A.chain_lnp = ctx->ens_chain_lnp;
+      A.chain_n0 = ctx->ens_chain_n;
+      A.chain_origin = ctx->ens_chain_origin;
+      A.chain_every = ctx->ens_chain_every;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, s));
+    CUDA_TRY(ctx, launch_k1_coop_persist(ctx->k1, FB, A, s));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, s));
+    ctx->k1_timed = true;
+    ctx->last_k1_kernel = 1;
+    ctx->launches += 1;
+    ctx->ens_step += n_steps;
+    ctx->ens_chain_n += n_rec;
+    if (ctx->ens_hist.hist) ctx->ens_hist_samples += n_thin * st.W;
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return 0;
+  }
   for (int64_t it = 0; it < n_steps; ++it) {
     if (st.split) {
       CUDA_TRY(ctx, launch_k3_split(st, ctx->ens_step, s));

@@ -75,6 +75,42 @@ __device__ __forceinline__ double pow2_64(double t, uint32_t tab_s) {
   return __hiloint2double(__double2hiint(v) + ((k >> P2_SHIFT) << 20), __double2loint(v));
 }
 
+// ---- pinned forms -------------------------------------------------------------------------------------------------
+// The cooperative kernel's arithmetic leaves the multiply-add contraction of a few expressions to the compiler; what
+// it compiles to (read off its SASS) is spelled out here for the kernels that must reproduce it bit for bit in other
+// instantiations (persistent sampler, gather4 kernel), where the compiler's own choice can differ by an ulp:
+//   a*b + c*d [+ e*f + g*h]   ->  fma(.., fma(e, f, fma(a, b, c*d)))      (the SECOND product is the plain multiply)
+//   2^(a b / D), band loop    ->  t = a*b rounded, integer part from t + magic (not fused)
+//   10^x, normalisations      ->  t = x C rounded for the remainder, integer part from fma(x, C, magic)
+__device__ __forceinline__ double sum2_pinned(double a, double b, double c, double d) {
+  return __fma_rn(a, b, __dmul_rn(c, d));
+}
+__device__ __forceinline__ double sum4_pinned(double a, double b, double c, double d, double e, double f, double g,
+                                              double h) {
+  return __fma_rn(g, h, __fma_rn(e, f, __fma_rn(a, b, __dmul_rn(c, d))));
+}
+template <bool NB>
+__device__ __forceinline__ double pow10_pinned(double x, uint32_t tab_s, bool& bad) {
+  const double t = __dmul_rn(x, P2_LOG2_10_D);
+  if (NB) bad = bad || !(fabs(t) < 1000.0 * AGNF_POW2_DENOM);
+  else if (!(fabs(t) < 1000.0 * AGNF_POW2_DENOM)) return pow2_64_slow(t);
+  const double magic = 6755399441055744.0;
+  const double km = __fma_rn(x, P2_LOG2_10_D, magic);
+  const int k = __double2loint(km);
+  const double r = t - (km - magic);
+  double p = c_p2[P2_DEG - 1];
+#pragma unroll
+  for (int n = P2_DEG - 2; n >= 0; --n) p = fma(p, r, c_p2[n]);
+  p = fma(p, r, 1.0);
+  const double v = lds_f64_ro(tab_s + ((k << 3) & (8 * AGNF_POW2_DENOM - 8))) * p;
+  return __hiloint2double(__double2hiint(v) + ((k >> P2_SHIFT) << 20), __double2loint(v));
+}
+
+__device__ __forceinline__ double pow10_pinned_tile(double x, uint32_t tab_s) {
+  bool unused = false;
+  return pow10_pinned<false>(x, tab_s, unused);
+}
+
 // The same arithmetic without the range branch: out-of-range (or NaN) arguments raise `bad` and return garbage; the
 // caller repeats the evaluation through pow2_64 (straight-line band loops: k1_g4.cu)
 __device__ __forceinline__ double pow2_64_nb(double t, uint32_t tab_s, bool& bad) {
@@ -160,26 +196,27 @@ __device__ __forceinline__ int snap_dim_lut(const double* __restrict__ ext, cons
 // Gaussian_prior(mu, sigma, x) = log(1/(sqrt(2 pi) sigma)) - 0.5 (x-mu)^2 / sigma^2 (PRIORS_AGNfitter.py:428-430);
 // lognorm is evaluated once on the host (libm), inv_var = 1/sigma^2.
 __device__ __forceinline__ double gaussian_prior(double lognorm, double inv_var, double mu, double x) {
-  const double d = x - mu;
-  return lognorm - 0.5 * (d * d) * inv_var;
+  // every operation rounded on its own, no fused multiply-add: all kernels (and NumPy) round alike
+  const double d = __dsub_rn(x, mu);
+  return __dsub_rn(lognorm, __dmul_rn(__dmul_rn(0.5, __dmul_rn(d, d)), inv_var));
 }
 
 // prior_midIR_UV (PRIORS_AGNfitter.py:327-357).  tor6 = torus band flux at 6 um times 10^TO; bb2500 = band flux of
 // the unreddened disc template at 2500 A times 10^BB; lumf = 4. pi dlum^2. (:331); lumf_bb = 4 pi (dlum)^2 (:346)
 __device__ __forceinline__ double prior_midir_uv(const K1Params& P, double tor6, double bb2500, double BB, double lumf,
                                                  double lumf_bb) {
-  const double x = log10(tor6 * lumf) - 27.30103;
-  const double to_model = (16.2530786 + 1.024 * x - 0.047 * (x * x)) / 0.643;
+  const double x = __dsub_rn(log10(__dmul_rn(tor6, lumf)), 27.30103);
+  const double to_model = __dsub_rn(__dadd_rn(16.2530786, __dmul_rn(1.024, x)), __dmul_rn(0.047, __dmul_rn(x, x))) / 0.643;
   if (BB != 0.0) bb2500 = bb2500 * lumf_bb;                   // decided by VALUE (:345)
-  return gaussian_prior(P.lognorm_s06, 1.0 / (0.6 * 0.6), 0.0, log10(bb2500) - to_model);
+  return gaussian_prior(P.lognorm_s06, 1.0 / (0.6 * 0.6), 0.0, __dsub_rn(log10(bb2500), to_model));
 }
 
 // prior_IR_XRays (PRIORS_AGNfitter.py:302-324).  logf_data = log10(F_2-10keV,data * lumfactor) (:317-318, host)
 __device__ __forceinline__ double prior_ir_xrays(const K1Params& P, double tor6, double lumf, double logf_data) {
   const double nuLnu = (P.xp_c6um * tor6) * lumf;
   const double x = log10(nuLnu / 1e41);
-  const double logf_model = 22.9494264 + 1.024 * x - 0.047 * (x * x);
-  return gaussian_prior(P.lognorm_s05, 1.0 / (0.5 * 0.5), 0.0, logf_data - logf_model);
+  const double logf_model = __dsub_rn(__dadd_rn(22.9494264, __dmul_rn(1.024, x)), __dmul_rn(0.047, __dmul_rn(x, x)));
+  return gaussian_prior(P.lognorm_s05, 1.0 / (0.5 * 0.5), 0.0, __dsub_rn(logf_data, logf_model));
 }
 
 }  // namespace agnf

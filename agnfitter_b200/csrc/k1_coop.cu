@@ -61,17 +61,14 @@ struct CoopPlan {
   int32_t per_warp;       // doubles per warp: 32 records + max(params block, partial planes) [+ proposals]
   int32_t q_off;          // doubles from the partial-sum area to the proposal rows (ensemble mode), else 0
   int32_t smem_bytes;
+  int32_t walkers_off;    // persistent sampler: bytes from the start of shared memory to the source's walkers
 };
 
 template <bool EXT>
-CoopPlan make_plan(const K1Params& P, bool ens) {
+CoopPlan make_plan(const K1Params& P, bool ens, int n_warps = KC_WARPS) {
   CoopPlan c;
   const bool eb_free = P.cfg.ga_free_ebv != 0 && P.cfg.eb_mode != 0;
-#ifdef KC_OLD_SNAP
-  c.stage_pad = (P.stage_bytes + 15) & ~15;
-#else
   c.stage_pad = (P.stage2_bytes + 15) & ~15;
-#endif
   c.cpr = P.nbp / 2;
   c.cprp = c.cpr | 1;
   const int a = 32 * c.cprp * (eb_free ? 2 : 1), b = 32 * P.cfg.n_par;
@@ -80,8 +77,77 @@ CoopPlan make_plan(const K1Params& P, bool ens) {
   const int part = (((ens || a > b) ? a : b) + 1) & ~1;
   c.q_off = ens ? part : 0;
   c.per_warp = 32 * Rec<EXT>::STRIDE + part + (ens ? ((32 * P.cfg.n_par + 1) & ~1) : 0);
-  c.smem_bytes = 64 * 8 /*exp2 table*/ + 16 * 8 /*mbarriers*/ + c.stage_pad + KC_WARPS * c.per_warp * 8;
+  c.smem_bytes = 64 * 8 /*exp2 table*/ + 16 * 8 /*mbarriers*/ + c.stage_pad + n_warps * c.per_warp * 8;
+  c.walkers_off = c.smem_bytes;
   return c;
+}
+
+// ---- per-step work of the persistent sampler, each the per-source form of a K3 kernel (k3_ensemble.cu) --------------
+// k3_split_kernel: rank the source's W walkers by their Philox key of this step (ties by walker index)
+__device__ __forceinline__ void persist_split(uint16_t* out, uint32_t* keys, int W, int64_t step, int64_t src_global,
+                                              uint64_t seed, int lane) {
+  const int W4 = (W + 3) & ~3;
+  for (int q = lane; q < W4 / 4; q += 32) {
+    uint32_t x[4];
+    philox4x32_10((uint32_t)step, K3_SPLIT_TAG, (uint32_t)src_global, (uint32_t)q, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+    keys[4 * q] = x[0];
+    keys[4 * q + 1] = x[1];
+    keys[4 * q + 2] = x[2];
+    keys[4 * q + 3] = x[3];
+  }
+  __syncwarp();
+  for (int w0 = lane; w0 < W; w0 += 32) {
+    const uint32_t k0 = keys[w0];
+    int r0 = 0;
+    for (int j = 0; j < W; ++j) {
+      const uint32_t kj = keys[j];
+      r0 += (kj < k0) || (kj == k0 && j < w0);
+    }
+    out[r0] = (uint16_t)w0;
+  }
+  __syncwarp();
+}
+
+// k3_best_kernel: the first walker with the largest lnp, if it beats the stored best
+__device__ __forceinline__ void persist_best(const double* pos, const double* lnp, int W, int n_par, double* best_pos,
+                                             double* best_lnp, int lane) {
+  double bv = -INFINITY;
+  int bk = -1;
+  for (int k = lane; k < W; k += 32) {
+    const double v = lnp[k];
+    if (v > bv) {
+      bv = v;
+      bk = k;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+    if (ok >= 0 && (bk < 0 || ov > bv || (ov == bv && ok < bk))) {
+      bv = ov;
+      bk = ok;
+    }
+  }
+  if (bk >= 0 && bv > *best_lnp) {          // every lane holds the same (bv, bk)
+    for (int c = lane; c < n_par; c += 32) best_pos[c] = pos[(int64_t)bk * n_par + c];
+    __syncwarp();
+    if (lane == 0) *best_lnp = bv;
+  }
+}
+
+// k3_hist_kernel for one source
+__device__ __forceinline__ void persist_hist(const double* pos, int W, int n_par, uint32_t* hist, const double2* pbox,
+                                             int n_bins, int64_t src) {
+  for (int e = threadIdx.x; e < W * n_par; e += blockDim.x) {
+    const int c = e % n_par;
+    const double2 mm = pbox[src * n_par + c];
+    const double v = pos[e];
+    const double f = (v - mm.x) / (mm.y - mm.x) * (double)n_bins;
+    int b = (int)f;
+    b = max(0, min(n_bins - 1, b));
+    if (v == v) atomicAdd(hist + (src * n_par + c) * n_bins + b, 1u);
+  }
 }
 
 // CPR_T: chunks per row as a compile-time constant (fully unrolled band phase), or 0 = runtime
@@ -91,6 +157,7 @@ CoopPlan make_plan(const K1Params& P, bool ens) {
 template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS, int MINB>
 __global__ void __launch_bounds__(KC_THREADS, MINB)
 k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPlan C) {
+  constexpr bool PERSIST = false;
   constexpr bool EXT = GA_FREE || RADIO || BB_MODE >= 2;
   constexpr int STRIDE = Rec<EXT>::STRIDE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -103,23 +170,16 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   const uint32_t tab_s = smem_u32(smem_raw);                 // 64 doubles
   const uint32_t bar_s = tab_s + 64 * 8;                     // [0] blob, [1 + w] warp w
   const uint32_t stage_s = bar_s + 16 * 8;
-#ifdef KC_OLD_SNAP
-  const uint32_t ext_s = stage_s + P.stage_off_grid, eperm_s = stage_s + P.stage_off_perm,
-                 lut_s = stage_s + P.stage_off_lut;
-  const unsigned char* stage_generic = smem_raw + 64 * 8 + 16 * 8;
-#else
   const uint32_t dlut_s = stage_s + P.stage2_off_dlut, brec_s = stage_s + P.stage2_off_brec,
                  perm_s = stage_s + P.stage2_off_perm;
-#endif
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t scal_s = stage_s + C.stage_pad + (unsigned)warp * (unsigned)C.per_warp * 8u;
   const uint32_t part_s = scal_s + 32 * STRIDE * 8;
+  const uint32_t q_s = part_s + 8u * (unsigned)C.q_off;        // params / proposal rows of the warp
 
   const int64_t row0 = ((int64_t)blockIdx.x * KC_WARPS + warp) * 32;
   const int rows_here = (int)max((int64_t)0, min((int64_t)32, B.n - row0));
-  const uint32_t q_s = part_s + 8u * (unsigned)C.q_off;        // params / proposal rows of the warp
-  const int n_dbl = rows_here * n_par;
-  const uint32_t par_bytes = ENS ? 0u : (uint32_t)(n_dbl >> 1) * 16u;
+  const uint32_t par_bytes = ENS ? 0u : (uint32_t)((rows_here * n_par) >> 1) * 16u;
 
   if (threadIdx.x == 0) {
     for (int w = 0; w <= KC_WARPS; ++w) mbar_init(bar_s + 8u * w, 1);
@@ -128,413 +188,113 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   if (threadIdx.x < AGNF_POW2_DENOM)
     sts_f64(tab_s + 8u * threadIdx.x, c_exp2_tab[threadIdx.x * (64 / AGNF_POW2_DENOM)]);
   __syncthreads();
-  // one bulk copy brings the grids + cell tables; one per warp brings that warp's params rows
-#ifdef KC_OLD_SNAP
-  if (threadIdx.x == 0 && P.stage_bytes > 0) {
-    mbar_expect_tx(bar_s, (uint32_t)P.stage_bytes);
-    bulk_g2s(stage_s, P.stage, (uint32_t)P.stage_bytes, bar_s);
-  }
-#else
+  // one bulk copy brings the snap decision tables; one per warp brings that warp's params rows
   if (threadIdx.x == 0 && P.stage2_bytes > 0) {
     mbar_expect_tx(bar_s, (uint32_t)P.stage2_bytes);
     bulk_g2s(stage_s, P.stage2, (uint32_t)P.stage2_bytes, bar_s);
   }
-#endif
   if (lane == 0 && par_bytes > 0) {
     mbar_expect_tx(bar_s + 8u + 8u * warp, par_bytes);
     bulk_g2s(q_s, B.params + row0 * n_par, par_bytes, bar_s + 8u + 8u * warp);   // 256-byte aligned source
   }
-  if (rows_here == 0) return;
-  const bool live = lane < rows_here;
-  const int my = live ? lane : rows_here - 1;      // tail lanes shadow the last row
-  const int64_t i = row0 + my;
+  double* const w_pos = B.ens.pos;      // walker state (ensemble mode): global memory
+  double* const w_lnp = B.ens.lnp;
+  const int64_t e_step = B.ens.step;
+  const int e_half = B.ens.half;
+#define TILE_EXIT return
+#include "k1_coop_tile.inc"
+#undef TILE_EXIT
+}
 
-  // ================================ phase 1: thread per evaluation =================================
-  int s;
-  int64_t wrow = 0;                 // ensemble mode: this walker's row in pos / lnp / n_acc
-  double ens_factor = 0.0, ens_lnu = 0.0, ens_lnp_old = 0.0;
-  if (ENS) {
-    // the proposal is drawn here instead of being read: q = c_j - (c_j - x_k) zz (k3_common.cuh)
-    const int H = B.ens.W >> 1;
-    const int64_t src = i / H;
-    const int kw = (int)(i - src * H);
-    const StretchDraw d = stretch_draw(B.ens.seed, B.ens.a, B.ens.step, B.ens.half, src + B.ens.src_offset, kw, H);
-    s = (int)src;
-    wrow = src * B.ens.W + split_walker(B.ens.split, src, B.ens.W, (B.ens.half ? H : 0) + kw);
-    const int my_w = (int)wrow;
-    const int my_c = (int)(src * B.ens.W + split_walker(B.ens.split, src, B.ens.W, (B.ens.half ? 0 : H) + d.j));
-    ens_lnp_old = B.ens.lnp[wrow];          // needed only by the acceptance test: in flight during the evaluation
-    {
-      // Both walker rows are fetched by the whole warp: element e of the flat [32][n_par] block goes to lane
-      // e % 32, so consecutive lanes read consecutive coordinates of one walker (a per-thread row read would
-      // touch 32 different lines per load).  The proposal q = c - (c - x) zz is formed right here, element by
-      // element (the row's stretch factor comes by shuffle), and only q is stored.  Four block rows per round:
-      // their eight loads are issued back to back before the stores (a store to shared memory orders the loads
-      // before it, so load-store pairs would serialise 2 n_par memory round trips).
-      const int d_row = 32 / n_par, d_col = 32 - d_row * n_par;
-      int row = lane / n_par, col = lane - row * n_par;
-      for (int r0 = 0; r0 < n_par; r0 += 4) {
-        double xv[4], cv[4], zv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          xv[u] = 0.0;
-          cv[u] = 0.0;
-          zv[u] = 0.0;
-          if (r0 + u < n_par) {
-            const int wr = __shfl_sync(0xffffffffu, my_w, row), cr = __shfl_sync(0xffffffffu, my_c, row);
-            zv[u] = __shfl_sync(0xffffffffu, d.zz, row);
-            xv[u] = B.ens.pos[(int64_t)wr * n_par + col];
-            cv[u] = B.ens.pos[(int64_t)cr * n_par + col];
-            row += d_row;
-            col += d_col;
-            if (col >= n_par) {
-              col -= n_par;
-              ++row;
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (r0 + u < n_par) sts_f64(q_s + 8u * (unsigned)((r0 + u) * 32 + lane), stretch_coord(cv[u], xv[u], zv[u]));
-        }
-      }
-    }
-    __syncwarp();
-    ens_factor = (double)(n_par - 1) * log(d.zz);
-    ens_lnu = d.lnu;
-  } else {
-    s = __ldg(B.source_id + i);
-    if ((n_dbl & 1) && lane == 0) sts_f64(q_s + 8u * (n_dbl - 1), __ldg(B.params + row0 * n_par + n_dbl - 1));
-    if (par_bytes > 0) mbar_wait(bar_s + 8u + 8u * warp, 0);
-  }
-  const int zi = __ldg(P.zi + s);
-  const uint64_t valid = __ldg(P.valid + s);
-  const double inv4pidl2 = __ldg(P.consts + (int64_t)s * P.n_const);
-  __syncwarp();
-  const uint32_t p_s = q_s + 8u * (unsigned)(my * n_par);
+// The persistent per-source sampler (ensemble mode): one CTA per source runs `A.n_steps` whole stretch-move steps — both
+// half-steps, the per-step split, best tracking, histograms and chain recording — inside ONE launch (see K1Persist).
+// The source's walkers and log-posteriors live in shared memory for the whole launch.
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
+__global__ void __launch_bounds__(KC_THREADS, KC_MINBLOCKS)
+k1_coop_persist_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPlan C, const K1Persist A) {
+  constexpr bool ENS = true, PERSIST = true;
+  constexpr bool EXT = GA_FREE || RADIO || BB_MODE >= 2;
+  constexpr int STRIDE = Rec<EXT>::STRIDE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const agnf_config& cfg = P.cfg;
+  const int n_par = cfg.n_par, n_b = cfg.n_b, nbp = P.nbp;
+  const bool eb_free = GA_FREE && cfg.eb_mode != 0;
+  const int CPR = CPR_T ? CPR_T : C.cpr;
+  const int CPRP = CPR | 1;
+  // shared-window addresses
+  const uint32_t tab_s = smem_u32(smem_raw);                 // 64 doubles
+  const uint32_t bar_s = tab_s + 64 * 8;                     // [0] blob, [1 + w] warp w
+  const uint32_t stage_s = bar_s + 16 * 8;
+  const uint32_t dlut_s = stage_s + P.stage2_off_dlut, brec_s = stage_s + P.stage2_off_brec,
+                 perm_s = stage_s + P.stage2_off_perm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t scal_s = stage_s + C.stage_pad + (unsigned)warp * (unsigned)C.per_warp * 8u;
+  const uint32_t part_s = scal_s + 32 * STRIDE * 8;
+  const uint32_t q_s = part_s + 8u * (unsigned)C.q_off;        // params / proposal rows of the warp
 
-  bool inbox = true;
-  {
-    const double2* __restrict__ box = P.pbox + (int64_t)s * n_par;
-    int c = 0;
-    if ((n_par & 1) == 0) {          // even row length: rows are 16-byte aligned -> conflict-free 128-bit reads
-      for (; c < n_par; c += 2) {
-        const double2 v = lds_v2f64(p_s + 8u * c);
-        const double2 m0 = __ldg(box + c), m1 = __ldg(box + c + 1);
-        inbox = inbox && (m0.x <= v.x) && (v.x <= m0.y) && (m1.x <= v.y) && (v.y <= m1.y);
+  const int n_warps = (int)(blockDim.x >> 5);
+  if (threadIdx.x == 0) {
+    for (int w = 0; w <= n_warps; ++w) mbar_init(bar_s + 8u * w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (threadIdx.x < AGNF_POW2_DENOM)
+    sts_f64(tab_s + 8u * threadIdx.x, c_exp2_tab[threadIdx.x * (64 / AGNF_POW2_DENOM)]);
+  __syncthreads();
+  if (threadIdx.x == 0 && P.stage2_bytes > 0) {
+    mbar_expect_tx(bar_s, (uint32_t)P.stage2_bytes);
+    bulk_g2s(stage_s, P.stage2, (uint32_t)P.stage2_bytes, bar_s);
+  }
+  const int64_t p_src = blockIdx.x;
+  const int p_W = B.ens.W, p_H = p_W >> 1;
+  // global walker indices address the shared-memory copy
+  double* const w_pos = reinterpret_cast<double*>(smem_raw + C.walkers_off) - p_src * p_W * n_par;
+  double* const w_lnp = reinterpret_cast<double*>(smem_raw + C.walkers_off) + (int64_t)p_W * n_par - p_src * p_W;
+  double* const my_pos = w_pos + p_src * p_W * n_par;
+  double* const my_lnp = w_lnp + p_src * p_W;
+  int64_t n_rec = 0;
+  for (int e = threadIdx.x; e < p_W * n_par; e += blockDim.x) my_pos[e] = B.ens.pos[p_src * p_W * n_par + e];
+  for (int e = threadIdx.x; e < p_W; e += blockDim.x) my_lnp[e] = B.ens.lnp[p_src * p_W + e];
+  __syncthreads();
+  const int64_t row0 = p_src * p_H + warp * 32;
+  const int rows_here = (int)max((int64_t)0, min((int64_t)32, (p_src + 1) * p_H - row0));
+  constexpr uint32_t par_bytes = 0;      // ensemble mode reads no params block
+  for (int64_t pass = 0; pass < 2 * A.n_steps; ++pass) {
+    const int64_t e_step = A.step0 + (pass >> 1);
+    const int e_half = (int)(pass & 1);
+    if (e_half == 0 && B.ens.split) {   // this step's split of the source's walkers (k3_split_kernel's ranking)
+      uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw + (part_s - tab_s));     // warp 0's partial-sum area
+      if (warp == 0)
+        persist_split(const_cast<uint16_t*>(B.ens.split) + p_src * p_W, keys, p_W, e_step, p_src + B.ens.src_offset,
+                      B.ens.seed, lane);
+      __syncthreads();
+    }
+    do {
+#define TILE_EXIT break
+#define TILE_PINNED
+#include "k1_coop_tile.inc"
+#undef TILE_PINNED
+#undef TILE_EXIT
+    } while (0);
+    __syncthreads();                     // the other half (and the per-step work) reads what this pass wrote
+    if (e_half == 1) {
+      const int64_t k = pass >> 1;
+      const bool thinned = A.hist_every > 0 && ((k + 1) % A.hist_every) == 0;
+      if (A.track_best == 1 || (A.track_best == 2 && thinned)) {
+        if (warp == 0) persist_best(my_pos, my_lnp, p_W, n_par, A.best_pos + p_src * n_par, A.best_lnp + p_src, lane);
       }
-    }
-    for (; c < n_par; ++c) {
-      const double v = lds_f64(p_s + 8u * c);
-      const double2 mm = __ldg(box + c);
-      inbox = inbox && (mm.x <= v) && (v <= mm.y);
-    }
-  }
-
-#ifdef KC_OLD_SNAP
-  if (P.stage_bytes > 0) mbar_wait(bar_s, 0);
-  const double* ext_g = reinterpret_cast<const double*>(stage_generic + P.stage_off_grid);
-  const int32_t* eperm_g = reinterpret_cast<const int32_t*>(stage_generic + P.stage_off_perm);
-  int row[AGNF_MAX_FAMILIES], grow[AGNF_MAX_FAMILIES];
-#pragma unroll
-  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
-    row[f] = 0;
-    grow[f] = 0;
-    if (f < (RADIO ? 5 : 4)) {
-      const FamDesc& F = P.fam[f];
-      int r = 0;
-      for (int t = 0; t < F.n_snap; ++t) {
-        const SnapTask& T = F.snap[t];
-        r += snap_task(T, lds_f64(p_s + 8u * T.col), ext_s, eperm_s, lut_s, ext_g, eperm_g) * T.stride;
+      if (thinned && A.hist) persist_hist(my_pos, p_W, n_par, A.hist, A.pbox, A.n_bins, p_src);
+      if (A.chain && ((e_step - A.chain_origin) % A.chain_every) == 0) {
+        const int64_t entry = A.chain_n0 + n_rec++;
+        const int64_t nw = A.S * p_W;
+        double* dst = A.chain + (entry * nw + p_src * p_W) * n_par;
+        for (int e = threadIdx.x; e < p_W * n_par; e += blockDim.x) dst[e] = my_pos[e];
+        for (int e = threadIdx.x; e < p_W; e += blockDim.x) A.chain_lnp[entry * nw + p_src * p_W + e] = my_lnp[e];
       }
-      row[f] = r;
-      grow[f] = zi * (int)F.T + r;
+      __syncthreads();
     }
   }
-#else
-  if (P.stage2_bytes > 0) mbar_wait(bar_s, 0);
-  // the snaps of all families through the decision tables (k1_dev.cuh::snap_fast: one 16-bit read, plus one 16-byte
-  // read when the cell straddles a switch point), four at a time as one straight-line block
-  int row[AGNF_MAX_FAMILIES], grow[AGNF_MAX_FAMILIES];
-#pragma unroll
-  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) row[f] = 0;
-  bool slow = false;
-  for (int t0 = 0; t0 < P.n_tasks; t0 += KC_SNAP_GROUP) {
-    int idx[KC_SNAP_GROUP];
-    bool sl[KC_SNAP_GROUP];
-#pragma unroll
-    for (int u = 0; u < KC_SNAP_GROUP; ++u) {
-      const SnapTask& T = P.tasks[min(t0 + u, P.n_tasks - 1)];
-      sl[u] = false;
-      idx[u] = snap_fast(T, lds_f64(p_s + 8u * T.col), dlut_s, brec_s, perm_s, sl[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < KC_SNAP_GROUP; ++u) {
-      const SnapTask& T = P.tasks[min(t0 + u, P.n_tasks - 1)];
-      const bool on = t0 + u < P.n_tasks;
-      const int add = on ? idx[u] * T.stride : 0;
-      slow = slow || (on && sl[u]);
-#pragma unroll
-      for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) row[f] += (T.fam == f) ? add : 0;
-    }
-  }
-  if (slow) {        // NaN, huge values, crowded cells: the binary search over the full grids (global memory)
-#pragma unroll
-    for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) {
-      if (f < (RADIO ? 5 : 4)) row[f] = snap_family_slow(P, f, p_s);
-    }
-  }
-#pragma unroll
-  for (int f = 0; f < AGNF_MAX_FAMILIES; ++f) grow[f] = f < (RADIO ? 5 : 4) ? zi * (int)P.fam[f].T + row[f] : 0;
-#endif
-  // start the only DRAM-bound gather early: this evaluation's galaxy row -> L2
-  {
-    const char* ga = reinterpret_cast<const char*>(P.fam[0].table + (int64_t)grow[0] * P.fam[0].pitch);
-    prefetch_l2(ga);
-    prefetch_l2(ga + 8 * n_b - 8);
-  }
-
-  const int no = P.norm_offset;
-  const double GA = lds_f64(p_s + 8u * no), SB = lds_f64(p_s + 8u * no + 8u), TO = lds_f64(p_s + 8u * no + 16u);
-  int kk = 3;
-  double BB = 0.0, RAD = 0.0;
-  if (cfg.bbb_has_norm) BB = lds_f64(p_s + 8u * (no + kk++));
-  if (RADIO) RAD = lds_f64(p_s + 8u * (no + kk++));
-  double ebv_gal = 0.0, ebv_bbb = 0.0, alpha = 0.0;
-  if (GA_FREE) ebv_gal = lds_f64(p_s + 8u * (P.fam[0].par_offset + P.fam[0].n_dim - 1));
-  if (BB_MODE == 1) ebv_bbb = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 1));
-  if (BB_MODE == 2) {
-    ebv_bbb = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 2));
-    alpha = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 1));
-  }
-  if (BB_MODE == 3) {
-    ebv_bbb = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 3));
-    alpha = lds_f64(p_s + 8u * (P.fam[3].par_offset + P.fam[3].n_dim - 2));
-  }
-  const double nGA = pow10_via2(GA, tab_s), nSB = pow10_via2(SB, tab_s), nTO = pow10_via2(TO, tab_s);
-  const double nBB = cfg.bbb_has_norm ? pow10_via2(BB, tab_s) : 1.0;
-  const double nRAD = RADIO ? pow10_via2(RAD, tab_s) : 0.0;
-  const double cBB = cfg.bbb_has_norm ? 1.0 : inv4pidl2;
-  const double xfac = (BB_MODE >= 2) ? pow10_via2(alpha / 0.3838, tab_s) : 1.0;
-  {
-    const uint32_t rec = scal_s + (unsigned)lane * (STRIDE * 8);
-    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};\n" ::"r"(rec), "r"(grow[0] * (P.fam[0].pitch >> 1)),
-                 "r"(grow[1] * (P.fam[1].pitch >> 1)), "r"(grow[2] * (P.fam[2].pitch >> 1)),
-                 "r"(grow[3] * (P.fam[3].pitch >> 1))
-                 : "memory");
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(rec + 16), "d"(nGA), "d"(nSB) : "memory");
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(rec + 32), "d"(nTO), "d"(nBB * cBB) : "memory");
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(rec + 48), "d"(ebv_bbb), "d"(xfac) : "memory");
-    asm volatile("st.shared.v2.u64 [%0], {%1, %2};\n" ::"r"(rec + 64),
-                 "l"((unsigned long long)(unsigned)(s * CPR) | ((unsigned long long)(unsigned)(zi * CPR) << 32)),
-                 "l"((unsigned long long)valid)
-                 : "memory");
-    if (EXT) {
-      asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(rec + 80), "d"(ebv_gal), "d"(nRAD) : "memory");
-      asm volatile("st.shared.v2.u64 [%0], {%1, %2};\n" ::"r"(rec + 96),
-                   "l"((unsigned long long)(unsigned)(RADIO ? grow[4] * (P.fam[4].pitch >> 1) : 0)),
-                   "l"((unsigned long long)(BB_MODE >= 2 ? __ldg(P.xray + zi) : 0ull))
-                   : "memory");
-    }
-  }
-  if (B.rows && live) {
-    for (int f = 0; f < cfg.n_fam; ++f) B.rows[i * cfg.n_fam + f] = row[f];
-  }
-  __syncwarp();      // records visible; the params block is dead and becomes the partial-sum area
-
-  // ================================== phase 2: lane per chunk ======================================
-  {
-    const double2* __restrict__ tGA = reinterpret_cast<const double2*>(P.fam[0].table);
-    const double2* __restrict__ tSB = reinterpret_cast<const double2*>(P.fam[1].table);
-    const double2* __restrict__ tTO = reinterpret_cast<const double2*>(P.fam[2].table);
-    const double2* __restrict__ tBB = reinterpret_cast<const double2*>(P.fam[3].table);
-    const double2* __restrict__ tRAD = reinterpret_cast<const double2*>(P.fam[RADIO ? 4 : 0].table);
-    const double2* __restrict__ y2 = reinterpret_cast<const double2*>(P.y);
-    const double2* __restrict__ i2 = reinterpret_cast<const double2*>(P.isig);
-    const double2* __restrict__ cb2 = reinterpret_cast<const double2*>(P.cbbb64);
-    const double2* __restrict__ cg2 = reinterpret_cast<const double2*>(P.cgal64);
-    const double2* __restrict__ om2 = reinterpret_cast<const double2*>(P.omega);
-    int e = lane / CPR;
-    int k = lane - e * CPR;
-    const int de = 32 / CPR, dk = 32 - de * CPR;
-#pragma unroll
-    for (int it = 0; it < CPR; ++it) {
-      const uint32_t rec = scal_s + (unsigned)e * (STRIDE * 8);
-      const int4 g = lds_v4s32(rec);
-      const double2 n01 = lds_v2f64(rec + 16);
-      const double2 n23 = lds_v2f64(rec + 32);
-      const int4 sv = lds_v4s32(rec + 64);                  // {s*CPR, zi*CPR, valid lo, valid hi}
-      const double2 dga = __ldg(tGA + (unsigned)(g.x + k));
-      const double2 dsb = __ldg(tSB + (unsigned)(g.y + k));
-      const double2 dto = __ldg(tTO + (unsigned)(g.z + k));
-      const double2 dbb = __ldg(tBB + (unsigned)(g.w + k));
-      const double2 yv = __ldg(y2 + (unsigned)(sv.x + k));
-      const double2 iv = __ldg(i2 + (unsigned)(sv.x + k));
-      double2 drad = make_double2(0.0, 0.0);
-      double c_ebvgal = 0.0, c_nrad = 0.0;
-      if (GA_FREE || RADIO) {
-        const double2 x = lds_v2f64(rec + 80);
-        c_ebvgal = x.x;
-        c_nrad = x.y;
-      }
-      if (RADIO) drad = __ldg(tRAD + (unsigned)(lds_s32(rec + 96) + k));
-      double bb0 = dbb.x, bb1 = dbb.y;
-      if (BB_MODE != 0) {
-        const double2 eb = lds_v2f64(rec + 48);
-        const double2 cb = __ldg(cb2 + (unsigned)(sv.y + k));
-        const double w0 = dbb.x * pow2_64(cb.x * eb.x, tab_s);
-        const double w1 = dbb.y * pow2_64(cb.y * eb.x, tab_s);
-        bb0 = (w0 != w0) ? dbb.x : w0;                        // NaN -> unreddened (MODEL:1211)
-        bb1 = (w1 != w1) ? dbb.y : w1;
-        if (BB_MODE >= 2) {
-          const unsigned xr = (unsigned)(lds_u64(rec + 104) >> (2 * k));
-          if (xr & 1u) bb0 = dbb.x * eb.y;
-          if (xr & 2u) bb1 = dbb.y * eb.y;
-        }
-      }
-      double ga0 = dga.x, ga1 = dga.y;
-      if (GA_FREE) {
-        const double2 cg = __ldg(cg2 + (unsigned)(sv.y + k));
-        const double rg0 = pow2_64(cg.x * c_ebvgal, tab_s), rg1 = pow2_64(cg.y * c_ebvgal, tab_s);
-        if (eb_free) {
-          const double2 om = __ldg(om2 + (unsigned)(sv.y + k));
-          sts_f64(part_s + 8u * (unsigned)(32 * CPRP + e * CPRP + k),
-                  om.x * (((dga.x * 1e18) * rg0) * 3.826e33) + om.y * (((dga.y * 1e18) * rg1) * 3.826e33));
-        }
-        ga0 = dga.x * rg0;
-        ga1 = dga.y * rg1;
-      }
-      double m0 = n01.y * dsb.x + n23.y * bb0 + n01.x * ga0 + n23.x * dto.x;
-      double m1 = n01.y * dsb.y + n23.y * bb1 + n01.x * ga1 + n23.x * dto.y;
-      if (RADIO) {
-        m0 += c_nrad * drad.x;
-        m1 += c_nrad * drad.y;
-      }
-      const unsigned long long vmask = ((unsigned long long)(unsigned)sv.w << 32) | (unsigned)sv.z;
-      const unsigned vb = (unsigned)(vmask >> (2 * k));
-      const double r0 = (yv.x - m0) * iv.x, r1 = (yv.y - m1) * iv.y;
-      const double c0 = (vb & 1u) ? r0 * r0 : 0.0;
-      sts_f64(part_s + 8u * (unsigned)(e * CPRP + k), (vb & 2u) ? fma(r1, r1, c0) : c0);
-      if (B.ymodel && row0 + e < B.n) {
-        double* ym = B.ymodel + (row0 + e) * n_b + 2 * k;
-        ym[0] = m0;
-        if (2 * k + 1 < n_b) ym[1] = m1;
-      }
-      k += dk;
-      e += de;
-      if (k >= CPR) {
-        k -= CPR;
-        ++e;
-      }
-    }
-  }
-  __syncwarp();
-
-  // ================================ phase 3: thread per evaluation =================================
-  if (!live && !ENS) return;          // ensemble mode keeps tail lanes for the cooperative write-back
-  double chi = 0.0, ebA = 0.0, ebB = 0.0;
-  {
-    const uint32_t mine = part_s + 8u * (unsigned)(lane * CPRP);
-#pragma unroll
-    for (int k = 0; k < CPR; ++k) chi += lds_f64(mine + 8u * k);
-    if (eb_free) {
-      for (int k = 0; k < CPR; ++k) ebB += lds_f64(mine + 8u * (32 * CPRP + k));
-    }
-  }
-  const double lnlike = -0.5 * chi;
-
-  double prior = 0.0;
-  if (cfg.eb_mode != 0) {
-    double L_att;
-    if (GA_FREE) {
-      ebA = __ldg(P.eb0 + (int64_t)grow[0]);      // the unreddened integral of this galaxy row (walker-independent)
-      L_att = fabs((ebA - ebB) * nGA);
-    }
-    else L_att = __ldg(P.fam[0].aux + row[0]) * nGA;
-    const double L_sb = __ldg(P.fam[1].aux + row[1]) * nSB;
-    double pr;
-    if (L_sb < L_att) pr = -9999.0;
-    else if (L_sb >= L_att)
-      pr = (cfg.eb_mode == 1) ? 0.0 : gaussian_prior(P.lognorm_s01, 100.0, 0.0, log10(L_sb / L_att));
-    else pr = NAN;   // unordered: the reference has no branch for it
-    prior += pr;
-  }
-  if (cfg.prior_agnfrac) {
-    const int j = __ldg(P.j1500 + zi);
-    double ga_r = __ldg(P.fam[0].table + (int64_t)grow[0] * P.fam[0].pitch + j);
-    if (GA_FREE) ga_r = ga_r * pow2_64(__ldg(P.cgal64 + (int64_t)zi * nbp + j) * ebv_gal, tab_s);
-    const double dbb = __ldg(P.fam[3].table + (int64_t)grow[3] * P.fam[3].pitch + j);
-    double bb_r = dbb;
-    if (BB_MODE != 0) {
-      if (BB_MODE >= 2 && ((__ldg(P.xray + zi) >> j) & 1ull)) {
-        bb_r = dbb * xfac;
-      } else {
-        const double w = dbb * pow2_64(__ldg(P.cbbb64 + (int64_t)zi * nbp + j) * ebv_bbb, tab_s);
-        bb_r = (w != w) ? dbb : w;
-      }
-    }
-    double bbj = bb_r * nBB;
-    if (BB == 0.0) bbj = bbj * inv4pidl2;          // decided by VALUE (PRIORS:177)
-    const double frac = log10(bbj / (ga_r * nGA));
-    double pr;
-    if (__ldg(P.agn_branch + s) == 0) pr = gaussian_prior(P.lognorm_s2, 0.25, -2.0, frac);
-    else pr = (frac < 0.0) ? -9999.0 : gaussian_prior(P.lognorm_s2, 0.25, 2.0, frac);
-    prior += pr + gaussian_prior(P.lognorm_s15, 1.0 / 2.25, 4.5, GA);
-  }
-  double tor6 = 0.0, lumf = 0.0;
-  if (P.xp_midir_uv | P.xp_ir_xray) {
-    tor6 = __ldg(P.fam[2].table + (int64_t)grow[2] * P.fam[2].pitch + P.xp_j6) * nTO;
-    lumf = __ldg(P.consts + (int64_t)s * P.n_const + 1);
-  }
-  if (P.xp_midir_uv) {
-    const int64_t dr = (int64_t)zi * P.fam[3].T + __ldg(P.xp_bb_dered + row[3]);
-    const double bb2500 = __ldg(P.fam[3].table + dr * P.fam[3].pitch + P.xp_j2500) * nBB;
-    prior += prior_midir_uv(P, tor6, bb2500, BB, lumf, __ldg(P.consts + (int64_t)s * P.n_const + 3));
-  }
-  if (RADIO) {
-    const int mode = __ldg(P.irsyn_mode + s);
-    if (mode != 0) {
-      const int j = __ldg(P.irsyn_j + s);
-      const double sb_ir = __ldg(P.fam[1].table + (int64_t)grow[1] * P.fam[1].pitch + j) * nSB;
-      const double syn_ir = __ldg(P.fam[4].table + (int64_t)grow[4] * P.fam[4].pitch + j) * nRAD;
-      prior += gaussian_prior(P.lognorm_s2, 0.25, mode > 0 ? 2.0 : -2.0, log10(syn_ir / sb_ir));
-    }
-  }
-  if (P.xp_ir_xray) prior += prior_ir_xrays(P, tor6, lumf, __ldg(P.consts + (int64_t)s * P.n_const + 2));
-  const double lnprior = inbox ? prior : -INFINITY;
-  const bool fin = (lnprior - lnprior) == 0.0;     // isfinite
-  const double lnp_new = fin ? lnprior + lnlike : -INFINITY;
-  if (ENS) {
-    // emcee's acceptance rule, in place: only this thread touches walker `wrow` during the launch, and the
-    // partners it read belong to the other (frozen) half
-    const double lnpdiff = ens_factor + lnp_new - ens_lnp_old;
-    const bool accept = live && (lnpdiff > ens_lnu);          // false for NaN and for -inf proposals
-    if (accept) {
-      B.ens.lnp[wrow] = lnp_new;
-      atomicAdd(B.ens.n_acc + wrow, 1);                       // result unused: a fire-and-forget reduction
-    }
-    // accepted rows go back to `pos` the way they came: consecutive lanes store consecutive coordinates
-    const unsigned acc_mask = __ballot_sync(0xffffffffu, accept);
-    if (acc_mask) {
-      const int my_w = (int)wrow;
-      const int d_row = 32 / n_par, d_col = 32 - d_row * n_par;
-      int row = lane / n_par, col = lane - row * n_par;
-      for (int r = 0; r < n_par; ++r) {
-        const int wr = __shfl_sync(0xffffffffu, my_w, row);
-        if ((acc_mask >> row) & 1u) B.ens.pos[(int64_t)wr * n_par + col] = lds_f64(q_s + 8u * (unsigned)(r * 32 + lane));
-        row += d_row;
-        col += d_col;
-        if (col >= n_par) {
-          col -= n_par;
-          ++row;
-        }
-      }
-    }
-    return;
-  }
-  B.lnp[i] = lnp_new;
-  if (B.lnprior) B.lnprior[i] = lnprior;
-  if (B.lnlike) B.lnlike[i] = lnlike;
+  for (int e = threadIdx.x; e < p_W * n_par; e += blockDim.x) B.ens.pos[p_src * p_W * n_par + e] = my_pos[e];
+  for (int e = threadIdx.x; e < p_W; e += blockDim.x) B.ens.lnp[p_src * p_W + e] = my_lnp[e];
 }
 
 template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS, int MINB>
@@ -551,6 +311,25 @@ cudaError_t launch_coop_ens(const K1Params& P, const K1Batch& B, cudaStream_t st
   }
   const int64_t blocks = (B.n + KC_THREADS - 1) / KC_THREADS;
   kern<<<(unsigned)blocks, KC_THREADS, (size_t)C.smem_bytes, stream>>>(P, B, C);
+  return cudaGetLastError();
+}
+
+// the persistent per-source sampler: one CTA of ceil(W/2 / 32) warps per source
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
+cudaError_t launch_coop_persist(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream) {
+  auto kern = k1_coop_persist_kernel<GA_FREE, BB_MODE, RADIO, CPR_T>;
+  const int n_warps = ((B.ens.W >> 1) + 31) / 32;
+  CoopPlan C = make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, true, n_warps);
+  C.smem_bytes += (B.ens.W * (P.cfg.n_par + 1) * 8 + 15) & ~15;          // the source's walkers + log-posteriors
+  static int attr_bytes[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || C.smem_bytes > attr_bytes[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C.smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_bytes[dev] = C.smem_bytes;
+  }
+  kern<<<(unsigned)A.S, 32 * n_warps, (size_t)C.smem_bytes, stream>>>(P, B, C, A);
   return cudaGetLastError();
 }
 
@@ -614,11 +393,11 @@ bool k1_coop_profitable(const K1Params& P, const K1Batch& B) {
   return 2 * coop_smem_bytes(P, B.ens.pos != nullptr) <= 220 * 1024;
 }
 
-bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why) {
+// everything but the shared-memory footprint of the 8-warp CTA
+static const char* coop_basic_checks(const K1Params& P, const K1Batch& B) {
   const char* w = nullptr;
   if (P.nbp & 1) w = "band pitch is odd";
   else if (!B.ens.pos && (reinterpret_cast<uintptr_t>(B.params) & 15)) w = "params is not 16-byte aligned";
-  else if (coop_smem_bytes(P, B.ens.pos != nullptr) > 200 * 1024) w = "grids + per-warp tiles exceed shared memory";
   else if (B.ens.pos && P.S * (int64_t)B.ens.W >= (int64_t)INT32_MAX) w = "too many walkers for 32-bit row indices";
   else if (P.S * (int64_t)(P.nbp / 2) >= (int64_t)INT32_MAX) w = "too many sources for 32-bit chunk offsets";
   else if (P.cfg.ga_free_ebv && P.cfg.eb_mode != 0 && !P.eb0) w = "the unreddened galaxy integrals have not been built";
@@ -630,6 +409,22 @@ bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why) {
         w = "a family table has 2^31 16-byte chunks or more";
     }
   }
+  return w;
+}
+
+bool k1_coop_persist_supported(const K1Params& P, const K1Batch& B) {
+  if (!B.ens.pos || B.ens.W < 2 || (B.ens.W >> 1) > KC_THREADS || coop_basic_checks(P, B)) return false;
+  const bool ext = P.cfg.ga_free_ebv != 0 || P.cfg.radio != 0 || P.cfg.bb_mode >= 2;
+  const int n_warps = ((B.ens.W >> 1) + 31) / 32;
+  const CoopPlan C = ext ? make_plan<true>(P, true, n_warps) : make_plan<false>(P, true, n_warps);
+  // warp 0's partial-sum area doubles as the key buffer of the per-step split
+  const int64_t key_bytes = 4 * (int64_t)((B.ens.W + 3) & ~3);
+  return (size_t)C.smem_bytes + (size_t)B.ens.W * (P.cfg.n_par + 1) * 8 <= 200 * 1024 && key_bytes <= (int64_t)C.q_off * 8;
+}
+
+bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why) {
+  const char* w = coop_basic_checks(P, B);
+  if (!w && coop_smem_bytes(P, B.ens.pos != nullptr) > 200 * 1024) w = "grids + per-warp tiles exceed shared memory";
   if (why) *why = w;
   return w == nullptr;
 }
@@ -656,7 +451,7 @@ __global__ void k1_eb0_kernel(K1Params P, double* __restrict__ eb0) {
   double acc = 0.0;
   for (int k = 0; k < P.nbp / 2; ++k) {
     const double2 d = row[k], o = om[k];
-    acc += o.x * (d.x * 3.826e33) + o.y * (d.y * 3.826e33);
+    acc += sum2_pinned(o.x, d.x * 3.826e33, o.y, d.y * 3.826e33);
   }
   eb0[i] = acc;
 }
@@ -684,6 +479,25 @@ cudaError_t launch_exp10_fast(const double* x, double* y, int64_t n, cudaStream_
 }
 
 #else   // K1_COOP_ENS_TU
+
+template <bool GA_FREE, bool RADIO>
+cudaError_t launch_persist_bb(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream) {
+  const bool c9 = P.nbp / 2 == 9;
+  switch (P.cfg.bb_mode) {
+    case 0: return c9 ? launch_coop_persist<GA_FREE, 0, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 0, RADIO, 0>(P, B, A, stream);
+    case 1: return c9 ? launch_coop_persist<GA_FREE, 1, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 1, RADIO, 0>(P, B, A, stream);
+    case 2: return c9 ? launch_coop_persist<GA_FREE, 2, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 2, RADIO, 0>(P, B, A, stream);
+    default: return c9 ? launch_coop_persist<GA_FREE, 3, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 3, RADIO, 0>(P, B, A, stream);
+  }
+}
+
+cudaError_t launch_k1_coop_persist(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream) {
+  if (A.S <= 0 || A.n_steps <= 0) return cudaSuccess;
+  const bool gf = P.cfg.ga_free_ebv != 0, rad = P.cfg.radio != 0;
+  if (gf) return rad ? launch_persist_bb<true, true>(P, B, A, stream) : launch_persist_bb<true, false>(P, B, A, stream);
+  return rad ? launch_persist_bb<false, true>(P, B, A, stream) : launch_persist_bb<false, false>(P, B, A, stream);
+}
+
 
 cudaError_t launch_k1_coop_ens(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
   const bool gf = P.cfg.ga_free_ebv != 0, rad = P.cfg.radio != 0;

@@ -333,19 +333,19 @@ k1_g4_kernel(const __grid_constant__ K1Params P, const __grid_constant__ K1Tenso
     // 10^x of the normalisations: branch-free first, repeated through the range-checked routine if any argument
     // was out of range (results are identical whenever the fast path applies)
     bool bad_n = false;
-    F.nGA = pow2_64_nb(GA * P2_LOG2_10_D, tab_s, bad_n);
-    F.nSB = pow2_64_nb(SB * P2_LOG2_10_D, tab_s, bad_n);
-    F.nTO = pow2_64_nb(TO * P2_LOG2_10_D, tab_s, bad_n);
-    F.nBB = cfg.bbb_has_norm ? pow2_64_nb(BB * P2_LOG2_10_D, tab_s, bad_n) : 1.0;
-    F.nRAD = RADIO ? pow2_64_nb(RAD * P2_LOG2_10_D, tab_s, bad_n) : 0.0;
-    F.xfac = (BB_MODE >= 2) ? pow2_64_nb((alpha / 0.3838) * P2_LOG2_10_D, tab_s, bad_n) : 1.0;
+    F.nGA = pow10_pinned<true>(GA, tab_s, bad_n);
+    F.nSB = pow10_pinned<true>(SB, tab_s, bad_n);
+    F.nTO = pow10_pinned<true>(TO, tab_s, bad_n);
+    F.nBB = cfg.bbb_has_norm ? pow10_pinned<true>(BB, tab_s, bad_n) : 1.0;
+    F.nRAD = RADIO ? pow10_pinned<true>(RAD, tab_s, bad_n) : 0.0;
+    F.xfac = (BB_MODE >= 2) ? pow10_pinned<true>((alpha / 0.3838), tab_s, bad_n) : 1.0;
     if (bad_n) {
-      F.nGA = pow10_via2(GA, tab_s);
-      F.nSB = pow10_via2(SB, tab_s);
-      F.nTO = pow10_via2(TO, tab_s);
-      if (cfg.bbb_has_norm) F.nBB = pow10_via2(BB, tab_s);
-      if (RADIO) F.nRAD = pow10_via2(RAD, tab_s);
-      if (BB_MODE >= 2) F.xfac = pow10_via2(alpha / 0.3838, tab_s);
+      F.nGA = pow10_pinned_tile(GA, tab_s);
+      F.nSB = pow10_pinned_tile(SB, tab_s);
+      F.nTO = pow10_pinned_tile(TO, tab_s);
+      if (cfg.bbb_has_norm) F.nBB = pow10_pinned_tile(BB, tab_s);
+      if (RADIO) F.nRAD = pow10_pinned_tile(RAD, tab_s);
+      if (BB_MODE >= 2) F.xfac = pow10_pinned_tile(alpha / 0.3838, tab_s);
     }
     F.nBBc = F.nBB * (cfg.bbb_has_norm ? 1.0 : F.inv4pidl2);
     if (B.rows && F.live) {
@@ -433,8 +433,8 @@ k1_g4_kernel(const __grid_constant__ K1Params P, const __grid_constant__ K1Tenso
         double bb0 = dbb.x, bb1 = dbb.y;
         if (BB_MODE != 0) {
           const double2 cb = __ldg(cb2 + kg);
-          const double w0 = dbb.x * pw2(cb.x * ebv_bbb);
-          const double w1 = dbb.y * pw2(cb.y * ebv_bbb);
+          const double w0 = dbb.x * pw2(__dmul_rn(cb.x, ebv_bbb));
+          const double w1 = dbb.y * pw2(__dmul_rn(cb.y, ebv_bbb));
           bb0 = (w0 != w0) ? dbb.x : w0;                        // NaN -> unreddened (MODEL:1211)
           bb1 = (w1 != w1) ? dbb.y : w1;
           if (BB_MODE >= 2) {
@@ -446,19 +446,20 @@ k1_g4_kernel(const __grid_constant__ K1Params P, const __grid_constant__ K1Tenso
         double ga0 = dga.x, ga1 = dga.y;
         if (GA_FREE) {
           const double2 cg = __ldg(cg2 + kg);
-          const double rg0 = pw2(cg.x * ebv_gal), rg1 = pw2(cg.y * ebv_gal);
+          const double rg0 = pw2(__dmul_rn(cg.x, ebv_gal)), rg1 = pw2(__dmul_rn(cg.y, ebv_gal));
           if (eb_free) {
             const double2 om = __ldg(om2 + kg);
-            ebB += om.x * (((dga.x * 1e18) * rg0) * 3.826e33) + om.y * (((dga.y * 1e18) * rg1) * 3.826e33);
+            ebB += sum2_pinned(om.x, ((dga.x * 1e18) * rg0) * 3.826e33, om.y, ((dga.y * 1e18) * rg1) * 3.826e33);
           }
           ga0 = dga.x * rg0;
           ga1 = dga.y * rg1;
         }
-        double m0 = nSB * dsb.x + nBBc * bb0 + nGA * ga0 + nTO * dto.x;
-        double m1 = nSB * dsb.y + nBBc * bb1 + nGA * ga1 + nTO * dto.y;
+        // the cooperative kernel's contraction, spelled out (k1_common.cuh: pinned forms)
+        double m0 = sum4_pinned(nSB, dsb.x, nBBc, bb0, nGA, ga0, nTO, dto.x);
+        double m1 = sum4_pinned(nSB, dsb.y, nBBc, bb1, nGA, ga1, nTO, dto.y);
         if (RADIO) {
-          m0 += nRAD * drad.x;
-          m1 += nRAD * drad.y;
+          m0 = __fma_rn(nRAD, drad.x, m0);
+          m1 = __fma_rn(nRAD, drad.y, m1);
         }
         const unsigned vb = (unsigned)(valid >> (2 * kg));
         const double r0 = (yv.x - m0) * iv.x, r1 = (yv.y - m1) * iv.y;
@@ -507,14 +508,14 @@ k1_g4_kernel(const __grid_constant__ K1Params P, const __grid_constant__ K1Tenso
     if (cfg.prior_agnfrac) {
       const int j = j15;
       double ga_r = cap_ga;
-      if (GA_FREE) ga_r = ga_r * pow2_64(__ldg(P.cgal64 + (int64_t)zi * nbp + j) * ebv_gal, tab_s);
+      if (GA_FREE) ga_r = ga_r * pow2_64(__dmul_rn(__ldg(P.cgal64 + (int64_t)zi * nbp + j), ebv_gal), tab_s);
       const double dbb = cap_bb;
       double bb_r = dbb;
       if (BB_MODE != 0) {
         if (BB_MODE >= 2 && ((xray >> j) & 1ull)) {
           bb_r = dbb * xfac;
         } else {
-          const double w = dbb * pow2_64(__ldg(P.cbbb64 + (int64_t)zi * nbp + j) * ebv_bbb, tab_s);
+          const double w = dbb * pow2_64(__dmul_rn(__ldg(P.cbbb64 + (int64_t)zi * nbp + j), ebv_bbb), tab_s);
           bb_r = (w != w) ? dbb : w;
         }
       }

@@ -169,6 +169,25 @@ struct K1Ensemble {
   const uint16_t* split = nullptr;   // [S, W] this step's split (k3_ensemble.cuh), or nullptr = fixed halves
 };
 
+// Persistent per-source sampler (k1_coop_kernel<..., PERSIST>): one CTA per source runs n_steps whole steps in one
+// launch, with everything agnf_ens_run does per step done in the kernel (see agnfit_capi.cu::agnf_ens_run).
+struct K1Persist {
+  int64_t step0 = 0, n_steps = 0;   // stretch-move steps step0 .. step0 + n_steps - 1
+  int32_t hist_every = 0;           // every hist_every-th step of this launch is a thinned step
+  int32_t track_best = 0;           // 0 off, 1 every step, 2 thinned steps
+  uint32_t* hist = nullptr;         // [S, n_par, n_bins] or nullptr
+  const double2* pbox = nullptr;    // [S, n_par]
+  int32_t n_bins = 0, pad = 0;
+  double* best_pos = nullptr;       // [S, n_par]
+  double* best_lnp = nullptr;       // [S]
+  double* chain = nullptr;          // recording buffer [cap, S, W, n_par] or nullptr
+  double* chain_lnp = nullptr;      // [cap, S, W]
+  int64_t chain_n0 = 0;             // entries recorded before this launch
+  int64_t chain_origin = 0;         // step index of the first recorded step
+  int32_t chain_every = 1, pad2 = 0;
+  int64_t S = 0;
+};
+
 struct K1Batch {
   const double* params;       // [n, n_par]  (ignored in ensemble mode)
   const int32_t* source_id;   // [n]         (ignored in ensemble mode)
@@ -198,6 +217,9 @@ cudaError_t launch_k1_g4(const K1Params& P, const K1TensorMaps& M, const K1Batch
 bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why);
 bool k1_coop_profitable(const K1Params& P, const K1Batch& B);   // false: the per-thread kernel is expected to win
 cudaError_t launch_k1_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream);
+// persistent per-source sampler; B.ens describes the ensemble, B.n is ignored
+bool k1_coop_persist_supported(const K1Params& P, const K1Batch& B);
+cudaError_t launch_k1_coop_persist(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream);
 // eb0[z, t] for the galaxy family (see K1Params::eb0), chunk sums in the order the kernel used to add them
 cudaError_t launch_k1_eb0(const K1Params& P, double* eb0, cudaStream_t stream);
 cudaError_t launch_exp10_fast(const double* x, double* y, int64_t n, cudaStream_t stream);

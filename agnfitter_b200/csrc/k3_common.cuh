@@ -52,8 +52,12 @@ __device__ __forceinline__ StretchDraw stretch_draw(uint64_t seed, double a, int
 // `split` [S, W] lists, per source, the walkers of set 0 in slots [0, W/2) and of set 1 in slots [W/2, W)
 // (k3_split_kernel); nullptr = the fixed first-half / second-half split.
 constexpr uint32_t K3_SPLIT_TAG = 0xFFFFFFFFu;     // second counter word of the split's Philox stream
-__device__ __forceinline__ int split_walker(const uint16_t* __restrict__ split, int64_t s_local, int W, int slot) {
-  return split ? (int)split[s_local * W + slot] : slot;
+// COHERENT: the table is rewritten inside the running kernel (persistent sampler): no read-only-cache loads
+template <bool COHERENT = false>
+__device__ __forceinline__ int split_walker(const uint16_t* split, int64_t s_local, int W, int slot) {
+  if (!split) return slot;
+  if (COHERENT) return (int)*(reinterpret_cast<const volatile uint16_t*>(split) + s_local * W + slot);
+  return (int)__ldg(split + s_local * W + slot);
 }
 
 // q = c - (c - x) * zz, no contraction

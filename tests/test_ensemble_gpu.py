@@ -42,16 +42,19 @@ def _setup(case):
 
 
 @pytest.mark.parametrize("split", ["random", "fixed"])
-@pytest.mark.parametrize("fused", [1, 3, 0])
+@pytest.mark.parametrize("fused", [1, 4, 3, 0])
 @pytest.mark.parametrize("case", ["classic18", "cat49_catalog_example"])
 def test_ensemble_matches_oracle_step_for_step(case, fused, split):
-    """fused = 1: one K1 launch per half-step draws, evaluates and accepts (cooperative kernel, the default); 3: the
-    same through the gather4 kernel; 0: propose / K1 / accept kernels.
+    """fused = 1: the default — for a shard this small the persistent per-source kernel (one launch per run() call,
+    one CTA per source); 4: one cooperative K1 launch per half-step that draws, evaluates and accepts (what large
+    shards run); 3: the same through the gather4 kernel; 0: propose / K1 / accept kernels.
     split: emcee 3's per-step random division of the walkers (default) or the fixed halves."""
     ms, eng, src, lnprob = _setup(case)
     eng.set_option("ens_fused", 1 if fused else 0)
     if fused == 3:
         eng.set_option("k1_variant", 3)
+    if fused == 4:
+        eng.set_option("ens_persist", 0)
     W, seed, n_steps = 24, 20260101, 40
     rng = np.random.default_rng(5)
     pos0 = src.pmin[:, None, :] + rng.uniform(size=(src.S, W, ms.n_par)) * (src.pmax - src.pmin)[:, None, :]
@@ -72,7 +75,9 @@ def test_ensemble_matches_oracle_step_for_step(case, fused, split):
         fin = np.isfinite(olnp)
         assert np.allclose(glnp[fin], olnp[fin], rtol=1e-10, atol=0)
     assert oacc.sum() > 0, "the test must exercise accepted moves"
-    assert eng.get_option("k1_last_kernel") == (2 if fused == 3 else 1), "the requested kernel must be the one that ran"
+    if fused:
+        assert eng.get_option("k1_last_kernel") == (2 if fused == 3 else 1), "the requested kernel must be the one that ran"
+        assert eng.get_option("ens_last_persist") == (1 if fused == 1 else 0)
 
 
 def test_ensemble_percentiles_and_best():
@@ -385,3 +390,33 @@ def test_reference_schedule_exact_percentiles():
             assert np.array_equal(b["lnp_percentiles"][s], np.percentile(lnflat, REFERENCE_PERCENTILES))
             assert lnflat.max() == b["best_lnp"][s]
             assert np.array_equal(eng.lnprob(b["best_pos"][s][None, :], np.array([s], dtype=np.int32)), [lnflat.max()])
+
+
+@pytest.mark.parametrize("case", ["classic18", "radio_xray49"])
+def test_persistent_sampler_equals_lock_step(case):
+    """One launch for a whole run() call (one CTA per source, steps looped inside the kernel) against the lock-step
+    path: same walkers, acceptance counters, best sample, histograms and recorded chain, bit for bit — over calls
+    with thinned steps, every-step best tracking and chain recording with a stride."""
+    ms, eng, src, _ = _setup(case)
+    W = 20
+    rng = np.random.default_rng(8)
+    pos0 = src.pmin[:, None, :] + rng.uniform(size=(src.S, W, ms.n_par)) * (src.pmax - src.pmin)[:, None, :]
+    got = {}
+    for persist in (1, 0):
+        eng.set_sources(src)
+        eng.set_option("ens_persist", persist)
+        ens = EnsembleSampler(eng, W, seed=31, n_bins=128)
+        ens.set_positions(pos0)
+        ens.run(7, track_best=True)
+        ens.record(9, every=3)
+        ens.run(25, hist_every=5, track_best='thinned')
+        assert eng.get_option("ens_last_persist") == persist
+        ens.run(1)
+        got[persist] = (ens.state(), ens.best(), ens.percentiles(), ens.chain())
+    a, b = got[1], got[0]
+    for x, y in zip(a[0], b[0]):
+        assert np.array_equal(x, y, equal_nan=True)
+    assert np.array_equal(a[1][0], b[1][0]) and np.array_equal(a[1][1], b[1][1])
+    assert np.array_equal(a[2], b[2], equal_nan=True)
+    assert a[3][0].shape[2] == 9 and np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1], b[3][1], equal_nan=True)
+    assert a[0][2].sum() > 0

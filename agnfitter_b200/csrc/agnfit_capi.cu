@@ -796,6 +796,10 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "k1_table_crowded_cells") == 0) *value = ctx->snap_crowded;
   else if (strcmp(name, "k1_tasks_without_table") == 0) *value = ctx->snap_no_table;
   else if (strncmp(name, "k2_prof", 7) == 0 && name[7] >= '0' && name[7] <= '9') *value = (int64_t)ctx->k2_prof[name[7] - '0'];
+  else if (strncmp(name, "kc_prof", 7) == 0) {
+    cudaStreamSynchronize(ctx->stream);
+    *value = (int64_t)k1_coop_prof_read(name[7] - '0');
+  }
   else if (strncmp(name, "g4_prof", 7) == 0) {
     cudaStreamSynchronize(ctx->stream);
     *value = (int64_t)k1_g4_prof_read(name[7] - '0', name[8] == 'r');

@@ -82,6 +82,9 @@ CoopPlan make_plan(const K1Params& P, bool ens, int n_warps = KC_WARPS) {
   return c;
 }
 
+#ifdef KC_PROF
+__device__ unsigned long long kc_prof[8];
+#endif
 // ---- per-step work of the persistent sampler, each the per-source form of a K3 kernel (k3_ensemble.cu) --------------
 // k3_split_kernel: rank the source's W walkers by their Philox key of this step (ties by walker index)
 __device__ __forceinline__ void persist_split(uint16_t* out, uint32_t* keys, int W, int64_t step, int64_t src_global,
@@ -210,7 +213,7 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
 // half-steps, the per-step split, best tracking, histograms and chain recording — inside ONE launch (see K1Persist).
 // The source's walkers and log-posteriors live in shared memory for the whole launch.
 template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
-__global__ void __launch_bounds__(KC_THREADS, KC_MINBLOCKS)
+__global__ void __launch_bounds__(KC_THREADS, 2)
 k1_coop_persist_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPlan C, const K1Persist A) {
   constexpr bool ENS = true, PERSIST = true;
   constexpr bool EXT = GA_FREE || RADIO || BB_MODE >= 2;
@@ -258,6 +261,10 @@ k1_coop_persist_kernel(const __grid_constant__ K1Params P, const K1Batch B, cons
   const int64_t row0 = p_src * p_H + warp * 32;
   const int rows_here = (int)max((int64_t)0, min((int64_t)32, (p_src + 1) * p_H - row0));
   constexpr uint32_t par_bytes = 0;      // ensemble mode reads no params block
+  // per-warp landing tile of the galaxy rows (after the walkers), its mbarrier = the warp's params barrier
+  const uint32_t ga_tile_s = tab_s + (uint32_t)C.walkers_off + (uint32_t)(((p_W * (n_par + 1) * 8) + 15) & ~15) +
+                             (uint32_t)warp * 32u * (uint32_t)P.fam[0].pitch * 8u;
+  uint32_t ga_parity = 0;
   for (int64_t pass = 0; pass < 2 * A.n_steps; ++pass) {
     const int64_t e_step = A.step0 + (pass >> 1);
     const int e_half = (int)(pass & 1);
@@ -268,14 +275,33 @@ k1_coop_persist_kernel(const __grid_constant__ K1Params P, const K1Batch B, cons
                       B.ens.seed, lane);
       __syncthreads();
     }
+#ifdef KC_PROF
+    long long tick__ = clock64();
+#endif
     do {
 #define TILE_EXIT break
 #define TILE_PINNED
+#define TILE_PERSIST
 #include "k1_coop_tile.inc"
+#undef TILE_PERSIST
 #undef TILE_PINNED
 #undef TILE_EXIT
     } while (0);
+#ifdef KC_PROF
+    {
+      const long long now__ = clock64();
+      if (lane == 0 && warp == 0) atomicAdd(&kc_prof[4], (unsigned long long)(now__ - tick__));
+      tick__ = now__;
+    }
+#endif
     __syncthreads();                     // the other half (and the per-step work) reads what this pass wrote
+#ifdef KC_PROF
+    {
+      const long long now__ = clock64();
+      if (lane == 0 && warp == 0) atomicAdd(&kc_prof[5], (unsigned long long)(now__ - tick__));
+      tick__ = now__;
+    }
+#endif
     if (e_half == 1) {
       const int64_t k = pass >> 1;
       const bool thinned = A.hist_every > 0 && ((k + 1) % A.hist_every) == 0;
@@ -321,6 +347,7 @@ cudaError_t launch_coop_persist(const K1Params& P, const K1Batch& B, const K1Per
   const int n_warps = ((B.ens.W >> 1) + 31) / 32;
   CoopPlan C = make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, true, n_warps);
   C.smem_bytes += (B.ens.W * (P.cfg.n_par + 1) * 8 + 15) & ~15;          // the source's walkers + log-posteriors
+  C.smem_bytes += n_warps * 32 * P.fam[0].pitch * 8;                     // landing tiles of the galaxy rows
   static int attr_bytes[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -419,7 +446,8 @@ bool k1_coop_persist_supported(const K1Params& P, const K1Batch& B) {
   const CoopPlan C = ext ? make_plan<true>(P, true, n_warps) : make_plan<false>(P, true, n_warps);
   // warp 0's partial-sum area doubles as the key buffer of the per-step split
   const int64_t key_bytes = 4 * (int64_t)((B.ens.W + 3) & ~3);
-  return (size_t)C.smem_bytes + (size_t)B.ens.W * (P.cfg.n_par + 1) * 8 <= 200 * 1024 && key_bytes <= (int64_t)C.q_off * 8;
+  return (size_t)C.smem_bytes + (size_t)B.ens.W * (P.cfg.n_par + 1) * 8 + (size_t)n_warps * 32 * P.fam[0].pitch * 8 <=
+             200 * 1024 && key_bytes <= (int64_t)C.q_off * 8;
 }
 
 bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why) {
@@ -489,6 +517,17 @@ cudaError_t launch_persist_bb(const K1Params& P, const K1Batch& B, const K1Persi
     case 2: return c9 ? launch_coop_persist<GA_FREE, 2, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 2, RADIO, 0>(P, B, A, stream);
     default: return c9 ? launch_coop_persist<GA_FREE, 3, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 3, RADIO, 0>(P, B, A, stream);
   }
+}
+
+unsigned long long k1_coop_prof_read(int i) {
+#ifdef KC_PROF
+  unsigned long long h[8] = {0};
+  cudaMemcpyFromSymbol(h, kc_prof, sizeof(h));
+  return (i >= 0 && i < 8) ? h[i] : 0;
+#else
+  (void)i;
+  return 0;
+#endif
 }
 
 cudaError_t launch_k1_coop_persist(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream) {

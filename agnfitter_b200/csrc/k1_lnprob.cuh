@@ -218,6 +218,7 @@ bool k1_coop_supported(const K1Params& P, const K1Batch& B, const char** why);
 bool k1_coop_profitable(const K1Params& P, const K1Batch& B);   // false: the per-thread kernel is expected to win
 cudaError_t launch_k1_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream);
 // persistent per-source sampler; B.ens describes the ensemble, B.n is ignored
+unsigned long long k1_coop_prof_read(int i);     // -DKC_PROF builds only (else 0)
 bool k1_coop_persist_supported(const K1Params& P, const K1Batch& B);
 cudaError_t launch_k1_coop_persist(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream);
 // eb0[z, t] for the galaxy family (see K1Params::eb0), chunk sums in the order the kernel used to add them

@@ -11,7 +11,8 @@ ms, g = load_k1("classic18")
 data, models, P = reference_objects(ms, g, 0)
 tmp = tempfile.mkdtemp()
 data.output_folder, data.name = tmp + "/", "src0"
-mc = dict(Nwalkers=100, Nburnsets=2, Nburn=12000, Nmcmc=25000, Nthin=10, iprint=1000, sampling_algorithm='emcee')
+mc = dict(Nwalkers=100, Nburnsets=2, Nburn=12000, Nmcmc=25000, Nthin=10, iprint=1000, sampling_algorithm="emcee",
+          chain_pickle_protocol=int(os.environ.get("CHAIN_PROTOCOL", "2")))
 dropin.main(data, models, P, dict(mc, Nburn=10, Nmcmc=10), seed=1)      # warm-up: context, module load
 t0 = time.perf_counter()
 out = dropin.main(data, models, P, mc, seed=1)

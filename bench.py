@@ -592,6 +592,13 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    # ... and keep warming until the clocks / power management have seen ~0.25 s of this load: at N = 8 the first tens
+    # of milliseconds after an idle phase run under a transient power cap (the sustained leg below shows the plateau)
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.25:
+        for _ in range(10):
+            step_resident()
+        torch.cuda.synchronize(dev)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()

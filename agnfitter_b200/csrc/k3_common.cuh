@@ -60,6 +60,69 @@ __device__ __forceinline__ int split_walker(const uint16_t* split, int64_t s_loc
   return (int)__ldg(split + s_local * W + slot);
 }
 
+// The split ranking of one source by one warp: out[rank(w)] = w, rank = position of walker w's 32-bit Philox key among
+// the source's W keys, ties by walker index.  Keys are uniform, so they are dropped into 128 buckets by their top seven
+// bits (shared-memory histogram, warp scan, scatter) and a key is compared only against its own bucket (W/128
+// candidates instead of W): the result is the same ranking the all-pairs count gives, for any key values.
+// `scratch`: split_scratch_words(W) 32-bit words of shared memory owned by the warp.  OUT16 = uint16_t (may be global).
+__host__ __device__ constexpr int split_scratch_words(int W) { return ((W + 3) & ~3) + 256 + W + (W + 1) / 2; }
+__device__ __forceinline__ void split_rank_warp(uint16_t* out, uint32_t* scratch, int W, int64_t step,
+                                                int64_t src_global, uint64_t seed, int lane) {
+  const int W4 = (W + 3) & ~3;
+  uint32_t* keys = scratch;                 // [W4]
+  uint32_t* cnt = scratch + W4;             // [128] entries per bucket
+  uint32_t* fill = cnt + 128;               // [128] bucket start, advanced to the bucket end by the scatter
+  uint32_t* skey = fill + 128;              // [W] keys in bucket order
+  uint16_t* sidx = reinterpret_cast<uint16_t*>(skey + W);      // [W] their walkers
+  for (int q = lane; q < W4 / 4; q += 32) {
+    uint32_t x[4];
+    philox4x32_10((uint32_t)step, K3_SPLIT_TAG, (uint32_t)src_global, (uint32_t)q, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+    keys[4 * q] = x[0];
+    keys[4 * q + 1] = x[1];
+    keys[4 * q + 2] = x[2];
+    keys[4 * q + 3] = x[3];
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) cnt[lane + 32 * u] = 0u;
+  __syncwarp();
+  for (int w = lane; w < W; w += 32) atomicAdd(cnt + (keys[w] >> 25), 1u);
+  __syncwarp();
+  {
+    // exclusive scan of the 128 counts: lane owns buckets 4 lane .. 4 lane + 3
+    const uint32_t c0 = cnt[4 * lane], c1 = cnt[4 * lane + 1], c2 = cnt[4 * lane + 2], c3 = cnt[4 * lane + 3];
+    uint32_t incl = c0 + c1 + c2 + c3;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t base = incl - (c0 + c1 + c2 + c3);
+    fill[4 * lane] = base;
+    fill[4 * lane + 1] = base + c0;
+    fill[4 * lane + 2] = base + c0 + c1;
+    fill[4 * lane + 3] = base + c0 + c1 + c2;
+  }
+  __syncwarp();
+  for (int w = lane; w < W; w += 32) {
+    const uint32_t k = keys[w];
+    const uint32_t at = atomicAdd(fill + (k >> 25), 1u);
+    skey[at] = k;
+    sidx[at] = (uint16_t)w;
+  }
+  __syncwarp();
+  for (int w = lane; w < W; w += 32) {
+    const uint32_t k = keys[w], b = k >> 25;
+    const uint32_t end = fill[b], n = cnt[b];
+    uint32_t r = end - n;
+    for (uint32_t e = end - n; e < end; ++e) {
+      const uint32_t ke = skey[e];
+      r += (ke < k) || (ke == k && (int)sidx[e] < w);
+    }
+    out[r] = (uint16_t)w;
+  }
+  __syncwarp();
+}
+
 // q = c - (c - x) * zz, no contraction
 __device__ __forceinline__ double stretch_coord(double c, double x, double zz) {
   return __dsub_rn(c, __dmul_rn(__dsub_rn(c, x), zz));

@@ -53,41 +53,14 @@ __global__ void __launch_bounds__(K3_THREADS) k3_accept_kernel(K3State st, K3Scr
   }
 }
 
-// one warp per source: rank every walker's key among the source's W keys (ties by walker index)
+// one warp per source: rank every walker's key among the source's W keys (ties by walker index), k3_common.cuh
 __global__ void __launch_bounds__(K3_THREADS) k3_split_kernel(K3State st, int64_t step) {
-  extern __shared__ uint32_t s_keys[];                    // [warps per CTA][W rounded up to 4]
+  extern __shared__ uint32_t s_split[];                   // [warps per CTA][split_scratch_words(W)]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t s = (int64_t)blockIdx.x * (K3_THREADS / 32) + warp;
   if (s >= st.S) return;
-  const int W = st.W, W4 = (W + 3) & ~3;
-  uint32_t* keys = s_keys + warp * W4;
-  for (int q = lane; q < W4 / 4; q += 32) {
-    uint32_t x[4];
-    philox4x32_10((uint32_t)step, K3_SPLIT_TAG, (uint32_t)(s + st.src_offset), (uint32_t)q, (uint32_t)st.seed,
-                  (uint32_t)(st.seed >> 32), x);
-    keys[4 * q] = x[0];
-    keys[4 * q + 1] = x[1];
-    keys[4 * q + 2] = x[2];
-    keys[4 * q + 3] = x[3];
-  }
-  __syncwarp();
-  for (int w0 = lane; w0 < W; w0 += 128) {               // four walkers per lane and pass
-    const int w1 = w0 + 32, w2 = w0 + 64, w3 = w0 + 96;
-    const uint32_t k0 = keys[w0], k1 = w1 < W ? keys[w1] : 0u, k2 = w2 < W ? keys[w2] : 0u, k3 = w3 < W ? keys[w3] : 0u;
-    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-    for (int j = 0; j < W; ++j) {
-      const uint32_t kj = keys[j];
-      r0 += (kj < k0) || (kj == k0 && j < w0);
-      r1 += (kj < k1) || (kj == k1 && j < w1);
-      r2 += (kj < k2) || (kj == k2 && j < w2);
-      r3 += (kj < k3) || (kj == k3 && j < w3);
-    }
-    uint16_t* out = st.split + s * W;
-    out[r0] = (uint16_t)w0;
-    if (w1 < W) out[r1] = (uint16_t)w1;
-    if (w2 < W) out[r2] = (uint16_t)w2;
-    if (w3 < W) out[r3] = (uint16_t)w3;
-  }
+  split_rank_warp(st.split + s * st.W, s_split + warp * split_scratch_words(st.W), st.W, step, s + st.src_offset,
+                  st.seed, lane);
 }
 
 // one thread per (source, walker, parameter)
@@ -289,7 +262,11 @@ cudaError_t launch_k3_fill_sid(int32_t* sid, int64_t S, int32_t half, cudaStream
 cudaError_t launch_k3_split(const K3State& st, int64_t step, cudaStream_t stream) {
   if (!st.split || st.S == 0) return cudaSuccess;
   const int wpc = K3_THREADS / 32;
-  const size_t smem = (size_t)wpc * ((st.W + 3) & ~3) * sizeof(uint32_t);
+  const size_t smem = (size_t)wpc * split_scratch_words(st.W) * sizeof(uint32_t);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k3_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
   k3_split_kernel<<<(unsigned)((st.S + wpc - 1) / wpc), K3_THREADS, smem, stream>>>(st, step);
   return cudaGetLastError();
 }

@@ -86,31 +86,6 @@ CoopPlan make_plan(const K1Params& P, bool ens, int n_warps = KC_WARPS) {
 __device__ unsigned long long kc_prof[8];
 #endif
 // ---- per-step work of the persistent sampler, each the per-source form of a K3 kernel (k3_ensemble.cu) --------------
-// k3_split_kernel: rank the source's W walkers by their Philox key of this step (ties by walker index)
-__device__ __forceinline__ void persist_split(uint16_t* out, uint32_t* keys, int W, int64_t step, int64_t src_global,
-                                              uint64_t seed, int lane) {
-  const int W4 = (W + 3) & ~3;
-  for (int q = lane; q < W4 / 4; q += 32) {
-    uint32_t x[4];
-    philox4x32_10((uint32_t)step, K3_SPLIT_TAG, (uint32_t)src_global, (uint32_t)q, (uint32_t)seed, (uint32_t)(seed >> 32), x);
-    keys[4 * q] = x[0];
-    keys[4 * q + 1] = x[1];
-    keys[4 * q + 2] = x[2];
-    keys[4 * q + 3] = x[3];
-  }
-  __syncwarp();
-  for (int w0 = lane; w0 < W; w0 += 32) {
-    const uint32_t k0 = keys[w0];
-    int r0 = 0;
-    for (int j = 0; j < W; ++j) {
-      const uint32_t kj = keys[j];
-      r0 += (kj < k0) || (kj == k0 && j < w0);
-    }
-    out[r0] = (uint16_t)w0;
-  }
-  __syncwarp();
-}
-
 // k3_best_kernel: the first walker with the largest lnp, if it beats the stored best
 __device__ __forceinline__ void persist_best(const double* pos, const double* lnp, int W, int n_par, double* best_pos,
                                              double* best_lnp, int lane) {
@@ -269,10 +244,10 @@ k1_coop_persist_kernel(const __grid_constant__ K1Params P, const K1Batch B, cons
     const int64_t e_step = A.step0 + (pass >> 1);
     const int e_half = (int)(pass & 1);
     if (e_half == 0 && B.ens.split) {   // this step's split of the source's walkers (k3_split_kernel's ranking)
-      uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw + (part_s - tab_s));     // warp 0's partial-sum area
+      uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw + (part_s - tab_s));     // warp 0's partial-sum area
       if (warp == 0)
-        persist_split(const_cast<uint16_t*>(B.ens.split) + p_src * p_W, keys, p_W, e_step, p_src + B.ens.src_offset,
-                      B.ens.seed, lane);
+        split_rank_warp(const_cast<uint16_t*>(B.ens.split) + p_src * p_W, scratch, p_W, e_step,
+                        p_src + B.ens.src_offset, B.ens.seed, lane);
       __syncthreads();
     }
 #ifdef KC_PROF
@@ -394,12 +369,17 @@ cudaError_t launch_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream
 
 template <bool GA_FREE, bool RADIO>
 cudaError_t launch_coop_bb(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
+#ifdef KC_DEV          // quick development builds (tools/dev_build.sh): the classic model set only
+  if (GA_FREE || RADIO || P.cfg.bb_mode != 1) return cudaErrorNotSupported;
+  return launch_coop<false, 1, false>(P, B, stream);
+#else
   switch (P.cfg.bb_mode) {
     case 0: return launch_coop<GA_FREE, 0, RADIO>(P, B, stream);
     case 1: return launch_coop<GA_FREE, 1, RADIO>(P, B, stream);
     case 2: return launch_coop<GA_FREE, 2, RADIO>(P, B, stream);
     default: return launch_coop<GA_FREE, 3, RADIO>(P, B, stream);
   }
+#endif
 }
 
 #ifndef K1_COOP_ENS_TU
@@ -445,7 +425,7 @@ bool k1_coop_persist_supported(const K1Params& P, const K1Batch& B) {
   const int n_warps = ((B.ens.W >> 1) + 31) / 32;
   const CoopPlan C = ext ? make_plan<true>(P, true, n_warps) : make_plan<false>(P, true, n_warps);
   // warp 0's partial-sum area doubles as the key buffer of the per-step split
-  const int64_t key_bytes = 4 * (int64_t)((B.ens.W + 3) & ~3);
+  const int64_t key_bytes = 4 * (int64_t)split_scratch_words(B.ens.W);
   return (size_t)C.smem_bytes + (size_t)B.ens.W * (P.cfg.n_par + 1) * 8 + (size_t)n_warps * 32 * P.fam[0].pitch * 8 <=
              200 * 1024 && key_bytes <= (int64_t)C.q_off * 8;
 }
@@ -511,12 +491,17 @@ cudaError_t launch_exp10_fast(const double* x, double* y, int64_t n, cudaStream_
 template <bool GA_FREE, bool RADIO>
 cudaError_t launch_persist_bb(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream) {
   const bool c9 = P.nbp / 2 == 9;
+#ifdef KC_DEV
+  if (GA_FREE || RADIO || P.cfg.bb_mode != 1) return cudaErrorNotSupported;
+  return c9 ? launch_coop_persist<false, 1, false, 9>(P, B, A, stream) : launch_coop_persist<false, 1, false, 0>(P, B, A, stream);
+#else
   switch (P.cfg.bb_mode) {
     case 0: return c9 ? launch_coop_persist<GA_FREE, 0, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 0, RADIO, 0>(P, B, A, stream);
     case 1: return c9 ? launch_coop_persist<GA_FREE, 1, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 1, RADIO, 0>(P, B, A, stream);
     case 2: return c9 ? launch_coop_persist<GA_FREE, 2, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 2, RADIO, 0>(P, B, A, stream);
     default: return c9 ? launch_coop_persist<GA_FREE, 3, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 3, RADIO, 0>(P, B, A, stream);
   }
+#endif
 }
 
 unsigned long long k1_coop_prof_read(int i) {

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import sources as _sources
 from .engine import Engine, DictBuilder
-from .flatten import modelset_from_modelsdicts, ModelSet
+from .flatten import modelset_from_modelsdicts, ModelSet, save_modelset, load_modelset
 
 
 def params_transform(cube, pmin, pmax):
@@ -46,6 +46,56 @@ def check_P(ms: ModelSet, P, pmin, pmax):
         raise ValueError("P['min']/P['max'] differ from the bounds Pdict gives for this dictionary and redshift")
 
 
+# ---- dense on-disk dictionary beside the legacy pickle -----------------------------------------
+# RUN_AGNfitter_multi.py:203-213 caches a source's dictionary as a pickle of Python dicts (`zdict.filename`), and
+# every later run of that source unpickles it and walks the dicts again.  The dense form -- the ModelSet the kernels
+# consume: key tables, snapping grids and one [T, n_b] fp64 table per family, `flatten.save_modelset` -- is written
+# next to it as `<zdict.filename>.b200.npz`; `Posterior` loads it instead of flattening the dicts when it is there and
+# describes the same dictionary.  The pickle stays: PLOTandWRITE reads the Python dicts.
+def cache_path(md):
+    fn = getattr(md, 'filename', None)
+    if fn is None:
+        return None
+    if isinstance(fn, bytes):
+        fn = fn.decode()
+    return str(fn) + '.b200.npz'
+
+
+def save_dictionary_cache(md, settings=None):
+    """Write the dense dictionary of the MODELSDICT `md` (built by the reference or by `build`) beside its pickle.
+    `settings`: the models settings (default `md.modelsettings`).  Returns the path written."""
+    path = cache_path(md)
+    if path is None:
+        raise ValueError("the MODELSDICT has no filename (DICTIONARIES_AGNfitter.py:60)")
+    ms = modelset_from_modelsdicts([md], md.modelsettings if settings is None else settings)
+    save_modelset(path, ms)
+    return path
+
+
+def load_dictionary_cache(md, settings):
+    """The ModelSet stored by save_dictionary_cache if it exists and describes `md` (same redshift, bands, families
+    and template counts, same settings of the prior branches); None otherwise (the caller flattens the dicts)."""
+    import os
+    path = cache_path(md)
+    if path is None or not os.path.lexists(path):
+        return None
+    try:
+        ms = load_modelset(path)
+    except Exception:
+        return None
+    counts = {"GA": "GALAXYFdict", "SB": "STARBURSTFdict", "TO": "TORUSFdict", "BB": "BBBFdict", "RAD": "AGN_RADFdict"}
+    ok = ms.n_z == 1 and float(ms.z_grid[0]) == float(md.z)
+    for f in ms.families:
+        d = getattr(md, counts[f.name], None)
+        ok = ok and d is not None and len(d) == f.T
+    if ok:
+        first = next(iter(md.GALAXYFdict.values()))
+        ok = np.array_equal(np.asarray(first[0], dtype=np.float64), ms.bands)
+    import json
+    ok = ok and json.loads(json.dumps(dict(settings))) == ms.settings
+    return ms if ok else None
+
+
 class Posterior:
     """ln_probab for ONE source, bound to the reference's (data, models, P) triple.
 
@@ -56,7 +106,10 @@ class Posterior:
 
     def __init__(self, data, models, P, device=0, ctx=None):
         md = models.dict_modelfluxes                     # the MODELSDICT instance (MODEL_AGNfitter.py:1483-1490)
-        self.ms = modelset_from_modelsdicts([md], models.settings)
+        self.ms = load_dictionary_cache(md, models.settings)      # dense .npz beside the pickle, when present
+        self.from_cache = self.ms is not None
+        if self.ms is None:
+            self.ms = modelset_from_modelsdicts([md], models.settings)
         if float(md.z) != float(data.z):
             raise ValueError("the dictionary was built for z=%r, the source is at z=%r" % (md.z, data.z))
         self.engine = Engine(self.ms, device=device, ctx=ctx)

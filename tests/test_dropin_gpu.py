@@ -36,6 +36,27 @@ def test_posterior_matches_reference(case):
         assert np.all(t >= np.asarray(P['min'])) and np.all(t <= np.asarray(P['max']))
 
 
+@pytest.mark.parametrize("case", ["classic18", "radio2_sn12_49"])
+def test_posterior_from_the_dense_dictionary_cache(case, tmp_path):
+    """with `<zdict.filename>.b200.npz` beside the pickle (dropin.save_dictionary_cache, written by the
+    patched RUN_AGNfitter_multi.py) the Posterior loads the dense arrays instead of flattening the Python dicts, and
+    evaluates the same bits."""
+    ms, g = load_k1(case)
+    data, models, P = _reference_objects(ms, g, 0)
+    md = models.dict_modelfluxes
+    md.modelsettings = models.settings
+    sel = np.nonzero(g["source_id"] == 0)[0]
+    plain = dropin.Posterior(data, models, P)
+    assert not plain.from_cache
+    want = plain.ln_probab_batch(g["pars"][sel])
+    md.filename = str(tmp_path / "MODELSDICT_z")
+    dropin.save_dictionary_cache(md)
+    cached = dropin.Posterior(data, models, P)
+    assert cached.from_cache
+    assert np.array_equal(cached.ln_probab_batch(g["pars"][sel]), want, equal_nan=True)
+    assert_close_with_specials(want, g["ref_lnp"][sel], what="ln_probab_batch")
+
+
 def test_fill_modelsdict_matches_reference_dictionary():
     g = load_k2("default18")
     bands, off = g["bands"], g["filt_offset"]

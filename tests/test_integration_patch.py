@@ -34,7 +34,8 @@ def patched_tree(tmp_path):
 
 def test_patch_applies_and_touches_only_the_two_call_sites(patched_tree):
     for rel, needle in (("functions/MCMC_AGNfitter.py", "mc.get('backend') == 'b200'"),
-                        ("RUN_AGNfitter_multi.py", "b200.build(zdict)")):
+                        ("RUN_AGNfitter_multi.py", "b200.build(zdict)"),
+                        ("RUN_AGNfitter_multi.py", "b200.save_dictionary_cache(zdict)")):
         new = open(patched_tree / rel).read()
         old = open(os.path.join(REF, rel)).read()
         assert needle in new and needle not in old

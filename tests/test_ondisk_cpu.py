@@ -43,3 +43,39 @@ def test_plotset_npz_roundtrip(tmp_path):
     _, a = SO.realization_fluxes(ms, ps, rows, z0, d0)
     _, b = SO.realization_fluxes(ms, back, rows, z0, d0)
     assert all(np.array_equal(a[c], b[c], equal_nan=True) for c in a)
+
+
+def test_dictionary_cache_beside_the_pickle(tmp_path):
+    """dropin.save_dictionary_cache / load_dictionary_cache: the dense `.npz` written next to the reference's dictionary
+    pickle (RUN_AGNfitter_multi.py:203-213) gives back the flattened dictionary bit for bit, and is ignored when it
+    describes another dictionary (other redshift, other template count, other settings) or is unreadable."""
+    from helpers import reference_objects
+    from agnfitter_b200 import dropin
+    ms, g = load_k1("classic18")
+    data, models, P = reference_objects(ms, g, 0)
+    md = models.dict_modelfluxes
+    md.modelsettings = models.settings
+    assert dropin.cache_path(md) is None and dropin.load_dictionary_cache(md, models.settings) is None
+    md.filename = str(tmp_path / "dict_z.pickle").encode()         # RUN_AGNfitter_multi.py:191 passes bytes around
+    assert dropin.load_dictionary_cache(md, models.settings) is None
+    path = dropin.save_dictionary_cache(md)
+    assert path == str(tmp_path / "dict_z.pickle") + ".b200.npz"
+    back = dropin.load_dictionary_cache(md, models.settings)
+    flat = flatten.modelset_from_modelsdicts([md], models.settings)
+    assert back is not None and back.par_names == flat.par_names
+    for a, b in zip(flat.families, back.families):
+        assert np.array_equal(a.table, b.table) and np.array_equal(a.keys_float, b.keys_float)
+        assert np.array_equal(a.stride, b.stride) and (a.aux is None or np.array_equal(a.aux, b.aux))
+    other = dict(models.settings)
+    other['PRIOR_AGNfraction'] = not (other.get('PRIOR_AGNfraction') == True)
+    assert dropin.load_dictionary_cache(md, other) is None          # other prior settings
+    z_true = md.z
+    md.z = z_true + 0.5
+    assert dropin.load_dictionary_cache(md, models.settings) is None  # other redshift
+    md.z = z_true
+    k = next(iter(md.TORUSFdict))
+    dropped = md.TORUSFdict.pop(k)
+    assert dropin.load_dictionary_cache(md, models.settings) is None  # other template count
+    md.TORUSFdict[k] = dropped
+    open(path, "wb").write(b"not an npz")
+    assert dropin.load_dictionary_cache(md, models.settings) is None  # unreadable: fall back to the dicts

@@ -9,7 +9,7 @@ from collections import defaultdict
 
 rep, kern, inst = sys.argv[1], sys.argv[2], sys.argv[3]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = os.path.join(ROOT, "agnfitter_b200", "csrc", "libagnfit_b200.so")
+lib = os.path.abspath(os.environ.get("AGNFIT_B200_LIB") or os.path.join(ROOT, "agnfitter_b200", "csrc", "libagnfit_b200.so"))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 seq = None

@@ -94,6 +94,7 @@ struct agnf_ctx {
   double* ens_best_pos = nullptr;
   double* ens_best_lnp = nullptr;
   int64_t ens_step = 0;              // stretch-move steps taken since agnf_ens_create (Philox counter)
+  int ens_persist_rows = 0;          // persistent sampler: walkers per warp (1..32); 0 automatic (see agnf_ens_run)
   int ens_persist = -1;              // persistent per-source sampler: -1 automatic (small shards), 0 never, 1 whenever possible
   int ens_last_persist = 0;          // whether the last agnf_ens_run took the persistent kernel
   int ens_fused = 1;                 // 1: one fused K1 launch per half-step; 0: propose / K1 / accept kernels
@@ -745,6 +746,11 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     ctx->k2_shared_window = (int)value;
     return 0;
   }
+  if (strcmp(name, "ens_persist_rows") == 0) {
+    if (value < 0 || value > 32) return fail(ctx, "ens_persist_rows must be 0 (automatic) or 1..32 walkers per warp");
+    ctx->ens_persist_rows = (int)value;
+    return 0;
+  }
   if (strcmp(name, "ens_persist") == 0) {
     if (value < -1 || value > 1) return fail(ctx, "ens_persist must be -1 (automatic), 0 or 1");
     ctx->ens_persist = (int)value;
@@ -810,6 +816,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   else if (strcmp(name, "zero_copy_rows") == 0) *value = ctx->zero_copy_rows;
   else if (strcmp(name, "ens_fused") == 0) *value = ctx->ens_fused;
   else if (strcmp(name, "ens_persist") == 0) *value = ctx->ens_persist;
+  else if (strcmp(name, "ens_persist_rows") == 0) *value = ctx->ens_persist_rows;
   else if (strcmp(name, "ens_last_persist") == 0) *value = ctx->ens_last_persist;
   else if (strcmp(name, "ens_split") == 0) *value = ctx->ens_split;
   else if (strcmp(name, "k2_shared_window") == 0) *value = ctx->k2_shared_window;
@@ -1646,8 +1653,16 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
   // pays ~5 launches per step, which is all a shard of a few hundred sources costs.  Same Philox counters, same
   // arithmetic: the chain is identical bit for bit (tests/test_ensemble_gpu.py).
   const int v = ctx->k1_variant;
+  // A half-step of one source is a chain of dependent memory round trips, so its latency falls with the rows a warp
+  // owns: up to two CTAs of eight warps fit an SM, which serves shards of <= 296 sources; larger ones keep 32 rows per
+  // warp (more CTAs per SM, better throughput).
+  int rpw = ctx->ens_persist_rows;
+  if (rpw <= 0) {
+    rpw = st.S <= 2 * 148 ? std::max(1, ((int)(st.W >> 1) + 7) / 8) : 32;
+    if (rpw != 32 && !k1_coop_persist_supported(ctx->k1, FB, rpw)) rpw = 32;
+  }
   const bool persist = ctx->ens_fused && v != 0 && v != 3 && n_steps > 0 && ctx->ens_persist != 0 &&
-                       k1_coop_persist_supported(ctx->k1, FB) && (ctx->ens_persist == 1 || st.S <= 1184);
+                       k1_coop_persist_supported(ctx->k1, FB, rpw) && (ctx->ens_persist == 1 || st.S <= 1184);
   ctx->ens_last_persist = persist ? 1 : 0;
   if (persist) {
     K1Persist A;
@@ -1661,6 +1676,7 @@ AGNF_API int agnf_ens_run(agnf_ctx* ctx, int64_t n_steps, int32_t hist_every, in
     A.best_pos = ctx->ens_best_pos;
     A.best_lnp = ctx->ens_best_lnp;
     A.S = st.S;
+    A.rows_per_warp = rpw;
     int64_t n_rec = 0, n_thin = 0;
     if (hist_every > 0) n_thin = n_steps / hist_every;
     if (ctx->ens_chain) {

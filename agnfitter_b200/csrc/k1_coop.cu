@@ -82,8 +82,11 @@ CoopPlan make_plan(const K1Params& P, bool ens, int n_warps = KC_WARPS) {
   return c;
 }
 
+// shared-memory copy of the snap tasks (persistent sampler)
+constexpr uint32_t KC_TASK_BYTES = (AGNF_MAX_FAMILIES * AGNF_MAX_DIMS * sizeof(SnapTask) + 15) & ~15u;
+
 #ifdef KC_PROF
-__device__ unsigned long long kc_prof[8];
+__device__ unsigned long long kc_prof[12];
 #endif
 // ---- per-step work of the persistent sampler, each the per-source form of a K3 kernel (k3_ensemble.cu) --------------
 // k3_best_kernel: the first walker with the largest lnp, if it beats the stored best
@@ -177,6 +180,7 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
   }
   double* const w_pos = B.ens.pos;      // walker state (ensemble mode): global memory
   double* const w_lnp = B.ens.lnp;
+  const uint16_t* const split_tab = B.ens.split;
   const int64_t e_step = B.ens.step;
   const int e_half = B.ens.half;
 #define TILE_EXIT return
@@ -233,11 +237,21 @@ k1_coop_persist_kernel(const __grid_constant__ K1Params P, const K1Batch B, cons
   for (int e = threadIdx.x; e < p_W * n_par; e += blockDim.x) my_pos[e] = B.ens.pos[p_src * p_W * n_par + e];
   for (int e = threadIdx.x; e < p_W; e += blockDim.x) my_lnp[e] = B.ens.lnp[p_src * p_W + e];
   __syncthreads();
-  const int64_t row0 = p_src * p_H + warp * 32;
-  const int rows_here = (int)max((int64_t)0, min((int64_t)32, (p_src + 1) * p_H - row0));
+  const int64_t row0 = p_src * p_H + warp * A.rows_per_warp;
+  const int rows_here = max(0, min(A.rows_per_warp, p_H - warp * A.rows_per_warp));
   constexpr uint32_t par_bytes = 0;      // ensemble mode reads no params block
   // per-warp landing tile of the galaxy rows (after the walkers), its mbarrier = the warp's params barrier
-  const uint32_t ga_tile_s = tab_s + (uint32_t)C.walkers_off + (uint32_t)(((p_W * (n_par + 1) * 8) + 15) & ~15) +
+  // this step's split of the source's walkers: shared memory too (the table in global memory is not used)
+  const uint32_t split_off = (uint32_t)C.walkers_off + (uint32_t)(((p_W * (n_par + 1) * 8) + 15) & ~15);
+  uint16_t* const my_split = reinterpret_cast<uint16_t*>(smem_raw + split_off);
+  const uint16_t* const split_tab = B.ens.split ? my_split - p_src * p_W : nullptr;
+  // the snap tasks, copied out of the parameter block (k1_coop_tile.inc: TILE_TASKS)
+  const uint32_t tasks_off = split_off + (uint32_t)((p_W * 2 + 15) & ~15);
+  SnapTask* const task_tab = reinterpret_cast<SnapTask*>(smem_raw + tasks_off);
+  for (int e = threadIdx.x; e < P.n_tasks * (int)(sizeof(SnapTask) / 4); e += blockDim.x)
+    reinterpret_cast<int32_t*>(task_tab)[e] = reinterpret_cast<const int32_t*>(P.tasks)[e];
+  __syncthreads();
+  const uint32_t ga_tile_s = tab_s + tasks_off + KC_TASK_BYTES +
                              (uint32_t)warp * 32u * (uint32_t)P.fam[0].pitch * 8u;
   uint32_t ga_parity = 0;
   for (int64_t pass = 0; pass < 2 * A.n_steps; ++pass) {
@@ -246,7 +260,7 @@ k1_coop_persist_kernel(const __grid_constant__ K1Params P, const K1Batch B, cons
     if (e_half == 0 && B.ens.split) {   // this step's split of the source's walkers (k3_split_kernel's ranking)
       uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw + (part_s - tab_s));     // warp 0's partial-sum area
       if (warp == 0)
-        split_rank_warp(const_cast<uint16_t*>(B.ens.split) + p_src * p_W, scratch, p_W, e_step,
+        split_rank_warp(my_split, scratch, p_W, e_step,
                         p_src + B.ens.src_offset, B.ens.seed, lane);
       __syncthreads();
     }
@@ -315,13 +329,18 @@ cudaError_t launch_coop_ens(const K1Params& P, const K1Batch& B, cudaStream_t st
   return cudaGetLastError();
 }
 
-// the persistent per-source sampler: one CTA of ceil(W/2 / 32) warps per source
+// warps of a persistent CTA: the half-ensemble cut into groups of rows_per_warp walkers
+inline int persist_warps(int W, int rows_per_warp) { return ((W >> 1) + rows_per_warp - 1) / rows_per_warp; }
+
+// the persistent per-source sampler: one CTA of ceil(W/2 / rows_per_warp) warps per source
 template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
 cudaError_t launch_coop_persist(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream) {
   auto kern = k1_coop_persist_kernel<GA_FREE, BB_MODE, RADIO, CPR_T>;
-  const int n_warps = ((B.ens.W >> 1) + 31) / 32;
+  const int n_warps = persist_warps(B.ens.W, A.rows_per_warp);
   CoopPlan C = make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, true, n_warps);
   C.smem_bytes += (B.ens.W * (P.cfg.n_par + 1) * 8 + 15) & ~15;          // the source's walkers + log-posteriors
+  C.smem_bytes += (B.ens.W * 2 + 15) & ~15;                              // this step's split
+  C.smem_bytes += KC_TASK_BYTES;                                         // the snap tasks
   C.smem_bytes += n_warps * 32 * P.fam[0].pitch * 8;                     // landing tiles of the galaxy rows
   static int attr_bytes[64] = {0};
   int dev = 0;
@@ -419,14 +438,16 @@ static const char* coop_basic_checks(const K1Params& P, const K1Batch& B) {
   return w;
 }
 
-bool k1_coop_persist_supported(const K1Params& P, const K1Batch& B) {
-  if (!B.ens.pos || B.ens.W < 2 || (B.ens.W >> 1) > KC_THREADS || coop_basic_checks(P, B)) return false;
+bool k1_coop_persist_supported(const K1Params& P, const K1Batch& B, int rows_per_warp) {
+  if (rows_per_warp < 1 || rows_per_warp > 32) return false;
+  const int n_warps = ((B.ens.W >> 1) + rows_per_warp - 1) / rows_per_warp;
+  if (!B.ens.pos || B.ens.W < 2 || n_warps * 32 > KC_THREADS || coop_basic_checks(P, B)) return false;
   const bool ext = P.cfg.ga_free_ebv != 0 || P.cfg.radio != 0 || P.cfg.bb_mode >= 2;
-  const int n_warps = ((B.ens.W >> 1) + 31) / 32;
   const CoopPlan C = ext ? make_plan<true>(P, true, n_warps) : make_plan<false>(P, true, n_warps);
   // warp 0's partial-sum area doubles as the key buffer of the per-step split
   const int64_t key_bytes = 4 * (int64_t)split_scratch_words(B.ens.W);
-  return (size_t)C.smem_bytes + (size_t)B.ens.W * (P.cfg.n_par + 1) * 8 + (size_t)n_warps * 32 * P.fam[0].pitch * 8 <=
+  return (size_t)C.smem_bytes + (size_t)B.ens.W * (P.cfg.n_par + 1) * 8 + 32 + (size_t)B.ens.W * 2 + KC_TASK_BYTES +
+                 (size_t)n_warps * 32 * P.fam[0].pitch * 8 <=
              200 * 1024 && key_bytes <= (int64_t)C.q_off * 8;
 }
 
@@ -506,9 +527,9 @@ cudaError_t launch_persist_bb(const K1Params& P, const K1Batch& B, const K1Persi
 
 unsigned long long k1_coop_prof_read(int i) {
 #ifdef KC_PROF
-  unsigned long long h[8] = {0};
+  unsigned long long h[12] = {0};
   cudaMemcpyFromSymbol(h, kc_prof, sizeof(h));
-  return (i >= 0 && i < 8) ? h[i] : 0;
+  return (i >= 0 && i < 12) ? h[i] : 0;
 #else
   (void)i;
   return 0;

@@ -177,7 +177,8 @@ struct K1Persist {
   int32_t track_best = 0;           // 0 off, 1 every step, 2 thinned steps
   uint32_t* hist = nullptr;         // [S, n_par, n_bins] or nullptr
   const double2* pbox = nullptr;    // [S, n_par]
-  int32_t n_bins = 0, pad = 0;
+  int32_t n_bins = 0;
+  int32_t rows_per_warp = 32;       // walkers of a half-ensemble per warp (1..32): fewer rows, more warps, shorter steps
   double* best_pos = nullptr;       // [S, n_par]
   double* best_lnp = nullptr;       // [S]
   double* chain = nullptr;          // recording buffer [cap, S, W, n_par] or nullptr
@@ -219,7 +220,7 @@ bool k1_coop_profitable(const K1Params& P, const K1Batch& B);   // false: the pe
 cudaError_t launch_k1_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream);
 // persistent per-source sampler; B.ens describes the ensemble, B.n is ignored
 unsigned long long k1_coop_prof_read(int i);     // -DKC_PROF builds only (else 0)
-bool k1_coop_persist_supported(const K1Params& P, const K1Batch& B);
+bool k1_coop_persist_supported(const K1Params& P, const K1Batch& B, int rows_per_warp = 32);
 cudaError_t launch_k1_coop_persist(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream);
 // eb0[z, t] for the galaxy family (see K1Params::eb0), chunk sums in the order the kernel used to add them
 cudaError_t launch_k1_eb0(const K1Params& P, double* eb0, cudaStream_t stream);

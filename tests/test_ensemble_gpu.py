@@ -402,9 +402,12 @@ def test_persistent_sampler_equals_lock_step(case):
     rng = np.random.default_rng(8)
     pos0 = src.pmin[:, None, :] + rng.uniform(size=(src.S, W, ms.n_par)) * (src.pmax - src.pmin)[:, None, :]
     got = {}
-    for persist in (1, 0):
+    # (persist, walkers per warp): automatic (ceil(H / 8): eight warps share a half-step), 32 (one warp per 32 rows)
+    # and an uneven cut (3: the last warp owns a single row)
+    for persist, rows in ((1, 0), (1, 32), (1, 3), (0, 0)):
         eng.set_sources(src)
         eng.set_option("ens_persist", persist)
+        eng.set_option("ens_persist_rows", rows)
         ens = EnsembleSampler(eng, W, seed=31, n_bins=128)
         ens.set_positions(pos0)
         ens.run(7, track_best=True)
@@ -412,11 +415,15 @@ def test_persistent_sampler_equals_lock_step(case):
         ens.run(25, hist_every=5, track_best='thinned')
         assert eng.get_option("ens_last_persist") == persist
         ens.run(1)
-        got[persist] = (ens.state(), ens.best(), ens.percentiles(), ens.chain())
-    a, b = got[1], got[0]
-    for x, y in zip(a[0], b[0]):
-        assert np.array_equal(x, y, equal_nan=True)
-    assert np.array_equal(a[1][0], b[1][0]) and np.array_equal(a[1][1], b[1][1])
-    assert np.array_equal(a[2], b[2], equal_nan=True)
-    assert a[3][0].shape[2] == 9 and np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1], b[3][1], equal_nan=True)
+        got[(persist, rows)] = (ens.state(), ens.best(), ens.percentiles(), ens.chain())
+    eng.set_option("ens_persist_rows", 0)
+    b = got[(0, 0)]
+    for key in ((1, 0), (1, 32), (1, 3)):
+        a = got[key]
+        for x, y in zip(a[0], b[0]):
+            assert np.array_equal(x, y, equal_nan=True), key
+        assert np.array_equal(a[1][0], b[1][0]) and np.array_equal(a[1][1], b[1][1]), key
+        assert np.array_equal(a[2], b[2], equal_nan=True), key
+        assert a[3][0].shape[2] == 9 and np.array_equal(a[3][0], b[3][0]), key
+        assert np.array_equal(a[3][1], b[3][1], equal_nan=True), key
     assert a[0][2].sum() > 0

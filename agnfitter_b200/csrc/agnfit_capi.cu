@@ -48,6 +48,7 @@ struct agnf_ctx {
   int k1_variant = 1;                          // 1: automatic (the cooperative kernel when profitable, else
                                                // per-thread); 0: per-thread kernel; 2: cooperative whenever
                                                // supported; 3: gather4 (TMA) kernel whenever supported
+  int coop_line = 1;                           // cooperative kernel: line form of the band phase (0: pair form; 2: forced)
   int last_k1_kernel = -1;                     // which kernel the last K1 launch used (0 / 1 cooperative / 2 gather4)
 
   bool have_cfg = false;
@@ -725,6 +726,13 @@ AGNF_API int agnf_set_option(agnf_ctx* ctx, const char* name, int64_t value) {
     ctx->k1_variant = (int)value;
     return 0;
   }
+  if (strcmp(name, "coop_line") == 0) {
+    if (value < 0 || value > 2)
+      return fail(ctx, "coop_line must be 0 (pair form), 1 (line form where it is the faster one) or 2 (line form wherever it runs)");
+    ctx->coop_line = (int)value;
+    ctx->k1.coop_line = ctx->coop_line;
+    return 0;
+  }
   if (strcmp(name, "ens_source_offset") == 0) {
     if (value < 0) return fail(ctx, "ens_source_offset must be >= 0");
     ctx->ens_src_offset = value;
@@ -797,6 +805,7 @@ AGNF_API int agnf_get_option(agnf_ctx* ctx, const char* name, int64_t* value) {
   if (!ctx || !name || !value) return 1;
   if (strcmp(name, "k1_variant") == 0) *value = ctx->k1_variant;
   else if (strcmp(name, "k1_last_kernel") == 0) *value = ctx->last_k1_kernel;
+  else if (strcmp(name, "coop_line") == 0) *value = ctx->coop_line;
   else if (strcmp(name, "k1_table_bytes") == 0) *value = ctx->k1.stage2_bytes;
   else if (strcmp(name, "k1_table_cells") == 0) *value = ctx->snap_cells;
   else if (strcmp(name, "k1_table_crowded_cells") == 0) *value = ctx->snap_crowded;
@@ -899,6 +908,7 @@ AGNF_API int agnf_modelset_config(agnf_ctx* ctx, const agnf_config* cfg) {
   const int n_norm = 3 + (cfg->bbb_has_norm ? 1 : 0) + (cfg->radio ? 1 : 0);
   ctx->k1.norm_offset = cfg->n_par - n_norm;
   ctx->k1.nbp = (cfg->n_b + 1) & ~1;
+  ctx->k1.coop_line = ctx->coop_line;
   // log(1 / (sqrt(2 pi) sigma)) as PRIORS_AGNfitter.py:429 writes it, in host libm
   ctx->k1.lognorm_s2 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 2.0));
   ctx->k1.lognorm_s15 = std::log(1.0 / (std::sqrt(2.0 * 3.141592653589793) * 1.5));

@@ -64,6 +64,14 @@ struct CoopPlan {
   int32_t walkers_off;    // persistent sampler: bytes from the start of shared memory to the source's walkers
 };
 
+// The line form of the band phase (k1_coop_tile.inc) wants at least one full group of eight chunks per row.  It is the
+// default where it is the faster one -- the 18-band sets with their unrolled instantiation (C3: 1.36 -> 1.19 ms per
+// 1e7 rows, free-E(B-V) galaxies 0.449 -> 0.424 ms per 2e6); on the 49-band sets (three groups + 1 chunk, runtime
+// trip counts) the pair form stays 1-6 % ahead.  coop_line = 2 forces it wherever it can run (tests).
+inline bool coop_line_ok(const K1Params& P) {
+  return P.nbp >= 16 && (P.coop_line == 2 || (P.coop_line == 1 && P.nbp / 2 == 9));
+}
+
 template <bool EXT>
 CoopPlan make_plan(const K1Params& P, bool ens, int n_warps = KC_WARPS) {
   CoopPlan c;
@@ -135,7 +143,8 @@ __device__ __forceinline__ void persist_hist(const double* pos, int W, int n_par
 // ENS: fused stretch-move launch (propose -> ln_probab -> accept), see K1Ensemble
 // MINB: CTAs per SM the register allocation is sized for (3: 80 registers; 2: 128, for shapes whose per-warp tiles
 // leave room for two CTAs anyway)
-template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS, int MINB>
+// LINE: the line form of the band phase (eight lanes per 128 bytes of a row, k1_coop_tile.inc)
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS, int MINB, bool LINE>
 __global__ void __launch_bounds__(KC_THREADS, MINB)
 k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPlan C) {
   constexpr bool PERSIST = false;
@@ -191,7 +200,7 @@ k1_coop_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPl
 // The persistent per-source sampler (ensemble mode): one CTA per source runs `A.n_steps` whole stretch-move steps — both
 // half-steps, the per-step split, best tracking, histograms and chain recording — inside ONE launch (see K1Persist).
 // The source's walkers and log-posteriors live in shared memory for the whole launch.
-template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool LINE>
 __global__ void __launch_bounds__(KC_THREADS, 2)
 k1_coop_persist_kernel(const __grid_constant__ K1Params P, const K1Batch B, const CoopPlan C, const K1Persist A) {
   constexpr bool ENS = true, PERSIST = true;
@@ -312,9 +321,9 @@ k1_coop_persist_kernel(const __grid_constant__ K1Params P, const K1Batch B, cons
   for (int e = threadIdx.x; e < p_W; e += blockDim.x) B.ens.lnp[p_src * p_W + e] = my_lnp[e];
 }
 
-template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS, int MINB>
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool ENS, int MINB, bool LINE>
 cudaError_t launch_coop_ens(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
-  auto kern = k1_coop_kernel<GA_FREE, BB_MODE, RADIO, CPR_T, ENS, MINB>;
+  auto kern = k1_coop_kernel<GA_FREE, BB_MODE, RADIO, CPR_T, ENS, MINB, LINE>;
   const CoopPlan C = make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, B.ens.pos != nullptr);
   static int attr_bytes[64] = {0};   // per instantiation and device
   int dev = 0;
@@ -333,9 +342,9 @@ cudaError_t launch_coop_ens(const K1Params& P, const K1Batch& B, cudaStream_t st
 inline int persist_warps(int W, int rows_per_warp) { return ((W >> 1) + rows_per_warp - 1) / rows_per_warp; }
 
 // the persistent per-source sampler: one CTA of ceil(W/2 / rows_per_warp) warps per source
-template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool LINE>
 cudaError_t launch_coop_persist(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream) {
-  auto kern = k1_coop_persist_kernel<GA_FREE, BB_MODE, RADIO, CPR_T>;
+  auto kern = k1_coop_persist_kernel<GA_FREE, BB_MODE, RADIO, CPR_T, LINE>;
   const int n_warps = persist_warps(B.ens.W, A.rows_per_warp);
   CoopPlan C = make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, true, n_warps);
   C.smem_bytes += (B.ens.W * (P.cfg.n_par + 1) * 8 + 15) & ~15;          // the source's walkers + log-posteriors
@@ -362,27 +371,41 @@ constexpr bool TU_ENS = true;
 constexpr bool TU_ENS = false;
 #endif
 
-template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T>
+template <bool GA_FREE, int BB_MODE, bool RADIO, int CPR_T, bool LINE>
 cudaError_t launch_coop_cpr(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
-  if (CPR_T == 0) {
+  const size_t smem = (size_t)make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, B.ens.pos != nullptr).smem_bytes;
+  if constexpr (LINE && !TU_ENS && CPR_T != 0) {
+    // The line form leaves the L1 data pipe unsaturated, so resident warps are what it runs on: four CTAs of 64
+    // registers (32 warps per SM) beat three of 80 when they fit the 196 KB carve-out (C3: 1.28 -> 1.19 ms per 1e7
+    // rows).  The fused stretch-move instantiations carry their proposal rows and stay at three.
+    if (4 * (smem + 1024) <= 196 * 1024) return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, 4, LINE>(P, B, stream);
+  }
+  if constexpr (CPR_T == 0) {
     // Three CTAs of this shape on an SM only if they fit the 196 KB shared-memory carve-out: at the next step (228 KB)
     // the L1 keeps 28 KB and the gathers of the small families miss (measured on the 49-band set: 0.81 ms per 2e6
     // rows with three CTAs of 80 registers, 0.70 ms with two of 114)
-    const size_t smem = (size_t)make_plan<(GA_FREE || RADIO || BB_MODE >= 2)>(P, B.ens.pos != nullptr).smem_bytes;
 #ifndef KC_FORCE_MINB3
-    if (3 * (smem + 1024) > 196 * 1024) return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, 2>(P, B, stream);
+    if (3 * (smem + 1024) > 196 * 1024) return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, 2, LINE>(P, B, stream);
 #endif
   }
-  return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, KC_MINBLOCKS>(P, B, stream);
+  return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, KC_MINBLOCKS, LINE>(P, B, stream);
 }
 
-// the default 18-band set has a fully unrolled instantiation; every other band count runs the
-// runtime-trip-count instantiation
+// the default 18-band set has fully unrolled instantiations; every other band count runs a runtime-trip-count one
 template <bool GA_FREE, int BB_MODE, bool RADIO>
 cudaError_t launch_coop(const K1Params& P, const K1Batch& B, cudaStream_t stream) {
+  const bool line = coop_line_ok(P);
   switch (P.nbp / 2) {
-    case 9: return launch_coop_cpr<GA_FREE, BB_MODE, RADIO, 9>(P, B, stream);
-    default: return launch_coop_cpr<GA_FREE, BB_MODE, RADIO, 0>(P, B, stream);
+    case 9:
+      if (line) return launch_coop_cpr<GA_FREE, BB_MODE, RADIO, 9, true>(P, B, stream);
+#ifdef KC_KEEP_PAIR9      // the unrolled pair form of round 1 (A/B builds; the runtime-trip-count one serves otherwise)
+      return launch_coop_cpr<GA_FREE, BB_MODE, RADIO, 9, false>(P, B, stream);
+#else
+      return launch_coop_cpr<GA_FREE, BB_MODE, RADIO, 0, false>(P, B, stream);
+#endif
+    default:
+      if (line) return launch_coop_cpr<GA_FREE, BB_MODE, RADIO, 0, true>(P, B, stream);
+      return launch_coop_cpr<GA_FREE, BB_MODE, RADIO, 0, false>(P, B, stream);
   }
 }
 
@@ -511,18 +534,24 @@ cudaError_t launch_exp10_fast(const double* x, double* y, int64_t n, cudaStream_
 
 template <bool GA_FREE, bool RADIO>
 cudaError_t launch_persist_bb(const K1Params& P, const K1Batch& B, const K1Persist& A, cudaStream_t stream) {
+  const bool line = coop_line_ok(P);
   const bool c9 = P.nbp / 2 == 9;
+#define PERSIST_GO(BB) \
+  (line ? (c9 ? launch_coop_persist<GA_FREE, BB, RADIO, 9, true>(P, B, A, stream) : launch_coop_persist<GA_FREE, BB, RADIO, 0, true>(P, B, A, stream)) \
+        : launch_coop_persist<GA_FREE, BB, RADIO, 0, false>(P, B, A, stream))
 #ifdef KC_DEV
   if (GA_FREE || RADIO || P.cfg.bb_mode != 1) return cudaErrorNotSupported;
-  return c9 ? launch_coop_persist<false, 1, false, 9>(P, B, A, stream) : launch_coop_persist<false, 1, false, 0>(P, B, A, stream);
+  return line ? (c9 ? launch_coop_persist<false, 1, false, 9, true>(P, B, A, stream) : launch_coop_persist<false, 1, false, 0, true>(P, B, A, stream))
+              : launch_coop_persist<false, 1, false, 0, false>(P, B, A, stream);
 #else
   switch (P.cfg.bb_mode) {
-    case 0: return c9 ? launch_coop_persist<GA_FREE, 0, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 0, RADIO, 0>(P, B, A, stream);
-    case 1: return c9 ? launch_coop_persist<GA_FREE, 1, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 1, RADIO, 0>(P, B, A, stream);
-    case 2: return c9 ? launch_coop_persist<GA_FREE, 2, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 2, RADIO, 0>(P, B, A, stream);
-    default: return c9 ? launch_coop_persist<GA_FREE, 3, RADIO, 9>(P, B, A, stream) : launch_coop_persist<GA_FREE, 3, RADIO, 0>(P, B, A, stream);
+    case 0: return PERSIST_GO(0);
+    case 1: return PERSIST_GO(1);
+    case 2: return PERSIST_GO(2);
+    default: return PERSIST_GO(3);
   }
 #endif
+#undef PERSIST_GO
 }
 
 unsigned long long k1_coop_prof_read(int i) {

@@ -40,6 +40,11 @@ __device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
   asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(a), "d"(v) : "memory");
 }
+// Store without the compiler-level memory barrier: for values nobody reads before the next __syncwarp() (the band
+// phase's partial sums), so that the loads of the following pass may be scheduled above it.
+__device__ __forceinline__ void sts_f64_nb(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(a), "d"(v));
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
 }

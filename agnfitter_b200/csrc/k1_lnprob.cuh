@@ -104,7 +104,8 @@ struct K1Params {
   int32_t n_grid_vals;        // total grid values
   int32_t norm_offset;        // column of GA in a params row
   int32_t nbp;                // pitch of every library-owned per-band array: n_b rounded up to even
-  int32_t pad0;
+  int32_t coop_line;          // cooperative kernel: band phase in line form (k1_coop_tile.inc) -- 1: where it is the
+                              // faster one (k1_coop.cu::coop_line_ok), 2: wherever it runs, 0: never (pair form)
   const double* grid_sorted;  // [n_grid_vals]  (per-thread kernel)
   const int32_t* grid_perm;   // [n_grid_vals]
   // cooperative kernel: one blob a CTA pulls into shared memory with a single bulk copy:

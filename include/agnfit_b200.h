@@ -147,6 +147,9 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
  * 2 = cooperative whenever the preconditions hold; 0 = per-thread K1 kernel (no preconditions).
  * agnf_get_option also answers "k1_last_kernel" (which kernel the last K1 launch ran: 1 / 0, -1 none)
  * and "band_pitch" (n_b rounded up to even: the pitch to ask agnf_dict_build for).
+ * "coop_line" (default 1): band phase of the cooperative kernel in line form (eight lanes per 128 bytes of one
+ * evaluation's row, per-source operands cached in registers) where that is the faster mapping (18-band sets);
+ * 2 = wherever it can run (>= 16 bands); 0 = round 1's lane-per-chunk pair form.  Same results bit for bit.
  * "pipeline_rows" (default 2^20): agnf_lnprob_batch with only lnp requested cuts batches larger than
  * this into chunks whose upload / kernel / download overlap on three streams; 0 = one shot.
  * "small_rows" (default 4096): batches of at most this many rows (what emcee / ultranest send per call) go
@@ -161,6 +164,10 @@ AGNF_API int agnf_lnprob_batch_device(agnf_ctx* ctx, const double* d_params, con
  * "ens_fused" (default 1): agnf_ens_run issues one fused launch per half-step (the cooperative K1 kernel
  * draws the proposal, evaluates it and applies the acceptance rule in place); 0 = separate propose / K1 /
  * accept kernels (same chain, bit for bit).
+ * "ens_persist" (default -1): one launch per agnf_ens_run call, one CTA per source, for shards of <= 1184 sources
+ * (1: whenever possible, 0: never); "ens_persist_rows" (default 0 = automatic): walkers of a half-ensemble per warp of
+ * that kernel (1..32) -- fewer rows per warp shorten a step (one source: 25 -> 16 us), more CTAs per SM serve larger
+ * shards.  Same chain bit for bit whatever the cut.
  * "ens_source_offset" (default 0): catalogue row of the first uploaded source; it is added to the source index
  * in the sampler's Philox counter, so a shard of a catalogue draws what a single-GPU run draws for the same
  * sources (results do not depend on how the catalogue is split over GPUs). */

@@ -47,6 +47,30 @@ def test_k1_matches_reference_golden(case, variant):
     assert np.array_equal(fast[ok], lnp[ok])
 
 
+@pytest.mark.parametrize("case", K1_CASES)
+def test_k1_line_form_equals_pair_form(case):
+    """The cooperative kernel's two band-phase mappings (`coop_line` 2: eight lanes per 128 bytes of a row, per-source
+    operands cached in registers -- forced here, the default takes it for the 18-band sets only; 0: round 1's
+    lane-per-chunk pair form) evaluate the same arithmetic per (row, chunk):
+    every output is the same bit for bit, in batches that mix sources inside a warp and end in a ragged tile."""
+    ms, g = load_k1(case)
+    eng, src = _engine(ms, g, 2)
+    rng = np.random.default_rng(4242)
+    n = 7013
+    sid = rng.integers(src.S, size=n).astype(np.int32)          # unsorted: the cached operands change row by row
+    pars = src.pmin[sid] + rng.uniform(-0.01, 1.01, size=(n, ms.n_par)) * (src.pmax[sid] - src.pmin[sid])
+    pars = np.concatenate([pars, g["pars"]])
+    sid = np.concatenate([sid, g["source_id"].astype(np.int32)])
+    got = {}
+    for line in (2, 0):
+        eng.set_option("coop_line", line)
+        got[line] = eng.lnprob(pars, sid, detail=True) + (eng.lnprob(pars, sid),)
+        assert eng.get_option("k1_last_kernel") == 1
+    eng.set_option("coop_line", 1)
+    for a, b in zip(got[2], got[0]):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
 @pytest.mark.parametrize("case", ["classic18", "freeebv_xray49", "radio4_sn12_49"])
 def test_k1_matches_oracle_on_fresh_positions(case):
     ms, g = load_k1(case)

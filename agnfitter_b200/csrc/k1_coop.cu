@@ -36,6 +36,9 @@ namespace {
 #ifndef KC_MINBLOCKS
 #define KC_MINBLOCKS 3
 #endif
+#ifndef KC_LINE_MINB
+#define KC_LINE_MINB 4      // CTAs per SM of the plain line-form launch
+#endif
 #ifndef KC_SNAP_GROUP
 #define KC_SNAP_GROUP 2
 #endif
@@ -378,7 +381,8 @@ cudaError_t launch_coop_cpr(const K1Params& P, const K1Batch& B, cudaStream_t st
     // The line form leaves the L1 data pipe unsaturated, so resident warps are what it runs on: four CTAs of 64
     // registers (32 warps per SM) beat three of 80 when they fit the 196 KB carve-out (C3: 1.28 -> 1.19 ms per 1e7
     // rows).  The fused stretch-move instantiations carry their proposal rows and stay at three.
-    if (4 * (smem + 1024) <= 196 * 1024) return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, 4, LINE>(P, B, stream);
+    if (KC_LINE_MINB * (smem + 1024) <= 196 * 1024)
+      return launch_coop_ens<GA_FREE, BB_MODE, RADIO, CPR_T, TU_ENS, KC_LINE_MINB, LINE>(P, B, stream);
   }
   if constexpr (CPR_T == 0) {
     // Three CTAs of this shape on an SM only if they fit the 196 KB shared-memory carve-out: at the next step (228 KB)

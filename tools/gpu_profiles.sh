@@ -4,13 +4,16 @@ mkdir -p gpurun_out
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_coop_kernel --launch-skip 4 -c 1 -f -o gpurun_out/k1_r02_coop_full python tools/k1_target.py plain --steps 3 > gpurun_out/ncu_plain.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_coop_kernel --launch-skip 14 -c 1 -f -o gpurun_out/k1_r02_ens_full python tools/k1_target.py ens --steps 3 > gpurun_out/ncu_ens.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:k2_contract_mma -c 1 -f -o gpurun_out/k2_r02_mma_full python tools/k2_wall.py > gpurun_out/ncu_k2.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:k3_split_kernel --launch-skip 3 -c 1 -f -o gpurun_out/k3_r02_split_full python tools/k1_target.py ens --steps 3 > gpurun_out/ncu_k3split.log 2>&1
+python tools/ncu_summary.py gpurun_out/k3_r02_split_full.ncu-rep gpurun_out/k3_r02_split_ncu.md > /dev/null 2>&1
+rm -f gpurun_out/k3_r02_split_full.ncu-rep
 timeout 600 ncu --set full --clock-control none -k regex:k3_select_kernel -c 1 -f -o gpurun_out/k3_r02_select_full python -m pytest tests/test_ensemble_gpu.py -q -m gpu -k exact_percentiles_match > gpurun_out/ncu_k3.log 2>&1
 python tools/ncu_summary.py gpurun_out/k1_r02_coop_full.ncu-rep gpurun_out/k1_r02_coop_ncu.md --traffic k1_coop_kernel 10000000 > /dev/null 2>&1
-cp profiles/k1_traffic.json gpurun_out/k1_traffic.json 2>/dev/null
-python tools/ncu_l1.py gpurun_out/k1_r02_coop_full.ncu-rep k1_coop_kernel 'ILb0ELi1ELb0ELi9ELb0ELi3' 1e7 > gpurun_out/k1_r02_coop_l1.txt 2>&1
-python tools/ncu_lines.py gpurun_out/k1_r02_coop_full.ncu-rep k1_coop_kernel 'ILb0ELi1ELb0ELi9ELb0ELi3' > gpurun_out/k1_r02_coop_lines.txt 2>&1
+python tools/ncu_l1.py gpurun_out/k1_r02_coop_full.ncu-rep k1_coop_kernel 'ILb0ELi1ELb0ELi9ELb0ELi4ELb1' 1e7 > gpurun_out/k1_r02_coop_l1.txt 2>&1
+python tools/ncu_lines.py gpurun_out/k1_r02_coop_full.ncu-rep k1_coop_kernel 'ILb0ELi1ELb0ELi9ELb0ELi4ELb1' > gpurun_out/k1_r02_coop_lines.txt 2>&1
 python tools/ncu_summary.py gpurun_out/k1_r02_ens_full.ncu-rep gpurun_out/k1_r02_ens_ncu.md > /dev/null 2>&1
-python tools/ncu_l1.py gpurun_out/k1_r02_ens_full.ncu-rep k1_coop_kernel 'ILb0ELi1ELb0ELi9ELb1ELi3' 5e6 > gpurun_out/k1_r02_ens_l1.txt 2>&1
+python tools/ncu_lines.py gpurun_out/k1_r02_ens_full.ncu-rep k1_coop_kernel 'ILb0ELi1ELb0ELi9ELb1ELi3ELb1' > gpurun_out/k1_r02_ens_lines.txt 2>&1
+python tools/ncu_l1.py gpurun_out/k1_r02_ens_full.ncu-rep k1_coop_kernel 'ILb0ELi1ELb0ELi9ELb1ELi3ELb1' 5e6 > gpurun_out/k1_r02_ens_l1.txt 2>&1
 python tools/ncu_summary.py gpurun_out/k2_r02_mma_full.ncu-rep gpurun_out/k2_r02_mma_ncu.md > /dev/null 2>&1
 python tools/ncu_summary.py gpurun_out/k3_r02_select_full.ncu-rep gpurun_out/k3_r02_select_ncu.md > /dev/null 2>&1
 rm -f gpurun_out/k1_r02_ens_full.ncu-rep

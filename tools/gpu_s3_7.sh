@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
+echo "main lib (4 CTAs):"; timeout 300 python tools/k1_target.py plain --steps 2000 2>&1 | grep -v Warn | tail -1
 export AGNFIT_B200_LIB=$PWD/build_alt/libagnfit_b200.so
-timeout 600 python tools/line_check.py --ens > gpurun_out/s3_line.txt 2>&1
-grep -v Warn gpurun_out/s3_line.txt | tail -8
+echo "3 CTAs:"; timeout 300 python tools/k1_target.py plain --steps 2000 2>&1 | grep -v Warn | tail -1
+timeout 300 python tools/k1_target.py plain --steps 2000 --opt coop_line=0 2>&1 | grep -v Warn | tail -1

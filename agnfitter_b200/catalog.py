@@ -41,7 +41,7 @@ def build_modelset_on_device(templates, filterdict, z_grid, settings, builder):
         if kf.ndim == 1:
             kf = kf[None, :]
         fitted = not (short == "RAD" and keys == ['-99.9'])
-        tab = builder.build_family(fam["F"], z_grid, on_device=True)
+        tab = builder.build_family(fam["F"], z_grid, on_device=True, reuse_staging=True)
         aux = None if fam.get("aux") is None else np.array([float(fam["aux"][k]) for k in keys])
         if short == "GA" and 'free' in fam["types"]:
             aux = None
@@ -124,10 +124,12 @@ def fit_catalog(templates, filterdict, settings, z, dlum, nus, fluxes, fluxerrs,
             memory_budget_bytes = 0.6 * free
         bounds = _chunk_bounds(zs_all, per_source, per_slice, float(memory_budget_bytes), max_sources_per_chunk)
         chunks = []
+        staging = {}      # the grouped, pinned template blocks, shared by the chunks' builders (DictBuilder.build_family)
         for c0, c1 in zip(bounds[:-1], bounds[1:]):
             sel = mine[c0:c1]
             zs = z[sel]
             builder = DictBuilder(filterdict, device=device)
+            builder._tpl_cache = staging
             ms, dev = build_modelset_on_device(templates, filterdict, np.unique(zs), settings, builder)
             eng = Engine(ms, device=device, ctx=builder.ctx, device_tables=dev)
             src = _sources.make_sources(ms, zs, dlum[sel], nus if nus.ndim == 1 else nus[sel],

@@ -192,7 +192,8 @@ def build_modelset(templates, filterdict, z_grid, builder, settings=CLASSIC_SETT
         arr = np.array(keys)
         kf = arr.T.astype(float)
         t0 = time.perf_counter()
-        tab = builder.build_family(fam["F"], z_grid, on_device=on_device)     # synchronous (the ctx stream is drained)
+        tab = builder.build_family(fam["F"], z_grid, on_device=on_device,      # synchronous (the ctx stream is drained)
+                                   reuse_staging=True)
         builder.k2_wall_s = getattr(builder, "k2_wall_s", 0.0) + time.perf_counter() - t0
         builder.k2_contract_ms = getattr(builder, "k2_contract_ms", 0.0) + builder.contract_ms
         aux = None if fam["aux"] is None else np.array([fam["aux"][k] for k in keys])

@@ -942,7 +942,8 @@ def run_ours(args):
                                  "modelset_wall_s": info["modelset_wall_s"],
                                  "what": "DictBuilder.build_family over every family and every distinct z of the shard: "
                                          "template dictionaries in NumPy -> band-flux tables in HBM; wall time incl. "
-                                         "host preparation, uploads, helper kernels, second build of the process "
+                                         "host preparation, uploads, helper kernels, second build of the process (the grouped, pinned "
+                                         "template blocks of the first are reused, as fit_catalog does from chunk to chunk) "
                                          "(first_build_wall_s: the first, which also allocates the pinned staging "
                                          "block, the scratch pool and the output; modelset_wall_s adds the parsing "
                                          "of the key strings into snapping grids)",

@@ -190,3 +190,30 @@ def test_k2_full_dense_zgrid_is_slice_independent():
         got = dense[zi, ti].cpu().numpy()
         assert np.array_equal(got == 0.0, want == 0.0)
         assert_close_with_specials(got, want, what="z=%g t=%d" % (z[zi], ti))
+
+
+def test_k2_staged_templates_are_reused_and_revalidated():
+    """build_family(reuse_staging=True) keeps the grouped, pinned template blocks of a family and reuses them when the
+    same dict comes again (catalogue chunks, rebuilds for other redshifts): same tables bit for bit, for ragged
+    families too; a dict whose values changed is staged afresh."""
+    g = load_k2("default18")
+    builder = DictBuilder(_filterdict(g), device=0)
+    fams = [str(x) for x in g["family_names"]]
+    ragged = {}
+    for fam in fams[:3]:                                  # three families merged: several frequency grids in one dict
+        for i in range(g[fam + "_ref"].shape[1]):
+            n = int(g[fam + "_len"][i])
+            ragged[(fam, i)] = (g[fam + "_lognu"][i, :n], g[fam + "_Fnu"][i, :n])
+    for tpl in (ragged, {k: v for k, v in list(ragged.items())[:7]}):
+        want = builder.build_family(tpl, g["z"])
+        first = builder.build_family(tpl, g["z"], reuse_staging=True)
+        staged = builder._tpl_cache[id(tpl)][2]
+        again = builder.build_family(tpl, g["z"][::-1].copy(), reuse_staging=True)[::-1]
+        assert builder._tpl_cache[id(tpl)][2] is staged, "the second call must reuse the staged blocks"
+        assert np.array_equal(first, want, equal_nan=True) and np.array_equal(again, want, equal_nan=True)
+        k0 = next(iter(tpl))
+        tpl[k0] = (tpl[k0][0], tpl[k0][1] * 2.0)            # a new value tuple: the cache entry no longer matches
+        doubled = builder.build_family(tpl, g["z"], reuse_staging=True)
+        assert builder._tpl_cache[id(tpl)][2] is not staged
+        assert np.array_equal(doubled, builder.build_family(tpl, g["z"]), equal_nan=True)
+        assert not np.array_equal(doubled[:, 0], want[:, 0])

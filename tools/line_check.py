@@ -1,5 +1,6 @@
-"""A/B of the cooperative K1 kernel's pair form (band pitch 2) and line form (band pitch 16: rows on their own 128-byte lines) on bench.py's
-C3 workload: bit equality of lnp on the same rows, then launch times (plain and fused ensemble).
+"""A/B of the two band-phase mappings of the cooperative K1 kernel (option coop_line: 0 pair form, 1 line form where it
+is the default, 2 line form forced) on bench.py's workloads: bit equality of lnp on the same rows, then launch times
+(plain and, with --ens, the fused ensemble step).
 
     python tools/line_check.py [--sources N] [--bands 49] [--c4] [--ga-free]
 """
@@ -9,7 +10,6 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import bench
-from agnfitter_b200 import engine as _engine
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--sources", type=int, default=100000)
@@ -26,8 +26,7 @@ a.scaling, a.no_sort_z = "weak", False
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev)
 ref = None
-for mult, quads in ((2, (0, 1)),):
-    _engine.BAND_PITCH_MULT = mult
+for quads in ((0, 1, 2),):
     eng, ms, dev_tables, raw, pars, sid, info = bench.make_workload(a, 0, 0)
     n = len(pars)
     d_p = torch.from_numpy(pars).to(dev)
@@ -50,8 +49,8 @@ for mult, quads in ((2, (0, 1)),):
         if ref is None:
             ref = out
         same = np.array_equal(ref, out, equal_nan=True)
-        msg = "pitch mult %d line %d: plain %.4f ms per %d rows = %.4g evals/s  identical to the pair form: %s" % (
-            mult, q, t, n, n / t * 1e3, same)
+        msg = "coop_line %d: plain %.4f ms per %d rows = %.4g evals/s  identical to the pair form: %s" % (
+            q, t, n, n / t * 1e3, same)
         if a.ens:
             from agnfitter_b200.ensemble import EnsembleSampler
             ens = EnsembleSampler(eng, a.walkers, seed=20260101, n_bins=256)

@@ -126,9 +126,12 @@ def test_random_modelsets_match_the_oracle(seed):
     src = sources.make_sources(ms, z, dlum, nus, fl, fe)
     rng = np.random.default_rng(seed)
     n_per = 1500
-    for variant in (3, 2, 0):
+    # (kernel, band-phase mapping of the cooperative kernel): gather4, cooperative with the line form forced wherever it
+    # can run (>= 16 bands; the default takes it for the 18-band sets only), cooperative pair form, per-thread
+    for variant, line in ((3, 1), (2, 2), (2, 0), (0, 1)):
         eng = Engine(ms, device=0)
         eng.set_option("k1_variant", variant)
+        eng.set_option("coop_line", line)
         eng.set_sources(src)
         for s in range(src.S):
             pars = _positions(np.random.default_rng(seed * 10 + s), ms, src.pmin[s], src.pmax[s], n_per)
@@ -138,7 +141,7 @@ def test_random_modelsets_match_the_oracle(seed):
             osrc = dict(z=float(z[s]), dlum=float(dlum[s]), nus=nus, fluxes=fl[s], fluxerrs=fe[s], pmin=src.pmin[s],
                         pmax=src.pmax[s], zi=zi)
             o_lnp, o_ym, o_rows, o_lpr, o_lll = O.ln_probab(ms, osrc, pars, return_parts=True)
-            tag = "seed %d variant %d n_b %d" % (seed, variant, ms.n_b)
+            tag = "seed %d variant %d line %d n_b %d" % (seed, variant, line, ms.n_b)
             assert np.array_equal(rows, o_rows), tag
             assert_close_with_specials(ym, o_ym, what="ymodel " + tag)
             assert_close_with_specials(lll, o_lll, what="lnlike " + tag)

@@ -3,7 +3,7 @@
 # use with AGNFIT_B200_LIB=build_alt/libagnfit_b200.so.  Extra nvcc flags: $EXTRA.
 set -e
 cd "$(dirname "$0")/../agnfitter_b200/csrc"
-OUT=../../build_alt
+OUT=${OUT:-../../build_alt}
 mkdir -p $OUT
 F="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $EXTRA"
 nvcc $F -Xptxas -v -DKC_DEV -c k1_coop.cu -o $OUT/k1_coop.o > $OUT/k1_coop.log 2>&1 &

@@ -17,6 +17,11 @@ __device__ __forceinline__ int4 lds_v4s32(uint32_t a) {
   asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
 }
+__device__ __forceinline__ int2 lds_v2s32(uint32_t a) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ int lds_s32(uint32_t a) {
   int v;
   asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a));

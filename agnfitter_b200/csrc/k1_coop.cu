@@ -7,18 +7,19 @@
 //            contiguous params rows.  Each thread box-tests its row, snaps every family (decision
 //            table, k1_dev.cuh::snap_fast), evaluates the normalisations 10^x, leaves a 10- or
 //            14-double record in shared memory and prefetches its galaxy-template row into L2.
-//   phase 2  lane-per-chunk.  The 32 x nbp tile of band values is cut into 16-byte chunks
-//            (2 bands); chunk c = e * nbp/2 + k goes to lane c % 32 of iteration c / 32, so the
-//            nbp/2 iterations keep all 32 lanes busy and consecutive lanes read consecutive
-//            chunks of the same template row: each 144-byte row costs 2 L1 wavefronts (the
-//            per-thread kernel pays 9).  A lane fetches its evaluation's record (LDS.128,
-//            conflict-free: record strides 10 and 14 doubles map 8 consecutive evaluations to
-//            disjoint banks), gathers one double2 per family plus y, 1/sigma and the reddening
-//            coefficients, forms the model flux of its two bands and their masked chi^2 terms,
-//            and stores the partial sum to shared memory.
+//   phase 2  band phase, lanes over the 16-byte chunks (2 bands) of the warp's 32 x nbp tile.  A lane
+//            fetches its evaluation's hand-off record, gathers one double2 per family plus y, 1/sigma
+//            and the reddening coefficients, forms the model flux of its two bands and their masked
+//            chi^2 terms, and stores the partial sum to shared memory.  Two lane mappings, same
+//            arithmetic per (row, chunk), same results bit for bit (k1_coop_tile.inc):
+//            line form (default for the 18-band sets): eight lanes take eight consecutive chunks of
+//            ONE row, four rows per pass -- a quarter-warp's gather stays inside one row (1-2 lines) and
+//            the lane's chunk is fixed, so the per-source operands stay in registers;
+//            pair form: chunk c = e * nbp/2 + k goes to lane c % 32 of iteration c / 32.
 //   phase 3  thread-per-evaluation again: sums its nbp/2 partials in band order (deterministic),
-//            re-reads the two band values prior_AGNfraction needs (L1 hits), evaluates the
-//            priors and writes lnP.
+//            re-reads the two band values prior_AGNfraction needs (L1 hits) and -- line form -- its own
+//            record (normalisations, E(B-V), row offsets: cheaper than carrying them in registers
+//            through phase 2), evaluates the priors and writes lnP.
 //
 // Only __syncwarp() separates the phases; the CTA synchronises once, to publish the mbarriers.
 #include "k1_lnprob.cuh"

@@ -92,7 +92,7 @@ def load_dictionary_cache(md, settings):
         first = next(iter(md.GALAXYFdict.values()))
         ok = np.array_equal(np.asarray(first[0], dtype=np.float64), ms.bands)
     import json
-    ok = ok and json.loads(json.dumps(dict(settings))) == ms.settings
+    ok = ok and json.loads(json.dumps(dict(settings), default=str)) == ms.settings
     return ms if ok else None
 
 

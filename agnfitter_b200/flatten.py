@@ -255,7 +255,7 @@ def modelset_from_modelsdicts(mds, settings):
 # ----------------------------------------------------------------------------
 def modelset_to_arrays(ms: ModelSet, prefix=""):
     import json
-    out = {prefix + "settings_json": np.array(json.dumps(ms.settings)),
+    out = {prefix + "settings_json": np.array(json.dumps(ms.settings, default=str)),      # odd values as their str()
            prefix + "bands": ms.bands, prefix + "z_grid": ms.z_grid,
            prefix + "family_names": np.array([f.name for f in ms.families])}
     for f in ms.families:
